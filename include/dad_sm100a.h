@@ -1,0 +1,180 @@
+/* libdad_sm100a.so -- C ABI of the B200 (sm_100a) DAD training-step kernels.
+ *
+ * The reference (TMZZ22331/Robust-Speech-Emotion-Recognition-via-Dynamic-Asymmetric-Distillation-in-Noisy-Environments)
+ * is pure Python/PyTorch and has no FFI of its own; each entry point below replaces the ATen call
+ * sequence of the cited reference lines.  I/ = IEMOCAP/DAD-train-IEMOCAP/ (the CASIA / EMODB copies are identical
+ * on this path except where noted).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller (outputs and workspace
+ *    included); nothing is allocated, freed or retained by the library;
+ *  - every op enqueues on `stream` (a cudaStream_t passed as void*), never synchronises the host and is CUDA-graph
+ *    capturable; state that advances (DACP thresholds, Adam moments, step counter, parameters) is updated in place;
+ *  - return value 0 = ok, negative = error (dad_last_error() holds a thread-local message); nothing throws or aborts;
+ *  - workspaces must be zero-initialised once when allocated (they hold self-resetting arrival counters);
+ *    use a separate workspace per concurrently-running op;
+ *  - fp32 tensors are contiguous row-major and 16-byte aligned; D = 768, H = 256, C = 4 are compile-time widths
+ *    (I/config.py:54-55,48).
+ */
+#ifndef DAD_SM100A_H
+#define DAD_SM100A_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAD_ABI_VERSION 1
+#define DAD_D 768
+#define DAD_H 256
+#define DAD_C 4
+#define DAD_NPARAM 197892 /* flat parameter buffer: [W 256x768 | b 256 | Wc 4x256 | bc 4] */
+
+/* GEMM arithmetic of the encoder kernels */
+#define DAD_GEMM_FP32 0      /* CUDA-core fp32 FMA: exact path, any B,T */
+#define DAD_GEMM_TC_BF16X3 1 /* tcgen05 (5th-gen tensor core, TMEM accumulators) bf16 hi/lo split, 3 products, fp32 accumulate */
+
+int dad_abi_version(void);
+const char* dad_last_error(void);
+/* 0 when the current CUDA device is compute capability 10.x, else an error */
+int dad_device_check(void);
+
+/* ---- augmentation parameters (I/utils.py:317-375 DataAugmentation) ------------------------------------------- */
+typedef struct dad_aug {
+    int32_t mode;       /* 0 none, 1 weak (noise only), 2 strong (noise + feature keep + temporal span) */
+    int32_t noise_src;  /* 0 = supplied `noise` tensor (parity mode, bit-exact), 1 = in-kernel Philox4x32-10 + Box-Muller */
+    const float* noise; /* [B,T,D] unit normal draws (noise_src 0) */
+    uint64_t seed;      /* Philox key (noise_src 1) */
+    uint64_t stream;    /* Philox stream id: weak and strong views use different streams */
+    float sigma;        /* WEAK_NOISE_STD / STRONG_NOISE_STD: out = x + (n*sigma), two fp32 roundings */
+    const float* feat_keep;  /* [D] 0/1 multiplier shared by the whole batch, no rescale (I/utils.py:343-344); NULL = none */
+    const int32_t* t_start;  /* [B] temporal span starts (I/utils.py:371); NULL = none */
+    int32_t mask_len;        /* int(T_padded * TEMPORAL_MASK_RATIO) (I/utils.py:366); rows [s, s+len) := +0 */
+    const int64_t* step_ptr; /* nullable device counter mixed into the Philox key, so a replayed CUDA graph draws fresh noise
+                                every step while the forward and backward kernels of one step regenerate identical noise */
+} dad_aug;
+
+/* per-step device-side draws for the throughput mode (replaces the host RNG calls of I/model.py:62 nn.Dropout x2,
+ * I/utils.py:343 torch.rand(D) and I/utils.py:371 B x torch.randint): keep_* [B,H] 0/1 with P(keep)=1-p_drop,
+ * feat_keep [D] 0/1 with P(keep)=1-feat_rate, t_start [B] uniform in [0, max(1, T-mask_len+1)).  Any output may be NULL. */
+int dad_step_rng(uint64_t seed, const int64_t* step_ptr, float* keep_clean, float* keep_strong, int64_t B, float p_drop,
+                 float* feat_keep, float feat_rate, int32_t* t_start, int64_t T, int32_t mask_len, void* stream);
+
+/* replaces DataAugmentation.weak_augment / strong_augment (I/utils.py:328-375): out[B,T,D] = aug(x) */
+int dad_augment(const float* x, float* out, const dad_aug* aug, int64_t B, int64_t T, void* stream);
+
+/* ---- encoder (I/model.py:18-41 Emotion2VecEncoder.forward) and its autograd backward ------------------------- */
+size_t dad_encoder_fwd_workspace_bytes(int64_t B, int64_t T, int32_t gemm_mode);
+/* emb[B,H] = masked-mean_t relu(W aug(x)[b,t,:] + bias).  pad: [B,T] uint8, 1 = padded frame, NULL = none.
+ * relu_bits (nullable): [B*T, H/32] uint32, bit j of word w of frame n = (pre[n, 32w+j] > 0) -- all the backward needs.
+ * lens (nullable): [B] valid length clamped to >= 1 (I/model.py:36).  W_hi/W_lo: bf16 [H,D] splits (TC mode only). */
+int dad_encoder_fwd(const float* x, const uint8_t* pad, const float* W, const float* bias, const void* W_hi,
+                    const void* W_lo, const dad_aug* aug, float* emb, uint32_t* relu_bits, float* lens, void* ws,
+                    size_t ws_bytes, int64_t B, int64_t T, int32_t gemm_mode, void* stream);
+
+int32_t dad_encoder_bwd_splits(int64_t B, int64_t T, int32_t gemm_mode);
+/* split-K partials: dW_part[splits, H, D], db_part[splits, H]; dad_grad_reduce sums them in fixed order.
+ * g_emb[B,H] = dL/d emb; x / pad / aug identical to the forward call (the augmented view is regenerated). */
+int dad_encoder_bwd(const float* x, const uint8_t* pad, const dad_aug* aug, const uint32_t* relu_bits,
+                    const float* g_emb, const float* lens, float* dW_part, float* db_part, int32_t splits, void* ws,
+                    size_t ws_bytes, int64_t B, int64_t T, int32_t gemm_mode, void* stream);
+size_t dad_encoder_bwd_workspace_bytes(int64_t B, int64_t T, int32_t gemm_mode);
+
+/* ---- the per-step exchange buffer ("pack"): what the single all-gather of the data-parallel step moves ------- *
+ * per rank, 4-byte words: [emb_clean B_local*H f32][emb_strong B_local*H f32][score B_local f32][pred B_local i32][label B_local i32] */
+typedef struct dad_pack {
+    float* base;      /* world * dad_pack_rank_words(B_local) words */
+    int32_t B_local;
+    int32_t world;
+} dad_pack;
+int64_t dad_pack_rank_words(int32_t B_local);
+
+/* ---- classifier heads + CE + teacher certainty (I/model.py:54-64, I/train.py:399-400,408-410,439-440, I/utils.py:400-428) */
+typedef struct dad_head_fwd_args {
+    dad_pack pack;
+    int32_t rank, B_local, noisy, use_entropy;
+    const float* emb_teacher;              /* [B_local,H] teacher embedding of the weak view (noisy != 0) */
+    const float *Wc, *bc, *tWc, *tbc;      /* student / teacher classifier [C,H],[C] */
+    const float *keep_clean, *keep_strong; /* [B_local,H] dropout keep masks (0/1) or NULL (eval, p = 0) */
+    float drop_scale;                      /* fl32(1/(1-p)) (ATen dropout: x * (keep / (1-p))) */
+    float label_smoothing, inv_B_global;
+    float *dz_clean, *probs, *logq;        /* out [B_local,C]: dCE/dlogits (/B_global), teacher probs, student log-probs */
+    float* ce_part;                        /* out [dad_head_grid(B_local)] per-CTA CE sums */
+} dad_head_fwd_args;
+int32_t dad_head_grid(int32_t B_local);
+int dad_head_fwd(const dad_head_fwd_args* a, void* stream);
+
+/* ---- DACP (I/utils.py:449-507 DACPManager.calculate_mask; fixed-threshold branch I/train.py:417-420) ---------- */
+typedef struct dad_dacp_args {
+    dad_pack pack;
+    int32_t use_dacp, npow2_;              /* npow2_: filled by the library */
+    float gamma;                           /* fl32(q_start + (q_end-q_start)*epoch/EPOCHS) */
+    float sens_k, calib_lambda, alpha, one_minus_alpha, fixed_thr;
+    const float* quality;                  /* [C] class_quality_scores Q (state, read) */
+    const float* anchors;                  /* [C] calibrated anchors */
+    float* ema_thr;                        /* [C] ema_thresholds (state, updated in place when use_dacp) */
+    uint8_t* mask;                         /* out [B_global] */
+    float *out_w, *out_thr;                /* out [C] class weights W_c, thresholds applied */
+    int32_t* out_nmask;                    /* out [1] number of masked-in samples */
+    double* epoch_sum;                     /* [C] state: running per-class score sums of the epoch (I/utils.py:503-505) */
+    int64_t* epoch_cnt;                    /* [C] */
+} dad_dacp_args;
+int dad_dacp_mask(const dad_dacp_args* a, void* stream);
+
+/* ---- KD + head backward (I/train.py:444-447 and autograd through I/model.py:62-63) ---------------------------- */
+typedef struct dad_head_bwd_args {
+    dad_pack pack;
+    int32_t rank, B_local, noisy, n_ce_part;
+    const float* Wc;
+    const float *keep_clean, *keep_strong;
+    float drop_scale, w_kd, inv_B_global;
+    const float *dz_clean, *probs, *logq, *ce_part;
+    const uint8_t* mask;                   /* [B_global] */
+    const int32_t* nmask;                  /* [1] */
+    float *g_clean, *g_strong;             /* out [B_local,H] dL/d emb (head part; dad_ecda accumulates on top) */
+    float *dWc, *dbc;                      /* out [C,H],[C] */
+    float* part;                           /* workspace [dad_head_grid, C*H+C+1] */
+    float* loss_out;                       /* out [0] CE share, [1] KD share of this rank (shares sum to the global loss) */
+    uint32_t* counter;                     /* [1] zero-initialised arrival counter */
+} dad_head_bwd_args;
+int dad_head_bwd(const dad_head_bwd_args* a, void* stream);
+
+/* ---- ECDA forward+backward (I/utils.py:510-652 ECDALoss; gate I/train.py:444,450) ----------------------------- */
+typedef struct dad_ecda_args {
+    dad_pack pack;
+    int32_t rank, class_aware;             /* class_aware 0 = global-MMD ablation (I/utils.py:633-650) */
+    const uint8_t* mask;                   /* [B_global] */
+    const int32_t* nmask;                  /* [1]; ECDA runs only if > 1 */
+    const float* w_class;                  /* [C] DACP class weights (ones for the fixed-threshold path) */
+    float lambda_cls, gamma_comp, delta_rep, w_ecda;
+    float *g_clean, *g_strong;             /* [B_local,H] accumulated: += w_ecda * dECDA/d emb for the rows this rank owns */
+    float* loss_out;                       /* out [2] = this rank's share of the (unweighted) ECDA loss */
+    void* ws;
+    size_t ws_bytes;
+} dad_ecda_args;
+size_t dad_ecda_workspace_bytes(int32_t B_local, int32_t world);
+int dad_ecda(const dad_ecda_args* a, void* stream);
+
+/* ---- optimiser tail (I/train.py:487-492; I/model.py:211-223) --------------------------------------------------- */
+/* g[DAD_NPARAM] = fixed-order sum of the encoder split-K partials (up to two backward launches) ++ head grads */
+int dad_grad_reduce(const float* dW_part0, const float* db_part0, int32_t splits0, const float* dW_part1,
+                    const float* db_part1, int32_t splits1, const float* dWc, const float* dbc, float* g, void* stream);
+/* global L2 norm -> scal[0] norm, [1] clip coef (max_norm <= 0: no clipping), [2] lr/(1-b1^t), [3] sqrt(1-b2^t); ++*step */
+int dad_grad_norm(const float* g, double* part_ws /*[128]*/, uint32_t* counter, int64_t* step, const double* lr,
+                  float* scal, float max_norm, void* stream);
+/* clip -> Adam (betas .9/.999, eps 1e-8, coupled L2 wd) -> EMA teacher (do_ema) -> bf16 hi/lo splits of W, teacher W (nullable).
+ * loss_src (nullable) = [CE, KD, ECDA] of this step: loss_last[4] = {total, CE, KD, ECDA}, loss_acc[5] += {.., 1}
+ * (device-side replacement of the per-step .item() reads of I/train.py:494-495; total = CE + w_kd KD + w_ecda ECDA). */
+int dad_adam_ema(float* p, float* t, float* m, float* v, const float* g, const float* scal, float wd, float ema_m,
+                 float ema_1m, int32_t do_ema, void* s_hi, void* s_lo, void* t_hi, void* t_lo, const float* loss_src,
+                 float* loss_last, double* loss_acc, float w_kd, float w_ecda, void* stream);
+/* SSRLModel.update_teacher_ema on a flat buffer: t = t*m + s*(1-m) (two muls + add, no FMA) */
+int dad_ema(float* t, const float* s, float ema_m, float ema_1m, int64_t n, void* stream);
+/* bf16 hi/lo split of an fp32 weight matrix: hi = bf16(w), lo = bf16(w - hi) */
+int dad_split_bf16(const float* w, void* hi, void* lo, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAD_SM100A_H */

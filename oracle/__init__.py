@@ -1,0 +1,5 @@
+"""CPU oracle of the DAD training step -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this package.  The product package never does: it fails loudly when the CUDA library is missing.
+"""

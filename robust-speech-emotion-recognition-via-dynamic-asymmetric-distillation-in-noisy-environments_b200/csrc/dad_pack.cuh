@@ -1,0 +1,64 @@
+// The per-step exchange buffer ("pack") and kernel argument blocks shared between the .cu files.
+//
+// Pack layout, one block per rank, ranks concatenated (this is exactly what the single NCCL all-gather of the
+// data-parallel step moves; world == 1 on one GPU).  Per rank, in 4-byte words:
+//   [ emb_clean : B_local*256 f32 ][ emb_strong : B_local*256 f32 ][ score : B_local f32 ][ pred : B_local i32 ][ label : B_local i32 ]
+// Global sample index gi = rank*B_local + i.
+#pragma once
+#include "dad_common.cuh"
+
+typedef dad_pack Pack;
+__host__ __device__ __forceinline__ int64_t pack_rank_words(int B_local) { return (int64_t)B_local * (2 * DAD_H + 3); }
+__device__ __forceinline__ float* pack_rank_base(const Pack& p, int gi, int& i) {
+    const int r = gi / p.B_local;
+    i = gi - r * p.B_local;
+    return p.base + (int64_t)r * pack_rank_words(p.B_local);
+}
+__device__ __forceinline__ float* pack_emb_clean(const Pack& p, int gi) { int i; float* b = pack_rank_base(p, gi, i); return b + (int64_t)i * DAD_H; }
+__device__ __forceinline__ float* pack_emb_strong(const Pack& p, int gi) { int i; float* b = pack_rank_base(p, gi, i); return b + (int64_t)(p.B_local + i) * DAD_H; }
+__device__ __forceinline__ float& pack_score(const Pack& p, int gi) { int i; float* b = pack_rank_base(p, gi, i); return b[(int64_t)2 * p.B_local * DAD_H + i]; }
+__device__ __forceinline__ int& pack_pred(const Pack& p, int gi) { int i; float* b = pack_rank_base(p, gi, i); return reinterpret_cast<int*>(b)[(int64_t)2 * p.B_local * DAD_H + p.B_local + i]; }
+__device__ __forceinline__ int& pack_label(const Pack& p, int gi) { int i; float* b = pack_rank_base(p, gi, i); return reinterpret_cast<int*>(b)[(int64_t)2 * p.B_local * DAD_H + 2 * p.B_local + i]; }
+
+typedef dad_head_fwd_args HeadFwdArgs;
+typedef dad_dacp_args DacpArgs;
+typedef dad_head_bwd_args HeadBwdArgs;
+
+// ---- ECDA
+constexpr int ECDA_TR = 32;  // rows (members of one class) per CTA tile
+constexpr int ECDA_MAXC = 4;
+struct EcdaTile { int cls, row_begin, row_count, feasible; };
+
+struct EcdaStats {  // written by k_ecda_prep's last CTA, read by k_ecda_pairs
+    int n_s[ECDA_MAXC], n_t[ECDA_MAXC], feasible[ECDA_MAXC], list_off[ECDA_MAXC];
+    float inv_beta[ECDA_MAXC][5];                             // 1/(bw*2^r + 1e-8)
+    float c_ss[ECDA_MAXC], c_tt[ECDA_MAXC], c_st[ECDA_MAXC];  // 1/(D_ss+1e-8), 1/(D_tt+1e-8), 1/(D_st+1e-8)
+    float att[ECDA_MAXC];                                     // class attention a_c
+    float comp[ECDA_MAXC];                                    // compactness per class
+    float rep;                                                // repulsion loss (<= 0)
+    float rho;                                                // delta * sum_{feasible} a_c
+    int n_tiles, any_feasible, n_classes, active;
+};
+
+struct EcdaArgs {
+    Pack pack;
+    int rank, class_aware;  // class_aware 0 -> global-MMD ablation (I/utils.py:633-650)
+    const uint8_t* mask;    // [B_global]
+    const int* nmask;       // [1] (gate: > 1, I/train.py:444)
+    const float* w_class;   // [4] W_c from DACP (ones for the fixed-threshold path)
+    float lambda_cls, gamma_comp, delta_rep, w_ecda;
+    // workspace
+    float* part_vec;        // [G][8][256]
+    double* part_sc;        // [G][8][2]  (sq-norm sum, weight sum)
+    int* part_cnt;          // [G][8]
+    EcdaStats* stats;
+    int* lists;             // [2*B_global] member lists; per class: clean members then noisy members (row ids: clean gi, noisy B_global+gi)
+    EcdaTile* tiles;        // [max_tiles]
+    float* mu_t;            // [4][256] noisy centroids
+    float* rep_grad;        // [4][256] rho * d rep / d z_i for noisy members of class c
+    float* tile_sums;       // [max_tiles][3]
+    float *g_clean, *g_strong;  // [B_local,256], accumulated (+=)
+    float* loss_out;        // [2] = ecda loss share, [3] = full-batch ecda loss when world == 1
+    unsigned* counter;      // [2] zero-initialised, self-resetting
+    int max_tiles, prep_grid;
+};

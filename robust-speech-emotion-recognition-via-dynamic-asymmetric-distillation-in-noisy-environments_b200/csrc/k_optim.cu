@@ -1,0 +1,154 @@
+// Optimiser tail as multi-tensor, bandwidth-bound kernels over ONE flat parameter buffer
+//   flat layout (fp32): [ W 256x768 | b 256 | Wc 4x256 | bc 4 ]  = 197 892 elements (student, teacher, m, v, grad)
+//   k_grad_reduce : fixed-order sum of the split-K dW/db partials of the two encoder backward launches + head grads
+//   k_grad_norm   : global L2 norm (fp64 partials, last CTA) -> clip coefficient, Adam step scalars (step counter on device)
+//   k_adam_ema    : clip * grad -> coupled-L2 Adam -> EMA teacher update, plus the bf16 hi/lo split of W and teacher W
+//                   that feeds the next step's tcgen05 encoder kernels.
+// Reference: I/train.py:487-492 (clip_grad_norm_, Adam.step), I/train.py:362 (Adam, wd 1e-5), I/model.py:211-223 (EMA).
+#include "dad_common.cuh"
+#include "dad_optim.cuh"
+#include <cuda_bf16.h>
+
+constexpr int NP_W = DAD_H * DAD_D;          // 196608
+constexpr int NP_B = DAD_H;                  // 256
+constexpr int NP_WC = DAD_C * DAD_H;         // 1024
+constexpr int NP_BC = DAD_C;                 // 4
+constexpr int NP = NP_W + NP_B + NP_WC + NP_BC;  // 197892
+constexpr int OPT_THREADS = 256;
+
+
+__global__ void __launch_bounds__(OPT_THREADS) k_grad_reduce(GradReduceArgs a) {
+    const int e = blockIdx.x * OPT_THREADS + threadIdx.x;
+    if (e >= NP) return;
+    float s = 0.f;
+    if (e < NP_W) {
+#pragma unroll
+        for (int l = 0; l < 2; ++l)
+            if (a.dWp[l])
+                for (int k = 0; k < a.splits[l]; ++k) s += __ldg(a.dWp[l] + (int64_t)k * NP_W + e);
+    } else if (e < NP_W + NP_B) {
+        const int h = e - NP_W;
+#pragma unroll
+        for (int l = 0; l < 2; ++l)
+            if (a.dbp[l])
+                for (int k = 0; k < a.splits[l]; ++k) s += __ldg(a.dbp[l] + (int64_t)k * NP_B + h);
+    } else if (e < NP_W + NP_B + NP_WC) {
+        s = a.dWc[e - NP_W - NP_B];
+    } else {
+        s = a.dbc[e - NP_W - NP_B - NP_WC];
+    }
+    a.g[e] = s;
+}
+
+
+__global__ void __launch_bounds__(OPT_THREADS) k_grad_norm(NormArgs a) {
+    __shared__ double s_red[OPT_THREADS / 32];
+    __shared__ int s_last;
+    double acc = 0.0;
+    for (int e = blockIdx.x * OPT_THREADS + threadIdx.x; e < NP; e += gridDim.x * OPT_THREADS) {
+        const double v = (double)a.g[e];
+        acc += v * v;
+    }
+    acc = warp_sum_d(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < OPT_THREADS / 32; ++w) t += s_red[w];
+        a.part[blockIdx.x] = t;
+        __threadfence();
+        const unsigned prev = atomicAdd(a.counter, 1u);
+        s_last = (prev == gridDim.x - 1u);
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    double tot = 0.0;
+    for (unsigned gI = 0; gI < gridDim.x; ++gI) tot += __ldcg(a.part + gI);
+    const float norm = (float)sqrt(tot);
+    float coef = 1.0f;
+    if (a.max_norm > 0.f) coef = fminf(a.max_norm / (norm + 1e-6f), 1.0f);  // clip_grad_norm_: clamp(max/(norm+1e-6), max=1)
+    const long long t = *a.step + 1;
+    *a.step = t;
+    const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
+    a.scal[0] = norm;
+    a.scal[1] = coef;
+    a.scal[2] = (float)(*a.lr / bc1);
+    a.scal[3] = (float)sqrt(bc2);
+    *a.counter = 0u;
+}
+
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__global__ void __launch_bounds__(OPT_THREADS) k_adam_ema(AdamArgs a) {
+    const int e = blockIdx.x * OPT_THREADS + threadIdx.x;
+    if (e >= NP) return;
+    if (e == 0 && a.loss_src) {  // device-side loss bookkeeping: no per-step host sync (replaces the .item() calls of I/train.py:494-495)
+        const float ce = a.loss_src[0], kd = a.loss_src[1], ec = a.loss_src[2];
+        const float tot = ce + a.w_kd * kd + a.w_ecda * ec;  // I/train.py:462-466
+        a.loss_last[0] = tot; a.loss_last[1] = ce; a.loss_last[2] = kd; a.loss_last[3] = ec;
+        a.loss_acc[0] += tot; a.loss_acc[1] += ce; a.loss_acc[2] += kd; a.loss_acc[3] += ec; a.loss_acc[4] += 1.0;
+    }
+    const float coef = a.scal[1], step_size = a.scal[2], bc2s = a.scal[3];
+    float p = a.p[e];
+    float g = a.g[e] * coef;                 // clip: g.mul_(coef)
+    g = fmaf(a.wd, p, g);                    // grad.add(param, alpha=wd)
+    float m = a.m[e], v = a.v[e];
+    m = m + 0.1f * (g - m);                  // exp_avg.lerp_(grad, 1-beta1)
+    v = v * 0.999f + 0.001f * g * g;         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+    const float denom = sqrtf(v) / bc2s + 1e-8f;
+    p = p - step_size * (m / denom);         // param.addcdiv_(exp_avg, denom, value=-step_size)
+    a.m[e] = m; a.v[e] = v; a.p[e] = p;
+    float t = a.t[e];
+    if (a.do_ema) {
+        t = __fadd_rn(__fmul_rn(t, a.ema_m), __fmul_rn(p, a.ema_1m));  // t*m + s*(1-m): two muls, one add (model.py:218-223)
+        a.t[e] = t;
+    }
+    if (e < NP_W && a.s_hi) {
+        split_bf16(p, reinterpret_cast<__nv_bfloat16*>(a.s_hi)[e], reinterpret_cast<__nv_bfloat16*>(a.s_lo)[e]);
+        split_bf16(t, reinterpret_cast<__nv_bfloat16*>(a.t_hi)[e], reinterpret_cast<__nv_bfloat16*>(a.t_lo)[e]);
+    }
+}
+
+// standalone EMA (SSRLModel.update_teacher_ema) and weight split (after loading weights)
+__global__ void __launch_bounds__(OPT_THREADS) k_ema(float* t, const float* s, float ema_m, float ema_1m, int n) {
+    const int e = blockIdx.x * OPT_THREADS + threadIdx.x;
+    if (e < n) t[e] = __fadd_rn(__fmul_rn(t[e], ema_m), __fmul_rn(s[e], ema_1m));
+}
+__global__ void __launch_bounds__(OPT_THREADS) k_split_bf16(const float* w, __nv_bfloat16* hi, __nv_bfloat16* lo, int n) {
+    const int e = blockIdx.x * OPT_THREADS + threadIdx.x;
+    if (e < n) split_bf16(w[e], hi[e], lo[e]);
+}
+
+int launch_grad_reduce(const GradReduceArgs& a, cudaStream_t st) {
+    k_grad_reduce<<<ceil_div(NP, OPT_THREADS), OPT_THREADS, 0, st>>>(a);
+    DAD_CHECK_LAUNCH("k_grad_reduce");
+    return DAD_OK;
+}
+constexpr int NORM_GRID = 96;
+int launch_grad_norm(const NormArgs& a, cudaStream_t st) {
+    k_grad_norm<<<NORM_GRID, OPT_THREADS, 0, st>>>(a);
+    DAD_CHECK_LAUNCH("k_grad_norm");
+    return DAD_OK;
+}
+int launch_adam_ema(const AdamArgs& a, cudaStream_t st) {
+    k_adam_ema<<<ceil_div(NP, OPT_THREADS), OPT_THREADS, 0, st>>>(a);
+    DAD_CHECK_LAUNCH("k_adam_ema");
+    return DAD_OK;
+}
+int launch_ema(float* t, const float* s, float ema_m, float ema_1m, int n, cudaStream_t st) {
+    if (n == 0) return DAD_OK;
+    k_ema<<<ceil_div(n, OPT_THREADS), OPT_THREADS, 0, st>>>(t, s, ema_m, ema_1m, n);
+    DAD_CHECK_LAUNCH("k_ema");
+    return DAD_OK;
+}
+int launch_split_bf16(const float* w, void* hi, void* lo, int n, cudaStream_t st) {
+    if (n == 0) return DAD_OK;
+    k_split_bf16<<<ceil_div(n, OPT_THREADS), OPT_THREADS, 0, st>>>(w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+    DAD_CHECK_LAUNCH("k_split_bf16");
+    return DAD_OK;
+}

@@ -1,0 +1,425 @@
+"""The fused DAD training step on one B200 (or one rank of a batch-sharded data-parallel job).
+
+One call of `DADStepEngine.step(epoch)` = the body of the reference's hot loop, I/train.py:484-492:
+    zero_grad -> train_step (I/train.py:397-471) -> backward -> clip_grad_norm_ -> Adam.step -> update_teacher_ema
+executed as ~15 hand-written sm_100a kernels through the C ABI, with no host synchronisation, no autograd tape and
+no [N,256] activation tensor; the sequence is captured once into a CUDA graph and replayed.
+
+Data layout in HBM (all fp32 unless noted; N = B_local*T):
+    x_clean / x_noisy [B,T,768]   inputs (static buffers, refreshed by set_inputs)          2 x N x 3072 B
+    relu bits         [N,8] u32   1 bit per (frame, hidden unit), clean + strong views       2 x N x 32 B
+    pack              [world, B*(2*256+3)]  emb_clean | emb_strong | score | pred | label    the all-gather payload
+    flat params x5    [197892]    student, teacher, Adam m, Adam v, grad (+8 loss words)      the all-reduce payload = grad
+    dW split-K partials [S,256,768] x2
+Under data parallelism (world > 1): one packed all-gather after the forwards, one all-reduce of the flat grad;
+DACP runs redundantly on the global batch, ECDA rows are sharded by owner rank (see csrc/k_ecda.cu)."""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (D_HID, D_IN, GEMM_FP32, GEMM_TC, N_CLS, NPARAM, OFF_B, OFF_BC, OFF_W, OFF_WC, Aug, DacpArgs, DadError,
+                   EcdaArgs, HeadBwdArgs, HeadFwdArgs, Pack, check, lib, make_aug, ptr)
+
+PARAM_KEYS = ("encoder.pre_net.weight", "encoder.pre_net.bias", "classifier.fc_layer.weight", "classifier.fc_layer.bias")
+_SLICES = ((OFF_W, OFF_B, (D_HID, D_IN)), (OFF_B, OFF_WC, (D_HID,)), (OFF_WC, OFF_BC, (N_CLS, D_HID)), (OFF_BC, NPARAM, (N_CLS,)))
+
+
+def _f32(x):
+    return float(np.float32(x))
+
+
+class StepScalars:
+    """Everything the step reads from cfg for a given epoch (read LIVE from the cfg module so the runners'
+    setattr-overrides are honoured, I/run_granular_ablations.py:25-44)."""
+
+    def __init__(self, cfg, epoch, dataset):
+        g = lambda k, d=None: getattr(cfg, k, d)
+        self.epoch = epoch
+        self.warmup = epoch < g("WARMUP_EPOCHS")
+        # loss-weight schedule (I/train.py:380-395)
+        if self.warmup:
+            self.w_kd, self.w_ecda = 0.0, 0.0
+        else:
+            if g("PROGRESSIVE_TRAINING"):
+                prog = min(1.0, (epoch - g("WARMUP_EPOCHS")) / g("WEIGHT_RAMP_EPOCHS"))
+                self.w_kd = g("INITIAL_CONSISTENCY_WEIGHT") + (g("FINAL_CONSISTENCY_WEIGHT") - g("INITIAL_CONSISTENCY_WEIGHT")) * prog
+            else:
+                self.w_kd = g("WEIGHT_CONSISTENCY")
+            self.w_ecda = g("WEIGHT_ECDA") * min(1.0, (epoch - g("ECDA_START_EPOCH")) / g("WEIGHT_RAMP_EPOCHS")) \
+                if epoch >= g("ECDA_START_EPOCH") else 0.0
+        emodb = dataset == "emodb"  # E/train_emodb.py:418-437 has no USE_DACP / USE_ECDA switches
+        iemocap = dataset == "iemocap"  # only I/utils.py honours USE_ENTROPY_IN_SCORE / USE_CLASS_AWARE_MMD
+        self.use_dacp = True if emodb else bool(g("USE_DACP", True))
+        self.use_ecda = (True if emodb else bool(g("USE_ECDA", True))) and self.w_ecda > 0
+        self.use_entropy = (bool(g("USE_ENTROPY_IN_SCORE", True)) if iemocap else True) if self.use_dacp else False
+        self.class_aware = bool(g("USE_CLASS_AWARE_MMD", True)) if iemocap else True
+        self.gamma = _f32(g("DACP_QUANTILE_START") + (g("DACP_QUANTILE_END") - g("DACP_QUANTILE_START")) * (epoch / g("EPOCHS")))
+        self.sens_k = _f32(g("DACP_SENSITIVITY_K"))
+        self.calib_lambda = _f32(g("DACP_CALIBRATION_STRENGTH_LAMBDA"))
+        self.alpha = _f32(g("DACP_THRESHOLD_SMOOTHING_ALPHA"))
+        self.one_minus_alpha = _f32(1 - g("DACP_THRESHOLD_SMOOTHING_ALPHA"))
+        self.fixed_thr = _f32(g("FIXED_CONFIDENCE_THRESHOLD", 0.9))
+        self.label_smoothing = _f32(g("LABEL_SMOOTHING_FACTOR")) if g("USE_LABEL_SMOOTHING") else 0.0
+        self.drop_p = float(g("DROPOUT_RATE"))
+        self.drop_scale = _f32(np.float32(1.0) / np.float32(1.0 - self.drop_p)) if self.drop_p > 0 else 1.0
+        self.weak_std, self.strong_std = _f32(g("WEAK_NOISE_STD")), _f32(g("STRONG_NOISE_STD"))
+        self.mask_ratio = float(g("TEMPORAL_MASK_RATIO"))
+        self.feat_rate = self.drop_p  # DataAugmentation(dropout_rate=None) -> cfg.DROPOUT_RATE (I/utils.py:325)
+        self.lambda_cls = _f32(g("ECDA_CLASS_ATTENTION_LAMBDA"))
+        self.gamma_comp = _f32(g("ECDA_COMPACTNESS_WEIGHT_GAMMA"))
+        self.delta_rep = _f32(g("ECDA_REPULSION_WEIGHT_DELTA"))
+        self.max_norm = _f32(g("MAX_GRAD_NORM")) if g("GRADIENT_CLIPPING") else -1.0
+        self.wd = _f32(g("WEIGHT_DECAY"))
+        self.ema_m, self.ema_1m = _f32(g("EMA_MOMENTUM")), _f32(1.0 - g("EMA_MOMENTUM"))
+
+    def key(self):
+        return tuple(sorted((k, v) for k, v in self.__dict__.items() if k != "epoch"))
+
+
+class DADStepEngine:
+    def __init__(self, cfg, B_local, T, device=None, dataset="iemocap", world=1, rank=0, process_group=None, gemm_mode=None,
+                 use_graph=True, seed=42, noise_mode="philox"):
+        _lib.require_device()
+        self.cfg, self.dataset = cfg, dataset
+        self.B, self.T = int(B_local), int(T)
+        self.world, self.rank, self.pg = int(world), int(rank), process_group
+        self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.gemm_mode = GEMM_FP32 if gemm_mode is None else gemm_mode
+        if self.gemm_mode == GEMM_TC and self.T < 32:
+            raise DadError("tcgen05 encoder path needs T >= 32; use gemm_mode=GEMM_FP32")
+        self.use_graph = use_graph
+        self.seed = int(seed)
+        if noise_mode not in ("philox", "supplied"):
+            raise DadError("noise_mode must be 'philox' or 'supplied'")
+        self.noise_mode = noise_mode
+        B, T, dev = self.B, self.T, self.dev
+        Bg = B * self.world
+        self.Bg = Bg
+        f32 = dict(dtype=torch.float32, device=dev)
+        z = lambda *s, **k: torch.zeros(*s, **({**f32, **k}))
+        # ---- parameters and optimiser state (flat)
+        self.p, self.t, self.m, self.v = z(NPARAM), z(NPARAM), z(NPARAM), z(NPARAM)
+        self.g_ext = z(NPARAM + 8)
+        self.hi_lo = torch.zeros(4, D_HID * D_IN, dtype=torch.bfloat16, device=dev)  # s_hi, s_lo, t_hi, t_lo
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.lr = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.scal = z(8)
+        self.loss_last = z(4)
+        self.loss_acc = torch.zeros(5, dtype=torch.float64, device=dev)
+        # ---- DACP state (I/utils.py:391-395)
+        self.quality = torch.full((N_CLS,), 0.5, **f32)
+        self.ema_thr = torch.full((N_CLS,), 0.5, **f32)
+        self.anchors = torch.full((N_CLS,), 0.05, **f32)
+        self.epoch_sum = torch.zeros(N_CLS, dtype=torch.float64, device=dev)
+        self.epoch_cnt = torch.zeros(N_CLS, dtype=torch.int64, device=dev)
+        # ---- inputs (static buffers)
+        self.x_clean, self.x_noisy = z(B, T, D_IN), z(B, T, D_IN)
+        self.pad_clean = torch.zeros(B, T, dtype=torch.uint8, device=dev)
+        self.pad_noisy = torch.zeros(B, T, dtype=torch.uint8, device=dev)
+        self.keep_clean, self.keep_strong = torch.ones(B, D_HID, **f32), torch.ones(B, D_HID, **f32)
+        self.feat_keep = torch.ones(D_IN, **f32)
+        self.t_start = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.n_weak = self.n_strong = None
+        if noise_mode == "supplied":
+            self.n_weak, self.n_strong = z(B, T, D_IN), z(B, T, D_IN)
+        # ---- activations / exchange
+        rw = _lib.pack_rank_words(B)
+        self.pack = z(self.world * rw)
+        self.pack_i32 = self.pack.view(torch.int32)
+        self._rw = rw
+        self.emb_teacher = z(B, D_HID)
+        self.bits_clean = torch.zeros(B * T, D_HID // 32, dtype=torch.int32, device=dev)
+        self.bits_strong = torch.zeros(B * T, D_HID // 32, dtype=torch.int32, device=dev)
+        self.lens_clean, self.lens_noisy, self.lens_scratch = z(B), z(B), z(B)
+        self.dz_clean, self.probs, self.logq = z(B, N_CLS), z(B, N_CLS), z(B, N_CLS)
+        self.n_head = lib().dad_head_grid(B)
+        self.ce_part = z(self.n_head)
+        self.mask = torch.zeros(Bg, dtype=torch.uint8, device=dev)
+        self.nmask = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.out_w, self.out_thr = torch.ones(N_CLS, **f32), z(N_CLS)
+        self.g_clean, self.g_strong = z(B, D_HID), z(B, D_HID)
+        self.dWc_dbc = z(N_CLS * D_HID + N_CLS)
+        self.head_part = z(self.n_head * (N_CLS * D_HID + N_CLS + 1))
+        self.counters = torch.zeros(16, dtype=torch.int32, device=dev)
+        self.norm_part = torch.zeros(128, dtype=torch.float64, device=dev)
+        self.ecda_ws = torch.zeros(lib().dad_ecda_workspace_bytes(B, self.world), dtype=torch.uint8, device=dev)
+        nb = max(lib().dad_encoder_fwd_workspace_bytes(B, T, self.gemm_mode), 256)
+        self.enc_ws = torch.zeros(nb, dtype=torch.uint8, device=dev)
+        self.bwd_ws = torch.zeros(max(lib().dad_encoder_bwd_workspace_bytes(B, T, self.gemm_mode), 256), dtype=torch.uint8, device=dev)
+        self.S = lib().dad_encoder_bwd_splits(B, T, self.gemm_mode)
+        self.dWp = z(2, self.S, D_HID * D_IN)
+        self.dbp = z(2, self.S, D_HID)
+        self._graphs = {}
+        self._scalars = None
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------ parameters
+    def views(self, flat):
+        return [flat[a:b].view(shape) for a, b, shape in _SLICES]
+
+    def load_state_dict(self, sd, reset_optimizer=True):
+        """sd: SSRLModel.state_dict() keys (student_*/teacher_*; teacher keys optional -> copy of the student)."""
+        with torch.no_grad():
+            for v, k in zip(self.views(self.p), PARAM_KEYS):
+                v.copy_(sd["student_" + k])
+            for v, k in zip(self.views(self.t), PARAM_KEYS):
+                v.copy_(sd["teacher_" + k] if ("teacher_" + k) in sd else sd["student_" + k])
+            if reset_optimizer:
+                self.m.zero_(); self.v.zero_(); self.step_count.zero_()
+        self.refresh_splits()
+
+    def state_dict(self):
+        out = {}
+        for prefix, flat in (("student_", self.p), ("teacher_", self.t)):
+            for v, k in zip(self.views(flat), PARAM_KEYS):
+                out[prefix + k] = v.detach().clone()
+        return out
+
+    def init_teacher(self):
+        """SSRLModel._init_teacher_network (I/model.py:200-209)."""
+        self.t.copy_(self.p)
+        self.refresh_splits()
+
+    def refresh_splits(self):
+        """bf16 hi/lo operand copies of W and teacher W for the tcgen05 path (kept current by the Adam kernel afterwards)."""
+        n = D_HID * D_IN
+        s = _lib.stream_ptr()
+        check(lib().dad_split_bf16(self.p.data_ptr(), self.hi_lo[0].data_ptr(), self.hi_lo[1].data_ptr(), n, s))
+        check(lib().dad_split_bf16(self.t.data_ptr(), self.hi_lo[2].data_ptr(), self.hi_lo[3].data_ptr(), n, s))
+
+    def set_lr(self, lr):
+        self.lr.fill_(float(lr))
+
+    # ------------------------------------------------------------------ inputs
+    def set_inputs(self, clean_batch, noisy_batch=None, rng=None):
+        """Copy one (clean, noisy) batch pair -- reference collator layout (I/dataload_clean.py:177-193) -- and, in the
+        supplied-noise mode, the step's RNG draws into the static device buffers."""
+        B, T = self.B, self.T
+        xc = clean_batch["net_input"]["feats"]
+        if tuple(xc.shape) != (B, T, D_IN):
+            raise DadError(f"clean feats {tuple(xc.shape)} != {(B, T, D_IN)} (engine is shape-specialised)")
+        self.x_clean.copy_(xc, non_blocking=True)
+        self.pad_clean.copy_(clean_batch["net_input"]["padding_mask"], non_blocking=True)
+        lab = self.pack_i32[self.rank * self._rw + 2 * B * D_HID + 2 * B: self.rank * self._rw + 2 * B * D_HID + 3 * B]
+        lab.copy_(clean_batch["labels"], non_blocking=True)
+        if noisy_batch is not None:
+            self.x_noisy.copy_(noisy_batch["net_input"]["feats"], non_blocking=True)
+            self.pad_noisy.copy_(noisy_batch["net_input"]["padding_mask"], non_blocking=True)
+        if rng is not None:
+            if self.noise_mode != "supplied":
+                raise DadError("rng inputs given but the engine was built with noise_mode='philox'")
+            drop_p = float(getattr(self.cfg, "DROPOUT_RATE"))
+            self.keep_clean.copy_(rng["drop_clean"], non_blocking=True)
+            self.keep_strong.copy_(rng["drop_strong"], non_blocking=True)
+            self.n_weak.copy_(rng["n_weak"], non_blocking=True)
+            self.n_strong.copy_(rng["n_strong"], non_blocking=True)
+            self.feat_keep.copy_((rng["feat_keep_u"] > drop_p).float(), non_blocking=True)
+            self.t_start.copy_(rng["t_start"], non_blocking=True)
+
+    # ------------------------------------------------------------------ the step
+    def _pack_struct(self):
+        return Pack(self.pack.data_ptr(), self.B, self.world)
+
+    def _aug(self, mode, sc):
+        if mode == 0:
+            return None
+        L = int(self.T * sc.mask_ratio)
+        supplied = self.noise_mode == "supplied"
+        if mode == 1:
+            return make_aug(1, noise=self.n_weak if supplied else None, sigma=sc.weak_std, seed=self.seed, stream=1,
+                            step_ptr=self.step_count.data_ptr())
+        return make_aug(2, noise=self.n_strong if supplied else None, sigma=sc.strong_std,
+                        feat_keep=self.feat_keep if sc.feat_rate > 0 else None,
+                        t_start=self.t_start if (sc.mask_ratio > 0 and L > 0) else None, mask_len=L, seed=self.seed, stream=2,
+                        step_ptr=self.step_count.data_ptr())
+
+    def _enc_fwd(self, x, pad, teacher, aug, emb_ptr, bits, lens, s):
+        flat = self.t if teacher else self.p
+        hi, lo = (self.hi_lo[2], self.hi_lo[3]) if teacher else (self.hi_lo[0], self.hi_lo[1])
+        check(lib().dad_encoder_fwd(x.data_ptr(), pad.data_ptr(), flat.data_ptr() + OFF_W * 4, flat.data_ptr() + OFF_B * 4,
+                                    hi.data_ptr(), lo.data_ptr(), C.byref(aug) if aug is not None else None, emb_ptr,
+                                    bits.data_ptr() if bits is not None else None, lens.data_ptr(), self.enc_ws.data_ptr(),
+                                    self.enc_ws.numel(), self.B, self.T, self.gemm_mode, s))
+        self.launches_per_step += 1
+
+    def _enc_bwd(self, x, pad, aug, bits, g, lens, slot, s):
+        check(lib().dad_encoder_bwd(x.data_ptr(), pad.data_ptr(), C.byref(aug) if aug is not None else None, bits.data_ptr(),
+                                    g.data_ptr(), lens.data_ptr(), self.dWp[slot].data_ptr(), self.dbp[slot].data_ptr(), self.S,
+                                    self.bwd_ws.data_ptr(), self.bwd_ws.numel(), self.B, self.T, self.gemm_mode, s))
+        self.launches_per_step += 1
+
+    def _enqueue(self, sc):
+        """Enqueue one full step on the current stream (eager or under graph capture)."""
+        L = lib()
+        s = _lib.stream_ptr()
+        B, T = self.B, self.T
+        self.launches_per_step = 0
+        pk = self._pack_struct()
+        rbase = self.pack.data_ptr() + self.rank * self._rw * 4
+        emb_clean_ptr, emb_strong_ptr = rbase, rbase + B * D_HID * 4
+        noisy = not sc.warmup
+        philox = self.noise_mode == "philox"
+        inv_Bg = _f32(1.0 / self.Bg)
+        drop = sc.drop_p > 0
+        if philox and (drop or noisy):
+            Lm = int(T * sc.mask_ratio)
+            check(L.dad_step_rng(self.seed, self.step_count.data_ptr(), self.keep_clean.data_ptr() if drop else None,
+                                 self.keep_strong.data_ptr() if (drop and noisy) else None, B, sc.drop_p,
+                                 self.feat_keep.data_ptr() if noisy else None, sc.feat_rate,
+                                 self.t_start.data_ptr() if noisy else None, T, Lm, s))
+            self.launches_per_step += 1
+        # ---- forwards (I/train.py:399, 409, 439)
+        self._enc_fwd(self.x_clean, self.pad_clean, False, None, emb_clean_ptr, self.bits_clean, self.lens_clean, s)
+        aug_w = aug_s = None
+        if noisy:
+            aug_w, aug_s = self._aug(1, sc), self._aug(2, sc)
+            self._enc_fwd(self.x_noisy, self.pad_noisy, True, aug_w, self.emb_teacher.data_ptr(), None, self.lens_scratch, s)
+            self._enc_fwd(self.x_noisy, self.pad_noisy, False, aug_s, emb_strong_ptr, self.bits_strong, self.lens_noisy, s)
+        # ---- heads
+        hf = HeadFwdArgs()
+        hf.pack, hf.rank, hf.B_local, hf.noisy, hf.use_entropy = pk, self.rank, B, int(noisy), int(sc.use_entropy)
+        hf.emb_teacher = self.emb_teacher.data_ptr()
+        hf.Wc, hf.bc = self.p.data_ptr() + OFF_WC * 4, self.p.data_ptr() + OFF_BC * 4
+        hf.tWc, hf.tbc = self.t.data_ptr() + OFF_WC * 4, self.t.data_ptr() + OFF_BC * 4
+        hf.keep_clean = self.keep_clean.data_ptr() if drop else None
+        hf.keep_strong = self.keep_strong.data_ptr() if drop else None
+        hf.drop_scale, hf.label_smoothing, hf.inv_B_global = sc.drop_scale, sc.label_smoothing, inv_Bg
+        hf.dz_clean, hf.probs, hf.logq, hf.ce_part = (self.dz_clean.data_ptr(), self.probs.data_ptr(), self.logq.data_ptr(),
+                                                      self.ce_part.data_ptr())
+        check(L.dad_head_fwd(C.byref(hf), s))
+        self.launches_per_step += 1
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.pack, self.pack[self.rank * self._rw:(self.rank + 1) * self._rw], group=self.pg)
+        if noisy:
+            da = DacpArgs()
+            da.pack, da.use_dacp = pk, int(sc.use_dacp)
+            da.gamma, da.sens_k, da.calib_lambda, da.alpha, da.one_minus_alpha, da.fixed_thr = (
+                sc.gamma, sc.sens_k, sc.calib_lambda, sc.alpha, sc.one_minus_alpha, sc.fixed_thr)
+            da.quality, da.anchors, da.ema_thr = self.quality.data_ptr(), self.anchors.data_ptr(), self.ema_thr.data_ptr()
+            da.mask, da.out_w, da.out_thr, da.out_nmask = (self.mask.data_ptr(), self.out_w.data_ptr(), self.out_thr.data_ptr(),
+                                                            self.nmask.data_ptr())
+            da.epoch_sum, da.epoch_cnt = self.epoch_sum.data_ptr(), self.epoch_cnt.data_ptr()
+            check(L.dad_dacp_mask(C.byref(da), s))
+            self.launches_per_step += 1
+        hb = HeadBwdArgs()
+        hb.pack, hb.rank, hb.B_local, hb.noisy, hb.n_ce_part = pk, self.rank, B, int(noisy), self.n_head
+        hb.Wc = self.p.data_ptr() + OFF_WC * 4
+        hb.keep_clean, hb.keep_strong = hf.keep_clean, hf.keep_strong
+        hb.drop_scale, hb.w_kd, hb.inv_B_global = sc.drop_scale, _f32(sc.w_kd), inv_Bg
+        hb.dz_clean, hb.probs, hb.logq, hb.ce_part = hf.dz_clean, hf.probs, hf.logq, hf.ce_part
+        hb.mask, hb.nmask = self.mask.data_ptr(), self.nmask.data_ptr()
+        hb.g_clean, hb.g_strong = self.g_clean.data_ptr(), self.g_strong.data_ptr()
+        hb.dWc, hb.dbc = self.dWc_dbc.data_ptr(), self.dWc_dbc.data_ptr() + N_CLS * D_HID * 4
+        hb.part, hb.loss_out, hb.counter = self.head_part.data_ptr(), self.g_ext.data_ptr() + NPARAM * 4, self.counters.data_ptr()
+        check(L.dad_head_bwd(C.byref(hb), s))
+        self.launches_per_step += 1
+        if noisy and sc.use_ecda:
+            ea = EcdaArgs()
+            ea.pack, ea.rank, ea.class_aware = pk, self.rank, int(sc.class_aware)
+            ea.mask, ea.nmask, ea.w_class = self.mask.data_ptr(), self.nmask.data_ptr(), self.out_w.data_ptr()
+            ea.lambda_cls, ea.gamma_comp, ea.delta_rep, ea.w_ecda = sc.lambda_cls, sc.gamma_comp, sc.delta_rep, _f32(sc.w_ecda)
+            ea.g_clean, ea.g_strong, ea.loss_out = hb.g_clean, hb.g_strong, hb.loss_out
+            ea.ws, ea.ws_bytes = self.ecda_ws.data_ptr(), self.ecda_ws.numel()
+            check(L.dad_ecda(C.byref(ea), s))
+            self.launches_per_step += 2
+        else:
+            self.g_ext[NPARAM + 2:NPARAM + 3].zero_()
+        # ---- backward of the two student encoder calls (I/train.py:486)
+        self._enc_bwd(self.x_clean, self.pad_clean, None, self.bits_clean, self.g_clean, self.lens_clean, 0, s)
+        if noisy:
+            self._enc_bwd(self.x_noisy, self.pad_noisy, aug_s, self.bits_strong, self.g_strong, self.lens_noisy, 1, s)
+        check(L.dad_grad_reduce(self.dWp[0].data_ptr(), self.dbp[0].data_ptr(), self.S,
+                                self.dWp[1].data_ptr() if noisy else None, self.dbp[1].data_ptr() if noisy else None, self.S,
+                                hb.dWc, hb.dbc, self.g_ext.data_ptr(), s))
+        self.launches_per_step += 1
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.g_ext, group=self.pg)
+        # ---- clip + Adam + EMA (I/train.py:487-492)
+        check(L.dad_grad_norm(self.g_ext.data_ptr(), self.norm_part.data_ptr(), self.counters.data_ptr() + 4 * 4,
+                              self.step_count.data_ptr(), self.lr.data_ptr(), self.scal.data_ptr(), sc.max_norm, s))
+        tc = self.gemm_mode == GEMM_TC
+        check(L.dad_adam_ema(self.p.data_ptr(), self.t.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.g_ext.data_ptr(),
+                             self.scal.data_ptr(), sc.wd, sc.ema_m, sc.ema_1m, int(noisy),
+                             self.hi_lo[0].data_ptr() if tc else None, self.hi_lo[1].data_ptr() if tc else None,
+                             self.hi_lo[2].data_ptr() if tc else None, self.hi_lo[3].data_ptr() if tc else None,
+                             self.g_ext.data_ptr() + NPARAM * 4, self.loss_last.data_ptr(), self.loss_acc.data_ptr(),
+                             _f32(sc.w_kd), _f32(sc.w_ecda), s))
+        self.launches_per_step += 2
+
+    def scalars(self, epoch):
+        return StepScalars(self.cfg, epoch, self.dataset)
+
+    def step(self, epoch):
+        """Run one optimisation step on the buffers filled by set_inputs().  No host sync."""
+        sc = self.scalars(epoch)
+        self._scalars = sc
+        if not self.use_graph:
+            self._enqueue(sc)
+            return
+        key = sc.key()
+        ent = self._graphs.get(key)
+        if ent is None:
+            # warm-up run on a side stream (sets func attributes, NCCL lazy init), then capture
+            state = self._snapshot()
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._enqueue(sc)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(self.dev)
+            self._restore(state)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue(sc)
+            ent = (g, self.launches_per_step)
+            if len(self._graphs) > 8:
+                self._graphs.clear()
+            self._graphs[key] = ent
+        ent[0].replay()
+        self.launches_per_step = ent[1]
+
+    _STATE = ("p", "t", "m", "v", "step_count", "ema_thr", "quality", "epoch_sum", "epoch_cnt", "loss_acc", "hi_lo")
+
+    def _snapshot(self):
+        return {k: getattr(self, k).clone() for k in self._STATE}
+
+    def _restore(self, st):
+        for k, v in st.items():
+            getattr(self, k).copy_(v)
+
+    # ------------------------------------------------------------------ epoch bookkeeping / read-back
+    def losses(self):
+        """Loss dict of the last step (one D2H read; the reference does one .item() per loss per step)."""
+        v = self.loss_last.tolist()
+        return {"total_loss": v[0], "supervised_ce_loss": v[1], "consistency_loss": v[2], "ecda_loss": v[3]}
+
+    def pop_epoch_losses(self):
+        """Mean losses since the last call (train_epoch's return value, I/train.py:520) and reset."""
+        a = self.loss_acc.tolist()
+        self.loss_acc.zero_()
+        n = max(a[4], 1.0)
+        return {"total_loss": a[0] / n, "supervised_ce_loss": a[1] / n, "consistency_loss": a[2] / n, "ecda_loss": a[3] / n}
+
+    def end_epoch(self, epoch):
+        """DACPManager.update_class_quality_scores_epoch (I/utils.py:430-447) from the device accumulators."""
+        beta = getattr(self.cfg, "DACP_QUALITY_SMOOTHING_BETA")
+        if epoch >= getattr(self.cfg, "WARMUP_EPOCHS"):
+            cnt = self.epoch_cnt.tolist()
+            sm = self.epoch_sum.tolist()
+            q = self.quality.tolist()
+            cur = torch.tensor([np.float32(sm[c] / cnt[c]) if cnt[c] > 0 else q[c] for c in range(N_CLS)], dtype=torch.float32)
+            newq = beta * torch.tensor(q, dtype=torch.float32) + (1 - beta) * cur
+            self.quality.copy_(newq)
+            self.epoch_sum.zero_()
+            self.epoch_cnt.zero_()
+
+    def cosine_lr(self, epoch):
+        lr0, total = getattr(self.cfg, "LEARNING_RATE"), getattr(self.cfg, "EPOCHS")
+        if getattr(self.cfg, "LEARNING_RATE_SCHEDULER", "cosine") != "cosine":
+            return lr0
+        return 0.5 * lr0 * (1 + math.cos(math.pi * epoch / total))

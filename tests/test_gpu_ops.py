@@ -1,0 +1,177 @@
+"""GPU (-m gpu): op-level parity of the CUDA kernels, called through the C ABI, against the oracle and the
+reference-generated golden vectors.  Augmentation must be BIT-EXACT; floating-point ops within the stated tolerances."""
+import pytest
+import torch
+
+from helpers import load_golden, pretrained_state
+from dad_b200 import synth
+
+pytestmark = pytest.mark.gpu
+MODES = ["fp32", "tc"]
+
+
+def _mode(name):
+    from dad_b200 import _lib
+    return {"fp32": _lib.GEMM_FP32, "tc": _lib.GEMM_TC}[name]
+
+
+def _inputs(B, T, seed, variable=True):
+    c, n = synth.make_batches(B, T, seed, variable_len=variable)
+    rng = synth.make_rng_inputs(B, T, seed + 1)
+    return c, n, rng
+
+
+def test_library_loaded_and_device_ok():
+    from dad_b200 import _lib
+    _lib.require_device()
+    assert _lib.lib().dad_abi_version() == 1
+
+
+@pytest.mark.parametrize("B,T", [(6, 20), (3, 7), (2, 200), (1, 1)])
+def test_augment_bit_exact_vs_oracle(B, T):
+    from dad_b200 import ops
+    from oracle import dad_oracle as O
+    c, n, rng = _inputs(B, T, 777)
+    x = n["net_input"]["feats"]
+    dev = "cuda"
+    weak = ops.augment(x.to(dev), 0.01, noise=rng["n_weak"].to(dev))
+    assert torch.equal(weak.cpu(), O.weak_augment(x, rng["n_weak"], 0.01))
+    L = int(T * 0.1)
+    keep = (rng["feat_keep_u"] > 0.1).float()
+    strong = ops.augment(x.to(dev), 0.05, noise=rng["n_strong"].to(dev), feat_keep=keep.to(dev),
+                         t_start=rng["t_start"].to(torch.int32).to(dev) if L > 0 else None, mask_len=L, strong=True)
+    ref = O.strong_augment(x, rng["n_strong"], 0.05, rng["feat_keep_u"], 0.1, rng["t_start"], 0.1)
+    # bit-exact including the sign of zeros (x*0 -> +-0, span := +0)
+    assert torch.equal(strong.cpu().view(torch.int32), ref.view(torch.int32))
+
+
+def test_augment_bit_exact_vs_reference_golden():
+    from dad_b200 import ops
+    g = load_golden("ops_small")
+    c, n = synth.make_batches(g["B"], g["T"], g["seed_batches"], variable_len=True)
+    rng = synth.make_rng_inputs(g["B"], g["T"], g["seed_rng"])
+    x = n["net_input"]["feats"].cuda()
+    weak = ops.augment(x, 0.01, noise=rng["n_weak"].cuda())
+    assert torch.equal(weak.cpu().view(torch.int32), g["weak"].view(torch.int32))
+    keep = (rng["feat_keep_u"] > 0.1).float().cuda()
+    strong = ops.augment(x, 0.05, noise=rng["n_strong"].cuda(), feat_keep=keep, t_start=rng["t_start"].to(torch.int32).cuda(),
+                         mask_len=int(g["T"] * 0.1), strong=True)
+    assert torch.equal(strong.cpu().view(torch.int32), g["strong"].view(torch.int32))
+    s2 = ops.augment(x[0], 0.05, noise=rng["n_strong"][0].cuda(), feat_keep=keep, t_start=rng["t_start"][:1].to(torch.int32).cuda(),
+                     mask_len=int(g["T"] * 0.1), strong=True)
+    assert torch.equal(s2.cpu().view(torch.int32), g["strong2d"].view(torch.int32))
+
+
+def test_augment_philox_statistics_and_determinism():
+    from dad_b200 import ops
+    x = torch.zeros(8, 64, 768, device="cuda")
+    a = ops.augment(x, 1.0, seed=5, stream=1)
+    b = ops.augment(x, 1.0, seed=5, stream=1)
+    c = ops.augment(x, 1.0, seed=5, stream=2)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert abs(float(a.mean())) < 5e-3 and abs(float(a.std()) - 1.0) < 5e-3
+    assert abs(float((a ** 4).mean()) - 3.0) < 0.05  # normal kurtosis
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_encoder_forward_vs_reference_golden(mode):
+    from dad_b200 import ops
+    g = load_golden("ops_small")
+    c, n = synth.make_batches(g["B"], g["T"], g["seed_batches"], variable_len=True)
+    st = pretrained_state()
+    W, b = st["student_encoder.pre_net.weight"].cuda(), st["student_encoder.pre_net.bias"].cuda()
+    if mode == "tc":
+        pytest.skip("T=20 < 32: tcgen05 path not applicable to this fixture")
+    x, pad = c["net_input"]["feats"].cuda(), c["net_input"]["padding_mask"].cuda()
+    emb, bits, lens = ops.encoder_pool_fwd(x, pad, W, b, gemm_mode=_mode(mode))
+    assert torch.allclose(emb.cpu(), g["emb_pad"], rtol=2e-5, atol=2e-6), (emb.cpu() - g["emb_pad"]).abs().max()
+    emb2, _, lens2 = ops.encoder_pool_fwd(x, None, W, b, gemm_mode=_mode(mode))
+    assert torch.allclose(emb2.cpu(), g["emb_nopad"], rtol=2e-5, atol=2e-6)
+    assert torch.equal(lens.cpu(), (~c["net_input"]["padding_mask"]).sum(1).float())
+    assert torch.equal(lens2.cpu(), torch.full((g["B"],), float(g["T"])))
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("B,T,aug", [(4, 64, 0), (5, 200, 2), (3, 97, 1), (2, 33, 2), (16, 40, 2), (1, 1, 0), (2, 5, 2)])
+def test_encoder_forward_backward_vs_oracle(mode, B, T, aug):
+    """emb, ReLU bits, dW, db against the oracle's autograd on the same (augmented) inputs."""
+    from dad_b200 import _lib, ops
+    from oracle import dad_oracle as O
+    if mode == "tc" and T < 32:
+        pytest.skip("tcgen05 path needs T >= 32")
+    c, n, rng = _inputs(B, T, 4242 + B * 1000 + T)
+    st = pretrained_state()
+    W0, b0 = st["student_encoder.pre_net.weight"], st["student_encoder.pre_net.bias"]
+    x, pad = n["net_input"]["feats"], n["net_input"]["padding_mask"]
+    L = int(T * 0.1)
+    keep = (rng["feat_keep_u"] > 0.1).float()
+    if aug == 0:
+        xa, a = x, None
+    elif aug == 1:
+        xa = O.weak_augment(x, rng["n_weak"], 0.01)
+        a = _lib.make_aug(1, noise=rng["n_weak"].cuda(), sigma=0.01)
+    else:
+        xa = O.strong_augment(x, rng["n_strong"], 0.05, rng["feat_keep_u"], 0.1, rng["t_start"], 0.1)
+        keep_d, ts_d, noise_d = keep.cuda(), rng["t_start"].to(torch.int32).cuda(), rng["n_strong"].cuda()
+        a = _lib.make_aug(2, noise=noise_d, sigma=0.05, feat_keep=keep_d, t_start=ts_d if L > 0 else None, mask_len=L)
+    W, b = W0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+    emb_ref = O.encoder(xa, pad, W, b)
+    gen = torch.Generator().manual_seed(9)
+    g_emb = torch.randn(B, 256, generator=gen)
+    (emb_ref * g_emb).sum().backward()
+    emb, bits, lens = ops.encoder_pool_fwd(x.cuda(), pad.cuda(), W0.cuda(), b0.cuda(), aug=a, gemm_mode=_mode(mode))
+    tol = dict(rtol=2e-5, atol=2e-6) if mode == "fp32" else dict(rtol=1e-4, atol=2e-5)
+    assert torch.allclose(emb.cpu(), emb_ref.detach(), **tol), (emb.cpu() - emb_ref.detach()).abs().max()
+    # ReLU sign bits against fp64 pre-activations (ignore |pre| < 1e-4: rounding may legitimately flip those)
+    pre = (xa.double() @ W0.double().t() + b0.double()).reshape(B * T, 256)
+    word = bits.cpu().view(B * T, 8).to(torch.int64) & 0xFFFFFFFF
+    got = ((word.unsqueeze(-1) >> torch.arange(32)) & 1).reshape(B * T, 256).bool()
+    sure = pre.abs() > 1e-4
+    assert torch.equal(got[sure], (pre > 0)[sure])
+    dW, db = ops.encoder_pool_bwd(x.cuda(), pad.cuda(), bits, g_emb.cuda(), lens, aug=a, gemm_mode=_mode(mode))
+    sW, sb = float(W.grad.abs().max()), float(b.grad.abs().max())
+    tolW = 2e-5 if mode == "fp32" else 1e-4
+    assert float((dW.cpu() - W.grad).abs().max()) <= tolW * sW + 1e-7, (float((dW.cpu() - W.grad).abs().max()), sW)
+    assert float((db.cpu() - b.grad).abs().max()) <= tolW * sb + 1e-7
+
+
+def test_encoder_rejects_bad_arguments():
+    from dad_b200 import _lib, ops
+    with pytest.raises(_lib.DadError):
+        ops.encoder_pool_fwd(torch.zeros(2, 4, 100, device="cuda"), None, torch.zeros(256, 768, device="cuda"), torch.zeros(256, device="cuda"))
+    with pytest.raises(_lib.DadError):
+        ops.encoder_pool_fwd(torch.zeros(2, 4, 768), None, torch.zeros(256, 768), torch.zeros(256))  # CPU tensors: no fallback
+    emb, bits, lens = ops.encoder_pool_fwd(torch.zeros(0, 4, 768, device="cuda"), None, torch.zeros(256, 768, device="cuda"),
+                                           torch.zeros(256, device="cuda"))
+    assert emb.shape == (0, 256)
+
+
+def test_ema_matches_reference_rounding():
+    from dad_b200 import ops
+    from oracle import dad_oracle as O
+    g = torch.Generator().manual_seed(3)
+    t, s = torch.randn(197892, generator=g), torch.randn(197892, generator=g)
+    out = ops.ema_(t.clone().cuda(), s.cuda(), 0.995)
+    assert torch.equal(out.cpu(), O.ema_update(t, s, 0.995))
+
+
+def test_autograd_module_path_matches_oracle():
+    """Drop-in module API: SSRLModel.student_encoder(x, pad) is differentiable through torch.ops.dad.encoder_pool."""
+    from dad_b200 import config as cfg
+    from dad_b200.model import SSRLModel
+    from oracle import dad_oracle as O
+    st = pretrained_state()
+    model = SSRLModel(cfg).cuda()
+    model.load_state_dict(st)
+    c, n, rng = _inputs(4, 50, 99)
+    x, pad = c["net_input"]["feats"], c["net_input"]["padding_mask"]
+    emb = model.student_encoder(x.cuda(), pad.cuda())
+    emb.square().sum().backward()
+    W = st["student_encoder.pre_net.weight"].clone().requires_grad_(True)
+    b = st["student_encoder.pre_net.bias"].clone().requires_grad_(True)
+    ref = O.encoder(x, pad, W, b)
+    ref.square().sum().backward()
+    assert torch.allclose(emb.detach().cpu(), ref.detach(), rtol=1e-4, atol=1e-5)
+    gW = model.student_encoder.pre_net.weight.grad.cpu()
+    assert float((gW - W.grad).abs().max()) <= 1e-4 * float(W.grad.abs().max())
+    assert model.teacher_encoder.pre_net.weight.grad is None

@@ -1,0 +1,150 @@
+"""GPU (-m gpu): step-level parity of the fused CUDA step against the oracle (itself pinned to the reference).
+
+Teacher-forced protocol: before every step the engine receives the oracle's full optimisation state, both run the
+same step on the same inputs (supplied noise / masks), and we compare losses (1e-4 relative, north_star), DACP masks
+and pseudo-labels (exact), gradients' effect = updated student + EMA weights (1e-5 absolute, north_star) and DACP
+thresholds.  The reference trajectory is chaotic at the ulp level (see DESIGN.md "Parity protocol"): a FREE-RUNNING
+100-step comparison is also made and bounded by the drift an fp64-accumulated CPU run of the same maths shows."""
+import pytest
+import torch
+
+from helpers import load_golden, make_oracle, push_oracle_state, rel, step_inputs
+from oracle import dad_oracle as O
+
+pytestmark = pytest.mark.gpu
+LOSS_KEYS = ("total_loss", "supervised_ce_loss", "consistency_loss", "ecda_loss")
+
+
+def _engine(cfg, meta, dataset, mode, graph=False):
+    from dad_b200 import _lib
+    from dad_b200.engine import DADStepEngine
+    gm = {"fp32": _lib.GEMM_FP32, "tc": _lib.GEMM_TC}[mode]
+    return DADStepEngine(cfg, meta["B"], meta["T"], dataset=dataset, gemm_mode=gm, use_graph=graph, noise_mode="supplied")
+
+
+def _to_dev(batch):
+    return {"net_input": {"feats": batch["net_input"]["feats"].cuda(), "padding_mask": batch["net_input"]["padding_mask"].cuda()},
+            "labels": batch["labels"].cuda()}
+
+
+def _run_teacher_forced(name, mode, max_steps=None, loss_tol=1e-4, w_tol=1e-5):
+    fix = load_golden(name)
+    meta = fix["meta"]
+    orc, cfg, hp = make_oracle(meta["dataset"], meta["overrides"])
+    eng = _engine(cfg, meta, meta["dataset"], mode)
+    worst = {"loss": 0.0, "w": 0.0, "t": 0.0, "thr": 0.0}
+    k = 0
+    for epoch in meta["epochs"]:
+        orc.lr = O.cosine_lr(hp.LEARNING_RATE, epoch, hp.EPOCHS)
+        for _ in range(meta["steps_per_epoch"]):
+            c, n, rng = step_inputs(meta, k, cfg)
+            push_oracle_state(eng, orc)
+            eng.set_inputs(_to_dev(c), _to_dev(n), {kk: v.cuda() for kk, v in rng.items()})
+            eng.step(epoch)
+            ref = orc.step(c, n, epoch, rng)
+            got = eng.losses()
+            for key in LOSS_KEYS:
+                r = abs(got[key] - ref[key]) / max(abs(ref[key]), 1e-3)
+                worst["loss"] = max(worst["loss"], r)
+                assert r <= loss_tol, (name, mode, k, key, got[key], ref[key])
+            if epoch >= hp.WARMUP_EPOCHS:
+                assert torch.equal(eng.mask.cpu().bool(), orc.last["mask"]), (name, mode, k, "mask")
+                B = meta["B"]
+                pred = eng.pack_i32[2 * B * 256 + B: 2 * B * 256 + 2 * B].cpu()
+                assert torch.equal(pred.long(), orc.last["pred"]), (name, mode, k, "pred")
+                dthr = float((eng.ema_thr.cpu() - orc.dacp.ema_thr).abs().max())
+                worst["thr"] = max(worst["thr"], dthr)
+                assert dthr <= 1e-6, (name, mode, k, "ema_thr", dthr)
+            sd, so = eng.state_dict(), orc.state_dict()
+            for key in so:
+                d = float((sd[key].cpu() - so[key]).abs().max())
+                worst["t" if key.startswith("teacher") else "w"] = max(worst["t" if key.startswith("teacher") else "w"], d)
+                assert d <= w_tol, (name, mode, k, key, d)
+            k += 1
+            if max_steps and k >= max_steps:
+                break
+        orc.end_epoch(epoch)
+        if max_steps and k >= max_steps:
+            break
+    print(f"[teacher-forced {name}/{mode}] steps={k} worst loss rel={worst['loss']:.2e} student dW={worst['w']:.2e} "
+          f"teacher={worst['t']:.2e} thr={worst['thr']:.2e}")
+    return worst
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+def test_iemocap_100_steps_teacher_forced(mode):
+    """north_star tolerances at every one of the 100 golden steps: losses 1e-4 rel, weights 1e-5."""
+    _run_teacher_forced("step_iemocap", mode)
+
+
+@pytest.mark.parametrize("name", ["step_iemocap_warmup", "step_iemocap_noentropy_globalmmd", "step_iemocap_fixedthr",
+                                  "step_casia_default", "step_casia_full", "step_emodb"])
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+def test_variants_teacher_forced(name, mode):
+    _run_teacher_forced(name, mode)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+def test_iemocap_100_steps_free_running(mode):
+    """Free-running drift over 100 steps vs the reference fixture.  The chaotic floor measured on CPU (fp64-accumulated
+    GEMMs, otherwise identical maths) is 1.3e-3 on losses / 6e-4 on weights; we allow 4x that."""
+    fix = load_golden("step_iemocap")
+    meta = fix["meta"]
+    orc, cfg, hp = make_oracle(meta["dataset"], meta["overrides"])
+    eng = _engine(cfg, meta, meta["dataset"], mode, graph=True)
+    push_oracle_state(eng, orc)
+    k, worst, flips = 0, 0.0, 0
+    for epoch in meta["epochs"]:
+        eng.set_lr(O.cosine_lr(hp.LEARNING_RATE, epoch, hp.EPOCHS))
+        for _ in range(meta["steps_per_epoch"]):
+            c, n, rng = step_inputs(meta, k, cfg)
+            eng.set_inputs(_to_dev(c), _to_dev(n), {kk: v.cuda() for kk, v in rng.items()})
+            eng.step(epoch)
+            got, ref = eng.losses(), fix["steps"][k]
+            worst = max(worst, max(abs(got[key] - ref[key]) / max(abs(ref[key]), 1e-3) for key in LOSS_KEYS))
+            flips += int((eng.mask.cpu() != fix["mask"][k]).sum())
+            k += 1
+        eng.end_epoch(epoch)
+    sd = eng.state_dict()
+    wd = max(float((sd[key].cpu() - ref).abs().max()) for key, ref in fix["final_state"].items())
+    thr = float((eng.ema_thr.cpu() - fix["dacp_ema_thr"]).abs().max())
+    q = float((eng.quality.cpu() - fix["dacp_quality"]).abs().max())
+    print(f"[free-running/{mode}] worst loss rel={worst:.2e} max weight diff={wd:.2e} mask flips={flips} thr diff={thr:.2e} Q diff={q:.2e}")
+    assert worst <= 6e-3 and wd <= 2.5e-3 and flips <= 2 and q <= 1e-4
+
+
+def test_graph_replay_equals_eager():
+    fix = load_golden("step_iemocap")
+    meta = fix["meta"]
+    res = []
+    for graph in (False, True):
+        orc, cfg, hp = make_oracle(meta["dataset"], meta["overrides"])
+        eng = _engine(cfg, meta, meta["dataset"], "fp32", graph=graph)
+        push_oracle_state(eng, orc)
+        for k in range(6):
+            c, n, rng = step_inputs(meta, k, cfg)
+            eng.set_inputs(_to_dev(c), _to_dev(n), {kk: v.cuda() for kk, v in rng.items()})
+            eng.step(40)
+        res.append((eng.p.clone(), eng.t.clone(), eng.ema_thr.clone(), eng.losses()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    assert res[0][3] == res[1][3]
+
+
+def test_philox_mode_runs_and_is_deterministic():
+    from dad_b200 import _lib, synth
+    from dad_b200.engine import DADStepEngine
+    from helpers import cfg_for, pretrained_state
+    cfg = cfg_for("iemocap")
+    outs = []
+    for _ in range(2):
+        eng = DADStepEngine(cfg, 32, 64, gemm_mode=_lib.GEMM_FP32, use_graph=True, noise_mode="philox", seed=7)
+        eng.load_state_dict(pretrained_state())
+        eng.set_lr(5e-4)
+        for k in range(5):
+            c, n = synth.make_batches(32, 64, 600 + k)
+            eng.set_inputs(_to_dev(c), _to_dev(n))
+            eng.step(45)
+        outs.append((eng.p.clone(), eng.losses()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    l = outs[0][1]
+    assert l["supervised_ce_loss"] > 0 and l["total_loss"] == l["total_loss"]  # finite

@@ -1,0 +1,110 @@
+"""CPU: pin oracle/dad_oracle.py against the golden vectors produced by the unmodified reference
+(tests/golden/*.pt, generator oracle/make_golden.py) and, when /root/reference is present, the live reference."""
+import pytest
+import torch
+
+from helpers import load_golden, make_oracle, pretrained_state, step_inputs
+from dad_b200 import synth
+from oracle import dad_oracle as O
+from oracle import ref_harness
+
+CASES = ["step_iemocap_warmup", "step_iemocap_noentropy_globalmmd", "step_iemocap_fixedthr", "step_casia_default",
+         "step_casia_full", "step_emodb", "step_iemocap"]
+
+
+def run_case(name, max_steps=None):
+    fix = load_golden(name)
+    meta = fix["meta"]
+    orc, cfg, hp = make_oracle(meta["dataset"], meta["overrides"])
+    k = 0
+    for epoch in meta["epochs"]:
+        orc.lr = O.cosine_lr(hp.LEARNING_RATE, epoch, hp.EPOCHS)
+        for _ in range(meta["steps_per_epoch"]):
+            c, n, rng = step_inputs(meta, k, cfg)
+            if k == 0:
+                cs = fix["input_checksums"][0]
+                assert abs(float(c["net_input"]["feats"].double().sum()) - cs["x_clean"][0]) < 1e-6, "synthetic input RNG drift"
+                assert rng["t_start"].tolist() == cs["t_start"]
+            out = orc.step(c, n, epoch, rng)
+            ref = fix["steps"][k]
+            for key in ("total_loss", "supervised_ce_loss", "consistency_loss", "ecda_loss", "grad_norm"):
+                assert abs(out[key] - ref[key]) <= 1e-6 * max(1.0, abs(ref[key])), (name, k, key, out[key], ref[key])
+            if fix["mask"] is not None and epoch >= hp.WARMUP_EPOCHS:
+                assert torch.equal(orc.last["mask"].to(torch.uint8), fix["mask"][k]), (name, k)
+                assert torch.equal(orc.last["pred"].to(torch.uint8), fix["pred"][k])
+            k += 1
+            if max_steps and k >= max_steps:
+                return
+        orc.end_epoch(epoch)
+    sd = orc.state_dict()
+    stride = fix["final_state_stride"]
+    for key, ref in fix["final_state"].items():
+        got = sd[key] if (stride == 1 or sd[key].numel() < 2048) else sd[key].flatten()[::stride]
+        assert torch.allclose(got, ref, rtol=0, atol=1e-7), (name, key, (got - ref).abs().max())
+    assert torch.allclose(orc.dacp.ema_thr, fix["dacp_ema_thr"], atol=1e-7)
+    assert torch.allclose(orc.dacp.quality, fix["dacp_quality"], atol=1e-7)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_step_matches_reference_golden(name):
+    run_case(name)
+
+
+def test_oracle_ops_match_reference_golden():
+    g = load_golden("ops_small")
+    cfg_drop, B, T = 0.1, g["B"], g["T"]
+    c, n = synth.make_batches(B, T, g["seed_batches"], variable_len=True)
+    rng = synth.make_rng_inputs(B, T, g["seed_rng"])
+    xn = n["net_input"]["feats"]
+    assert torch.equal(O.weak_augment(xn, rng["n_weak"], 0.01), g["weak"])
+    assert torch.equal(O.strong_augment(xn, rng["n_strong"], 0.05, rng["feat_keep_u"], cfg_drop, rng["t_start"], 0.1), g["strong"])
+    assert torch.equal(O.strong_augment(xn[0], rng["n_strong"][0], 0.05, rng["feat_keep_u"], cfg_drop, rng["t_start"][:1], 0.1), g["strong2d"])
+    st = pretrained_state()
+    W, b = st["student_encoder.pre_net.weight"], st["student_encoder.pre_net.bias"]
+    assert torch.equal(O.encoder(c["net_input"]["feats"], c["net_input"]["padding_mask"], W, b), g["emb_pad"])
+    assert torch.equal(O.encoder(c["net_input"]["feats"], None, W, b), g["emb_nopad"])
+    # DACP incl. an empty class, three consecutive calls + epoch update
+    hp = O.HParams()
+    d = g["dacp"]
+    stt = O.DACPState.fresh(4)
+    stt.quality = d["quality0"].clone()
+    for o in d["out"]:
+        m, s, w = O.dacp_mask(stt, d["P"], o["epoch"], d["anchors"], hp)
+        assert torch.equal(m, o["mask"]) and torch.equal(s, o["scores"]) and torch.equal(w, o["w"])
+        assert torch.equal(stt.ema_thr, o["ema_thr"])
+    O.dacp_epoch_update(stt, hp)
+    assert torch.allclose(stt.quality, d["quality_after_epoch"], atol=1e-7)
+    # ECDA forward + autograd grads, class-aware and global; and the fp64 Gram-form restatement
+    e = g["ecda"]
+    for aware, key in ((True, "aware"), (False, "global")):
+        hp2 = O.HParams(USE_CLASS_AWARE_MMD=aware)
+        fc, fn = e["fc"].clone().requires_grad_(True), e["fn"].clone().requires_grad_(True)
+        loss = O.ecda_loss(fc, fn, e["yc"], e["yn"], e["mask"], e["scores"], e["wce"], hp2)
+        loss.backward()
+        assert torch.equal(loss.detach(), e["out"][key]["loss"])
+        assert torch.allclose(fc.grad, e["out"][key]["g_clean"], atol=1e-9) and torch.allclose(fn.grad, e["out"][key]["g_noisy"], atol=1e-9)
+        l64 = O.ecda_loss_gram(e["fc"].double(), e["fn"].double(), e["yc"], e["yn"], e["mask"], e["scores"].double(), e["wce"].double(), hp2)
+        assert abs(float(l64) - float(e["out"][key]["loss"])) < 2e-5 * abs(float(e["out"][key]["loss"]))
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="/root/reference not mounted (GPU box)")
+def test_oracle_matches_live_reference():
+    """Bit-level lockstep with the imported reference on fresh seeds (beyond what the fixtures hold)."""
+    ov = {"WARMUP_EPOCHS": 1, "ECDA_START_EPOCH": 1, "WEIGHT_RAMP_EPOCHS": 2}
+    ref = ref_harness.RefStepper("iemocap", overrides=ov, state=pretrained_state())
+    orc, cfg, hp = make_oracle("iemocap", ov)
+    k = 0
+    for epoch in (0, 1, 2, 3):
+        for _ in range(3):
+            c, n = synth.make_batches(12, 24, 31000 + k, variable_len=True)
+            rng = synth.make_rng_inputs(12, 24, 32000 + k)
+            a, b = ref.step(c, n, epoch, rng), orc.step(c, n, epoch, rng)
+            for key in b:
+                assert a[key] == pytest.approx(b[key], rel=1e-6, abs=1e-7), (epoch, key)
+            k += 1
+        if epoch >= hp.WARMUP_EPOCHS:
+            ref.tr.dacp_manager.update_class_quality_scores_epoch(ref.tr.dacp_manager.batch_scores_per_class)
+        orc.end_epoch(epoch)
+    sd, so = ref.tr.model.state_dict(), orc.state_dict()
+    for key in sd:
+        assert torch.allclose(sd[key], so[key], atol=1e-7), key
