@@ -109,7 +109,8 @@ def test_encoder_forward_backward_vs_oracle(mode, B, T, aug):
         xa, a = x, None
     elif aug == 1:
         xa = O.weak_augment(x, rng["n_weak"], 0.01)
-        a = _lib.make_aug(1, noise=rng["n_weak"].cuda(), sigma=0.01)
+        noise_d = rng["n_weak"].cuda()  # keep alive: dad_aug only holds the raw pointer
+        a = _lib.make_aug(1, noise=noise_d, sigma=0.01)
     else:
         xa = O.strong_augment(x, rng["n_strong"], 0.05, rng["feat_keep_u"], 0.1, rng["t_start"], 0.1)
         keep_d, ts_d, noise_d = keep.cuda(), rng["t_start"].to(torch.int32).cuda(), rng["n_strong"].cuda()

@@ -2,8 +2,10 @@
 
 Teacher-forced protocol: before every step the engine receives the oracle's full optimisation state, both run the
 same step on the same inputs (supplied noise / masks), and we compare losses (1e-4 relative, north_star), DACP masks
-and pseudo-labels (exact), gradients' effect = updated student + EMA weights (1e-5 absolute, north_star) and DACP
-thresholds.  The reference trajectory is chaotic at the ulp level (see DESIGN.md "Parity protocol"): a FREE-RUNNING
+and pseudo-labels (exact), the clipped gradient (1e-5 of its max), DACP thresholds, and the updated student + EMA
+weights (1e-5 absolute, north_star) on every element whose Adam update is well conditioned (|g| >= 1e-6: for
+|g| ~ eps = 1e-8 the update lr*m/(sqrt(v)+eps) turns ulp-level gradient noise into O(lr) weight changes in ANY
+implementation, the reference on another BLAS included -- those elements are bounded by 2.5*lr and counted).  The reference trajectory is chaotic at the ulp level (see DESIGN.md "Parity protocol"): a FREE-RUNNING
 100-step comparison is also made and bounded by the drift an fp64-accumulated CPU run of the same maths shows."""
 import pytest
 import torch
@@ -32,7 +34,8 @@ def _run_teacher_forced(name, mode, max_steps=None, loss_tol=1e-4, w_tol=1e-5):
     meta = fix["meta"]
     orc, cfg, hp = make_oracle(meta["dataset"], meta["overrides"])
     eng = _engine(cfg, meta, meta["dataset"], mode)
-    worst = {"loss": 0.0, "w": 0.0, "t": 0.0, "thr": 0.0}
+    worst = {"loss": 0.0, "w": 0.0, "t": 0.0, "thr": 0.0, "g": 0.0, "w_ill": 0.0, "n_ill": 0}
+    g_tol = 1e-5 if mode == "fp32" else 3e-5
     k = 0
     for epoch in meta["epochs"]:
         orc.lr = O.cosine_lr(hp.LEARNING_RATE, epoch, hp.EPOCHS)
@@ -55,19 +58,31 @@ def _run_teacher_forced(name, mode, max_steps=None, loss_tol=1e-4, w_tol=1e-5):
                 dthr = float((eng.ema_thr.cpu() - orc.dacp.ema_thr).abs().max())
                 worst["thr"] = max(worst["thr"], dthr)
                 assert dthr <= 1e-6, (name, mode, k, "ema_thr", dthr)
-            sd, so = eng.state_dict(), orc.state_dict()
-            for key in so:
-                d = float((sd[key].cpu() - so[key]).abs().max())
-                worst["t" if key.startswith("teacher") else "w"] = max(worst["t" if key.startswith("teacher") else "w"], d)
-                assert d <= w_tol, (name, mode, k, key, d)
+            # clipped gradient (the oracle's .grad is clipped in place by clip_grad_norm)
+            g_orc = torch.cat([orc.p[key].grad.reshape(-1) for key in O.PARAM_KEYS])
+            g_eng = (eng.g_ext[:g_orc.numel()] * eng.scal[1]).cpu()
+            gd = float((g_eng - g_orc).abs().max()) / float(g_orc.abs().max())
+            worst["g"] = max(worst["g"], gd)
+            assert gd <= g_tol, (name, mode, k, "grad", gd)
+            well = (g_orc.abs() >= 1e-6)
+            p_orc = torch.cat([orc.p[key].detach().reshape(-1) for key in O.PARAM_KEYS])
+            t_orc = torch.cat([orc.t[key].reshape(-1) for key in O.TEACHER_KEYS])
+            dp, dt = (eng.p.cpu() - p_orc).abs(), (eng.t.cpu() - t_orc).abs()
+            worst["w"], worst["t"] = max(worst["w"], float(dp[well].max())), max(worst["t"], float(dt.max()))
+            worst["w_ill"] = max(worst["w_ill"], float(dp.max()))
+            worst["n_ill"] += int((dp > w_tol).sum())
+            assert float(dp[well].max()) <= w_tol, (name, mode, k, "student weights (well-conditioned)", float(dp[well].max()))
+            assert float(dp.max()) <= 2.5 * orc.lr, (name, mode, k, "student weights (all)", float(dp.max()))
+            assert float(dt.max()) <= w_tol, (name, mode, k, "teacher weights", float(dt.max()))
             k += 1
             if max_steps and k >= max_steps:
                 break
         orc.end_epoch(epoch)
         if max_steps and k >= max_steps:
             break
-    print(f"[teacher-forced {name}/{mode}] steps={k} worst loss rel={worst['loss']:.2e} student dW={worst['w']:.2e} "
-          f"teacher={worst['t']:.2e} thr={worst['thr']:.2e}")
+    print(f"[teacher-forced {name}/{mode}] steps={k} worst: loss rel={worst['loss']:.2e} grad rel-to-max={worst['g']:.2e} "
+          f"student w={worst['w']:.2e} (ill-conditioned elems: max {worst['w_ill']:.2e}, {worst['n_ill']} over 1e-5) "
+          f"teacher w={worst['t']:.2e} thr={worst['thr']:.2e}")
     return worst
 
 
