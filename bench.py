@@ -1,0 +1,311 @@
+#!/usr/bin/env python3
+"""DAD train samples/s on N B200s of one node (+ fraction of roofline, + the reference's CPU path beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] ...                # the reference's CPU implementation (oracle port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU (driver launches this for N > 1)
+
+One "step" = one full DAD training step (I/train.py:484-492) on one (clean, noisy) batch pair of synthetic features.
+Default workload = BASELINE.json configs[3]: IEMOCAP DAD-train, GLOBAL batch 4096, T=200, post-warm-up epoch 60 (full
+loss stack CE + DACP-masked KD + ECDA), sharded over the N ranks (strong scaling; at N=1 the whole 4096 fits one GPU).
+`--workload b64` selects configs[1] (batch 64).  One sample = one clean + one noisy utterance."""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D_IN = 768
+FLOPS_PER_PAIR_T = 10 * 768 * 256      # x T: 3 forward + 2 dW GEMMs
+BYTES_PER_PAIR_T = 16 * 768            # x T: clean + noisy fp32 features read once forward, once backward
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="g4096", choices=["g4096", "b64", "t1000"])
+    ap.add_argument("--gemm", default=os.environ.get("DAD_GEMM", "tc"), choices=["tc", "fp32"])
+    ap.add_argument("--epoch", type=int, default=60)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def workload(name, world):
+    if name == "g4096":
+        return dict(label="IEMOCAP DAD-train global batch 4096 (BASELINE configs[3]), T=200, epoch 60 full loss stack",
+                    Bg=4096, T=200, scaling="strong")
+    if name == "b64":
+        return dict(label="IEMOCAP DAD-train fold 0 batch 64 per GPU (BASELINE configs[1]), T=200, epoch 60 full loss stack",
+                    Bg=64 * world, T=200, scaling="weak")
+    return dict(label="long-utterance stress B=512 per GPU, T=1000 (BASELINE configs[4])", Bg=512 * world, T=1000, scaling="weak")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def device_batches(B, T, seed, dev, snr_db=10.0):
+    """Synthetic class-structured features generated ON the device (SURVEY.md 8d formulas; the CPU generator in
+    dad_b200.synth is used for parity tests, this one for throughput: 2 x B x T x 768 randn would take minutes on the host)."""
+    import torch
+    from dad_b200 import synth
+    g = torch.Generator(device=dev).manual_seed(seed)
+    mu = synth.class_means().to(dev)
+    out = []
+    for domain in ("clean", "noisy"):
+        y = torch.randint(0, 4, (B,), generator=g, device=dev)
+        x = mu[y][:, None, :] + torch.randn(B, T, D_IN, generator=g, device=dev)
+        if domain == "noisy":
+            P = (x * x).mean(dim=(1, 2))
+            x = x + torch.sqrt(P / (10.0 ** (snr_db / 10.0)))[:, None, None] * torch.randn(B, T, D_IN, generator=g, device=dev)
+        out.append({"net_input": {"feats": x.contiguous(), "padding_mask": torch.zeros(B, T, dtype=torch.bool, device=dev)}, "labels": y})
+    return out[0], out[1]
+
+
+def cpu_reference_steps(B, T, steps, warmup, epoch, threads=None):
+    """The reference's CPU step, restated op for op in oracle/dad_oracle.py (the Python reference cannot travel to the
+    GPU box; the oracle is bit-identical to it on CPU, tests/test_oracle_golden.py).  Returns seconds per step (median)."""
+    import torch
+    from dad_b200 import config as cfg, synth
+    from oracle import dad_oracle as O
+    torch.set_num_threads(threads or os.cpu_count())
+    hp = O.HParams.from_cfg(cfg)
+    st = synth.init_state(42)
+    orc = O.OracleStepper(st, hp)
+    c, n = synth.make_batches(B, T, 1)
+    gen = torch.Generator().manual_seed(2)
+    for i in range(30):  # CE-only "pretraining" so the teacher is confident and every branch executes
+        orc.step(c, n, 0, synth.make_rng_inputs(B, T, 1000 + i))
+    for ks, kt in zip(O.PARAM_KEYS, O.TEACHER_KEYS):
+        orc.t[kt] = orc.p[ks].detach().clone()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        # the reference draws its noise inside the step (torch.randn_like etc., I/utils.py:330-371): keep that cost inside
+        rng = {"drop_clean": (torch.rand(B, 256, generator=gen) >= 0.1).float(), "n_weak": torch.randn(B, T, D_IN, generator=gen),
+               "n_strong": torch.randn(B, T, D_IN, generator=gen), "feat_keep_u": torch.rand(D_IN, generator=gen),
+               "t_start": torch.randint(0, T - int(T * 0.1) + 1, (B,), generator=gen),
+               "drop_strong": (torch.rand(B, 256, generator=gen) >= 0.1).float()}
+        orc.step(c, n, epoch, rng)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return statistics.median(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = workload(args.workload, args.gpus)
+    Bs, T = 64, wl["T"]
+    steps = min(args.steps, 12 if T <= 200 else 3)
+    sec, threads = cpu_reference_steps(Bs, T, steps, min(args.warmup, 3), args.epoch)
+    val = Bs / sec
+    sample = f"each step = one B={Bs}, T={T} sub-batch of the workload (full loss stack, epoch {args.epoch}); {steps} timed steps, median"
+    print(json.dumps({
+        "impl": "reference", "metric": "DAD train samples/sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": wl["scaling"],
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["label"], "global_batch": wl["Bg"], "T": T, "device": "host CPU"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import torch
+    import dad_b200  # noqa: F401
+    from dad_b200 import _lib, config as cfg, synth
+    from dad_b200.engine import DADStepEngine
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    wl = workload(args.workload, world)
+    Bg, T = wl["Bg"], wl["T"]
+    assert Bg % world == 0
+    B = Bg // world
+    gm = _lib.GEMM_TC if args.gemm == "tc" else _lib.GEMM_FP32
+    eng = DADStepEngine(cfg, B, T, device=dev, world=world, rank=rank, process_group=pg, gemm_mode=gm, use_graph=not args.no_graph,
+                        noise_mode="philox", seed=42)
+    eng.load_state_dict(synth.init_state(42))
+    clean, noisy = device_batches(B, T, 1234 + rank, dev)
+    eng.set_inputs(clean, noisy)
+    eng.set_lr(cfg.LEARNING_RATE)
+    for _ in range(30):  # CE-only pretraining (epoch 0 < WARMUP_EPOCHS), then teacher := student, fresh Adam
+        eng.step(0)
+    eng.init_teacher()
+    eng.m.zero_(); eng.v.zero_(); eng.step_count.zero_()
+    eng.set_lr(eng.cosine_lr(args.epoch))
+    sync = lambda: (torch.cuda.synchronize(dev), world > 1 and torch.distributed.barrier())
+
+    # ---- device-timed steps: inputs resident in HBM
+    for _ in range(max(args.warmup, 3)):
+        eng.step(args.epoch)
+    sync()
+    sampler = ClockSampler(local)
+    sampler.start()
+    small = 2 * B * T * D_IN * 4 < 2 * 126e6  # working set not >> L2: flush L2 between steps and time steps individually
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev) if small else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if small:
+        tot = 0.0
+        for _ in range(args.steps):
+            flush.zero_()
+            e0.record(); eng.step(args.epoch); e1.record()
+            torch.cuda.synchronize(dev)
+            tot += e0.elapsed_time(e1)
+        ms = tot / args.steps
+    else:
+        e0.record()
+        for _ in range(args.steps):
+            eng.step(args.epoch)
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.summary()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t)
+    launches = eng.launches_per_step * args.steps
+    losses = eng.losses()
+    value = Bg / (ms * 1e-3)
+
+    # ---- dominant kernels alone (roofline): encoder forward (x3 per step) and encoder backward (x2 per step)
+    peaks, peak_src = measured_peaks()
+    kern = {}
+    sc = eng.scalars(args.epoch)
+    s = _lib.stream_ptr()
+    reps = 10 if not small else 40
+    for name, fn in (("encoder_fwd", lambda: eng._enc_fwd(eng.x_clean, eng.pad_clean, False, None, eng.pack.data_ptr(), eng.bits_clean, eng.lens_clean, s)),
+                     ("encoder_bwd", lambda: eng._enc_bwd(eng.x_clean, eng.pad_clean, None, eng.bits_clean, eng.g_clean, eng.lens_clean, 0, s))):
+        for _ in range(3):
+            fn()
+        tot = 0.0
+        for _ in range(reps):
+            if flush is not None:
+                flush.zero_()
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize(dev)
+            tot += e0.elapsed_time(e1)
+        t_ms = tot / reps
+        alg_bytes = B * T * D_IN * 4
+        alg_flops = 2 * B * T * D_IN * 256
+        kern[name] = {"ms": t_ms, "GBps": alg_bytes / t_ms / 1e6, "TFLOPs": alg_flops / t_ms / 1e9}
+    share = {"encoder_fwd": 3 * kern["encoder_fwd"]["ms"], "encoder_bwd": 2 * kern["encoder_bwd"]["ms"]}
+    dom = max(share, key=share.get)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": kern[dom]["GBps"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": B * T * D_IN * 4, "kernels": kern,
+                "step": {"algorithmic_bytes": BYTES_PER_PAIR_T * T * B, "algorithmic_flops": FLOPS_PER_PAIR_T * T * B,
+                         "hbm_roofline_ms": BYTES_PER_PAIR_T * T * B / (peaks["hbm_gbs"] * 1e6),
+                         "frac_of_hbm_roofline": (BYTES_PER_PAIR_T * T * B / (peaks["hbm_gbs"] * 1e6)) / ms,
+                         "tensor_3pass_roofline_ms": 3 * FLOPS_PER_PAIR_T * T * B / (peaks["bf16_tflops_sustained"] * 1e9)}}
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D of the step's inputs + D2H of its losses inside
+    e2e = None
+    if not args.no_e2e:
+        hb = []
+        for b in (clean, noisy):
+            hb.append({"net_input": {"feats": b["net_input"]["feats"].cpu().pin_memory(),
+                                     "padding_mask": b["net_input"]["padding_mask"].cpu().pin_memory()},
+                       "labels": b["labels"].cpu().pin_memory()})
+        h2d = sum(t.numel() * t.element_size() for b in hb for t in (b["net_input"]["feats"], b["net_input"]["padding_mask"], b["labels"]))
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(2):
+            eng.set_inputs(hb[0], hb[1]); eng.step(args.epoch); eng.losses()
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            eng.set_inputs(hb[0], hb[1])
+            eng.step(args.epoch)
+            eng.losses()  # D2H read of the step's losses (sync)
+        sync()
+        dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            dt = float(t)
+        e2e = {"value": Bg / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16, "ms_per_step": dt * 1e3}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, threads = cpu_reference_steps(64, T, 8 if T <= 200 else 2, 2, args.epoch)
+        cpu = {"value": 64 / sec, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"oracle port of the reference step, B=64, T={T}, full loss stack, median of {8 if T <= 200 else 2} steps"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "DAD train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+            "dtype": "f32 (bf16x3 split products on tcgen05, fp32 accumulate)" if args.gemm == "tc" else "f32", "data": "synthetic",
+            "config": {"workload": wl["label"], "global_batch": Bg, "per_gpu_batch": B, "T": T, "parallelism": f"dp{world}",
+                       "noise": "in-kernel Philox", "cuda_graph": not args.no_graph,
+                       "l2": "inputs >> L2 (126 MB)" if not small else "L2 flushed (256 MB write) between individually timed steps"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "losses_last_step": losses,
+        }))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
