@@ -379,10 +379,347 @@ int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W_hi, cons
     return DAD_OK;
 }
 
-// ---- backward on tensor cores: lands next; until then the mode reports unsupported (no silent fallback)
-int enc_bwd_tc_splits(int64_t) { return 1; }
-size_t enc_bwd_tc_ws_bytes(int64_t, int64_t) { return 256; }
-int launch_enc_bwd_tc(const float*, const uint8_t*, const AugParams&, const uint32_t*, const float*, const float*, float*, float*, int, void*,
-                      size_t, int64_t, int64_t, cudaStream_t) {
-    return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_bwd: DAD_GEMM_TC_BF16X3 backward not built yet");
+// =====================================================================================================================
+// Backward:  dW[256,768] = sum_n dpre[n,:] (x) aug(x)[n,:],   dpre[n,h] = relu_bit(n,h) * valid(n) * g[b(n),h] / len_b
+//   = a [256 x N] . [N x 768] GEMM whose reduction axis is the frame axis: BOTH operands are MN-major in shared memory
+//   (frame rows, 128-byte lines of 64 contiguous h / d elements, SWIZZLE_128B), so nothing is transposed.
+//   grid = (3 d-slices of 256, S frame-range splits); per CTA two 128 x 256 fp32 accumulators (all 512 TMEM columns).
+//   The A operand is never read from memory as numbers: it is SELECTED from a per-utterance table of pre-split
+//   g/len values (G_hi/G_lo, bf16) by the 1-bit ReLU mask of the forward.  Split partials are reduced in fixed order
+//   by dad_grad_reduce (deterministic, no fp32 atomics).
+// =====================================================================================================================
+namespace {
+
+constexpr int BWD_BK = 32, BWD_STAGES = 3, BWD_THREADS = 512;
+constexpr uint32_t BOP_BYTES = DAD_H * BWD_BK * 2;                  // 16 KB: one operand (hi or lo), 256 x 32 bf16
+constexpr uint32_t BSTAGE_BYTES = 4 * BOP_BYTES;                    // A_hi, A_lo, B_hi, B_lo = 64 KB
+constexpr uint32_t BOFF_AHI = 0, BOFF_ALO = BOP_BYTES, BOFF_BHI = 2 * BOP_BYTES, BOFF_BLO = 3 * BOP_BYTES;
+constexpr uint32_t BOFF_BARS = BWD_STAGES * BSTAGE_BYTES;
+constexpr uint32_t BWD_SMEM = BOFF_BARS + 128 + 1024;
+constexpr uint32_t MN_LBO = (BWD_BK / 8) * 1024;                    // pitch between 64-element M/N chunks (4 k-groups of 1 KB)
+constexpr uint32_t MN_SBO = 1024;                                   // pitch between 8-frame groups
+
+struct BwdParams {
+    const float* x;
+    const uint8_t* pad;
+    AugParams ap;
+    const uint32_t* bits;            // [N][8]
+    const __nv_bfloat16* g_hi;       // [B][256]  bf16(g/len)
+    const __nv_bfloat16* g_lo;       // [B][256]  bf16(g/len - hi)
+    float* dWp;                      // [S][256][768]
+    int64_t N;
+    int T;
+    int64_t rows_per_split;          // multiple of 32
+};
+
+// G_hi/G_lo = bf16 split of g_emb / len (division as in autograd of sum/len), one thread per (b,h)
+__global__ void __launch_bounds__(DAD_H) k_bwd_prep(const float* __restrict__ g_emb, const float* __restrict__ lens, __nv_bfloat16* __restrict__ g_hi,
+                                                    __nv_bfloat16* __restrict__ g_lo) {
+    const int64_t i = (int64_t)blockIdx.x * DAD_H + threadIdx.x;
+    const float v = g_emb[i] / lens[blockIdx.x];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    g_hi[i] = h;
+    g_lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// db[h]: sum over valid frames of relu_bit * g/len (fp32, exact selection).  grid = (S, sub): CTA (s, u) covers the u-th
+// slice of split s's frame range with 4 independent frames in flight per thread; k_bwd_db_fold sums the sub-partials.
+__global__ void __launch_bounds__(DAD_H) k_bwd_db(const uint32_t* __restrict__ bits, const uint8_t* __restrict__ pad, const float* __restrict__ g_emb,
+                                                  const float* __restrict__ lens, float* __restrict__ sub_part, int64_t N, int T,
+                                                  int64_t rows_per_split, int64_t rows_per_sub) {
+    const int h = threadIdx.x;
+    const int64_t s0 = (int64_t)blockIdx.x * rows_per_split;
+    const int64_t s1 = s0 + rows_per_split < N ? s0 + rows_per_split : N;
+    int64_t n0 = s0 + (int64_t)blockIdx.y * rows_per_sub;
+    int64_t n1 = n0 + rows_per_sub < s1 ? n0 + rows_per_sub : s1;
+    float acc = 0.f;
+    for (int64_t n = n0; n < n1; n += 4) {
+        uint32_t w[4];
+        bool on[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t m = n + u;
+            on[u] = m < n1 && !(pad && pad[m]);
+            w[u] = on[u] ? __ldg(bits + m * DAD_HW + (h >> 5)) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (on[u] && ((w[u] >> (h & 31)) & 1u)) {
+                const int64_t b = (n + u) / T;
+                acc += __ldg(g_emb + b * DAD_H + h) / __ldg(lens + b);
+            }
+        }
+    }
+    sub_part[((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * DAD_H + h] = acc;
+}
+__global__ void __launch_bounds__(DAD_H) k_bwd_db_fold(const float* __restrict__ sub_part, float* __restrict__ dbp, int nsub) {
+    float s = 0.f;
+    for (int u = 0; u < nsub; ++u) s += sub_part[((int64_t)blockIdx.x * nsub + u) * DAD_H + threadIdx.x];
+    dbp[(int64_t)blockIdx.x * DAD_H + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1) k_enc_bwd_tc(BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BOFF_BARS);
+    uint64_t* full = bars;                  // [3] 8 converter warps
+    uint64_t* empty = bars + BWD_STAGES;    // [3] 1 (tcgen05.commit)
+    uint64_t* tfull = bars + 2 * BWD_STAGES;  // [1]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * BWD_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dslice = blockIdx.x, split = blockIdx.y;
+    const int64_t n_begin = (int64_t)split * p.rows_per_split;
+    const int64_t n_end = n_begin + p.rows_per_split < p.N ? n_begin + p.rows_per_split : p.N;
+    const int nkb = n_end > n_begin ? (int)ceil_div64(n_end - n_begin, BWD_BK) : 0;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < BWD_STAGES; ++s) { tc::mbar_init(&full[s], N_CONV_WARPS); tc::mbar_init(&empty[s], 1); }
+        tc::mbar_init(tfull, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) {
+        tc::tmem_alloc(tmem_ptr, TMEM_COLS);
+        tc::tmem_relinquish();
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = tc::make_idesc_bf16(128, DAD_H, 1, 1);  // A and B both MN-major
+        for (int kb = 0; kb < nkb; ++kb) {
+            const uint32_t s = kb % BWD_STAGES, ph = (kb / BWD_STAGES) & 1;
+            tc::mbar_wait(&full[s], ph);
+            tc::tcgen05_fence_after();
+            if (lane == 0) {
+                const uint32_t base = tc::smem_u32(smem + s * BSTAGE_BYTES);
+#pragma unroll
+                for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+                    for (int prod = 0; prod < 3; ++prod) {
+                        const uint32_t a_off = ((prod == 2) ? BOFF_ALO : BOFF_AHI) + mh * 2 * MN_LBO;  // hi*hi, hi*lo, lo*hi
+                        const uint32_t b_off = (prod == 1) ? BOFF_BLO : BOFF_BHI;
+#pragma unroll
+                        for (int ks = 0; ks < BWD_BK / 16; ++ks) {
+                            const uint64_t ad = tc::make_smem_desc(base + a_off + ks * 2 * MN_SBO, MN_LBO, MN_SBO);
+                            const uint64_t bd = tc::make_smem_desc(base + b_off + ks * 2 * MN_SBO, MN_LBO, MN_SBO);
+                            tc::umma_bf16(tmem_base + mh * DAD_H, ad, bd, idesc, (kb | prod | ks) != 0);
+                        }
+                    }
+                tc::umma_commit(&empty[s]);
+                if (kb == nkb - 1) tc::umma_commit(tfull);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= CONV_WARP0 && warp < CONV_WARP0 + N_CONV_WARPS) {
+        // ===================== converters =====================
+        const int cw = warp - CONV_WARP0;
+        const int ctid = threadIdx.x - CONV_WARP0 * 32;  // 0..255
+        const AugParams& ap = p.ap;
+        const unsigned long long seed = (ap.mode && ap.noise_src == 1) ? aug_seed(ap) : 0ull;
+        const int mode = ap.mode;
+        // x operand: this thread converts float4 #f (f = half*32 + lane) of rows cw*4 + i/2, i = 0..7
+        // A operand: this thread generates the 16-byte chunks hq = hc + 8j (j = 0..3) of frame row ar
+        const int ar = ctid >> 3, hc = ctid & 7;
+        float4 cur[8], nxt[8];
+        uint32_t zc = 0, zn = 0;
+        uint32_t wcur[4], wnxt[4];
+        int64_t bcur = 0, bnxt = 0;
+
+        auto x_flags = [&](int kb) -> uint32_t {
+            uint32_t z = 0;
+#pragma unroll
+            for (int r4 = 0; r4 < 4; ++r4) {
+                const int64_t n = n_begin + (int64_t)kb * BWD_BK + cw * 4 + r4;
+                bool zr = n >= n_end;
+                if (!zr && mode == 2 && ap.t_start && ap.mask_len > 0) {
+                    const int b = (int)(n / p.T), t = (int)(n - (int64_t)b * p.T);
+                    const int s = __ldg(ap.t_start + b);
+                    zr = (t >= s && t < s + ap.mask_len);
+                }
+                z |= (zr ? 1u : 0u) << r4;
+            }
+            return z;
+        };
+        auto x_loads = [&](int kb, uint32_t z, float4 (&dst)[8]) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r4 = i >> 1, f = (i & 1) * 32 + lane;
+                const int64_t n = n_begin + (int64_t)kb * BWD_BK + cw * 4 + r4;
+                if (n < n_end && !((z >> r4) & 1u)) dst[i] = __ldg(reinterpret_cast<const float4*>(p.x + n * DAD_D + dslice * 256 + f * 4));
+                else dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto a_loads = [&](int kb, uint32_t (&w)[4], int64_t& b) {
+            const int64_t n = n_begin + (int64_t)kb * BWD_BK + ar;
+            const bool on = n < n_end && !(p.pad && p.pad[n]);
+            b = n < n_end ? n / p.T : 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int h = (hc + 8 * j) * 8;
+                const uint32_t word = on ? __ldg(p.bits + n * DAD_HW + (h >> 5)) : 0u;
+                w[j] = (word >> (h & 31)) & 0xFFu;
+            }
+        };
+
+        if (nkb > 0) {
+            zc = x_flags(0);
+            x_loads(0, zc, cur);
+            a_loads(0, wcur, bcur);
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+            const bool has_next = kb + 1 < nkb;
+            if (has_next) {
+                zn = x_flags(kb + 1);
+                x_loads(kb + 1, zn, nxt);
+                a_loads(kb + 1, wnxt, bnxt);
+            }
+            const uint32_t s = kb % BWD_STAGES, ph = (kb / BWD_STAGES) & 1;
+            tc::mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* st = smem + s * BSTAGE_BYTES;
+            // ---- A operand: dpre^T chunks selected from the pre-split g/len table by the ReLU bits
+            {
+                const uint32_t rofs = (uint32_t)(ar >> 3) * MN_SBO;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int hq = hc + 8 * j;  // 16-byte chunk index along h (0..31)
+                    const uint32_t byte = wcur[j];
+                    uint4 gh = make_uint4(0, 0, 0, 0), gl = make_uint4(0, 0, 0, 0);
+                    if (byte) {
+                        gh = __ldg(reinterpret_cast<const uint4*>(p.g_hi + bcur * DAD_H + hq * 8));
+                        gl = __ldg(reinterpret_cast<const uint4*>(p.g_lo + bcur * DAD_H + hq * 8));
+                        const uint32_t m0 = ((byte & 1u) ? 0x0000FFFFu : 0u) | ((byte & 2u) ? 0xFFFF0000u : 0u);
+                        const uint32_t m1 = ((byte & 4u) ? 0x0000FFFFu : 0u) | ((byte & 8u) ? 0xFFFF0000u : 0u);
+                        const uint32_t m2 = ((byte & 16u) ? 0x0000FFFFu : 0u) | ((byte & 32u) ? 0xFFFF0000u : 0u);
+                        const uint32_t m3 = ((byte & 64u) ? 0x0000FFFFu : 0u) | ((byte & 128u) ? 0xFFFF0000u : 0u);
+                        gh.x &= m0; gh.y &= m1; gh.z &= m2; gh.w &= m3;
+                        gl.x &= m0; gl.y &= m1; gl.z &= m2; gl.w &= m3;
+                    }
+                    const uint32_t off = (uint32_t)(hq >> 3) * MN_LBO + rofs + tc::sw128_offset(ar & 7, hq & 7);
+                    *reinterpret_cast<uint4*>(st + BOFF_AHI + off) = gh;
+                    *reinterpret_cast<uint4*>(st + BOFF_ALO + off) = gl;
+                }
+            }
+            // ---- B operand: aug(x) rows -> bf16 hi/lo
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r4 = i >> 1, f = (i & 1) * 32 + lane;
+                const int r = cw * 4 + r4;
+                float4 v = cur[i];
+                const bool zr = (zc >> r4) & 1u;
+                if (mode != 0 && !zr) {
+                    const int64_t n = n_begin + (int64_t)kb * BWD_BK + r;
+                    const int d = dslice * 256 + f * 4;
+                    const int64_t e = n * DAD_D + d;
+                    float4 nz;
+                    if (ap.noise_src == 1) nz = philox_normal4(seed, ap.stream, (unsigned long long)(e >> 2));
+                    else nz = __ldg(reinterpret_cast<const float4*>(ap.noise + e));
+                    v.x = aug_add_noise(v.x, nz.x, ap.sigma); v.y = aug_add_noise(v.y, nz.y, ap.sigma);
+                    v.z = aug_add_noise(v.z, nz.z, ap.sigma); v.w = aug_add_noise(v.w, nz.w, ap.sigma);
+                    if (mode == 2 && ap.feat_keep) {
+                        const float4 kp = __ldg(reinterpret_cast<const float4*>(ap.feat_keep + d));
+                        v.x = __fmul_rn(v.x, kp.x); v.y = __fmul_rn(v.y, kp.y); v.z = __fmul_rn(v.z, kp.z); v.w = __fmul_rn(v.w, kp.w);
+                    }
+                }
+                if (zr) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                uint32_t h01, l01, h23, l23;
+                tc::split2_bf16(v.x, v.y, h01, l01);
+                tc::split2_bf16(v.z, v.w, h23, l23);
+                const uint32_t off = (uint32_t)(f >> 4) * MN_LBO + (uint32_t)(r >> 3) * MN_SBO + tc::sw128_offset(r & 7, (f & 15) >> 1) + (f & 1) * 8;
+                *reinterpret_cast<uint2*>(st + BOFF_BHI + off) = make_uint2(h01, h23);
+                *reinterpret_cast<uint2*>(st + BOFF_BLO + off) = make_uint2(l01, l23);
+            }
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&full[s]);
+            if (has_next) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) wcur[j] = wnxt[j];
+                zc = zn;
+                bcur = bnxt;
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue: TMEM -> split-K partial dW =====================
+        const int q = warp - EPI_WARP0;
+        float* out = p.dWp + (int64_t)split * DAD_H * DAD_D;
+        if (nkb > 0) {
+            tc::mbar_wait(tfull, 0);
+            tc::tcgen05_fence_after();
+        }
+#pragma unroll 1
+        for (int mh = 0; mh < 2; ++mh) {
+            const int h = mh * 128 + q * 32 + lane;
+            float* row = out + (int64_t)h * DAD_D + dslice * 256;
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+                uint32_t r[32];
+                if (nkb > 0) {
+                    tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + mh * DAD_H + c * 32, r);
+                    tc::tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(row + c * 32 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            }
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc::tcgen05_fence_after();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace
+
+int enc_bwd_tc_splits(int64_t N) {
+    // grid = 3 d-slices x S: one wave of 147 CTAs at S = 49; keep >= 128 frames per split for small batches
+    int64_t s = N / 128;
+    if (s > 49) s = 49;
+    if (s < 1) s = 1;
+    return (int)s;
+}
+constexpr int DB_MAX_SUB = 32;
+size_t enc_bwd_tc_ws_bytes(int64_t B, int64_t) {
+    return (size_t)(2 * B * DAD_H * sizeof(__nv_bfloat16)) + 256 + (size_t)49 * DB_MAX_SUB * DAD_H * sizeof(float);
+}
+
+int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, const uint32_t* bits, const float* g_emb, const float* lens,
+                      float* dWp, float* dbp, int splits, void* ws, size_t ws_bytes, int64_t B, int64_t T, cudaStream_t st) {
+    if (ws_bytes < enc_bwd_tc_ws_bytes(B, T)) return dad_set_error(DAD_ERR_WS, "encoder_bwd(tc): workspace too small");
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_enc_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
+        if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "encoder_bwd(tc): cannot opt in to %u B shared memory: %s", BWD_SMEM, cudaGetErrorString(e));
+        attr = true;
+    }
+    __nv_bfloat16* g_hi = reinterpret_cast<__nv_bfloat16*>(ws);
+    __nv_bfloat16* g_lo = g_hi + B * DAD_H;
+    k_bwd_prep<<<(unsigned)B, DAD_H, 0, st>>>(g_emb, lens, g_hi, g_lo);
+    DAD_CHECK_LAUNCH("k_bwd_prep");
+    BwdParams p;
+    p.x = x; p.pad = pad; p.ap = ap; p.bits = bits; p.g_hi = g_hi; p.g_lo = g_lo; p.dWp = dWp;
+    p.N = B * T; p.T = (int)T;
+    p.rows_per_split = ceil_div64(ceil_div64(p.N, splits), BWD_BK) * BWD_BK;
+    k_enc_bwd_tc<<<dim3(DAD_D / 256, splits), BWD_THREADS, BWD_SMEM, st>>>(p);
+    DAD_CHECK_LAUNCH("k_enc_bwd_tc");
+    float* sub_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + (((size_t)(2 * B * DAD_H * sizeof(__nv_bfloat16)) + 255) & ~(size_t)255));
+    int nsub = (int)(p.rows_per_split / 64);
+    nsub = nsub < 1 ? 1 : (nsub > DB_MAX_SUB ? DB_MAX_SUB : nsub);
+    const int64_t rows_per_sub = ceil_div64(p.rows_per_split, nsub);
+    k_bwd_db<<<dim3(splits, nsub), DAD_H, 0, st>>>(bits, pad, g_emb, lens, sub_part, p.N, (int)T, p.rows_per_split, rows_per_sub);
+    DAD_CHECK_LAUNCH("k_bwd_db");
+    k_bwd_db_fold<<<splits, DAD_H, 0, st>>>(sub_part, dbp, nsub);
+    DAD_CHECK_LAUNCH("k_bwd_db_fold");
+    return DAD_OK;
 }
