@@ -34,9 +34,12 @@ def make_batches(B, T, seed, snr_db=10.0, variable_len=False, mu=None):
         lens = _lengths(B, T, g, variable_len)
         pad = torch.arange(T)[None, :] >= lens[:, None]
         if domain == "noisy":
-            valid = (~pad).unsqueeze(-1).float()
-            P = (x * x * valid).sum(dim=(1, 2)) / (lens.float() * D_IN)
-            sigma = torch.sqrt(P / (10.0 ** (snr_db / 10.0)))
+            # fp64 accumulation, rounded to fp32 once: the result does not depend on the host's SIMD reduction order,
+            # so fixtures generated in the build container reproduce bit-for-bit on the GPU box's CPU
+            valid = (~pad).unsqueeze(-1).double()
+            xd = x.double()
+            P = (xd * xd * valid).sum(dim=(1, 2)) / (lens.double() * D_IN)
+            sigma = torch.sqrt(P / (10.0 ** (snr_db / 10.0))).float()
             x = x + sigma[:, None, None] * torch.randn(B, T, D_IN, generator=g)
         x = x.masked_fill(pad.unsqueeze(-1), 0.0).contiguous()
         out.append({"id": torch.arange(B), "net_input": {"feats": x, "padding_mask": pad}, "labels": y})
