@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--pretrain-steps", type=int, default=30, help="CE-only steps before the timed region (SURVEY 8d); lower it under ncu")
     return ap.parse_args()
 
 
@@ -186,7 +187,7 @@ def run_ours(args):
     clean, noisy = device_batches(B, T, 1234 + rank, dev)
     eng.set_inputs(clean, noisy)
     eng.set_lr(cfg.LEARNING_RATE)
-    for _ in range(30):  # CE-only pretraining (epoch 0 < WARMUP_EPOCHS), then teacher := student, fresh Adam
+    for _ in range(args.pretrain_steps):  # CE-only pretraining (epoch 0 < WARMUP_EPOCHS), then teacher := student, fresh Adam
         eng.step(0)
     eng.init_teacher()
     eng.m.zero_(); eng.v.zero_(); eng.step_count.zero_()
@@ -292,7 +293,7 @@ def run_ours(args):
         print(json.dumps({
             "metric": "DAD train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
-            "dtype": "f32 (bf16x3 split products on tcgen05, fp32 accumulate)" if args.gemm == "tc" else "f32", "data": "synthetic",
+            "dtype": "f32 (scaled fp16 hi/lo split, 3 tcgen05 products per GEMM, fp32 accumulate)" if args.gemm == "tc" else "f32", "data": "synthetic",
             "config": {"workload": wl["label"], "global_batch": Bg, "per_gpu_batch": B, "T": T, "parallelism": f"dp{world}",
                        "noise": "in-kernel Philox", "cuda_graph": not args.no_graph,
                        "l2": "inputs >> L2 (126 MB)" if not small else "L2 flushed (256 MB write) between individually timed steps"},

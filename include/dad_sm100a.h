@@ -33,7 +33,7 @@ extern "C" {
 
 /* GEMM arithmetic of the encoder kernels */
 #define DAD_GEMM_FP32 0      /* CUDA-core fp32 FMA: exact path, any B,T */
-#define DAD_GEMM_TC_BF16X3 1 /* tcgen05 (5th-gen tensor core, TMEM accumulators) bf16 hi/lo split, 3 products, fp32 accumulate */
+#define DAD_GEMM_TC_F16X3 1  /* tcgen05 (5th-gen tensor core, TMEM accumulators): power-of-two scaled fp16 hi/lo split, 3 products, fp32 accumulate */
 
 int dad_abi_version(void);
 const char* dad_last_error(void);
@@ -68,7 +68,7 @@ int dad_augment(const float* x, float* out, const dad_aug* aug, int64_t B, int64
 size_t dad_encoder_fwd_workspace_bytes(int64_t B, int64_t T, int32_t gemm_mode);
 /* emb[B,H] = masked-mean_t relu(W aug(x)[b,t,:] + bias).  pad: [B,T] uint8, 1 = padded frame, NULL = none.
  * relu_bits (nullable): [B*T, H/32] uint32, bit j of word w of frame n = (pre[n, 32w+j] > 0) -- all the backward needs.
- * lens (nullable): [B] valid length clamped to >= 1 (I/model.py:36).  W_hi/W_lo: bf16 [H,D] splits (TC mode only). */
+ * lens (nullable): [B] valid length clamped to >= 1 (I/model.py:36).  W_hi/W_lo: fp16 [H,D] splits from dad_split_f16 (TC mode only). */
 int dad_encoder_fwd(const float* x, const uint8_t* pad, const float* W, const float* bias, const void* W_hi,
                     const void* W_lo, const dad_aug* aug, float* emb, uint32_t* relu_bits, float* lens, void* ws,
                     size_t ws_bytes, int64_t B, int64_t T, int32_t gemm_mode, void* stream);
@@ -163,7 +163,7 @@ int dad_grad_reduce(const float* dW_part0, const float* db_part0, int32_t splits
 /* global L2 norm -> scal[0] norm, [1] clip coef (max_norm <= 0: no clipping), [2] lr/(1-b1^t), [3] sqrt(1-b2^t); ++*step */
 int dad_grad_norm(const float* g, double* part_ws /*[128]*/, uint32_t* counter, int64_t* step, const double* lr,
                   float* scal, float max_norm, void* stream);
-/* clip -> Adam (betas .9/.999, eps 1e-8, coupled L2 wd) -> EMA teacher (do_ema) -> bf16 hi/lo splits of W, teacher W (nullable).
+/* clip -> Adam (betas .9/.999, eps 1e-8, coupled L2 wd) -> EMA teacher (do_ema) -> fp16 hi/lo splits of W, teacher W (nullable).
  * loss_src (nullable) = [CE, KD, ECDA] of this step: loss_last[4] = {total, CE, KD, ECDA}, loss_acc[5] += {.., 1}
  * (device-side replacement of the per-step .item() reads of I/train.py:494-495; total = CE + w_kd KD + w_ecda ECDA). */
 int dad_adam_ema(float* p, float* t, float* m, float* v, const float* g, const float* scal, float wd, float ema_m,
@@ -171,8 +171,8 @@ int dad_adam_ema(float* p, float* t, float* m, float* v, const float* g, const f
                  float* loss_last, double* loss_acc, float w_kd, float w_ecda, void* stream);
 /* SSRLModel.update_teacher_ema on a flat buffer: t = t*m + s*(1-m) (two muls + add, no FMA) */
 int dad_ema(float* t, const float* s, float ema_m, float ema_1m, int64_t n, void* stream);
-/* bf16 hi/lo split of an fp32 weight matrix: hi = bf16(w), lo = bf16(w - hi) */
-int dad_split_bf16(const float* w, void* hi, void* lo, int64_t n, void* stream);
+/* fp16 hi/lo split of an fp32 encoder weight matrix: hi = fp16(256 w), lo = fp16(256 w - hi) (saturating) */
+int dad_split_f16(const float* w, void* hi, void* lo, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ EXPORTS = (
     "dad_encoder_fwd", "dad_encoder_bwd_splits", "dad_encoder_bwd", "dad_encoder_bwd_workspace_bytes",
     "dad_pack_rank_words", "dad_head_grid", "dad_head_fwd", "dad_dacp_mask", "dad_head_bwd",
     "dad_ecda_workspace_bytes", "dad_ecda", "dad_grad_reduce", "dad_grad_norm", "dad_adam_ema", "dad_ema",
-    "dad_split_bf16", "dad_step_rng",
+    "dad_split_f16", "dad_step_rng",
 )
 
 
@@ -105,7 +105,7 @@ def lib():
     L.dad_grad_norm.argtypes = [vp, vp, vp, vp, vp, vp, f32, vp]
     L.dad_adam_ema.argtypes = [vp, vp, vp, vp, vp, vp, f32, f32, f32, i32, vp, vp, vp, vp, vp, vp, vp, f32, f32, vp]
     L.dad_ema.argtypes = [vp, vp, f32, f32, i64, vp]
-    L.dad_split_bf16.argtypes = [vp, vp, vp, i64, vp]
+    L.dad_split_f16.argtypes = [vp, vp, vp, i64, vp]
     L.dad_step_rng.argtypes = [C.c_uint64, vp, vp, vp, i64, f32, vp, f32, vp, i64, i32, vp]
     if L.dad_abi_version() != 1:
         raise DadError("libdad_sm100a.so ABI version mismatch")

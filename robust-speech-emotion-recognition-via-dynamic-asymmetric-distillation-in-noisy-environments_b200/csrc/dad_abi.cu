@@ -34,7 +34,7 @@ int launch_grad_reduce(const GradReduceArgs& a, cudaStream_t st);
 int launch_grad_norm(const NormArgs& a, cudaStream_t st);
 int launch_adam_ema(const AdamArgs& a, cudaStream_t st);
 int launch_ema(float* t, const float* s, float ema_m, float ema_1m, int n, cudaStream_t st);
-int launch_split_bf16(const float* w, void* hi, void* lo, int n, cudaStream_t st);
+int launch_split_f16(const float* w, void* hi, void* lo, int n, cudaStream_t st);
 
 // ---- error plumbing
 static thread_local char g_err[512] = "";
@@ -94,7 +94,7 @@ int dad_step_rng(uint64_t seed, const int64_t* step_ptr, float* keep_clean, floa
 // ---------------------------------------------------------------- encoder
 size_t dad_encoder_fwd_workspace_bytes(int64_t B, int64_t T, int32_t gemm_mode) {
     const size_t counters = align_up((size_t)(2 * B) * sizeof(unsigned), 256);
-    if (gemm_mode == DAD_GEMM_TC_BF16X3) return counters + enc_fwd_tc_ws_bytes(B, T);
+    if (gemm_mode == DAD_GEMM_TC_F16X3) return counters + enc_fwd_tc_ws_bytes(B, T);
     return counters + enc_fwd_simt_ws_bytes(B, T);
 }
 
@@ -119,18 +119,18 @@ int dad_encoder_fwd(const float* x, const uint8_t* pad, const float* W, const fl
     if (gemm_mode == DAD_GEMM_FP32) {
         DAD_REQUIRE(W && aligned16(W), "encoder_fwd: W null or unaligned");
         return launch_enc_fwd_simt(x, pad, W, bias, ap, emb, relu_bits, lens, reinterpret_cast<float*>(rest), counters, B, T, (cudaStream_t)stream);
-    } else if (gemm_mode == DAD_GEMM_TC_BF16X3) {
-        DAD_REQUIRE(W_hi && W_lo, "encoder_fwd: TC mode needs the bf16 hi/lo weight splits (dad_split_bf16)");
+    } else if (gemm_mode == DAD_GEMM_TC_F16X3) {
+        DAD_REQUIRE(W_hi && W_lo, "encoder_fwd: TC mode needs the bf16 hi/lo weight splits (dad_split_f16)");
         return launch_enc_fwd_tc(x, pad, W_hi, W_lo, bias, ap, emb, relu_bits, lens, rest, ws_bytes - (size_t)(rest - (char*)ws), B, T, (cudaStream_t)stream);
     }
     return dad_set_error(DAD_ERR_ARG, "encoder_fwd: unknown gemm_mode %d", gemm_mode);
 }
 
 int32_t dad_encoder_bwd_splits(int64_t B, int64_t T, int32_t gemm_mode) {
-    return gemm_mode == DAD_GEMM_TC_BF16X3 ? enc_bwd_tc_splits(B * T) : enc_bwd_simt_splits(B * T);
+    return gemm_mode == DAD_GEMM_TC_F16X3 ? enc_bwd_tc_splits(B * T) : enc_bwd_simt_splits(B * T);
 }
 size_t dad_encoder_bwd_workspace_bytes(int64_t B, int64_t T, int32_t gemm_mode) {
-    return gemm_mode == DAD_GEMM_TC_BF16X3 ? enc_bwd_tc_ws_bytes(B, T) : 256;
+    return gemm_mode == DAD_GEMM_TC_F16X3 ? enc_bwd_tc_ws_bytes(B, T) : 256;
 }
 
 int dad_encoder_bwd(const float* x, const uint8_t* pad, const dad_aug* aug, const uint32_t* relu_bits, const float* g_emb,
@@ -147,7 +147,7 @@ int dad_encoder_bwd(const float* x, const uint8_t* pad, const dad_aug* aug, cons
     if (aug) ap = *aug;
     if (gemm_mode == DAD_GEMM_FP32)
         return launch_enc_bwd_simt(x, pad, ap, relu_bits, g_emb, lens, dW_part, db_part, splits, B, T, (cudaStream_t)stream);
-    if (gemm_mode == DAD_GEMM_TC_BF16X3) {
+    if (gemm_mode == DAD_GEMM_TC_F16X3) {
         const size_t need = enc_bwd_tc_ws_bytes(B, T);
         if (!ws || ws_bytes < need) return dad_set_error(DAD_ERR_WS, "encoder_bwd: workspace %zu < %zu bytes", ws_bytes, need);
         return launch_enc_bwd_tc(x, pad, ap, relu_bits, g_emb, lens, dW_part, db_part, splits, ws, ws_bytes, B, T, (cudaStream_t)stream);
@@ -276,10 +276,10 @@ int dad_ema(float* t, const float* s, float ema_m, float ema_1m, int64_t n, void
     return launch_ema(t, s, ema_m, ema_1m, (int)n, (cudaStream_t)stream);
 }
 
-int dad_split_bf16(const float* w, void* hi, void* lo, int64_t n, void* stream) {
-    DAD_REQUIRE(n >= 0 && n < (1ll << 31), "split_bf16: bad n");
-    DAD_REQUIRE(n == 0 || (w && hi && lo), "split_bf16: null pointer");
-    return launch_split_bf16(w, hi, lo, (int)n, (cudaStream_t)stream);
+int dad_split_f16(const float* w, void* hi, void* lo, int64_t n, void* stream) {
+    DAD_REQUIRE(n >= 0 && n < (1ll << 31), "split_f16: bad n");
+    DAD_REQUIRE(n == 0 || (w && hi && lo), "split_f16: null pointer");
+    return launch_split_f16(w, hi, lo, (int)n, (cudaStream_t)stream);
 }
 
 }  // extern "C"

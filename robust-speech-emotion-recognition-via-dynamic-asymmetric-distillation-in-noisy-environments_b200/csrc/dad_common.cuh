@@ -29,6 +29,11 @@ int dad_set_error(int code, const char* fmt, ...);  // returns code
 // DAD_D = 768, DAD_H = 256, DAD_C = 4 come from dad_sm100a.h
 constexpr int DAD_HW = DAD_H / 32;  // ReLU bitmask words per frame
 
+// Power-of-two operand scales of the tcgen05 "f16x3" path (exact in fp32; see k_enc_tc.cu): features x 2^3, encoder weight x 2^8.
+constexpr float TC_XS = 8.0f;
+constexpr float TC_WS = 256.0f;
+constexpr float TC_INV_XW = 1.0f / (TC_XS * TC_WS);
+
 static __host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -71,16 +76,41 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     }
     return ctr;
 }
-// four unit normals for the aligned group of 4 consecutive elements starting at flat index 4*idx4
+// ---------------------------------------------------------------------------------------------
+// Canonical in-kernel noise field (throughput mode; the parity mode reads supplied noise instead).
+// One Philox4x32-10 call -- counter (n2, c4, stream, 0), key = seed -- yields the 8 unit normals of the float4 column
+// group c4 (columns 4*c4 .. 4*c4+3, c4 < 192) of the frame-row pair (2*n2, 2*n2+1): each 32-bit word feeds one
+// Box-Muller pair with a 16-bit radius uniform u = (k + 0.5) / 65536 and a 16-bit angle (|z| <= 4.86; the
+// truncated tail mass is 1.2e-6).  word j -> (r_j cos_j, r_j sin_j); words 0,1 belong to the even row, words 2,3 to the odd row.
+// Every kernel that needs the noise (materialising augment, CUDA-core and tcgen05 encoder forward AND backward)
+// regenerates it from this function, so the field is identical wherever it is consumed.
+// radius_k: -2 ln2 * sigma^2 folds the noise scale into the radius (r = sigma * sqrt(-2 ln u)); pass -2 ln2 for unit normals.
+// Cost: ~60 integer ops + 16 MUFU per 8 normals (no I2F: the uniforms are built in the mantissa of [1,2) floats).
+// ---------------------------------------------------------------------------------------------
+constexpr float NOISE_UNIT_K = -1.3862943611198906f;  // -2 ln 2
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+struct NoiseBM8 { float r[4], c[4], s[4]; };
+__device__ __forceinline__ void philox_bm8(unsigned long long seed, uint32_t stream, uint32_t n2, uint32_t c4, float radius_k, NoiseBM8& o) {
+    const uint4 w4 = philox4x32_10(make_uint4(n2, c4, stream, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float u = __uint_as_float(0x3f800040u | ((w[j] & 0xffffu) << 7)) - 1.0f;  // (k + 0.5) / 65536 in (0, 1)
+        o.r[j] = fast_sqrt(__log2f(u) * radius_k);
+        const float turns = __uint_as_float(0x3f800000u | ((w[j] >> 16) << 7));        // 1 + a / 65536: sin/cos are 1-periodic in turns
+        __sincosf(6.283185307179586f * turns, &o.s[j], &o.c[j]);
+    }
+}
+// four unit normals for the aligned group of 4 consecutive elements starting at flat index 4*idx4 of a [N, 768] tensor
 __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long stream, unsigned long long idx4) {
-    uint4 r = philox4x32_10(make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)),
-                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    const float k = 2.3283064365386963e-10f;  // 2^-32
-    float u0 = fmaf((float)r.x, k, k * 0.5f), u1 = (float)r.y * k;
-    float u2 = fmaf((float)r.z, k, k * 0.5f), u3 = (float)r.w * k;
-    float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
-    float s0, c0, s1, c1;
-    __sincosf(6.283185307179586f * u1, &s0, &c0);
-    __sincosf(6.283185307179586f * u3, &s1, &c1);
-    return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+    const unsigned long long n = idx4 / (DAD_D / 4);
+    const uint32_t c4 = (uint32_t)(idx4 - n * (DAD_D / 4));
+    NoiseBM8 z;
+    philox_bm8(seed, (uint32_t)stream, (uint32_t)(n >> 1), c4, NOISE_UNIT_K, z);
+    return (n & 1ull) ? make_float4(z.r[2] * z.c[2], z.r[2] * z.s[2], z.r[3] * z.c[3], z.r[3] * z.s[3])
+                      : make_float4(z.r[0] * z.c[0], z.r[0] * z.s[0], z.r[1] * z.c[1], z.r[1] * z.s[1]);
 }

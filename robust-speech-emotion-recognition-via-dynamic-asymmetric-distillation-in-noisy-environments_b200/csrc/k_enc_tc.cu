@@ -1,21 +1,25 @@
 // Encoder kernels on the 5th-gen tensor cores (tcgen05, accumulators in TMEM, weights fed by TMA).
 //
-// Arithmetic: every fp32 operand is split on the fly into bf16 hi + bf16 lo (hi = bf16(x), lo = bf16(x - hi)) and the
-// product is formed as  hi*hi + hi*lo + lo*hi  with fp32 accumulation in TMEM ("bf16x3", ~2^-17 relative per product;
-// parity evidence in DESIGN.md).  Only the dense contractions run here; everything else stays on CUDA cores.
+// Arithmetic ("f16x3"): every fp32 operand is scaled by a power of two (exact) and split on the fly into fp16 hi + fp16 lo
+// (hi = fp16(x), lo = fp16(x - hi): 22 significant bits together) and the product is formed as  hi*hi + hi*lo + lo*hi
+// with fp32 accumulation in TMEM (~2^-21 relative per product; the dropped lo*lo term is 2^-22).  Same tensor-pipe cost
+// as a bf16 split (kind::f16 runs fp16 and bf16 at one rate) but 16x tighter, which is what keeps the ECDA gradient and
+// the ReLU sign decisions inside the parity tolerance (DESIGN.md "Precision").  Scales: x by 2^3, W by 2^8 (fixed: |x| <
+// 8188, |W| < 255 before saturation), g/len by a per-launch power of two derived from its absmax.  Only the dense
+// contractions run here; everything else stays on CUDA cores.
 //
 // Forward  (I/model.py:18-41):  pre[N,256] = aug(x)[N,768] . W^T,  emb[b] = sum_t valid relu(pre + bias) / len_b
 //   persistent CTAs (one per SM), 128-frame x 256-unit tiles, K loop of 12 x 64.  Warp roles:
-//     warp 0      TMA producer: W_hi / W_lo k-blocks (bf16, SWIZZLE_128B) -> smem ring
+//     warp 0      TMA producer: W_hi / W_lo k-blocks (fp16, SWIZZLE_128B) -> smem ring
 //     warp 1      MMA issuer : 12 tcgen05.mma (3 products x 4 k-steps) per k-block into one of two TMEM accumulators
 //     warp 2      TMEM allocator
 //     warps 4-11  converters : coalesced LDG of fp32 x (+ fused weak/strong augmentation, I/utils.py:328-375),
-//                              bf16 hi/lo split, swizzled st.shared of the A operand (K-major, SWIZZLE_128B)
+//                              fp16 hi/lo split, swizzled st.shared of the A operand (K-major, SWIZZLE_128B)
 //     warps 12-15 epilogue   : tcgen05.ld -> bias + ReLU + padding mask -> 1-bit ReLU mask + per-32-frame pooled partial sums
 //   k_pool_finalize then sums the partials of each utterance in fixed order and divides by its valid length.
 #include "dad_common.cuh"
 #include "tc_ptx.cuh"
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <mutex>
 
 namespace {
@@ -44,6 +48,137 @@ struct FwdParams {
     int T;
     int num_tiles;
 };
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Converter warp body of the forward kernel.  Thread (cw, lane): 8-byte k-slot kq = lane & 15 of the 64-wide k-block and
+// the 8 CONSECUTIVE tile rows rbase = cw*16 + (lane>>4)*8 .. +7 (exactly one 8-row SWIZZLE_128B atom, 4 noise row pairs):
+//   - a warp-wide LDG.128 reads two fully used 256-byte row segments; the two shared-memory stores of a row hit all 32 banks once;
+//   - every address is  base + compile-time immediate  (no per-element index arithmetic);
+//   - two register sets ping-pong (flat (tile, k-block) iteration space unrolled by 2): the loads of iteration i+1 are in
+//     flight while iteration i is converted, and nothing is copied between the sets;
+//   - rows that contribute zeros (beyond N, or inside the temporal mask span of the strong view) are flagged per tile.
+// MODE 0 clean, 1 weak, 2 strong (I/utils.py:328-375); PHILOX: canonical in-kernel noise field, else supplied noise tensor.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int MODE, bool PHILOX>
+__device__ __forceinline__ void fwd_convert(const FwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, const int cw, const int lane) {
+    const int kq = lane & 15;
+    const int rbase = cw * 16 + (lane >> 4) * 8;
+    const uint32_t c16 = (uint32_t)kq >> 1;
+    const uint32_t sbase = (uint32_t)rbase * 128u + (uint32_t)(kq & 1) * 8u;
+    const AugParams& ap = p.ap;
+    const unsigned long long seed = (MODE != 0 && PHILOX) ? aug_seed(ap) : 0ull;
+    const float radius_k = NOISE_UNIT_K * ap.sigma * ap.sigma;
+    const int n_my_tiles = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_iter = n_my_tiles * KB;  // even (KB = 12)
+
+    auto tile_of = [&](int it) { return (int)blockIdx.x + (it / KB) * (int)gridDim.x; };
+    // bit i set: row rbase+i of `tile` contributes zeros
+    auto row_flags = [&](int tile) -> uint32_t {
+        const int64_t row0 = (int64_t)tile * BM + rbase;
+        uint32_t z = 0;
+        if (row0 + 8 > p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z |= (row0 + i >= p.N ? 1u : 0u) << i;
+        }
+        if (MODE == 2 && ap.t_start && ap.mask_len > 0 && row0 < p.N) {
+            const uint32_t r0 = (uint32_t)row0;  // N < 2^31 on this path (launch check)
+            uint32_t b = r0 / (uint32_t)p.T, t = r0 - b * (uint32_t)p.T;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if ((int64_t)r0 + i < p.N) {
+                    const int s0 = __ldg(ap.t_start + b);
+                    z |= (((int)t >= s0 && (int)t < s0 + ap.mask_len) ? 1u : 0u) << i;
+                }
+                if (++t == (uint32_t)p.T) { t = 0; ++b; }
+            }
+        }
+        return z;
+    };
+    auto load = [&](float4 (&dst)[8], int it) {
+        const int tile = tile_of(it), kb = it % KB;
+        const int64_t row0 = (int64_t)tile * BM + rbase;
+        const float* src = p.x + row0 * DAD_D + kb * BK + kq * 4;
+        if (row0 + 8 <= p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = __ldg(reinterpret_cast<const float4*>(src + i * DAD_D));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                dst[i] = (row0 + i < p.N) ? __ldg(reinterpret_cast<const float4*>(src + i * DAD_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto store_row = [&](uint8_t* a_hi, uint8_t* a_lo, const float4& v, int i, uint32_t zmask) {
+        uint32_t h01 = 0, l01 = 0, h23 = 0, l23 = 0;
+        if (!((zmask >> i) & 1u)) {
+            tc::split2_f16(v.x * TC_XS, v.y * TC_XS, h01, l01);
+            tc::split2_f16(v.z * TC_XS, v.w * TC_XS, h23, l23);
+        }
+        const uint32_t off = sbase + (uint32_t)i * 128u + ((c16 ^ (uint32_t)i) << 4);
+        *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(h01, h23);
+        *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(l01, l23);
+    };
+    auto convert = [&](float4 (&cur)[8], int it, uint32_t zmask) {
+        const int tile = tile_of(it), kb = it % KB;
+        const uint32_t s = (uint32_t)it % STAGES, ph = ((uint32_t)it / STAGES) & 1u;
+        tc::mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* a_hi = smem + s * STAGE_BYTES + OFF_AHI;
+        uint8_t* a_lo = smem + s * STAGE_BYTES + OFF_ALO;
+        if (MODE != 0) {
+            const int64_t row0 = (int64_t)tile * BM + rbase;
+            float4 keep = make_float4(1.f, 1.f, 1.f, 1.f);
+            const bool has_keep = MODE == 2 && ap.feat_keep != nullptr;
+            if (has_keep) keep = __ldg(reinterpret_cast<const float4*>(ap.feat_keep + kb * BK + kq * 4));
+#pragma unroll
+            for (int rp = 0; rp < 4; ++rp) {
+                float4& va = cur[2 * rp];
+                float4& vb = cur[2 * rp + 1];
+                if (PHILOX) {
+                    NoiseBM8 z;
+                    philox_bm8(seed, (uint32_t)ap.stream, (uint32_t)((row0 + 2 * rp) >> 1), (uint32_t)(kb * (BK / 4) + kq), radius_k, z);
+                    va.x = fmaf(z.r[0], z.c[0], va.x); va.y = fmaf(z.r[0], z.s[0], va.y); va.z = fmaf(z.r[1], z.c[1], va.z); va.w = fmaf(z.r[1], z.s[1], va.w);
+                    vb.x = fmaf(z.r[2], z.c[2], vb.x); vb.y = fmaf(z.r[2], z.s[2], vb.y); vb.z = fmaf(z.r[3], z.c[3], vb.z); vb.w = fmaf(z.r[3], z.s[3], vb.w);
+                } else {
+                    // parity mode: supplied unit normals, out = x + (n * sigma) with two fp32 roundings (bit-exact vs I/utils.py:330,338)
+                    const float* nz = ap.noise + (row0 + 2 * rp) * DAD_D + kb * BK + kq * 4;
+                    const bool ina = row0 + 2 * rp < p.N, inb = row0 + 2 * rp + 1 < p.N;
+                    const float4 na = ina ? __ldg(reinterpret_cast<const float4*>(nz)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 nb = inb ? __ldg(reinterpret_cast<const float4*>(nz + DAD_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    va.x = aug_add_noise(va.x, na.x, ap.sigma); va.y = aug_add_noise(va.y, na.y, ap.sigma);
+                    va.z = aug_add_noise(va.z, na.z, ap.sigma); va.w = aug_add_noise(va.w, na.w, ap.sigma);
+                    vb.x = aug_add_noise(vb.x, nb.x, ap.sigma); vb.y = aug_add_noise(vb.y, nb.y, ap.sigma);
+                    vb.z = aug_add_noise(vb.z, nb.z, ap.sigma); vb.w = aug_add_noise(vb.w, nb.w, ap.sigma);
+                }
+                if (has_keep) {
+                    va.x = __fmul_rn(va.x, keep.x); va.y = __fmul_rn(va.y, keep.y); va.z = __fmul_rn(va.z, keep.z); va.w = __fmul_rn(va.w, keep.w);
+                    vb.x = __fmul_rn(vb.x, keep.x); vb.y = __fmul_rn(vb.y, keep.y); vb.z = __fmul_rn(vb.z, keep.z); vb.w = __fmul_rn(vb.w, keep.w);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) store_row(a_hi, a_lo, cur[i], i, zmask);
+        tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&full[s]);
+    };
+
+    if (n_iter == 0) return;
+    float4 bufA[8], bufB[8];
+    uint32_t zcur = row_flags(tile_of(0));
+    load(bufA, 0);
+    for (int it = 0; it < n_iter; it += 2) {
+        // ---- even iteration: convert A while B's loads fly (it + 1 is always in the same tile: KB is even)
+        load(bufB, it + 1);
+        convert(bufA, it, zcur);
+        // ---- odd iteration: convert B while A's loads (possibly the first k-block of the next tile) fly
+        uint32_t znext = zcur;
+        if (it + 2 < n_iter) {
+            if ((it + 2) % KB == 0) znext = row_flags(tile_of(it + 2));
+            load(bufA, it + 2);
+        }
+        convert(bufB, it + 1, zcur);
+        zcur = znext;
+    }
+}
 
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo, FwdParams p) {
@@ -77,8 +212,12 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
     tc::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
+    // register budget follows the roles (setmaxnreg, one per role branch): 128 x 40 (control warps 0-3) + 256 x 168 (converters)
+    // + 128 x 128 (epilogue) <= 64 K registers
+
     if (warp == 0) {
         // ===================== TMA producer (weights) =====================
+        tc::reg_dec<40>();
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
@@ -92,7 +231,8 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = tc::make_idesc_bf16(BM, DAD_H, 0, 0);
+        tc::reg_dec<40>();
+        constexpr uint32_t idesc = tc::make_idesc_f16(BM, DAD_H, 0, 0);
         uint32_t it = 0, ti = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
             const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
@@ -113,7 +253,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
                         for (int k = 0; k < BK / 16; ++k) {
                             const uint64_t ad = tc::make_smem_desc(base + a_off + k * 32, 16, 1024);
                             const uint64_t bd = tc::make_smem_desc(base + b_off + k * 32, 16, 1024);
-                            tc::umma_bf16(d_tmem, ad, bd, idesc, (kb | prod | k) != 0);
+                            tc::umma_f16(d_tmem, ad, bd, idesc, (kb | prod | k) != 0);
                         }
                     }
                     tc::umma_commit(&empty[s]);                  // smem slot free once these MMAs retire
@@ -123,96 +263,16 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
             }
         }
     } else if (warp >= CONV_WARP0 && warp < CONV_WARP0 + N_CONV_WARPS) {
-        // ===================== converters: fp32 x (+ augmentation) -> bf16 hi/lo A operand =====================
+        // ===================== converters: fp32 x (+ augmentation) -> fp16 hi/lo A operand =====================
+        tc::reg_inc<168>();
         const int cw = warp - CONV_WARP0;
-        const int kq = lane & 15, rsub = lane >> 4;  // float4 index inside the 64-float k-block row segment; row parity
-        const AugParams& ap = p.ap;
-        const unsigned long long seed = (ap.mode && ap.noise_src == 1) ? aug_seed(ap) : 0ull;
-        const int mode = ap.mode;
-        uint32_t it = 0;
-        float4 cur[8], nxt[8];
-        uint32_t zero_cur = 0, zero_nxt = 0;  // bit i: row i of this thread is out of range (or temporally masked) -> contributes zeros
-
-        auto row_flags = [&](int tile) -> uint32_t {
-            uint32_t z = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t n = (int64_t)tile * BM + cw * 16 + 2 * i + rsub;
-                bool zr = n >= p.N;
-                if (!zr && mode == 2 && ap.t_start && ap.mask_len > 0) {
-                    const int b = (int)(n / p.T), t = (int)(n - (int64_t)b * p.T);
-                    const int s = __ldg(ap.t_start + b);
-                    zr = (t >= s && t < s + ap.mask_len);
-                }
-                z |= (zr ? 1u : 0u) << i;
-            }
-            return z;
-        };
-        auto issue_loads = [&](int tile, int kb, uint32_t zmask, float4 (&dst)[8]) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t n = (int64_t)tile * BM + cw * 16 + 2 * i + rsub;
-                if (n < p.N && !((zmask >> i) & 1u))
-                    dst[i] = __ldg(reinterpret_cast<const float4*>(p.x + n * DAD_D + kb * BK + kq * 4));
-                else
-                    dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-
-        int tile = blockIdx.x;
-        if (tile < p.num_tiles) {
-            zero_cur = row_flags(tile);
-            issue_loads(tile, 0, zero_cur, cur);
-        }
-        for (; tile < p.num_tiles; tile += gridDim.x) {
-            for (int kb = 0; kb < KB; ++kb, ++it) {
-                // prefetch the next k-block (possibly of the next tile) into registers before converting this one
-                int ntile = tile, nkb = kb + 1;
-                if (nkb == KB) { nkb = 0; ntile = tile + gridDim.x; }
-                const bool has_next = ntile < p.num_tiles;
-                if (has_next) {
-                    zero_nxt = (nkb == 0) ? row_flags(ntile) : zero_cur;
-                    issue_loads(ntile, nkb, zero_nxt, nxt);
-                }
-                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                tc::mbar_wait(&empty[s], ph ^ 1);
-                uint8_t* a_hi = smem + s * STAGE_BYTES + OFF_AHI;
-                uint8_t* a_lo = smem + s * STAGE_BYTES + OFF_ALO;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = cw * 16 + 2 * i + rsub;
-                    float4 v = cur[i];
-                    const bool zr = (zero_cur >> i) & 1u;
-                    if (mode != 0 && !zr) {
-                        const int64_t n = (int64_t)tile * BM + r;
-                        const int64_t e = n * DAD_D + kb * BK + kq * 4;
-                        float4 nz;
-                        if (ap.noise_src == 1) nz = philox_normal4(seed, ap.stream, (unsigned long long)(e >> 2));
-                        else nz = __ldg(reinterpret_cast<const float4*>(ap.noise + e));
-                        v.x = aug_add_noise(v.x, nz.x, ap.sigma); v.y = aug_add_noise(v.y, nz.y, ap.sigma);
-                        v.z = aug_add_noise(v.z, nz.z, ap.sigma); v.w = aug_add_noise(v.w, nz.w, ap.sigma);
-                        if (mode == 2 && ap.feat_keep) {
-                            const float4 kp = __ldg(reinterpret_cast<const float4*>(ap.feat_keep + kb * BK + kq * 4));
-                            v.x = __fmul_rn(v.x, kp.x); v.y = __fmul_rn(v.y, kp.y); v.z = __fmul_rn(v.z, kp.z); v.w = __fmul_rn(v.w, kp.w);
-                        }
-                    }
-                    if (zr) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    uint32_t h01, l01, h23, l23;
-                    tc::split2_bf16(v.x, v.y, h01, l01);
-                    tc::split2_bf16(v.z, v.w, h23, l23);
-                    const uint32_t off = tc::sw128_offset(r, kq >> 1) + (kq & 1) * 8;
-                    *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(h01, h23);
-                    *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(l01, l23);
-                }
-                tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&full[s]);
-                if (has_next) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-                    zero_cur = zero_nxt;
-                }
-            }
+        const int variant = p.ap.mode == 0 ? 0 : (p.ap.mode * 2 - 1 + (p.ap.noise_src == 1 ? 1 : 0));  // 0 | 1,2 weak | 3,4 strong (supplied, philox)
+        switch (variant) {
+            case 0: fwd_convert<0, false>(p, smem, full, empty, cw, lane); break;
+            case 1: fwd_convert<1, false>(p, smem, full, empty, cw, lane); break;
+            case 2: fwd_convert<1, true>(p, smem, full, empty, cw, lane); break;
+            case 3: fwd_convert<2, false>(p, smem, full, empty, cw, lane); break;
+            default: fwd_convert<2, true>(p, smem, full, empty, cw, lane); break;
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: TMEM -> bias + ReLU + mask -> ReLU bits + pooled partial sums =====================
@@ -240,7 +300,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
                 uint32_t w = 0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float pre = __uint_as_float(r[j]) + s_bias[c * 32 + j];
+                    const float pre = fmaf(__uint_as_float(r[j]), TC_INV_XW, s_bias[c * 32 + j]);  // exact power-of-two unscale, then + bias (one rounding, as fp32 x.W + b)
                     const bool pos = pre > 0.f;
                     w |= (pos ? 1u : 0u) << j;
                     scratch[lane * 33 + j] = (pos && valid) ? pre : 0.f;
@@ -263,6 +323,8 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
                 dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
             }
         }
+    } else {
+        tc::reg_dec<40>();  // warps 2, 3: same warpgroup as the TMA / MMA warps
     }
     tc::tcgen05_fence_before();
     __syncthreads();
@@ -319,15 +381,15 @@ PFN_encodeTiled get_encode() {
     return fn;
 }
 
-// bf16 [rows][cols] row-major, box = [box_rows][64 cols] (128 bytes inner), SWIZZLE_128B
-int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// fp16 [rows][cols] row-major, box = [box_rows][64 cols] (128 bytes inner), SWIZZLE_128B
+int make_tmap_f16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return dad_set_error(DAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {cols * 2};
     cuuint32_t box[2] = {64, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return dad_set_error(DAD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return DAD_OK;
@@ -354,13 +416,14 @@ size_t enc_fwd_tc_ws_bytes(int64_t B, int64_t T) {
 int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W_hi, const void* W_lo, const float* bias, const AugParams& ap, float* emb,
                       uint32_t* bits, float* lens_out, void* ws, size_t ws_bytes, int64_t B, int64_t T, cudaStream_t st) {
     if (T < 32) return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_fwd: the tcgen05 path needs T >= 32 (got %lld); use DAD_GEMM_FP32", (long long)T);
+    if (B * T >= (1ll << 31)) return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_fwd: the tcgen05 path indexes frames with 32 bits (B*T = %lld)", (long long)(B * T));
     if ((reinterpret_cast<uintptr_t>(W_hi) | reinterpret_cast<uintptr_t>(W_lo)) & 15u)
         return dad_set_error(DAD_ERR_ARG, "encoder_fwd: W_hi/W_lo must be 16-byte aligned (TMA)");
     if (ws_bytes < enc_fwd_tc_ws_bytes(B, T)) return dad_set_error(DAD_ERR_WS, "encoder_fwd(tc): workspace too small");
     CUtensorMap tm_hi, tm_lo;
-    int rc = make_tmap_bf16(&tm_hi, W_hi, DAD_H, DAD_D, DAD_H);
+    int rc = make_tmap_f16(&tm_hi, W_hi, DAD_H, DAD_D, DAD_H);
     if (rc) return rc;
-    rc = make_tmap_bf16(&tm_lo, W_lo, DAD_H, DAD_D, DAD_H);
+    rc = make_tmap_f16(&tm_lo, W_lo, DAD_H, DAD_D, DAD_H);
     if (rc) return rc;
     static bool attr = false;
     if (!attr) {
@@ -385,13 +448,13 @@ int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W_hi, cons
 //   (frame rows, 128-byte lines of 64 contiguous h / d elements, SWIZZLE_128B), so nothing is transposed.
 //   grid = (3 d-slices of 256, S frame-range splits); per CTA two 128 x 256 fp32 accumulators (all 512 TMEM columns).
 //   The A operand is never read from memory as numbers: it is SELECTED from a per-utterance table of pre-split
-//   g/len values (G_hi/G_lo, bf16) by the 1-bit ReLU mask of the forward.  Split partials are reduced in fixed order
+//   scaled g/len values (G_hi/G_lo, fp16) by the 1-bit ReLU mask of the forward.  Split partials are reduced in fixed order
 //   by dad_grad_reduce (deterministic, no fp32 atomics).
 // =====================================================================================================================
 namespace {
 
 constexpr int BWD_BK = 32, BWD_STAGES = 3, BWD_THREADS = 512;
-constexpr uint32_t BOP_BYTES = DAD_H * BWD_BK * 2;                  // 16 KB: one operand (hi or lo), 256 x 32 bf16
+constexpr uint32_t BOP_BYTES = DAD_H * BWD_BK * 2;                  // 16 KB: one operand (hi or lo), 256 x 32 fp16
 constexpr uint32_t BSTAGE_BYTES = 4 * BOP_BYTES;                    // A_hi, A_lo, B_hi, B_lo = 64 KB
 constexpr uint32_t BOFF_AHI = 0, BOFF_ALO = BOP_BYTES, BOFF_BHI = 2 * BOP_BYTES, BOFF_BLO = 3 * BOP_BYTES;
 constexpr uint32_t BOFF_BARS = BWD_STAGES * BSTAGE_BYTES;
@@ -404,58 +467,289 @@ struct BwdParams {
     const uint8_t* pad;
     AugParams ap;
     const uint32_t* bits;            // [N][8]
-    const __nv_bfloat16* g_hi;       // [B][256]  bf16(g/len)
-    const __nv_bfloat16* g_lo;       // [B][256]  bf16(g/len - hi)
+    const uint16_t* g_hi;            // [B][256]  fp16(s * g/len)
+    const uint16_t* g_lo;            // [B][256]  fp16(s * g/len - hi)
+    const float* unscale;            // [1] 1 / (s * TC_XS): applied to the accumulators in the epilogue (exact power of two)
     float* dWp;                      // [S][256][768]
     int64_t N;
     int T;
     int64_t rows_per_split;          // multiple of 32
 };
 
-// G_hi/G_lo = bf16 split of g_emb / len (division as in autograd of sum/len), one thread per (b,h)
-__global__ void __launch_bounds__(DAD_H) k_bwd_prep(const float* __restrict__ g_emb, const float* __restrict__ lens, __nv_bfloat16* __restrict__ g_hi,
-                                                    __nv_bfloat16* __restrict__ g_lo) {
-    const int64_t i = (int64_t)blockIdx.x * DAD_H + threadIdx.x;
-    const float v = g_emb[i] / lens[blockIdx.x];
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    g_hi[i] = h;
-    g_lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+constexpr int ABSMAX_GRID = 32;
+
+// per-CTA partial max of |g/len| (no atomics: the table scale must be bit-reproducible)
+__global__ void __launch_bounds__(DAD_H) k_bwd_absmax(const float* __restrict__ g_emb, const float* __restrict__ lens, float* __restrict__ part, int B) {
+    __shared__ float s_w[DAD_H / 32];
+    float m = 0.f;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) m = fmaxf(m, fabsf(g_emb[(int64_t)b * DAD_H + threadIdx.x] / lens[b]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < DAD_H / 32; ++w) m = fmaxf(m, s_w[w]);
+        part[blockIdx.x] = m;
+    }
 }
 
-// db[h]: sum over valid frames of relu_bit * g/len (fp32, exact selection).  grid = (S, sub): CTA (s, u) covers the u-th
-// slice of split s's frame range with 4 independent frames in flight per thread; k_bwd_db_fold sums the sub-partials.
+// G_hi/G_lo = fp16 split of s * g_emb / len (division as in autograd of sum/len), one thread per (b,h).
+// s = 2^(13-e) with 2^e <= absmax < 2^(e+1): the largest entry lands in [2^13, 2^14), 18 octaves of entries keep all 22 bits.
+__global__ void __launch_bounds__(DAD_H) k_bwd_prep(const float* __restrict__ g_emb, const float* __restrict__ lens, const float* __restrict__ part,
+                                                    uint16_t* __restrict__ g_hi, uint16_t* __restrict__ g_lo, float* __restrict__ unscale) {
+    __shared__ float s_scale;
+    if (threadIdx.x < 32) {
+        float m = threadIdx.x < ABSMAX_GRID ? part[threadIdx.x] : 0.f;
+        m = warp_max(m);
+        if (threadIdx.x == 0) {
+            float sc = 1.0f;
+            if (m > 0.f && m < 3.0e38f) {
+                int e = (int)((__float_as_uint(m) >> 23) & 0xFFu) - 127;  // floor(log2 m) for normal m
+                if (e < -100) e = -100;                                     // keep s and 1/s finite fp32 normals
+                sc = __uint_as_float((uint32_t)(127 + 13 - e) << 23);
+            }
+            s_scale = sc;
+            if (blockIdx.x == 0) unscale[0] = 1.0f / (sc * TC_XS);
+        }
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * DAD_H + threadIdx.x;
+    const float v = (g_emb[i] / lens[blockIdx.x]) * s_scale;
+    unsigned short h, l;
+    tc::split1_f16(v, h, l);
+    g_hi[i] = h;
+    g_lo[i] = l;
+}
+
+// db[h] = sum over valid frames of relu_bit(n,h) * g[b,h]/len_b = sum_b (g[b,h]/len_b) * count_b[h]:
+// one CTA per utterance counts its ReLU bits per hidden unit (warp ballots over 32-frame chunks), contrib[b][h] = count * g/len;
+// k_bwd_db_fold then sums utterance groups in fixed order into the split partials consumed by dad_grad_reduce.
 __global__ void __launch_bounds__(DAD_H) k_bwd_db(const uint32_t* __restrict__ bits, const uint8_t* __restrict__ pad, const float* __restrict__ g_emb,
-                                                  const float* __restrict__ lens, float* __restrict__ sub_part, int64_t N, int T,
-                                                  int64_t rows_per_split, int64_t rows_per_sub) {
-    const int h = threadIdx.x;
-    const int64_t s0 = (int64_t)blockIdx.x * rows_per_split;
-    const int64_t s1 = s0 + rows_per_split < N ? s0 + rows_per_split : N;
-    int64_t n0 = s0 + (int64_t)blockIdx.y * rows_per_sub;
-    int64_t n1 = n0 + rows_per_sub < s1 ? n0 + rows_per_sub : s1;
-    float acc = 0.f;
-    for (int64_t n = n0; n < n1; n += 4) {
-        uint32_t w[4];
-        bool on[4];
+                                                  const float* __restrict__ lens, float* __restrict__ contrib, int T) {
+    __shared__ int s_cnt[DAD_H / 32][DAD_H];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
+    int cnt[DAD_HW];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t m = n + u;
-            on[u] = m < n1 && !(pad && pad[m]);
-            w[u] = on[u] ? __ldg(bits + m * DAD_HW + (h >> 5)) : 0u;
+    for (int w = 0; w < DAD_HW; ++w) cnt[w] = 0;
+    for (int t0 = warp * 32; t0 < T; t0 += (DAD_H / 32) * 32) {
+        const int t = t0 + lane;
+        const int64_t n = (int64_t)b * T + t;
+        uint32_t wd[DAD_HW];
+        const bool on = t < T && !(pad && pad[n]);
+        if (on) {
+            const uint4 lo = __ldg(reinterpret_cast<const uint4*>(bits + n * DAD_HW));
+            const uint4 hi = __ldg(reinterpret_cast<const uint4*>(bits + n * DAD_HW) + 1);
+            wd[0] = lo.x; wd[1] = lo.y; wd[2] = lo.z; wd[3] = lo.w; wd[4] = hi.x; wd[5] = hi.y; wd[6] = hi.z; wd[7] = hi.w;
+        } else {
+#pragma unroll
+            for (int w = 0; w < DAD_HW; ++w) wd[w] = 0u;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (on[u] && ((w[u] >> (h & 31)) & 1u)) {
-                const int64_t b = (n + u) / T;
-                acc += __ldg(g_emb + b * DAD_H + h) / __ldg(lens + b);
+        for (int w = 0; w < DAD_HW; ++w) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const unsigned bal = __ballot_sync(0xffffffffu, (wd[w] >> j) & 1u);
+                if (lane == j) cnt[w] += __popc(bal);
             }
         }
     }
-    sub_part[((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * DAD_H + h] = acc;
+#pragma unroll
+    for (int w = 0; w < DAD_HW; ++w) s_cnt[warp][w * 32 + lane] = cnt[w];
+    __syncthreads();
+    const int h = threadIdx.x;
+    int c = 0;
+#pragma unroll
+    for (int w = 0; w < DAD_H / 32; ++w) c += s_cnt[w][h];
+    contrib[(int64_t)b * DAD_H + h] = (float)c * (g_emb[(int64_t)b * DAD_H + h] / lens[b]);
 }
-__global__ void __launch_bounds__(DAD_H) k_bwd_db_fold(const float* __restrict__ sub_part, float* __restrict__ dbp, int nsub) {
-    float s = 0.f;
-    for (int u = 0; u < nsub; ++u) s += sub_part[((int64_t)blockIdx.x * nsub + u) * DAD_H + threadIdx.x];
-    dbp[(int64_t)blockIdx.x * DAD_H + threadIdx.x] = s;
+__global__ void __launch_bounds__(DAD_H) k_bwd_db_fold(const float* __restrict__ contrib, float* __restrict__ dbp, int B, int per) {
+    const int b0 = blockIdx.x * per;
+    const int b1 = b0 + per < B ? b0 + per : B;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int b = b0;
+    for (; b + 3 < b1; b += 4) {
+        s0 += contrib[(int64_t)b * DAD_H + threadIdx.x];
+        s1 += contrib[(int64_t)(b + 1) * DAD_H + threadIdx.x];
+        s2 += contrib[(int64_t)(b + 2) * DAD_H + threadIdx.x];
+        s3 += contrib[(int64_t)(b + 3) * DAD_H + threadIdx.x];
+    }
+    for (; b < b1; ++b) s0 += contrib[(int64_t)b * DAD_H + threadIdx.x];
+    dbp[(int64_t)blockIdx.x * DAD_H + threadIdx.x] = (s0 + s1) + (s2 + s3);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Converter warp body of the backward kernel.  Warp cw owns the 4 consecutive frames cw*4 .. cw*4+3 of every 32-frame k-block
+// (two noise row pairs), for BOTH operands:
+//   B operand (aug(x), 256 d columns of this CTA's slice): lane -> float4 columns lane and lane+32 (two coalesced 512-byte loads per row);
+//   A operand (dpre^T, 256 hidden units): lane -> the 16-byte chunk of 8 hidden units hq = lane; one pre-split fp16 g/len table chunk
+//     per UTTERANCE serves all frames of that utterance, so it is fetched once per k-block together with the next k-block's
+//     data (no dependent load on the critical path); the ReLU byte of each frame masks it.
+// (utterance, frame-in-utterance) of the warp's first frame advance incrementally (T >= 32: at most one wrap per k-block).
+// Two register sets ping-pong over the k-blocks so the loads of k-block i+1 fly while k-block i is converted.
+// ---------------------------------------------------------------------------------------------------------------------
+struct BwdRegs {
+    float4 x[8];     // [r4*2 + half]
+    uint32_t w[4];   // ReLU mask word holding this lane's byte, per frame
+    uint4 gh, gl;    // table chunk of utterance b0
+    uint32_t flags;  // bits 0-3: x row contributes zeros; bits 4-7: A row active (in range and not padded)
+    int b0, t0;      // utterance / frame-in-utterance of the warp's first frame
+};
+
+template <int MODE, bool PHILOX>
+__device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, const int cw, const int lane,
+                                            const int dslice, const int64_t n_begin, const int64_t n_end, const int nkb) {
+    const AugParams& ap = p.ap;
+    const unsigned long long seed = (MODE != 0 && PHILOX) ? aug_seed(ap) : 0ull;
+    const float radius_k = NOISE_UNIT_K * ap.sigma * ap.sigma;
+    const int T = p.T;
+    // shared-memory offsets (MN-major, SWIZZLE_128B): frame r = cw*4 + j -> 8-frame group cw>>1, row-in-atom r7 = (cw&1)*4 + j
+    const uint32_t r7b = (uint32_t)(cw & 1) * 4u;
+    const uint32_t xoff0 = (uint32_t)(lane >> 4) * MN_LBO + (uint32_t)(cw >> 1) * MN_SBO + (uint32_t)(lane & 1) * 8u;  // + 2*MN_LBO for the second half
+    const uint32_t xc = (uint32_t)(lane & 15) >> 1;
+    const uint32_t aoff0 = (uint32_t)(lane >> 3) * MN_LBO + (uint32_t)(cw >> 1) * MN_SBO;
+    const uint32_t ac = (uint32_t)lane & 7u;
+    const uint32_t bshift = (uint32_t)(lane & 3) * 8u;
+    float4 keep0 = make_float4(1.f, 1.f, 1.f, 1.f), keep1 = keep0;
+    const bool has_keep = MODE == 2 && ap.feat_keep != nullptr;
+    if (has_keep) {
+        keep0 = __ldg(reinterpret_cast<const float4*>(ap.feat_keep + dslice * 256 + lane * 4));
+        keep1 = __ldg(reinterpret_cast<const float4*>(ap.feat_keep + dslice * 256 + (lane + 32) * 4));
+    }
+    // (utterance, frame) of frame n_begin + cw*4, advanced by 32 frames per k-block
+    int b_run, t_run;
+    {
+        const uint32_t n0 = (uint32_t)(n_begin + cw * 4);
+        b_run = (int)(n0 / (uint32_t)T);
+        t_run = (int)(n0 - (uint32_t)b_run * (uint32_t)T);
+    }
+
+    auto load = [&](BwdRegs& R, int kb) {
+        const int64_t n0 = n_begin + (int64_t)kb * BWD_BK + cw * 4;
+        R.b0 = b_run; R.t0 = t_run;
+        t_run += BWD_BK;
+        if (t_run >= T) { t_run -= T; ++b_run; }
+        uint32_t flags = 0;
+        const float* src = p.x + n0 * DAD_D + dslice * 256 + lane * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool in = n0 + j < n_end;
+            int t = R.t0 + j, b = R.b0;
+            if (t >= T) { t -= T; ++b; }
+            bool zx = !in;
+            if (MODE == 2 && in && ap.t_start && ap.mask_len > 0) {
+                const int s0 = __ldg(ap.t_start + b);
+                zx = (t >= s0 && t < s0 + ap.mask_len);
+            }
+            if (in) {
+                R.x[2 * j] = __ldg(reinterpret_cast<const float4*>(src + j * DAD_D));
+                R.x[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(src + j * DAD_D + 128));
+                R.w[j] = __ldg(p.bits + (n0 + j) * DAD_HW + (lane >> 2));
+            } else {
+                R.x[2 * j] = R.x[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                R.w[j] = 0u;
+            }
+            const bool on = in && !(p.pad && p.pad[n0 + j]);
+            flags |= (zx ? 1u : 0u) << j;
+            flags |= (on ? 1u : 0u) << (4 + j);
+        }
+        R.flags = flags;
+        const bool any = n0 < n_end;
+        R.gh = any ? __ldg(reinterpret_cast<const uint4*>(p.g_hi + (int64_t)R.b0 * DAD_H + lane * 8)) : make_uint4(0, 0, 0, 0);
+        R.gl = any ? __ldg(reinterpret_cast<const uint4*>(p.g_lo + (int64_t)R.b0 * DAD_H + lane * 8)) : make_uint4(0, 0, 0, 0);
+    };
+
+    auto convert = [&](BwdRegs& R, int kb) {
+        const uint32_t s = (uint32_t)kb % BWD_STAGES, ph = ((uint32_t)kb / BWD_STAGES) & 1u;
+        tc::mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* st = smem + s * BSTAGE_BYTES;
+        const int64_t n0 = n_begin + (int64_t)kb * BWD_BK + cw * 4;
+        // ---- A operand: dpre^T chunks = table chunk of the frame's utterance, masked by the frame's ReLU byte
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t byte = ((R.flags >> (4 + j)) & 1u) ? ((R.w[j] >> bshift) & 0xFFu) : 0u;
+            uint4 gh = make_uint4(0, 0, 0, 0), gl = make_uint4(0, 0, 0, 0);
+            if (byte) {
+                gh = R.gh; gl = R.gl;
+                if (R.t0 + j >= T) {  // this frame already belongs to the next utterance (once per utterance boundary)
+                    gh = __ldg(reinterpret_cast<const uint4*>(p.g_hi + (int64_t)(R.b0 + 1) * DAD_H + lane * 8));
+                    gl = __ldg(reinterpret_cast<const uint4*>(p.g_lo + (int64_t)(R.b0 + 1) * DAD_H + lane * 8));
+                }
+                const uint32_t m0 = ((byte & 1u) ? 0x0000FFFFu : 0u) | ((byte & 2u) ? 0xFFFF0000u : 0u);
+                const uint32_t m1 = ((byte & 4u) ? 0x0000FFFFu : 0u) | ((byte & 8u) ? 0xFFFF0000u : 0u);
+                const uint32_t m2 = ((byte & 16u) ? 0x0000FFFFu : 0u) | ((byte & 32u) ? 0xFFFF0000u : 0u);
+                const uint32_t m3 = ((byte & 64u) ? 0x0000FFFFu : 0u) | ((byte & 128u) ? 0xFFFF0000u : 0u);
+                gh.x &= m0; gh.y &= m1; gh.z &= m2; gh.w &= m3;
+                gl.x &= m0; gl.y &= m1; gl.z &= m2; gl.w &= m3;
+            }
+            const uint32_t r7 = r7b + (uint32_t)j;
+            const uint32_t off = aoff0 + r7 * 128u + ((ac ^ r7) << 4);
+            *reinterpret_cast<uint4*>(st + BOFF_AHI + off) = gh;
+            *reinterpret_cast<uint4*>(st + BOFF_ALO + off) = gl;
+        }
+        // ---- B operand: aug(x) rows -> fp16 hi/lo (scaled by TC_XS)
+        if (MODE != 0) {
+#pragma unroll
+            for (int rp = 0; rp < 2; ++rp) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float4& va = R.x[(2 * rp) * 2 + half];
+                    float4& vb = R.x[(2 * rp + 1) * 2 + half];
+                    const int f = lane + 32 * half;
+                    if (PHILOX) {
+                        NoiseBM8 z;
+                        philox_bm8(seed, (uint32_t)ap.stream, (uint32_t)((n0 + 2 * rp) >> 1), (uint32_t)(dslice * 64 + f), radius_k, z);
+                        va.x = fmaf(z.r[0], z.c[0], va.x); va.y = fmaf(z.r[0], z.s[0], va.y); va.z = fmaf(z.r[1], z.c[1], va.z); va.w = fmaf(z.r[1], z.s[1], va.w);
+                        vb.x = fmaf(z.r[2], z.c[2], vb.x); vb.y = fmaf(z.r[2], z.s[2], vb.y); vb.z = fmaf(z.r[3], z.c[3], vb.z); vb.w = fmaf(z.r[3], z.s[3], vb.w);
+                    } else {
+                        const float* nz = ap.noise + (n0 + 2 * rp) * DAD_D + dslice * 256 + f * 4;
+                        const bool ina = n0 + 2 * rp < n_end, inb = n0 + 2 * rp + 1 < n_end;
+                        const float4 na = ina ? __ldg(reinterpret_cast<const float4*>(nz)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 nb = inb ? __ldg(reinterpret_cast<const float4*>(nz + DAD_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        va.x = aug_add_noise(va.x, na.x, ap.sigma); va.y = aug_add_noise(va.y, na.y, ap.sigma);
+                        va.z = aug_add_noise(va.z, na.z, ap.sigma); va.w = aug_add_noise(va.w, na.w, ap.sigma);
+                        vb.x = aug_add_noise(vb.x, nb.x, ap.sigma); vb.y = aug_add_noise(vb.y, nb.y, ap.sigma);
+                        vb.z = aug_add_noise(vb.z, nb.z, ap.sigma); vb.w = aug_add_noise(vb.w, nb.w, ap.sigma);
+                    }
+                    if (has_keep) {
+                        const float4 kp = half ? keep1 : keep0;
+                        va.x = __fmul_rn(va.x, kp.x); va.y = __fmul_rn(va.y, kp.y); va.z = __fmul_rn(va.z, kp.z); va.w = __fmul_rn(va.w, kp.w);
+                        vb.x = __fmul_rn(vb.x, kp.x); vb.y = __fmul_rn(vb.y, kp.y); vb.z = __fmul_rn(vb.z, kp.z); vb.w = __fmul_rn(vb.w, kp.w);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t r7 = r7b + (uint32_t)j;
+            const uint32_t roff = xoff0 + r7 * 128u + ((xc ^ r7) << 4);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const float4 v = R.x[2 * j + half];
+                uint32_t h01 = 0, l01 = 0, h23 = 0, l23 = 0;
+                if (!((R.flags >> j) & 1u)) {
+                    tc::split2_f16(v.x * TC_XS, v.y * TC_XS, h01, l01);
+                    tc::split2_f16(v.z * TC_XS, v.w * TC_XS, h23, l23);
+                }
+                const uint32_t off = roff + (uint32_t)half * 2u * MN_LBO;
+                *reinterpret_cast<uint2*>(st + BOFF_BHI + off) = make_uint2(h01, h23);
+                *reinterpret_cast<uint2*>(st + BOFF_BLO + off) = make_uint2(l01, l23);
+            }
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&full[s]);
+    };
+
+    if (nkb == 0) return;
+    BwdRegs RA, RB;
+    load(RA, 0);
+    for (int kb = 0; kb < nkb; kb += 2) {
+        if (kb + 1 < nkb) load(RB, kb + 1);
+        convert(RA, kb);
+        if (kb + 1 < nkb) {
+            if (kb + 2 < nkb) load(RA, kb + 2);
+            convert(RB, kb + 1);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(BWD_THREADS, 1) k_enc_bwd_tc(BwdParams p) {
@@ -489,7 +783,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_enc_bwd_tc(BwdParams p) {
 
     if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = tc::make_idesc_bf16(128, DAD_H, 1, 1);  // A and B both MN-major
+        tc::reg_dec<40>();
+        constexpr uint32_t idesc = tc::make_idesc_f16(128, DAD_H, 1, 1);  // A and B both MN-major
         for (int kb = 0; kb < nkb; ++kb) {
             const uint32_t s = kb % BWD_STAGES, ph = (kb / BWD_STAGES) & 1;
             tc::mbar_wait(&full[s], ph);
@@ -506,7 +801,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_enc_bwd_tc(BwdParams p) {
                         for (int ks = 0; ks < BWD_BK / 16; ++ks) {
                             const uint64_t ad = tc::make_smem_desc(base + a_off + ks * 2 * MN_SBO, MN_LBO, MN_SBO);
                             const uint64_t bd = tc::make_smem_desc(base + b_off + ks * 2 * MN_SBO, MN_LBO, MN_SBO);
-                            tc::umma_bf16(tmem_base + mh * DAD_H, ad, bd, idesc, (kb | prod | ks) != 0);
+                            tc::umma_f16(tmem_base + mh * DAD_H, ad, bd, idesc, (kb | prod | ks) != 0);
                         }
                     }
                 tc::umma_commit(&empty[s]);
@@ -516,138 +811,21 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_enc_bwd_tc(BwdParams p) {
         }
     } else if (warp >= CONV_WARP0 && warp < CONV_WARP0 + N_CONV_WARPS) {
         // ===================== converters =====================
+        tc::reg_inc<168>();
         const int cw = warp - CONV_WARP0;
-        const int ctid = threadIdx.x - CONV_WARP0 * 32;  // 0..255
-        const AugParams& ap = p.ap;
-        const unsigned long long seed = (ap.mode && ap.noise_src == 1) ? aug_seed(ap) : 0ull;
-        const int mode = ap.mode;
-        // x operand: this thread converts float4 #f (f = half*32 + lane) of rows cw*4 + i/2, i = 0..7
-        // A operand: this thread generates the 16-byte chunks hq = hc + 8j (j = 0..3) of frame row ar
-        const int ar = ctid >> 3, hc = ctid & 7;
-        float4 cur[8], nxt[8];
-        uint32_t zc = 0, zn = 0;
-        uint32_t wcur[4], wnxt[4];
-        int64_t bcur = 0, bnxt = 0;
-
-        auto x_flags = [&](int kb) -> uint32_t {
-            uint32_t z = 0;
-#pragma unroll
-            for (int r4 = 0; r4 < 4; ++r4) {
-                const int64_t n = n_begin + (int64_t)kb * BWD_BK + cw * 4 + r4;
-                bool zr = n >= n_end;
-                if (!zr && mode == 2 && ap.t_start && ap.mask_len > 0) {
-                    const int b = (int)(n / p.T), t = (int)(n - (int64_t)b * p.T);
-                    const int s = __ldg(ap.t_start + b);
-                    zr = (t >= s && t < s + ap.mask_len);
-                }
-                z |= (zr ? 1u : 0u) << r4;
-            }
-            return z;
-        };
-        auto x_loads = [&](int kb, uint32_t z, float4 (&dst)[8]) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r4 = i >> 1, f = (i & 1) * 32 + lane;
-                const int64_t n = n_begin + (int64_t)kb * BWD_BK + cw * 4 + r4;
-                if (n < n_end && !((z >> r4) & 1u)) dst[i] = __ldg(reinterpret_cast<const float4*>(p.x + n * DAD_D + dslice * 256 + f * 4));
-                else dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        auto a_loads = [&](int kb, uint32_t (&w)[4], int64_t& b) {
-            const int64_t n = n_begin + (int64_t)kb * BWD_BK + ar;
-            const bool on = n < n_end && !(p.pad && p.pad[n]);
-            b = n < n_end ? n / p.T : 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int h = (hc + 8 * j) * 8;
-                const uint32_t word = on ? __ldg(p.bits + n * DAD_HW + (h >> 5)) : 0u;
-                w[j] = (word >> (h & 31)) & 0xFFu;
-            }
-        };
-
-        if (nkb > 0) {
-            zc = x_flags(0);
-            x_loads(0, zc, cur);
-            a_loads(0, wcur, bcur);
-        }
-        for (int kb = 0; kb < nkb; ++kb) {
-            const bool has_next = kb + 1 < nkb;
-            if (has_next) {
-                zn = x_flags(kb + 1);
-                x_loads(kb + 1, zn, nxt);
-                a_loads(kb + 1, wnxt, bnxt);
-            }
-            const uint32_t s = kb % BWD_STAGES, ph = (kb / BWD_STAGES) & 1;
-            tc::mbar_wait(&empty[s], ph ^ 1);
-            uint8_t* st = smem + s * BSTAGE_BYTES;
-            // ---- A operand: dpre^T chunks selected from the pre-split g/len table by the ReLU bits
-            {
-                const uint32_t rofs = (uint32_t)(ar >> 3) * MN_SBO;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int hq = hc + 8 * j;  // 16-byte chunk index along h (0..31)
-                    const uint32_t byte = wcur[j];
-                    uint4 gh = make_uint4(0, 0, 0, 0), gl = make_uint4(0, 0, 0, 0);
-                    if (byte) {
-                        gh = __ldg(reinterpret_cast<const uint4*>(p.g_hi + bcur * DAD_H + hq * 8));
-                        gl = __ldg(reinterpret_cast<const uint4*>(p.g_lo + bcur * DAD_H + hq * 8));
-                        const uint32_t m0 = ((byte & 1u) ? 0x0000FFFFu : 0u) | ((byte & 2u) ? 0xFFFF0000u : 0u);
-                        const uint32_t m1 = ((byte & 4u) ? 0x0000FFFFu : 0u) | ((byte & 8u) ? 0xFFFF0000u : 0u);
-                        const uint32_t m2 = ((byte & 16u) ? 0x0000FFFFu : 0u) | ((byte & 32u) ? 0xFFFF0000u : 0u);
-                        const uint32_t m3 = ((byte & 64u) ? 0x0000FFFFu : 0u) | ((byte & 128u) ? 0xFFFF0000u : 0u);
-                        gh.x &= m0; gh.y &= m1; gh.z &= m2; gh.w &= m3;
-                        gl.x &= m0; gl.y &= m1; gl.z &= m2; gl.w &= m3;
-                    }
-                    const uint32_t off = (uint32_t)(hq >> 3) * MN_LBO + rofs + tc::sw128_offset(ar & 7, hq & 7);
-                    *reinterpret_cast<uint4*>(st + BOFF_AHI + off) = gh;
-                    *reinterpret_cast<uint4*>(st + BOFF_ALO + off) = gl;
-                }
-            }
-            // ---- B operand: aug(x) rows -> bf16 hi/lo
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r4 = i >> 1, f = (i & 1) * 32 + lane;
-                const int r = cw * 4 + r4;
-                float4 v = cur[i];
-                const bool zr = (zc >> r4) & 1u;
-                if (mode != 0 && !zr) {
-                    const int64_t n = n_begin + (int64_t)kb * BWD_BK + r;
-                    const int d = dslice * 256 + f * 4;
-                    const int64_t e = n * DAD_D + d;
-                    float4 nz;
-                    if (ap.noise_src == 1) nz = philox_normal4(seed, ap.stream, (unsigned long long)(e >> 2));
-                    else nz = __ldg(reinterpret_cast<const float4*>(ap.noise + e));
-                    v.x = aug_add_noise(v.x, nz.x, ap.sigma); v.y = aug_add_noise(v.y, nz.y, ap.sigma);
-                    v.z = aug_add_noise(v.z, nz.z, ap.sigma); v.w = aug_add_noise(v.w, nz.w, ap.sigma);
-                    if (mode == 2 && ap.feat_keep) {
-                        const float4 kp = __ldg(reinterpret_cast<const float4*>(ap.feat_keep + d));
-                        v.x = __fmul_rn(v.x, kp.x); v.y = __fmul_rn(v.y, kp.y); v.z = __fmul_rn(v.z, kp.z); v.w = __fmul_rn(v.w, kp.w);
-                    }
-                }
-                if (zr) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                uint32_t h01, l01, h23, l23;
-                tc::split2_bf16(v.x, v.y, h01, l01);
-                tc::split2_bf16(v.z, v.w, h23, l23);
-                const uint32_t off = (uint32_t)(f >> 4) * MN_LBO + (uint32_t)(r >> 3) * MN_SBO + tc::sw128_offset(r & 7, (f & 15) >> 1) + (f & 1) * 8;
-                *reinterpret_cast<uint2*>(st + BOFF_BHI + off) = make_uint2(h01, h23);
-                *reinterpret_cast<uint2*>(st + BOFF_BLO + off) = make_uint2(l01, l23);
-            }
-            tc::fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&full[s]);
-            if (has_next) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) wcur[j] = wnxt[j];
-                zc = zn;
-                bcur = bnxt;
-            }
+        const int variant = p.ap.mode == 0 ? 0 : (p.ap.mode * 2 - 1 + (p.ap.noise_src == 1 ? 1 : 0));
+        switch (variant) {
+            case 0: bwd_convert<0, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 1: bwd_convert<1, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 2: bwd_convert<1, true>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 3: bwd_convert<2, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            default: bwd_convert<2, true>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: TMEM -> split-K partial dW =====================
         const int q = warp - EPI_WARP0;
         float* out = p.dWp + (int64_t)split * DAD_H * DAD_D;
+        const float unscale = __ldg(p.unscale);
         if (nkb > 0) {
             tc::mbar_wait(tfull, 0);
             tc::tcgen05_fence_after();
@@ -668,9 +846,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_enc_bwd_tc(BwdParams p) {
                 }
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<uint4*>(row + c * 32 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                    *reinterpret_cast<float4*>(row + c * 32 + j) = make_float4(__uint_as_float(r[j]) * unscale, __uint_as_float(r[j + 1]) * unscale,
+                                                                                __uint_as_float(r[j + 2]) * unscale, __uint_as_float(r[j + 3]) * unscale);
             }
         }
+    } else {
+        tc::reg_dec<40>();  // warps 0, 2, 3: same warpgroup as the MMA warp
     }
     tc::tcgen05_fence_before();
     __syncthreads();
@@ -689,37 +870,50 @@ int enc_bwd_tc_splits(int64_t N) {
     if (s < 1) s = 1;
     return (int)s;
 }
-constexpr int DB_MAX_SUB = 32;
-size_t enc_bwd_tc_ws_bytes(int64_t B, int64_t) {
-    return (size_t)(2 * B * DAD_H * sizeof(__nv_bfloat16)) + 256 + (size_t)49 * DB_MAX_SUB * DAD_H * sizeof(float);
+static inline size_t bwd_align(size_t v) { return (v + 255) & ~(size_t)255; }
+struct BwdCarve { size_t g_hi, g_lo, scal, contrib, total; };
+static BwdCarve bwd_carve(int64_t B) {
+    BwdCarve c;
+    size_t o = 0;
+    c.g_hi = o; o = bwd_align(o + (size_t)B * DAD_H * sizeof(uint16_t));
+    c.g_lo = o; o = bwd_align(o + (size_t)B * DAD_H * sizeof(uint16_t));
+    c.scal = o; o = bwd_align(o + 64 * sizeof(float));   // [0,32) absmax partials, [32] unscale
+    c.contrib = o; o = bwd_align(o + (size_t)B * DAD_H * sizeof(float));
+    c.total = o;
+    return c;
 }
+size_t enc_bwd_tc_ws_bytes(int64_t B, int64_t) { return bwd_carve(B).total; }
 
 int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, const uint32_t* bits, const float* g_emb, const float* lens,
                       float* dWp, float* dbp, int splits, void* ws, size_t ws_bytes, int64_t B, int64_t T, cudaStream_t st) {
-    if (ws_bytes < enc_bwd_tc_ws_bytes(B, T)) return dad_set_error(DAD_ERR_WS, "encoder_bwd(tc): workspace too small");
+    const BwdCarve cv = bwd_carve(B);
+    if (ws_bytes < cv.total) return dad_set_error(DAD_ERR_WS, "encoder_bwd(tc): workspace too small");
+    if (T < 32) return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_bwd: the tcgen05 path needs T >= 32 (got %lld); use DAD_GEMM_FP32", (long long)T);
+    if (B * T >= (1ll << 31)) return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_bwd: the tcgen05 path indexes frames with 32 bits (B*T = %lld)", (long long)(B * T));
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_enc_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
         if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "encoder_bwd(tc): cannot opt in to %u B shared memory: %s", BWD_SMEM, cudaGetErrorString(e));
         attr = true;
     }
-    __nv_bfloat16* g_hi = reinterpret_cast<__nv_bfloat16*>(ws);
-    __nv_bfloat16* g_lo = g_hi + B * DAD_H;
-    k_bwd_prep<<<(unsigned)B, DAD_H, 0, st>>>(g_emb, lens, g_hi, g_lo);
+    uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+    uint16_t* g_hi = reinterpret_cast<uint16_t*>(w8 + cv.g_hi);
+    uint16_t* g_lo = reinterpret_cast<uint16_t*>(w8 + cv.g_lo);
+    float* scal = reinterpret_cast<float*>(w8 + cv.scal);
+    float* contrib = reinterpret_cast<float*>(w8 + cv.contrib);
+    k_bwd_absmax<<<ABSMAX_GRID, DAD_H, 0, st>>>(g_emb, lens, scal, (int)B);
+    DAD_CHECK_LAUNCH("k_bwd_absmax");
+    k_bwd_prep<<<(unsigned)B, DAD_H, 0, st>>>(g_emb, lens, scal, g_hi, g_lo, scal + 32);
     DAD_CHECK_LAUNCH("k_bwd_prep");
     BwdParams p;
-    p.x = x; p.pad = pad; p.ap = ap; p.bits = bits; p.g_hi = g_hi; p.g_lo = g_lo; p.dWp = dWp;
+    p.x = x; p.pad = pad; p.ap = ap; p.bits = bits; p.g_hi = g_hi; p.g_lo = g_lo; p.unscale = scal + 32; p.dWp = dWp;
     p.N = B * T; p.T = (int)T;
     p.rows_per_split = ceil_div64(ceil_div64(p.N, splits), BWD_BK) * BWD_BK;
     k_enc_bwd_tc<<<dim3(DAD_D / 256, splits), BWD_THREADS, BWD_SMEM, st>>>(p);
     DAD_CHECK_LAUNCH("k_enc_bwd_tc");
-    float* sub_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + (((size_t)(2 * B * DAD_H * sizeof(__nv_bfloat16)) + 255) & ~(size_t)255));
-    int nsub = (int)(p.rows_per_split / 64);
-    nsub = nsub < 1 ? 1 : (nsub > DB_MAX_SUB ? DB_MAX_SUB : nsub);
-    const int64_t rows_per_sub = ceil_div64(p.rows_per_split, nsub);
-    k_bwd_db<<<dim3(splits, nsub), DAD_H, 0, st>>>(bits, pad, g_emb, lens, sub_part, p.N, (int)T, p.rows_per_split, rows_per_sub);
+    k_bwd_db<<<(unsigned)B, DAD_H, 0, st>>>(bits, pad, g_emb, lens, contrib, (int)T);
     DAD_CHECK_LAUNCH("k_bwd_db");
-    k_bwd_db_fold<<<splits, DAD_H, 0, st>>>(sub_part, dbp, nsub);
+    k_bwd_db_fold<<<splits, DAD_H, 0, st>>>(contrib, dbp, (int)B, (int)ceil_div64(B, splits));
     DAD_CHECK_LAUNCH("k_bwd_db_fold");
     return DAD_OK;
 }

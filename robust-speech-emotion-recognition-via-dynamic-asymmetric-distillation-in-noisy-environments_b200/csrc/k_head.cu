@@ -245,9 +245,9 @@ __global__ void __launch_bounds__(HD_THREADS) k_head_bwd(HeadBwdArgs a) {
     __shared__ float s_dWc[HD_THREADS / 32][DAD_C][DAD_H];  // 16 KB
     __shared__ float s_dbc[HD_THREADS / 32][DAD_C];
     __shared__ float s_kd[HD_THREADS / 32];
+    __shared__ float s_red[2][HD_THREADS];
     __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (HD_THREADS / 32) + warp;
     const int nmask = a.noisy ? a.nmask[0] : 0;
     const bool kd_on = a.noisy && nmask > 1;  // I/train.py:444
     const float kd_den = (float)nmask + 1e-8f;
@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(HD_THREADS) k_head_bwd(HeadBwdArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) dWc[c][j] = 0.f;
     float dbc = 0.f, kd_i = 0.f;
-    if (i < a.B_local) {
+    // persistent: warp w of CTA g owns samples g*4 + w, + 4*gridDim.x, ... (fixed order -> deterministic partials)
+    for (int i = blockIdx.x * (HD_THREADS / 32) + warp; i < a.B_local; i += gridDim.x * (HD_THREADS / 32)) {
         const int gi = a.rank * a.B_local + i;
         // ---- clean path
         {
@@ -281,9 +282,9 @@ __global__ void __launch_bounds__(HD_THREADS) k_head_bwd(HeadBwdArgs a) {
                 float w[8];
                 load8(a.Wc + c * DAD_H + lane * 8, w);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { g[j] = fmaf(dz[c], w[j], g[j]); dWc[c][j] = dz[c] * u[j]; }
+                for (int j = 0; j < 8; ++j) { g[j] = fmaf(dz[c], w[j], g[j]); dWc[c][j] = fmaf(dz[c], u[j], dWc[c][j]); }
             }
-            if (lane < DAD_C) dbc = dz[lane];
+            if (lane < DAD_C) dbc += dz[lane];
             float* go = a.g_clean + (int64_t)i * DAD_H + lane * 8;
             *reinterpret_cast<float4*>(go) = make_float4(g[0] * ks[0], g[1] * ks[1], g[2] * ks[2], g[3] * ks[3]);
             *reinterpret_cast<float4*>(go + 4) = make_float4(g[4] * ks[4], g[5] * ks[5], g[6] * ks[6], g[7] * ks[7]);
@@ -350,17 +351,32 @@ __global__ void __launch_bounds__(HD_THREADS) k_head_bwd(HeadBwdArgs a) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // ---- last CTA: fixed-order reduction of the G (<= SM count) CTA partials, 4 independent chains per element
     const int stride = DAD_C * DAD_H + DAD_C + 1;
     for (int e = threadIdx.x; e < DAD_C * DAD_H + DAD_C; e += HD_THREADS) {
-        float s = 0.f;
-        for (int g = 0; g < G; ++g) s += __ldcg(a.part + (int64_t)g * stride + e);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int g = 0;
+        for (; g + 3 < G; g += 4) {
+            s0 += __ldcg(a.part + (int64_t)g * stride + e);
+            s1 += __ldcg(a.part + (int64_t)(g + 1) * stride + e);
+            s2 += __ldcg(a.part + (int64_t)(g + 2) * stride + e);
+            s3 += __ldcg(a.part + (int64_t)(g + 3) * stride + e);
+        }
+        for (; g < G; ++g) s0 += __ldcg(a.part + (int64_t)g * stride + e);
+        const float s = (s0 + s1) + (s2 + s3);
         if (e < DAD_C * DAD_H) a.dWc[e] = s;
         else a.dbc[e - DAD_C * DAD_H] = s;
     }
+    // loss scalars: thread-strided partial sums, then a fixed-order sum over the 128 threads
+    float kd = 0.f, ce = 0.f;
+    for (int g = threadIdx.x; g < G; g += HD_THREADS) kd += __ldcg(a.part + (int64_t)g * stride + DAD_C * DAD_H + DAD_C);
+    for (int g = threadIdx.x; g < a.n_ce_part; g += HD_THREADS) ce += __ldcg(a.ce_part + g);
+    s_red[0][threadIdx.x] = kd;
+    s_red[1][threadIdx.x] = ce;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        float kd = 0.f, ce = 0.f;
-        for (int g = 0; g < G; ++g) kd += __ldcg(a.part + (int64_t)g * stride + DAD_C * DAD_H + DAD_C);
-        for (int g = 0; g < a.n_ce_part; ++g) ce += __ldcg(a.ce_part + g);
+        kd = 0.f; ce = 0.f;
+        for (int t = 0; t < HD_THREADS; ++t) { kd += s_red[0][t]; ce += s_red[1][t]; }
         a.loss_out[0] = ce * a.inv_B_global;         // supervised CE (local share under DP; summed by the all-reduce)
         a.loss_out[1] = kd_on ? kd / kd_den : 0.f;   // consistency (local share under DP)
         *a.counter = 0u;
@@ -395,7 +411,9 @@ int launch_dacp(DacpArgs a, cudaStream_t st) {
 
 int launch_head_bwd(const HeadBwdArgs& a, cudaStream_t st) {
     if (a.B_local == 0) return DAD_OK;
-    k_head_bwd<<<ceil_div(a.B_local, HD_THREADS / 32), HD_THREADS, 0, st>>>(a);
+    int grid = ceil_div(a.B_local, HD_THREADS / 32);  // <= dad_head_grid(B_local): the `part` workspace is sized for that
+    if (grid > 148) grid = 148;
+    k_head_bwd<<<grid, HD_THREADS, 0, st>>>(a);
     DAD_CHECK_LAUNCH("k_head_bwd");
     return DAD_OK;
 }

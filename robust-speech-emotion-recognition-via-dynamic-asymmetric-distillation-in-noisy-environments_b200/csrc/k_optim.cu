@@ -2,12 +2,12 @@
 //   flat layout (fp32): [ W 256x768 | b 256 | Wc 4x256 | bc 4 ]  = 197 892 elements (student, teacher, m, v, grad)
 //   k_grad_reduce : fixed-order sum of the split-K dW/db partials of the two encoder backward launches + head grads
 //   k_grad_norm   : global L2 norm (fp64 partials, last CTA) -> clip coefficient, Adam step scalars (step counter on device)
-//   k_adam_ema    : clip * grad -> coupled-L2 Adam -> EMA teacher update, plus the bf16 hi/lo split of W and teacher W
-//                   that feeds the next step's tcgen05 encoder kernels.
+//   k_adam_ema    : clip * grad -> coupled-L2 Adam -> EMA teacher update, plus the fp16 hi/lo split of W and teacher W
+//                   that feeds the next step's tcgen05 encoder kernels (fp16, scaled by 2^8).
 // Reference: I/train.py:487-492 (clip_grad_norm_, Adam.step), I/train.py:362 (Adam, wd 1e-5), I/model.py:211-223 (EMA).
 #include "dad_common.cuh"
 #include "dad_optim.cuh"
-#include <cuda_bf16.h>
+#include "tc_ptx.cuh"
 
 constexpr int NP_W = DAD_H * DAD_D;          // 196608
 constexpr int NP_B = DAD_H;                  // 256
@@ -79,10 +79,8 @@ __global__ void __launch_bounds__(OPT_THREADS) k_grad_norm(NormArgs a) {
 }
 
 
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
+// fp16 hi/lo operand split of an encoder weight, pre-scaled by TC_WS (dad_common.cuh)
+__device__ __forceinline__ void split_f16(float x, unsigned short& hi, unsigned short& lo) { tc::split1_f16(x * TC_WS, hi, lo); }
 
 __global__ void __launch_bounds__(OPT_THREADS) k_adam_ema(AdamArgs a) {
     const int e = blockIdx.x * OPT_THREADS + threadIdx.x;
@@ -109,8 +107,8 @@ __global__ void __launch_bounds__(OPT_THREADS) k_adam_ema(AdamArgs a) {
         a.t[e] = t;
     }
     if (e < NP_W && a.s_hi) {
-        split_bf16(p, reinterpret_cast<__nv_bfloat16*>(a.s_hi)[e], reinterpret_cast<__nv_bfloat16*>(a.s_lo)[e]);
-        split_bf16(t, reinterpret_cast<__nv_bfloat16*>(a.t_hi)[e], reinterpret_cast<__nv_bfloat16*>(a.t_lo)[e]);
+        split_f16(p, reinterpret_cast<unsigned short*>(a.s_hi)[e], reinterpret_cast<unsigned short*>(a.s_lo)[e]);
+        split_f16(t, reinterpret_cast<unsigned short*>(a.t_hi)[e], reinterpret_cast<unsigned short*>(a.t_lo)[e]);
     }
 }
 
@@ -119,9 +117,9 @@ __global__ void __launch_bounds__(OPT_THREADS) k_ema(float* t, const float* s, f
     const int e = blockIdx.x * OPT_THREADS + threadIdx.x;
     if (e < n) t[e] = __fadd_rn(__fmul_rn(t[e], ema_m), __fmul_rn(s[e], ema_1m));
 }
-__global__ void __launch_bounds__(OPT_THREADS) k_split_bf16(const float* w, __nv_bfloat16* hi, __nv_bfloat16* lo, int n) {
+__global__ void __launch_bounds__(OPT_THREADS) k_split_f16(const float* w, unsigned short* hi, unsigned short* lo, int n) {
     const int e = blockIdx.x * OPT_THREADS + threadIdx.x;
-    if (e < n) split_bf16(w[e], hi[e], lo[e]);
+    if (e < n) split_f16(w[e], hi[e], lo[e]);
 }
 
 int launch_grad_reduce(const GradReduceArgs& a, cudaStream_t st) {
@@ -146,9 +144,9 @@ int launch_ema(float* t, const float* s, float ema_m, float ema_1m, int n, cudaS
     DAD_CHECK_LAUNCH("k_ema");
     return DAD_OK;
 }
-int launch_split_bf16(const float* w, void* hi, void* lo, int n, cudaStream_t st) {
+int launch_split_f16(const float* w, void* hi, void* lo, int n, cudaStream_t st) {
     if (n == 0) return DAD_OK;
-    k_split_bf16<<<ceil_div(n, OPT_THREADS), OPT_THREADS, 0, st>>>(w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
-    DAD_CHECK_LAUNCH("k_split_bf16");
+    k_split_f16<<<ceil_div(n, OPT_THREADS), OPT_THREADS, 0, st>>>(w, (unsigned short*)hi, (unsigned short*)lo, n);
+    DAD_CHECK_LAUNCH("k_split_f16");
     return DAD_OK;
 }

@@ -20,19 +20,25 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// warp-specialised register reallocation (all 4 warps of a warpgroup execute the same one; counts are multiples of 8)
+template <uint32_t N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <uint32_t N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// try_wait with a suspend-time hint: a waiting warp is parked by the hardware (up to the hint) instead of spinning through the
+// issue slots that the converter warps of the same SM sub-partition need
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar_addr, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P1;\n\t}\n"
         : "=r"(ok)
-        : "r"(bar_addr), "r"(parity)
+        : "r"(bar_addr), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
@@ -50,6 +56,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 
 // ---------------------------------------------------------------- proxies / fences
 // generic-proxy st.shared -> visible to the async proxy (tcgen05.mma / TMA reads of shared memory)
+// bring [p, p+bytes) into L2 ahead of use (bytes % 16 == 0, p 16-byte aligned); no smem, no completion tracking
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -75,7 +85,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -107,8 +117,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor, SWIZZLE_128B.  Fields (PTX ISA, tcgen05 matrix descriptor):
 //   [0,14) start address >> 4   [16,30) leading-dim byte offset >> 4   [32,46) stride-dim byte offset >> 4
 //   [46,48) version = 1         [49,52) base offset = 0 (tiles are 1024-B aligned)   [61,64) layout: 2 = SWIZZLE_128B
-// K-major  (rows = M/N index, 128-B rows of 64 bf16 along K): SBO = 1024 B (8-row group pitch), LBO unused (=1).
-// MN-major (rows = K index, 128-B rows of 64 bf16 along M/N): SBO = pitch between 8-k groups, LBO = pitch between 64-element M/N chunks.
+// K-major  (rows = M/N index, 128-B rows of 64 fp16 along K): SBO = 1024 B (8-row group pitch), LBO unused (=1).
+// MN-major (rows = K index, 128-B rows of 64 fp16 along M/N): SBO = pitch between 8-k groups, LBO = pitch between 64-element M/N chunks.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
@@ -118,22 +128,33 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     d |= (uint64_t)2 << 61;
     return d;
 }
-// Instruction descriptor, kind::f16: bf16 x bf16 -> fp32.  [4,6) D fmt 1=F32  [7,10) A fmt 1=BF16  [10,13) B fmt 1=BF16
+// Instruction descriptor, kind::f16: fp16 x fp16 -> fp32.  [4,6) D fmt 1=F32  [7,10) A fmt 0=F16 (1=BF16)  [10,13) B fmt 0=F16
 // [15] A major (0=K,1=MN)  [16] B major  [17,23) N>>3  [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
 
 // byte offset of the 16-byte chunk `chunk16` (0..7) of 128-byte row `row` inside a SWIZZLE_128B tile (8-row / 1024-B atoms)
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16) { return row * 128u + ((chunk16 ^ (row & 7u)) << 4); }
 
-// packed bf16 hi/lo split of two floats: hi = bf16(x), lo = bf16(x - hi)
-__device__ __forceinline__ void split2_bf16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
-    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
+// Packed fp16 hi/lo split of two (pre-scaled) floats: hi = fp16(x), lo = fp16(x - hi).  hi carries 11 significant bits,
+// lo the next 11 (x - hi is exact in fp32), so hi + lo reproduces x to ~2^-22 relative while |x| stays inside fp16's
+// normal range [2^-14, 65504]; below that the absolute error is bounded by the subnormal spacing 2^-25.  Conversions
+// saturate (finite) instead of overflowing to inf.  Callers scale by a power of two first (exact) -- see k_enc_tc.cu.
+__device__ __forceinline__ void split2_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    float h0, h1;
+    asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(h0), "=f"(h1) : "r"(hi));
     const float r0 = x0 - h0, r1 = x1 - h1;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+// scalar version (weights / gradient tables)
+__device__ __forceinline__ void split1_f16(float x, unsigned short& hi, unsigned short& lo) {
+    uint32_t h, l;
+    split2_f16(x, 0.f, h, l);
+    hi = (unsigned short)(h & 0xFFFFu);
+    lo = (unsigned short)(l & 0xFFFFu);
 }
 
 }  // namespace tc

@@ -103,7 +103,7 @@ class DADStepEngine:
         # ---- parameters and optimiser state (flat)
         self.p, self.t, self.m, self.v = z(NPARAM), z(NPARAM), z(NPARAM), z(NPARAM)
         self.g_ext = z(NPARAM + 8)
-        self.hi_lo = torch.zeros(4, D_HID * D_IN, dtype=torch.bfloat16, device=dev)  # s_hi, s_lo, t_hi, t_lo
+        self.hi_lo = torch.zeros(4, D_HID * D_IN, dtype=torch.float16, device=dev)  # s_hi, s_lo, t_hi, t_lo
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self.lr = torch.zeros(1, dtype=torch.float64, device=dev)
         self.scal = z(8)
@@ -184,11 +184,11 @@ class DADStepEngine:
         self.refresh_splits()
 
     def refresh_splits(self):
-        """bf16 hi/lo operand copies of W and teacher W for the tcgen05 path (kept current by the Adam kernel afterwards)."""
+        """fp16 hi/lo operand copies (scaled by 2^8) of W and teacher W for the tcgen05 path (kept current by the Adam kernel)."""
         n = D_HID * D_IN
         s = _lib.stream_ptr()
-        check(lib().dad_split_bf16(self.p.data_ptr(), self.hi_lo[0].data_ptr(), self.hi_lo[1].data_ptr(), n, s))
-        check(lib().dad_split_bf16(self.t.data_ptr(), self.hi_lo[2].data_ptr(), self.hi_lo[3].data_ptr(), n, s))
+        check(lib().dad_split_f16(self.p.data_ptr(), self.hi_lo[0].data_ptr(), self.hi_lo[1].data_ptr(), n, s))
+        check(lib().dad_split_f16(self.t.data_ptr(), self.hi_lo[2].data_ptr(), self.hi_lo[3].data_ptr(), n, s))
 
     def set_lr(self, lr):
         self.lr.fill_(float(lr))

@@ -1,6 +1,6 @@
 """Tensor-level operators over the C ABI (libdad_sm100a.so) + their torch.library registration.
 
-Functional layer (no autograd): augment, encoder_pool_fwd, encoder_pool_bwd, ema_, split_bf16.
+Functional layer (no autograd): augment, encoder_pool_fwd, encoder_pool_bwd, ema_, split_f16.
 torch.library layer: `torch.ops.dad.encoder_pool` (autograd-aware; used by model.Emotion2VecEncoder so the
 reference's module API -- enc(x, padding_mask) -> [B,256], differentiable w.r.t. W, b -- stays drop-in) and
 `torch.ops.dad.augment`.  Nothing here has a CPU or eager-PyTorch fallback: CPU tensors raise DadError."""
@@ -29,7 +29,7 @@ def default_gemm_mode(T):
     mode = os.environ.get("DAD_GEMM", "").lower()
     if mode == "fp32":
         return GEMM_FP32
-    if mode in ("tc", "bf16x3"):
+    if mode in ("tc", "f16x3"):
         return GEMM_TC
     return GEMM_FP32
 
@@ -79,7 +79,7 @@ def encoder_pool_fwd(x, pad, W, b, aug=None, gemm_mode=None, want_bits=True, W_h
     if B == 0:
         return emb, bits, lens
     if mode == GEMM_TC and (W_hi is None or W_lo is None):
-        W_hi, W_lo = split_bf16(W)
+        W_hi, W_lo = split_f16(W)
     nb = lib().dad_encoder_fwd_workspace_bytes(B, T, mode)
     ws = _zeros_ws(nb, dev, "enc_fwd")
     check(lib().dad_encoder_fwd(ptr(x, torch.float32, "x"), ptr(pad8), ptr(W.contiguous(), torch.float32, "W"),
@@ -120,13 +120,13 @@ def ema_(teacher_flat, student_flat, momentum):
     return teacher_flat
 
 
-def split_bf16(W):
-    """(hi, lo) bf16 tensors with hi = bf16(W), lo = bf16(W - hi): operands of the 3-product tcgen05 GEMM."""
+def split_f16(W):
+    """(hi, lo) fp16 tensors with hi = fp16(256 W), lo = fp16(256 W - hi): operands of the 3-product tcgen05 GEMM."""
     _lib.require_device()
     W = W.contiguous()
-    hi = torch.empty(W.shape, dtype=torch.bfloat16, device=W.device)
+    hi = torch.empty(W.shape, dtype=torch.float16, device=W.device)
     lo = torch.empty_like(hi)
-    check(lib().dad_split_bf16(ptr(W, torch.float32, "W"), ptr(hi), ptr(lo), W.numel(), stream_ptr()))
+    check(lib().dad_split_f16(ptr(W, torch.float32, "W"), ptr(hi), ptr(lo), W.numel(), stream_ptr()))
     return hi, lo
 
 

@@ -43,7 +43,7 @@ if __name__ == "__main__":
     B, T = 512, 200
     x = torch.randn(B, T, 768, device="cuda"); st = synth.init_state(42)
     W, b = st["student_encoder.pre_net.weight"].cuda(), st["student_encoder.pre_net.bias"].cuda()
-    hi, lo = ops.split_bf16(W)
+    hi, lo = ops.split_f16(W)
     for mode in (_lib.GEMM_FP32, _lib.GEMM_TC):
         for _ in range(3): ops.encoder_pool_fwd(x, None, W, b, gemm_mode=mode, W_hi=hi, W_lo=lo)
         torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
