@@ -21,6 +21,7 @@
 #include "tc_ptx.cuh"
 #include <cuda_fp16.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace {
 
@@ -47,7 +48,24 @@ struct FwdParams {
     int64_t N;
     int T;
     int num_tiles;
+    int dbg;  // timing experiments only (DAD_TC_DBG): bit 0 one product instead of three, bit 1 W loaded for the first two k-blocks only
 };
+
+// Sum over the 32 lanes of each of the 32 per-lane values: on return lane j holds sum_lanes v[j] (fixed butterfly order).
+// Stage with partner lane^off: the lane whose `off` bit is set keeps the upper half of its live values, sends the lower half.
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], const int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? v[i] : v[i + off];
+            const float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Converter warp body of the forward kernel.  Thread (cw, lane): 8-byte k-slot kq = lane & 15 of the 64-wide k-block and
@@ -60,12 +78,14 @@ struct FwdParams {
 // MODE 0 clean, 1 weak, 2 strong (I/utils.py:328-375); PHILOX: canonical in-kernel noise field, else supplied noise tensor.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int MODE, bool PHILOX>
-__device__ __forceinline__ void fwd_convert(const FwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, const int cw, const int lane) {
+__device__ __forceinline__ void fwd_convert(const FwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, volatile int* progress, const int cw,
+                                            const int lane) {
     const int kq = lane & 15;
     const int rbase = cw * 16 + (lane >> 4) * 8;
     const uint32_t c16 = (uint32_t)kq >> 1;
     const uint32_t sbase = (uint32_t)rbase * 128u + (uint32_t)(kq & 1) * 8u;
     const AugParams& ap = p.ap;
+    const uint32_t smem_a = tc::smem_u32(smem);
     const unsigned long long seed = (MODE != 0 && PHILOX) ? aug_seed(ap) : 0ull;
     const float radius_k = NOISE_UNIT_K * ap.sigma * ap.sigma;
     const int n_my_tiles = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -94,11 +114,15 @@ __device__ __forceinline__ void fwd_convert(const FwdParams& p, uint8_t* smem, u
         }
         return z;
     };
+    float dbg_acc = 0.f;
     auto load = [&](float4 (&dst)[8], int it) {
         const int tile = tile_of(it), kb = it % KB;
         const int64_t row0 = (int64_t)tile * BM + rbase;
         const float* src = p.x + row0 * DAD_D + kb * BK + kq * 4;
-        if (row0 + 8 <= p.N) {
+        if (p.dbg & 8) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(1.f, 2.f, 3.f, (float)it);
+        } else if (row0 + 8 <= p.N) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) dst[i] = __ldg(reinterpret_cast<const float4*>(src + i * DAD_D));
         } else {
@@ -107,22 +131,22 @@ __device__ __forceinline__ void fwd_convert(const FwdParams& p, uint8_t* smem, u
                 dst[i] = (row0 + i < p.N) ? __ldg(reinterpret_cast<const float4*>(src + i * DAD_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
-    auto store_row = [&](uint8_t* a_hi, uint8_t* a_lo, const float4& v, int i, uint32_t zmask) {
-        uint32_t h01 = 0, l01 = 0, h23 = 0, l23 = 0;
-        if (!((zmask >> i) & 1u)) {
-            tc::split2_f16(v.x * TC_XS, v.y * TC_XS, h01, l01);
-            tc::split2_f16(v.z * TC_XS, v.w * TC_XS, h23, l23);
-        }
+    // zeroed rows (beyond N, temporal mask span) are multiplied by 0 instead of TC_XS: no branch, no select
+    auto store_row = [&](uint32_t a_hi, uint32_t a_lo, const float4& v, int i, uint32_t zmask) {
+        const float sc = ((zmask >> i) & 1u) ? 0.f : TC_XS;
+        uint32_t h01, l01, h23, l23;
+        tc::split2_f16(v.x * sc, v.y * sc, h01, l01);
+        tc::split2_f16(v.z * sc, v.w * sc, h23, l23);
         const uint32_t off = sbase + (uint32_t)i * 128u + ((c16 ^ (uint32_t)i) << 4);
-        *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(h01, h23);
-        *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(l01, l23);
+        tc::sts64(a_hi + off, h01, h23);
+        tc::sts64(a_lo + off, l01, l23);
     };
     auto convert = [&](float4 (&cur)[8], int it, uint32_t zmask) {
         const int tile = tile_of(it), kb = it % KB;
         const uint32_t s = (uint32_t)it % STAGES, ph = ((uint32_t)it / STAGES) & 1u;
         tc::mbar_wait(&empty[s], ph ^ 1u);
-        uint8_t* a_hi = smem + s * STAGE_BYTES + OFF_AHI;
-        uint8_t* a_lo = smem + s * STAGE_BYTES + OFF_ALO;
+        const uint32_t a_hi = smem_a + s * STAGE_BYTES + OFF_AHI;
+        const uint32_t a_lo = smem_a + s * STAGE_BYTES + OFF_ALO;
         if (MODE != 0) {
             const int64_t row0 = (int64_t)tile * BM + rbase;
             float4 keep = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -154,28 +178,40 @@ __device__ __forceinline__ void fwd_convert(const FwdParams& p, uint8_t* smem, u
                 }
             }
         }
+        if (p.dbg & 4) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) store_row(a_hi, a_lo, cur[i], i, zmask);
+            for (int i = 0; i < 8; ++i) dbg_acc += cur[i].x + cur[i].y + cur[i].z + cur[i].w;
+            if (dbg_acc == 1.2345f) store_row(a_hi, a_lo, cur[0], 0, zmask);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) store_row(a_hi, a_lo, cur[i], i, zmask);
+        }
         tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&full[s]);
     };
 
     if (n_iter == 0) return;
-    float4 bufA[8], bufB[8];
+    // Three register sets rotate over the flat iteration space (KB = 12 is a multiple of 3, so a group of three iterations never
+    // straddles a tile): the loads of iterations i+1 and i+2 (64 KB per SM) are in flight while iteration i is converted.  One set
+    // ahead was not enough: with ~2 us of loaded DRAM latency the kernel ran at one k-block per latency (ncu: converters
+    // stalled on the first use of the loaded registers, tensor pipe 55 % active).
+    float4 bufA[8], bufB[8], bufC[8];
     uint32_t zcur = row_flags(tile_of(0));
     load(bufA, 0);
-    for (int it = 0; it < n_iter; it += 2) {
-        // ---- even iteration: convert A while B's loads fly (it + 1 is always in the same tile: KB is even)
-        load(bufB, it + 1);
+    load(bufB, 1);
+    for (int it = 0; it < n_iter; it += 3) {
+        load(bufC, it + 2);
         convert(bufA, it, zcur);
-        // ---- odd iteration: convert B while A's loads (possibly the first k-block of the next tile) fly
         uint32_t znext = zcur;
-        if (it + 2 < n_iter) {
-            if ((it + 2) % KB == 0) znext = row_flags(tile_of(it + 2));
-            load(bufA, it + 2);
+        const bool more = it + 3 < n_iter;
+        if (more) {
+            if ((it + 3) % KB == 0) znext = row_flags(tile_of(it + 3));
+            load(bufA, it + 3);
         }
         convert(bufB, it + 1, zcur);
+        if (more) load(bufB, it + 4);
+        convert(bufC, it + 2, zcur);
         zcur = znext;
     }
 }
@@ -190,6 +226,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
     uint64_t* tfull = bars + 4;       // [2]       1 (tcgen05.commit)
     uint64_t* tempty = bars + 6;      // [2]       4 (epilogue warps)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+    volatile int* progress = reinterpret_cast<volatile int*>(bars + 9);  // flat (tile, k-block) iteration the converters have reached
     float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -199,6 +236,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
         tc::prefetch_tmap(&tm_wlo);
     }
     if (warp == 1 && lane == 0) {
+        *progress = 0;
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1 + N_CONV_WARPS); tc::mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], 4); }
         tc::fence_barrier_init();
@@ -224,6 +262,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     tc::mbar_wait(&empty[s], ph ^ 1);
+                    if ((p.dbg & 2) && it >= STAGES) { tc::mbar_arrive(&full[s]); continue; }
                     tc::mbar_arrive_expect_tx(&full[s], 2 * W_BYTES);
                     tc::tma_load_2d(smem + s * STAGE_BYTES + OFF_WHI, &tm_whi, &full[s], kb * BK, 0);
                     tc::tma_load_2d(smem + s * STAGE_BYTES + OFF_WLO, &tm_wlo, &full[s], kb * BK, 0);
@@ -247,6 +286,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
                     const uint32_t base = tc::smem_u32(smem + s * STAGE_BYTES);
 #pragma unroll
                     for (int prod = 0; prod < 3; ++prod) {
+                        if ((p.dbg & 1) && prod > 0) break;
                         const uint32_t a_off = (prod == 2) ? OFF_ALO : OFF_AHI;  // hi*hi, hi*lo, lo*hi
                         const uint32_t b_off = (prod == 1) ? OFF_WLO : OFF_WHI;
 #pragma unroll
@@ -268,16 +308,19 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
         const int cw = warp - CONV_WARP0;
         const int variant = p.ap.mode == 0 ? 0 : (p.ap.mode * 2 - 1 + (p.ap.noise_src == 1 ? 1 : 0));  // 0 | 1,2 weak | 3,4 strong (supplied, philox)
         switch (variant) {
-            case 0: fwd_convert<0, false>(p, smem, full, empty, cw, lane); break;
-            case 1: fwd_convert<1, false>(p, smem, full, empty, cw, lane); break;
-            case 2: fwd_convert<1, true>(p, smem, full, empty, cw, lane); break;
-            case 3: fwd_convert<2, false>(p, smem, full, empty, cw, lane); break;
-            default: fwd_convert<2, true>(p, smem, full, empty, cw, lane); break;
+            case 0: fwd_convert<0, false>(p, smem, full, empty, progress, cw, lane); break;
+            case 1: fwd_convert<1, false>(p, smem, full, empty, progress, cw, lane); break;
+            case 2: fwd_convert<1, true>(p, smem, full, empty, progress, cw, lane); break;
+            case 3: fwd_convert<2, false>(p, smem, full, empty, progress, cw, lane); break;
+            default: fwd_convert<2, true>(p, smem, full, empty, progress, cw, lane); break;
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: TMEM -> bias + ReLU + mask -> ReLU bits + pooled partial sums =====================
+        // Lane = frame row (tcgen05.ld 32x32b), 32 hidden units per chunk.  The per-utterance column sums over the 32 rows are a
+        // register transpose-reduce: 31 shuffles + 31 adds per 32 x 32 block leave lane j with the sum of column j -- no shared
+        // memory, no serial chain (the first version staged through smem with a 32-deep dependent add chain per chunk and made
+        // the whole kernel epilogue-bound at ~40 k cycles per tile; measured with the MMA / loads / conversion stubbed out).
         const int q = warp - EPI_WARP0;  // == warp % 4: this warp may touch TMEM lanes [32q, 32q+32)
-        float* scratch = reinterpret_cast<float*>(smem + OFF_SCRATCH) + q * 32 * 33;
         uint32_t ti = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
             const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
@@ -286,42 +329,56 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
             const bool in = n < p.N;
             const bool valid = in && !(p.pad && p.pad[n]);
             const int64_t b_first = n0 / p.T;
-            int64_t split64 = (b_first + 1) * p.T - n0;  // rows [0,split) belong to utterance b_first, the rest to b_first+1 (T >= 32)
+            const int64_t split64 = (b_first + 1) * p.T - n0;  // rows [0,split) belong to utterance b_first, the rest to b_first+1 (T >= 32)
             const int split = split64 > 32 ? 32 : (int)split64;
+            const bool first = lane < split;
             tc::mbar_wait(&tfull[acc], tph);
             tc::tcgen05_fence_after();
-            uint32_t words[8];
             const int64_t g = (int64_t)tile * 4 + q;
-#pragma unroll
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * DAD_H;
+            const uint32_t wstage = tc::smem_u32(smem + OFF_SCRATCH) + (uint32_t)(q * 32 * 9 + lane * 9) * 4u;  // [32 rows][8 words + 1 pad]
+            const uint32_t bias_a = tc::smem_u32(s_bias);
+            uint32_t r[32];
+            tc::tmem_ld_32x32(taddr, r);
+#pragma unroll 1  // keep the body small: the unrolled version (19 k SASS instructions in the kernel) was instruction-fetch bound
             for (int c = 0; c < 8; ++c) {
-                uint32_t r[32];
-                tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * DAD_H + c * 32, r);
                 tc::tmem_ld_wait();
+                float v[32];
                 uint32_t w = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float pre = fmaf(__uint_as_float(r[j]), TC_INV_XW, s_bias[c * 32 + j]);  // exact power-of-two unscale, then + bias (one rounding, as fp32 x.W + b)
-                    const bool pos = pre > 0.f;
-                    w |= (pos ? 1u : 0u) << j;
-                    scratch[lane * 33 + j] = (pos && valid) ? pre : 0.f;
+                for (int j4 = 0; j4 < 32; j4 += 4) {
+                    const uint4 bs = tc::lds128(bias_a + (uint32_t)(c * 32 + j4) * 4u);
+                    const float bj[4] = {__uint_as_float(bs.x), __uint_as_float(bs.y), __uint_as_float(bs.z), __uint_as_float(bs.w)};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float pre = fmaf(__uint_as_float(r[j4 + u]), TC_INV_XW, bj[u]);  // exact power-of-two unscale, then + bias
+                        const bool pos = pre > 0.f;
+                        w |= (pos ? 1u : 0u) << (j4 + u);
+                        v[j4 + u] = (pos && valid) ? pre : 0.f;
+                    }
                 }
-                words[c] = w;
-                __syncwarp();
-                float s0 = 0.f, s1 = 0.f;
-                for (int rr = 0; rr < split; ++rr) s0 += scratch[rr * 33 + lane];
-                for (int rr = split; rr < 32; ++rr) s1 += scratch[rr * 33 + lane];
+                tc::sts32(wstage + (uint32_t)c * 4u, w);
+                if (c + 1 < 8) tc::tmem_ld_32x32(taddr + (c + 1) * 32, r);  // next chunk flies while this one is reduced
+                float s0, s1 = 0.f;
+                if (split < 32) {  // the 32 rows straddle two utterances: a second masked reduction (warp-uniform branch)
+                    float v1[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { v1[j] = first ? 0.f : v[j]; v[j] = first ? v[j] : 0.f; }
+                    s1 = transpose_reduce32(v1, lane);
+                }
+                s0 = transpose_reduce32(v, lane);
                 p.part[(g * 2 + 0) * DAD_H + c * 32 + lane] = s0;
                 p.part[(g * 2 + 1) * DAD_H + c * 32 + lane] = s1;
-                __syncwarp();
             }
             tc::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tempty[acc]);
             if (p.bits && in) {
                 uint4* dst = reinterpret_cast<uint4*>(p.bits + n * DAD_HW);
-                dst[0] = make_uint4(words[0], words[1], words[2], words[3]);
-                dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
+                dst[0] = make_uint4(tc::lds32(wstage), tc::lds32(wstage + 4), tc::lds32(wstage + 8), tc::lds32(wstage + 12));
+                dst[1] = make_uint4(tc::lds32(wstage + 16), tc::lds32(wstage + 20), tc::lds32(wstage + 24), tc::lds32(wstage + 28));
             }
+            __syncwarp();
         }
     } else {
         tc::reg_dec<40>();  // warps 2, 3: same warpgroup as the TMA / MMA warps
@@ -434,6 +491,11 @@ int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W_hi, cons
     FwdParams p;
     p.x = x; p.pad = pad; p.bias = bias; p.ap = ap; p.part = reinterpret_cast<float*>(ws); p.bits = bits;
     p.N = B * T; p.T = (int)T; p.num_tiles = (int)ceil_div64(B * T, BM);
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("DAD_TC_DBG"); dbg = e ? atoi(e) : 0; }
+        p.dbg = dbg;
+    }
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
     k_enc_fwd_tc<<<grid, FWD_THREADS, FWD_SMEM, st>>>(tm_hi, tm_lo, p);
     DAD_CHECK_LAUNCH("k_enc_fwd_tc");
@@ -584,20 +646,23 @@ __global__ void __launch_bounds__(DAD_H) k_bwd_db_fold(const float* __restrict__
 //     per UTTERANCE serves all frames of that utterance, so it is fetched once per k-block together with the next k-block's
 //     data (no dependent load on the critical path); the ReLU byte of each frame masks it.
 // (utterance, frame-in-utterance) of the warp's first frame advance incrementally (T >= 32: at most one wrap per k-block).
-// Two register sets ping-pong over the k-blocks so the loads of k-block i+1 fly while k-block i is converted.
+// Three register sets rotate over the k-blocks so the loads of k-blocks i+1 and i+2 fly while k-block i is converted (see fwd_convert);
+// the table chunks live in two tagged slots (utterance b -> slot b & 1) refreshed at load time, with an inline reload
+// when a slot was recycled before use (only possible for T < 64).
 // ---------------------------------------------------------------------------------------------------------------------
 struct BwdRegs {
     float4 x[8];     // [r4*2 + half]
     uint32_t w[4];   // ReLU mask word holding this lane's byte, per frame
-    uint4 gh, gl;    // table chunk of utterance b0
     uint32_t flags;  // bits 0-3: x row contributes zeros; bits 4-7: A row active (in range and not padded)
     int b0, t0;      // utterance / frame-in-utterance of the warp's first frame
 };
+struct BwdTab { uint4 gh, gl; int b; };  // this lane's g/len table chunk (fp16 hi, lo) of utterance b; slot = b & 1
 
 template <int MODE, bool PHILOX>
-__device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, const int cw, const int lane,
+__device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, volatile int* progress, const int cw, const int lane,
                                             const int dslice, const int64_t n_begin, const int64_t n_end, const int nkb) {
     const AugParams& ap = p.ap;
+    const uint32_t smem_a = tc::smem_u32(smem);
     const unsigned long long seed = (MODE != 0 && PHILOX) ? aug_seed(ap) : 0ull;
     const float radius_k = NOISE_UNIT_K * ap.sigma * ap.sigma;
     const int T = p.T;
@@ -621,6 +686,12 @@ __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, u
         b_run = (int)(n0 / (uint32_t)T);
         t_run = (int)(n0 - (uint32_t)b_run * (uint32_t)T);
     }
+
+    const int n_utt = (int)(p.N / T);
+    BwdTab tab0, tab1;
+    tab0.b = tab1.b = -1;
+    tab0.gh = tab0.gl = tab1.gh = tab1.gl = make_uint4(0, 0, 0, 0);
+    auto tab_ldg = [&](const uint16_t* base, int b) { return __ldg(reinterpret_cast<const uint4*>(base + (int64_t)b * DAD_H + lane * 8)); };
 
     auto load = [&](BwdRegs& R, int kb) {
         const int64_t n0 = n_begin + (int64_t)kb * BWD_BK + cw * 4;
@@ -652,15 +723,22 @@ __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, u
             flags |= (on ? 1u : 0u) << (4 + j);
         }
         R.flags = flags;
-        const bool any = n0 < n_end;
-        R.gh = any ? __ldg(reinterpret_cast<const uint4*>(p.g_hi + (int64_t)R.b0 * DAD_H + lane * 8)) : make_uint4(0, 0, 0, 0);
-        R.gl = any ? __ldg(reinterpret_cast<const uint4*>(p.g_lo + (int64_t)R.b0 * DAD_H + lane * 8)) : make_uint4(0, 0, 0, 0);
+        if (n0 < n_end) {
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const int bb = R.b0 + d;
+                if (bb < n_utt) {
+                    if (bb & 1) { if (tab1.b != bb) { tab1.gh = tab_ldg(p.g_hi, bb); tab1.gl = tab_ldg(p.g_lo, bb); tab1.b = bb; } }
+                    else        { if (tab0.b != bb) { tab0.gh = tab_ldg(p.g_hi, bb); tab0.gl = tab_ldg(p.g_lo, bb); tab0.b = bb; } }
+                }
+            }
+        }
     };
 
     auto convert = [&](BwdRegs& R, int kb) {
         const uint32_t s = (uint32_t)kb % BWD_STAGES, ph = ((uint32_t)kb / BWD_STAGES) & 1u;
         tc::mbar_wait(&empty[s], ph ^ 1u);
-        uint8_t* st = smem + s * BSTAGE_BYTES;
+        const uint32_t st = smem_a + s * BSTAGE_BYTES;
         const int64_t n0 = n_begin + (int64_t)kb * BWD_BK + cw * 4;
         // ---- A operand: dpre^T chunks = table chunk of the frame's utterance, masked by the frame's ReLU byte
 #pragma unroll
@@ -668,10 +746,14 @@ __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, u
             const uint32_t byte = ((R.flags >> (4 + j)) & 1u) ? ((R.w[j] >> bshift) & 0xFFu) : 0u;
             uint4 gh = make_uint4(0, 0, 0, 0), gl = make_uint4(0, 0, 0, 0);
             if (byte) {
-                gh = R.gh; gl = R.gl;
-                if (R.t0 + j >= T) {  // this frame already belongs to the next utterance (once per utterance boundary)
-                    gh = __ldg(reinterpret_cast<const uint4*>(p.g_hi + (int64_t)(R.b0 + 1) * DAD_H + lane * 8));
-                    gl = __ldg(reinterpret_cast<const uint4*>(p.g_lo + (int64_t)(R.b0 + 1) * DAD_H + lane * 8));
+                const int bj = R.b0 + (R.t0 + j >= T ? 1 : 0);
+                const bool odd = bj & 1;
+                if ((odd ? tab1.b : tab0.b) == bj) {
+                    gh = odd ? tab1.gh : tab0.gh;
+                    gl = odd ? tab1.gl : tab0.gl;
+                } else {  // slot recycled before use (short utterances): reload in place
+                    gh = tab_ldg(p.g_hi, bj);
+                    gl = tab_ldg(p.g_lo, bj);
                 }
                 const uint32_t m0 = ((byte & 1u) ? 0x0000FFFFu : 0u) | ((byte & 2u) ? 0xFFFF0000u : 0u);
                 const uint32_t m1 = ((byte & 4u) ? 0x0000FFFFu : 0u) | ((byte & 8u) ? 0xFFFF0000u : 0u);
@@ -682,8 +764,8 @@ __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, u
             }
             const uint32_t r7 = r7b + (uint32_t)j;
             const uint32_t off = aoff0 + r7 * 128u + ((ac ^ r7) << 4);
-            *reinterpret_cast<uint4*>(st + BOFF_AHI + off) = gh;
-            *reinterpret_cast<uint4*>(st + BOFF_ALO + off) = gl;
+            tc::sts128(st + BOFF_AHI + off, gh);
+            tc::sts128(st + BOFF_ALO + off, gl);
         }
         // ---- B operand: aug(x) rows -> fp16 hi/lo (scaled by TC_XS)
         if (MODE != 0) {
@@ -724,14 +806,13 @@ __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, u
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const float4 v = R.x[2 * j + half];
-                uint32_t h01 = 0, l01 = 0, h23 = 0, l23 = 0;
-                if (!((R.flags >> j) & 1u)) {
-                    tc::split2_f16(v.x * TC_XS, v.y * TC_XS, h01, l01);
-                    tc::split2_f16(v.z * TC_XS, v.w * TC_XS, h23, l23);
-                }
+                const float sc = ((R.flags >> j) & 1u) ? 0.f : TC_XS;
+                uint32_t h01, l01, h23, l23;
+                tc::split2_f16(v.x * sc, v.y * sc, h01, l01);
+                tc::split2_f16(v.z * sc, v.w * sc, h23, l23);
                 const uint32_t off = roff + (uint32_t)half * 2u * MN_LBO;
-                *reinterpret_cast<uint2*>(st + BOFF_BHI + off) = make_uint2(h01, h23);
-                *reinterpret_cast<uint2*>(st + BOFF_BLO + off) = make_uint2(l01, l23);
+                tc::sts64(st + BOFF_BHI + off, h01, h23);
+                tc::sts64(st + BOFF_BLO + off, l01, l23);
             }
         }
         tc::fence_proxy_async_smem();
@@ -740,14 +821,19 @@ __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, u
     };
 
     if (nkb == 0) return;
-    BwdRegs RA, RB;
+    BwdRegs RA, RB, RC;
     load(RA, 0);
-    for (int kb = 0; kb < nkb; kb += 2) {
-        if (kb + 1 < nkb) load(RB, kb + 1);
+    if (nkb > 1) load(RB, 1);
+    for (int kb = 0; kb < nkb; kb += 3) {
+        if (kb + 2 < nkb) load(RC, kb + 2);
         convert(RA, kb);
         if (kb + 1 < nkb) {
-            if (kb + 2 < nkb) load(RA, kb + 2);
+            if (kb + 3 < nkb) load(RA, kb + 3);
             convert(RB, kb + 1);
+        }
+        if (kb + 2 < nkb) {
+            if (kb + 4 < nkb) load(RB, kb + 4);
+            convert(RC, kb + 2);
         }
     }
 }
@@ -760,6 +846,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_enc_bwd_tc(BwdParams p) {
     uint64_t* empty = bars + BWD_STAGES;    // [3] 1 (tcgen05.commit)
     uint64_t* tfull = bars + 2 * BWD_STAGES;  // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * BWD_STAGES + 1);
+    volatile int* progress = reinterpret_cast<volatile int*>(bars + 2 * BWD_STAGES + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dslice = blockIdx.x, split = blockIdx.y;
@@ -768,6 +855,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_enc_bwd_tc(BwdParams p) {
     const int nkb = n_end > n_begin ? (int)ceil_div64(n_end - n_begin, BWD_BK) : 0;
 
     if (warp == 1 && lane == 0) {
+        *progress = 0;
         for (int s = 0; s < BWD_STAGES; ++s) { tc::mbar_init(&full[s], N_CONV_WARPS); tc::mbar_init(&empty[s], 1); }
         tc::mbar_init(tfull, 1);
         tc::fence_barrier_init();
@@ -811,18 +899,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_enc_bwd_tc(BwdParams p) {
         }
     } else if (warp >= CONV_WARP0 && warp < CONV_WARP0 + N_CONV_WARPS) {
         // ===================== converters =====================
-        tc::reg_inc<168>();
+        tc::reg_inc<200>();  // 128 x 40 (control) + 256 x 200 (converters: three 39-register landing sets) + 128 x 64 (epilogue) <= 64 K
         const int cw = warp - CONV_WARP0;
         const int variant = p.ap.mode == 0 ? 0 : (p.ap.mode * 2 - 1 + (p.ap.noise_src == 1 ? 1 : 0));
         switch (variant) {
-            case 0: bwd_convert<0, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 1: bwd_convert<1, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 2: bwd_convert<1, true>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 3: bwd_convert<2, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
-            default: bwd_convert<2, true>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 0: bwd_convert<0, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 1: bwd_convert<1, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 2: bwd_convert<1, true>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 3: bwd_convert<2, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
+            default: bwd_convert<2, true>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: TMEM -> split-K partial dW =====================
+        tc::reg_dec<64>();
         const int q = warp - EPI_WARP0;
         float* out = p.dWp + (int64_t)split * DAD_H * DAD_D;
         const float unscale = __ldg(p.unscale);
