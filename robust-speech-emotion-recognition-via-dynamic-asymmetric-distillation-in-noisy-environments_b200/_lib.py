@@ -172,3 +172,27 @@ def make_aug(mode=0, noise=None, sigma=0.0, feat_keep=None, t_start=None, mask_l
 
 def pack_rank_words(B_local):
     return int(B_local) * (2 * D_HID + 3)
+
+
+def pack_offsets(B_local):
+    """Word offsets of the fields inside ONE rank's segment of the exchange buffer (include/dad_sm100a.h `dad_pack`):
+    [emb_clean B*H f32 | emb_strong B*H f32 | score B f32 | pred B i32 | label B i32]."""
+    B = int(B_local)
+    return {"emb_clean": 0, "emb_strong": B * D_HID, "score": 2 * B * D_HID, "pred": 2 * B * D_HID + B,
+            "label": 2 * B * D_HID + 2 * B, "words": pack_rank_words(B)}
+
+
+def pack_global_views(pack_f32, B_local, world):
+    """Global-batch views (rank-major sample order) of an all-gathered exchange buffer (any device):
+    -> dict(emb_clean [Bg,H] f32, emb_strong [Bg,H] f32, score [Bg] f32, pred [Bg] i32, label [Bg] i32).
+    These are strided views of `pack_f32` (no copy), so writes land in the buffer."""
+    B, o = int(B_local), pack_offsets(B_local)
+    seg = pack_f32.view(world, o["words"])
+    segi = pack_f32.view(torch.int32).view(world, o["words"])
+    return {
+        "emb_clean": seg[:, o["emb_clean"]:o["emb_clean"] + B * D_HID].unflatten(1, (B, D_HID)),
+        "emb_strong": seg[:, o["emb_strong"]:o["emb_strong"] + B * D_HID].unflatten(1, (B, D_HID)),
+        "score": seg[:, o["score"]:o["score"] + B],
+        "pred": segi[:, o["pred"]:o["pred"] + B],
+        "label": segi[:, o["label"]:o["label"] + B],
+    }

@@ -203,7 +203,7 @@ class DADStepEngine:
             raise DadError(f"clean feats {tuple(xc.shape)} != {(B, T, D_IN)} (engine is shape-specialised)")
         self.x_clean.copy_(xc, non_blocking=True)
         self.pad_clean.copy_(clean_batch["net_input"]["padding_mask"], non_blocking=True)
-        lab = self.pack_i32[self.rank * self._rw + 2 * B * D_HID + 2 * B: self.rank * self._rw + 2 * B * D_HID + 3 * B]
+        lab = _lib.pack_global_views(self.pack, B, self.world)["label"][self.rank]
         lab.copy_(clean_batch["labels"], non_blocking=True)
         if noisy_batch is not None:
             self.x_noisy.copy_(noisy_batch["net_input"]["feats"], non_blocking=True)
