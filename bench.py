@@ -301,7 +301,8 @@ def run_ours(args):
             "losses_last_step": losses,
         }))
     if world > 1:
-        torch.distributed.destroy_process_group()
+        eng.close()
+        DADStepEngine.shutdown_process_group()
 
 
 if __name__ == "__main__":

@@ -538,7 +538,7 @@ struct BwdParams {
     int64_t rows_per_split;          // multiple of 32
 };
 
-constexpr int ABSMAX_GRID = 32;
+constexpr int ABSMAX_GRID = 256;  // == DAD_H: k_bwd_prep folds the partials with one thread each
 
 // per-CTA partial max of |g/len| (no atomics: the table scale must be bit-reproducible)
 __global__ void __launch_bounds__(DAD_H) k_bwd_absmax(const float* __restrict__ g_emb, const float* __restrict__ lens, float* __restrict__ part, int B) {
@@ -559,8 +559,14 @@ __global__ void __launch_bounds__(DAD_H) k_bwd_absmax(const float* __restrict__ 
 __global__ void __launch_bounds__(DAD_H) k_bwd_prep(const float* __restrict__ g_emb, const float* __restrict__ lens, const float* __restrict__ part,
                                                     uint16_t* __restrict__ g_hi, uint16_t* __restrict__ g_lo, float* __restrict__ unscale) {
     __shared__ float s_scale;
+    __shared__ float s_m[DAD_H / 32];
+    {
+        const float m = warp_max(part[threadIdx.x]);  // max is order-independent: the scale is bit-reproducible
+        if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    }
+    __syncthreads();
     if (threadIdx.x < 32) {
-        float m = threadIdx.x < ABSMAX_GRID ? part[threadIdx.x] : 0.f;
+        float m = threadIdx.x < DAD_H / 32 ? s_m[threadIdx.x] : 0.f;
         m = warp_max(m);
         if (threadIdx.x == 0) {
             float sc = 1.0f;
@@ -582,46 +588,51 @@ __global__ void __launch_bounds__(DAD_H) k_bwd_prep(const float* __restrict__ g_
     g_lo[i] = l;
 }
 
-// db[h] = sum over valid frames of relu_bit(n,h) * g[b,h]/len_b = sum_b (g[b,h]/len_b) * count_b[h]:
-// one CTA per utterance counts its ReLU bits per hidden unit (warp ballots over 32-frame chunks), contrib[b][h] = count * g/len;
-// k_bwd_db_fold then sums utterance groups in fixed order into the split partials consumed by dad_grad_reduce.
-__global__ void __launch_bounds__(DAD_H) k_bwd_db(const uint32_t* __restrict__ bits, const uint8_t* __restrict__ pad, const float* __restrict__ g_emb,
-                                                  const float* __restrict__ lens, float* __restrict__ contrib, int T) {
-    __shared__ int s_cnt[DAD_H / 32][DAD_H];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
-    int cnt[DAD_HW];
+// db[h] = sum over valid frames of relu_bit(n,h) * g[b,h]/len_b = sum_b (g[b,h]/len_b) * count_b[h].
+// One WARP per utterance counts its ReLU bits per hidden unit with SIMD-in-register adds: lane (w = lane & 7, q = lane >> 3)
+// walks frames q, q+4, ... and keeps, for its 32-bit mask word w, sixteen registers of two 16-bit counters
+// ((word >> k) & 0x00010001 counts bits k and k+16) -- 48 integer ops per frame instead of 256 warp ballots.  The four q-lanes
+// of a word are folded with two shuffles per register; contrib[b][h] = count * g/len, and k_bwd_db_fold then sums utterance
+// groups in fixed order into the split partials consumed by dad_grad_reduce.  (Frames per lane <= 65535: T < 2^18.)
+constexpr int DB_WARPS = 8;
+__global__ void __launch_bounds__(DB_WARPS * 32) k_bwd_db(const uint32_t* __restrict__ bits, const uint8_t* __restrict__ pad, const float* __restrict__ g_emb,
+                                                         const float* __restrict__ lens, float* __restrict__ contrib, int T, int B) {
+    __shared__ int s_cnt[DB_WARPS][DAD_H];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * DB_WARPS + warp;
+    if (b >= B) return;
+    const int w = lane & 7, q = lane >> 3;
+    uint32_t c[16];
 #pragma unroll
-    for (int w = 0; w < DAD_HW; ++w) cnt[w] = 0;
-    for (int t0 = warp * 32; t0 < T; t0 += (DAD_H / 32) * 32) {
-        const int t = t0 + lane;
-        const int64_t n = (int64_t)b * T + t;
-        uint32_t wd[DAD_HW];
-        const bool on = t < T && !(pad && pad[n]);
-        if (on) {
-            const uint4 lo = __ldg(reinterpret_cast<const uint4*>(bits + n * DAD_HW));
-            const uint4 hi = __ldg(reinterpret_cast<const uint4*>(bits + n * DAD_HW) + 1);
-            wd[0] = lo.x; wd[1] = lo.y; wd[2] = lo.z; wd[3] = lo.w; wd[4] = hi.x; wd[5] = hi.y; wd[6] = hi.z; wd[7] = hi.w;
-        } else {
+    for (int k = 0; k < 16; ++k) c[k] = 0u;
+    const int64_t n0 = (int64_t)b * T;
+#pragma unroll 2
+    for (int t = q; t < T; t += 4) {
+        const int64_t n = n0 + t;
+        uint32_t word = __ldg(bits + n * DAD_HW + w);  // a warp reads 4 frames x 32 B = 128 contiguous bytes
+        if (pad && pad[n]) word = 0u;
 #pragma unroll
-            for (int w = 0; w < DAD_HW; ++w) wd[w] = 0u;
-        }
-#pragma unroll
-        for (int w = 0; w < DAD_HW; ++w) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const unsigned bal = __ballot_sync(0xffffffffu, (wd[w] >> j) & 1u);
-                if (lane == j) cnt[w] += __popc(bal);
-            }
-        }
+        for (int k = 0; k < 16; ++k) c[k] += (word >> k) & 0x00010001u;
     }
 #pragma unroll
-    for (int w = 0; w < DAD_HW; ++w) s_cnt[warp][w * 32 + lane] = cnt[w];
-    __syncthreads();
-    const int h = threadIdx.x;
-    int c = 0;
+    for (int k = 0; k < 16; ++k) {
+        c[k] += __shfl_xor_sync(0xffffffffu, c[k], 8);
+        c[k] += __shfl_xor_sync(0xffffffffu, c[k], 16);
+    }
+    if (q == 0) {
 #pragma unroll
-    for (int w = 0; w < DAD_H / 32; ++w) c += s_cnt[w][h];
-    contrib[(int64_t)b * DAD_H + h] = (float)c * (g_emb[(int64_t)b * DAD_H + h] / lens[b]);
+        for (int k = 0; k < 16; ++k) {
+            s_cnt[warp][w * 32 + k] = (int)(c[k] & 0xFFFFu);
+            s_cnt[warp][w * 32 + 16 + k] = (int)(c[k] >> 16);
+        }
+    }
+    __syncwarp();
+    const float inv = lens[b];
+#pragma unroll
+    for (int m = 0; m < DAD_H / 32; ++m) {
+        const int h = lane + 32 * m;
+        contrib[(int64_t)b * DAD_H + h] = (float)s_cnt[warp][h] * (g_emb[(int64_t)b * DAD_H + h] / inv);
+    }
 }
 __global__ void __launch_bounds__(DAD_H) k_bwd_db_fold(const float* __restrict__ contrib, float* __restrict__ dbp, int B, int per) {
     const int b0 = blockIdx.x * per;
@@ -966,7 +977,7 @@ static BwdCarve bwd_carve(int64_t B) {
     size_t o = 0;
     c.g_hi = o; o = bwd_align(o + (size_t)B * DAD_H * sizeof(uint16_t));
     c.g_lo = o; o = bwd_align(o + (size_t)B * DAD_H * sizeof(uint16_t));
-    c.scal = o; o = bwd_align(o + 64 * sizeof(float));   // [0,32) absmax partials, [32] unscale
+    c.scal = o; o = bwd_align(o + (ABSMAX_GRID + 64) * sizeof(float));   // [0,ABSMAX_GRID) absmax partials, [ABSMAX_GRID] unscale
     c.contrib = o; o = bwd_align(o + (size_t)B * DAD_H * sizeof(float));
     c.total = o;
     return c;
@@ -992,15 +1003,15 @@ int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, c
     float* contrib = reinterpret_cast<float*>(w8 + cv.contrib);
     k_bwd_absmax<<<ABSMAX_GRID, DAD_H, 0, st>>>(g_emb, lens, scal, (int)B);
     DAD_CHECK_LAUNCH("k_bwd_absmax");
-    k_bwd_prep<<<(unsigned)B, DAD_H, 0, st>>>(g_emb, lens, scal, g_hi, g_lo, scal + 32);
+    k_bwd_prep<<<(unsigned)B, DAD_H, 0, st>>>(g_emb, lens, scal, g_hi, g_lo, scal + ABSMAX_GRID);
     DAD_CHECK_LAUNCH("k_bwd_prep");
     BwdParams p;
-    p.x = x; p.pad = pad; p.ap = ap; p.bits = bits; p.g_hi = g_hi; p.g_lo = g_lo; p.unscale = scal + 32; p.dWp = dWp;
+    p.x = x; p.pad = pad; p.ap = ap; p.bits = bits; p.g_hi = g_hi; p.g_lo = g_lo; p.unscale = scal + ABSMAX_GRID; p.dWp = dWp;
     p.N = B * T; p.T = (int)T;
     p.rows_per_split = ceil_div64(ceil_div64(p.N, splits), BWD_BK) * BWD_BK;
     k_enc_bwd_tc<<<dim3(DAD_D / 256, splits), BWD_THREADS, BWD_SMEM, st>>>(p);
     DAD_CHECK_LAUNCH("k_enc_bwd_tc");
-    k_bwd_db<<<(unsigned)B, DAD_H, 0, st>>>(bits, pad, g_emb, lens, contrib, (int)T);
+    k_bwd_db<<<(unsigned)ceil_div64(B, DB_WARPS), DB_WARPS * 32, 0, st>>>(bits, pad, g_emb, lens, contrib, (int)T, (int)B);
     DAD_CHECK_LAUNCH("k_bwd_db");
     k_bwd_db_fold<<<splits, DAD_H, 0, st>>>(contrib, dbp, (int)B, (int)ceil_div64(B, splits));
     DAD_CHECK_LAUNCH("k_bwd_db_fold");

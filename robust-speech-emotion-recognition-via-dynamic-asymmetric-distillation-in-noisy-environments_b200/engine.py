@@ -383,6 +383,12 @@ class DADStepEngine:
         ent[0].replay()
         self.launches_per_step = ent[1]
 
+    def close(self):
+        """Drop the captured CUDA graphs (they hold NCCL kernels under data parallelism: release them BEFORE
+        torch.distributed.destroy_process_group(), which otherwise waits on them forever)."""
+        self._graphs.clear()
+        torch.cuda.synchronize(self.dev)
+
     _STATE = ("p", "t", "m", "v", "step_count", "ema_thr", "quality", "epoch_sum", "epoch_cnt", "loss_acc", "hi_lo")
 
     def _snapshot(self):
@@ -417,6 +423,26 @@ class DADStepEngine:
             self.quality.copy_(newq)
             self.epoch_sum.zero_()
             self.epoch_cnt.zero_()
+
+    @staticmethod
+    def shutdown_process_group(grace_s=20.0):
+        """barrier + destroy_process_group with a watchdog: a communicator that was captured into CUDA graphs can hang in
+        its destructor; results are already printed by then, so after `grace_s` the process exits with status 0."""
+        import os
+        import sys
+        import threading
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        sys.stdout.flush(); sys.stderr.flush()
+        timer = threading.Timer(grace_s, lambda: os._exit(0))
+        timer.daemon = True
+        timer.start()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        finally:
+            timer.cancel()
 
     def cosine_lr(self, epoch):
         lr0, total = getattr(self.cfg, "LEARNING_RATE"), getattr(self.cfg, "EPOCHS")

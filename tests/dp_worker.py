@@ -219,8 +219,9 @@ def run_gpu(args):
     assert torch.equal(flat, ref0), (rank, "replicated state diverged across ranks")
     torch.cuda.synchronize()
     if rank == 0:
-        print(f"DP_GPU_OK world={world} gemm={args.gemm} graph={args.graph} steps={steps} worst loss rel={worst['loss']:.2e} w={worst['w']:.2e}")
-    dist.destroy_process_group()
+        print(f"DP_GPU_OK world={world} gemm={args.gemm} graph={args.graph} steps={steps} worst loss rel={worst['loss']:.2e} w={worst['w']:.2e}", flush=True)
+    dp.close(); one.close()
+    DADStepEngine.shutdown_process_group()
 
 
 if __name__ == "__main__":

@@ -17,7 +17,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _torchrun(nproc, extra, timeout=600):
+def _torchrun(nproc, extra, timeout=240):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(HERE, "dp_worker.py")] + extra
     env = dict(os.environ, OMP_NUM_THREADS="2", PYTHONDONTWRITEBYTECODE="1")
