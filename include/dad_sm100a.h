@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DAD_ABI_VERSION 1
+#define DAD_ABI_VERSION 2
 #define DAD_D 768
 #define DAD_H 256
 #define DAD_C 4
@@ -68,17 +68,22 @@ int dad_augment(const float* x, float* out, const dad_aug* aug, int64_t B, int64
 size_t dad_encoder_fwd_workspace_bytes(int64_t B, int64_t T, int32_t gemm_mode);
 /* emb[B,H] = masked-mean_t relu(W aug(x)[b,t,:] + bias).  pad: [B,T] uint8, 1 = padded frame, NULL = none.
  * relu_bits (nullable): [B*T, H/32] uint32, bit j of word w of frame n = (pre[n, 32w+j] > 0) -- all the backward needs.
+ * xs_hi / xs_lo (nullable, TC mode only): OPERAND CACHE, two fp16 [B*T, D] buffers.  When given, the forward also writes the
+ *   hi/lo split of the augmented, power-of-two-scaled input it feeds to the tensor cores; dad_encoder_bwd given the same
+ *   buffers loads its B operand from them by TMA instead of re-reading x and regenerating the augmentation (same values,
+ *   bit-identical dW; trades one extra N*D*4-byte write + read for the converter work of the backward).
  * lens (nullable): [B] valid length clamped to >= 1 (I/model.py:36).  W_hi/W_lo: fp16 [H,D] splits from dad_split_f16 (TC mode only). */
 int dad_encoder_fwd(const float* x, const uint8_t* pad, const float* W, const float* bias, const void* W_hi,
-                    const void* W_lo, const dad_aug* aug, float* emb, uint32_t* relu_bits, float* lens, void* ws,
-                    size_t ws_bytes, int64_t B, int64_t T, int32_t gemm_mode, void* stream);
+                    const void* W_lo, const dad_aug* aug, float* emb, uint32_t* relu_bits, void* xs_hi, void* xs_lo,
+                    float* lens, void* ws, size_t ws_bytes, int64_t B, int64_t T, int32_t gemm_mode, void* stream);
 
 int32_t dad_encoder_bwd_splits(int64_t B, int64_t T, int32_t gemm_mode);
 /* split-K partials: dW_part[splits, H, D], db_part[splits, H]; dad_grad_reduce sums them in fixed order.
- * g_emb[B,H] = dL/d emb; x / pad / aug identical to the forward call (the augmented view is regenerated). */
-int dad_encoder_bwd(const float* x, const uint8_t* pad, const dad_aug* aug, const uint32_t* relu_bits,
-                    const float* g_emb, const float* lens, float* dW_part, float* db_part, int32_t splits, void* ws,
-                    size_t ws_bytes, int64_t B, int64_t T, int32_t gemm_mode, void* stream);
+ * g_emb[B,H] = dL/d emb; x / pad / aug identical to the forward call (the augmented view is regenerated) -- or, in TC
+ * mode, xs_hi / xs_lo = the operand cache the forward call filled (then x and aug are ignored and may be NULL). */
+int dad_encoder_bwd(const float* x, const uint8_t* pad, const dad_aug* aug, const uint32_t* relu_bits, const void* xs_hi,
+                    const void* xs_lo, const float* g_emb, const float* lens, float* dW_part, float* db_part,
+                    int32_t splits, void* ws, size_t ws_bytes, int64_t B, int64_t T, int32_t gemm_mode, void* stream);
 size_t dad_encoder_bwd_workspace_bytes(int64_t B, int64_t T, int32_t gemm_mode);
 
 /* ---- the per-step exchange buffer ("pack"): what the single all-gather of the data-parallel step moves ------- *

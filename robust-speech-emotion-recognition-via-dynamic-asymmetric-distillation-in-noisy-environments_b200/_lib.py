@@ -95,8 +95,8 @@ def lib():
     L.dad_head_grid.argtypes = [C.c_int32]
     vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
     L.dad_augment.argtypes = [vp, vp, C.POINTER(Aug), i64, i64, vp]
-    L.dad_encoder_fwd.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(Aug), vp, vp, vp, vp, C.c_size_t, i64, i64, i32, vp]
-    L.dad_encoder_bwd.argtypes = [vp, vp, C.POINTER(Aug), vp, vp, vp, vp, vp, i32, vp, C.c_size_t, i64, i64, i32, vp]
+    L.dad_encoder_fwd.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(Aug), vp, vp, vp, vp, vp, vp, C.c_size_t, i64, i64, i32, vp]
+    L.dad_encoder_bwd.argtypes = [vp, vp, C.POINTER(Aug), vp, vp, vp, vp, vp, vp, vp, i32, vp, C.c_size_t, i64, i64, i32, vp]
     L.dad_head_fwd.argtypes = [C.POINTER(HeadFwdArgs), vp]
     L.dad_dacp_mask.argtypes = [C.POINTER(DacpArgs), vp]
     L.dad_head_bwd.argtypes = [C.POINTER(HeadBwdArgs), vp]
@@ -107,7 +107,7 @@ def lib():
     L.dad_ema.argtypes = [vp, vp, f32, f32, i64, vp]
     L.dad_split_f16.argtypes = [vp, vp, vp, i64, vp]
     L.dad_step_rng.argtypes = [C.c_uint64, vp, vp, vp, i64, f32, vp, f32, vp, i64, i32, vp]
-    if L.dad_abi_version() != 1:
+    if L.dad_abi_version() != 2:
         raise DadError("libdad_sm100a.so ABI version mismatch")
     _lib = L
     return L

@@ -17,11 +17,13 @@ int launch_enc_bwd_simt(const float* x, const uint8_t* pad, const AugParams& ap,
                         float* dWp, float* dbp, int splits, int64_t B, int64_t T, cudaStream_t st);
 size_t enc_fwd_tc_ws_bytes(int64_t B, int64_t T);
 int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W_hi, const void* W_lo, const float* bias, const AugParams& ap,
-                      float* emb, uint32_t* bits, float* lens_out, void* ws, size_t ws_bytes, int64_t B, int64_t T, cudaStream_t st);
+                      float* emb, uint32_t* bits, void* xs_hi, void* xs_lo, float* lens_out, void* ws, size_t ws_bytes, int64_t B, int64_t T,
+                      cudaStream_t st);
 int enc_bwd_tc_splits(int64_t N);
 size_t enc_bwd_tc_ws_bytes(int64_t B, int64_t T);
-int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, const uint32_t* bits, const float* g_emb, const float* lens,
-                      float* dWp, float* dbp, int splits, void* ws, size_t ws_bytes, int64_t B, int64_t T, cudaStream_t st);
+int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, const uint32_t* bits, const void* xs_hi, const void* xs_lo,
+                      const float* g_emb, const float* lens, float* dWp, float* dbp, int splits, void* ws, size_t ws_bytes, int64_t B, int64_t T,
+                      cudaStream_t st);
 int launch_head_fwd(const HeadFwdArgs& a, cudaStream_t st);
 int head_grid(int B_local);
 int launch_dacp(DacpArgs a, cudaStream_t st);
@@ -99,8 +101,8 @@ size_t dad_encoder_fwd_workspace_bytes(int64_t B, int64_t T, int32_t gemm_mode) 
 }
 
 int dad_encoder_fwd(const float* x, const uint8_t* pad, const float* W, const float* bias, const void* W_hi, const void* W_lo,
-                    const dad_aug* aug, float* emb, uint32_t* relu_bits, float* lens, void* ws, size_t ws_bytes, int64_t B, int64_t T,
-                    int32_t gemm_mode, void* stream) {
+                    const dad_aug* aug, float* emb, uint32_t* relu_bits, void* xs_hi, void* xs_lo, float* lens, void* ws, size_t ws_bytes,
+                    int64_t B, int64_t T, int32_t gemm_mode, void* stream) {
     DAD_REQUIRE(B >= 0 && T >= 0, "encoder_fwd: negative size");
     if (B == 0) return DAD_OK;
     DAD_REQUIRE(T > 0, "encoder_fwd: T must be > 0");
@@ -121,7 +123,10 @@ int dad_encoder_fwd(const float* x, const uint8_t* pad, const float* W, const fl
         return launch_enc_fwd_simt(x, pad, W, bias, ap, emb, relu_bits, lens, reinterpret_cast<float*>(rest), counters, B, T, (cudaStream_t)stream);
     } else if (gemm_mode == DAD_GEMM_TC_F16X3) {
         DAD_REQUIRE(W_hi && W_lo, "encoder_fwd: TC mode needs the bf16 hi/lo weight splits (dad_split_f16)");
-        return launch_enc_fwd_tc(x, pad, W_hi, W_lo, bias, ap, emb, relu_bits, lens, rest, ws_bytes - (size_t)(rest - (char*)ws), B, T, (cudaStream_t)stream);
+        DAD_REQUIRE((xs_hi == nullptr) == (xs_lo == nullptr), "encoder_fwd: xs_hi and xs_lo must be given together");
+        DAD_REQUIRE(!xs_hi || (aligned16(xs_hi) && aligned16(xs_lo)), "encoder_fwd: xs_hi/xs_lo not 16-byte aligned");
+        return launch_enc_fwd_tc(x, pad, W_hi, W_lo, bias, ap, emb, relu_bits, xs_hi, xs_lo, lens, rest, ws_bytes - (size_t)(rest - (char*)ws), B, T,
+                                 (cudaStream_t)stream);
     }
     return dad_set_error(DAD_ERR_ARG, "encoder_fwd: unknown gemm_mode %d", gemm_mode);
 }
@@ -133,11 +138,14 @@ size_t dad_encoder_bwd_workspace_bytes(int64_t B, int64_t T, int32_t gemm_mode) 
     return gemm_mode == DAD_GEMM_TC_F16X3 ? enc_bwd_tc_ws_bytes(B, T) : 256;
 }
 
-int dad_encoder_bwd(const float* x, const uint8_t* pad, const dad_aug* aug, const uint32_t* relu_bits, const float* g_emb,
-                    const float* lens, float* dW_part, float* db_part, int32_t splits, void* ws, size_t ws_bytes, int64_t B, int64_t T,
-                    int32_t gemm_mode, void* stream) {
+int dad_encoder_bwd(const float* x, const uint8_t* pad, const dad_aug* aug, const uint32_t* relu_bits, const void* xs_hi, const void* xs_lo,
+                    const float* g_emb, const float* lens, float* dW_part, float* db_part, int32_t splits, void* ws, size_t ws_bytes,
+                    int64_t B, int64_t T, int32_t gemm_mode, void* stream) {
     DAD_REQUIRE(B > 0 && T > 0, "encoder_bwd: empty batch");
-    DAD_REQUIRE(x && aligned16(x) && relu_bits && g_emb && aligned16(g_emb) && lens, "encoder_bwd: null/unaligned input");
+    DAD_REQUIRE((xs_hi == nullptr) == (xs_lo == nullptr), "encoder_bwd: xs_hi and xs_lo must be given together");
+    const bool cached = xs_hi != nullptr && gemm_mode == DAD_GEMM_TC_F16X3;
+    DAD_REQUIRE(cached || (x && aligned16(x)), "encoder_bwd: x null/unaligned (and no operand cache given)");
+    DAD_REQUIRE(relu_bits && g_emb && aligned16(g_emb) && lens, "encoder_bwd: null/unaligned input");
     DAD_REQUIRE(dW_part && db_part && aligned16(dW_part), "encoder_bwd: null/unaligned partial buffers");
     DAD_REQUIRE(splits == dad_encoder_bwd_splits(B, T, gemm_mode), "encoder_bwd: splits must equal dad_encoder_bwd_splits()");
     int rc = check_aug(aug, false);
@@ -150,7 +158,7 @@ int dad_encoder_bwd(const float* x, const uint8_t* pad, const dad_aug* aug, cons
     if (gemm_mode == DAD_GEMM_TC_F16X3) {
         const size_t need = enc_bwd_tc_ws_bytes(B, T);
         if (!ws || ws_bytes < need) return dad_set_error(DAD_ERR_WS, "encoder_bwd: workspace %zu < %zu bytes", ws_bytes, need);
-        return launch_enc_bwd_tc(x, pad, ap, relu_bits, g_emb, lens, dW_part, db_part, splits, ws, ws_bytes, B, T, (cudaStream_t)stream);
+        return launch_enc_bwd_tc(x, pad, ap, relu_bits, xs_hi, xs_lo, g_emb, lens, dW_part, db_part, splits, ws, ws_bytes, B, T, (cudaStream_t)stream);
     }
     return dad_set_error(DAD_ERR_ARG, "encoder_bwd: unknown gemm_mode %d", gemm_mode);
 }

@@ -21,7 +21,7 @@
 #include "tc_ptx.cuh"
 #include <cuda_fp16.h>
 #include <mutex>
-#include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -45,10 +45,11 @@ struct FwdParams {
     AugParams ap;
     float* part;        // [num_groups][2][256]
     uint32_t* bits;     // [N][8] or null
+    int cache;          // operand cache on: every A tile (the fp16 hi/lo split of the augmented, scaled input) is also TMA-stored from
+                        //   shared memory to xs_hi / xs_lo [N][768] for the backward kernel (tm_xhi / tm_xlo), at no converter cost
     int64_t N;
     int T;
     int num_tiles;
-    int dbg;  // timing experiments only (DAD_TC_DBG): bit 0 one product instead of three, bit 1 W loaded for the first two k-blocks only
 };
 
 // Sum over the 32 lanes of each of the 32 per-lane values: on return lane j holds sum_lanes v[j] (fixed butterfly order).
@@ -114,15 +115,11 @@ __device__ __forceinline__ void fwd_convert(const FwdParams& p, uint8_t* smem, u
         }
         return z;
     };
-    float dbg_acc = 0.f;
     auto load = [&](float4 (&dst)[8], int it) {
         const int tile = tile_of(it), kb = it % KB;
         const int64_t row0 = (int64_t)tile * BM + rbase;
         const float* src = p.x + row0 * DAD_D + kb * BK + kq * 4;
-        if (p.dbg & 8) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_float4(1.f, 2.f, 3.f, (float)it);
-        } else if (row0 + 8 <= p.N) {
+        if (row0 + 8 <= p.N) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) dst[i] = __ldg(reinterpret_cast<const float4*>(src + i * DAD_D));
         } else {
@@ -178,14 +175,8 @@ __device__ __forceinline__ void fwd_convert(const FwdParams& p, uint8_t* smem, u
                 }
             }
         }
-        if (p.dbg & 4) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dbg_acc += cur[i].x + cur[i].y + cur[i].z + cur[i].w;
-            if (dbg_acc == 1.2345f) store_row(a_hi, a_lo, cur[0], 0, zmask);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) store_row(a_hi, a_lo, cur[i], i, zmask);
-        }
+        for (int i = 0; i < 8; ++i) store_row(a_hi, a_lo, cur[i], i, zmask);
         tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&full[s]);
@@ -217,12 +208,13 @@ __device__ __forceinline__ void fwd_convert(const FwdParams& p, uint8_t* smem, u
 }
 
 __global__ void __launch_bounds__(FWD_THREADS, 1)
-k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo, FwdParams p) {
+k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_xhi,
+             const __grid_constant__ CUtensorMap tm_xlo, FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
     uint64_t* full = bars;            // [STAGES]  1 (TMA expect_tx) + 8 (converter warps)
-    uint64_t* empty = bars + 2;       // [STAGES]  1 (tcgen05.commit)
+    uint64_t* empty = bars + 2;       // [STAGES]  1 (tcgen05.commit) + 1 (operand-cache store warp, when caching)
     uint64_t* tfull = bars + 4;       // [2]       1 (tcgen05.commit)
     uint64_t* tempty = bars + 6;      // [2]       4 (epilogue warps)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
@@ -237,7 +229,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         *progress = 0;
-        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1 + N_CONV_WARPS); tc::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1 + N_CONV_WARPS); tc::mbar_init(&empty[s], 1 + (p.cache ? 1 : 0)); }
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], 4); }
         tc::fence_barrier_init();
     }
@@ -262,7 +254,6 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     tc::mbar_wait(&empty[s], ph ^ 1);
-                    if ((p.dbg & 2) && it >= STAGES) { tc::mbar_arrive(&full[s]); continue; }
                     tc::mbar_arrive_expect_tx(&full[s], 2 * W_BYTES);
                     tc::tma_load_2d(smem + s * STAGE_BYTES + OFF_WHI, &tm_whi, &full[s], kb * BK, 0);
                     tc::tma_load_2d(smem + s * STAGE_BYTES + OFF_WLO, &tm_wlo, &full[s], kb * BK, 0);
@@ -286,7 +277,6 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
                     const uint32_t base = tc::smem_u32(smem + s * STAGE_BYTES);
 #pragma unroll
                     for (int prod = 0; prod < 3; ++prod) {
-                        if ((p.dbg & 1) && prod > 0) break;
                         const uint32_t a_off = (prod == 2) ? OFF_ALO : OFF_AHI;  // hi*hi, hi*lo, lo*hi
                         const uint32_t b_off = (prod == 1) ? OFF_WLO : OFF_WHI;
 #pragma unroll
@@ -380,8 +370,29 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
             }
             __syncwarp();
         }
+    } else if (warp == 3) {
+        // ===================== operand-cache store: A tiles shared -> global by TMA =====================
+        // The A tile of a stage ([128 frames][64 k] fp16, SWIZZLE_128B) is exactly one TMA box of xs_hi / xs_lo; the slot is handed
+        // back (second arrival on empty[s]) once the bulk store has finished READING shared memory.  Frames beyond N are clipped.
+        tc::reg_dec<40>();
+        if (p.cache && lane == 0) {
+            tc::prefetch_tmap(&tm_xhi);
+            tc::prefetch_tmap(&tm_xlo);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    tc::mbar_wait(&full[s], ph);
+                    tc::tma_store_2d(&tm_xhi, smem + s * STAGE_BYTES + OFF_AHI, kb * BK, tile * BM);
+                    tc::tma_store_2d(&tm_xlo, smem + s * STAGE_BYTES + OFF_ALO, kb * BK, tile * BM);
+                    tc::bulk_commit();
+                    tc::bulk_wait_read0();
+                    tc::mbar_arrive(&empty[s]);
+                }
+            tc::bulk_wait0();
+        }
     } else {
-        tc::reg_dec<40>();  // warps 2, 3: same warpgroup as the TMA / MMA warps
+        tc::reg_dec<40>();  // warp 2: same warpgroup as the TMA / MMA / store warps
     }
     tc::tcgen05_fence_before();
     __syncthreads();
@@ -471,7 +482,7 @@ size_t enc_fwd_tc_ws_bytes(int64_t B, int64_t T) {
 }
 
 int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W_hi, const void* W_lo, const float* bias, const AugParams& ap, float* emb,
-                      uint32_t* bits, float* lens_out, void* ws, size_t ws_bytes, int64_t B, int64_t T, cudaStream_t st) {
+                      uint32_t* bits, void* xs_hi, void* xs_lo, float* lens_out, void* ws, size_t ws_bytes, int64_t B, int64_t T, cudaStream_t st) {
     if (T < 32) return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_fwd: the tcgen05 path needs T >= 32 (got %lld); use DAD_GEMM_FP32", (long long)T);
     if (B * T >= (1ll << 31)) return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_fwd: the tcgen05 path indexes frames with 32 bits (B*T = %lld)", (long long)(B * T));
     if ((reinterpret_cast<uintptr_t>(W_hi) | reinterpret_cast<uintptr_t>(W_lo)) & 15u)
@@ -490,14 +501,21 @@ int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W_hi, cons
     }
     FwdParams p;
     p.x = x; p.pad = pad; p.bias = bias; p.ap = ap; p.part = reinterpret_cast<float*>(ws); p.bits = bits;
-    p.N = B * T; p.T = (int)T; p.num_tiles = (int)ceil_div64(B * T, BM);
-    {
-        static int dbg = -1;
-        if (dbg < 0) { const char* e = getenv("DAD_TC_DBG"); dbg = e ? atoi(e) : 0; }
-        p.dbg = dbg;
+    p.cache = (xs_hi && xs_lo) ? 1 : 0;
+    CUtensorMap tm_xhi, tm_xlo;
+    memset(&tm_xhi, 0, sizeof(tm_xhi));
+    memset(&tm_xlo, 0, sizeof(tm_xlo));
+    if (p.cache) {
+        if ((reinterpret_cast<uintptr_t>(xs_hi) | reinterpret_cast<uintptr_t>(xs_lo)) & 15u)
+            return dad_set_error(DAD_ERR_ARG, "encoder_fwd: xs_hi/xs_lo must be 16-byte aligned (TMA)");
+        rc = make_tmap_f16(&tm_xhi, xs_hi, (uint64_t)(B * T), DAD_D, BM);
+        if (rc) return rc;
+        rc = make_tmap_f16(&tm_xlo, xs_lo, (uint64_t)(B * T), DAD_D, BM);
+        if (rc) return rc;
     }
+    p.N = B * T; p.T = (int)T; p.num_tiles = (int)ceil_div64(B * T, BM);
     const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    k_enc_fwd_tc<<<grid, FWD_THREADS, FWD_SMEM, st>>>(tm_hi, tm_lo, p);
+    k_enc_fwd_tc<<<grid, FWD_THREADS, FWD_SMEM, st>>>(tm_hi, tm_lo, tm_xhi, tm_xlo, p);
     DAD_CHECK_LAUNCH("k_enc_fwd_tc");
     k_pool_finalize<<<(unsigned)B, DAD_H, 0, st>>>(p.part, pad, emb, lens_out, (int)T);
     DAD_CHECK_LAUNCH("k_pool_finalize");
@@ -536,6 +554,7 @@ struct BwdParams {
     int64_t N;
     int T;
     int64_t rows_per_split;          // multiple of 32
+    int use_xs;                      // B operand comes from the forward's operand cache by TMA (tm_xhi / tm_xlo); x / ap are not touched
 };
 
 constexpr int ABSMAX_GRID = 256;  // == DAD_H: k_bwd_prep folds the partials with one thread each
@@ -669,7 +688,7 @@ struct BwdRegs {
 };
 struct BwdTab { uint4 gh, gl; int b; };  // this lane's g/len table chunk (fp16 hi, lo) of utterance b; slot = b & 1
 
-template <int MODE, bool PHILOX>
+template <int MODE, bool PHILOX, bool XS>
 __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, volatile int* progress, const int cw, const int lane,
                                             const int dslice, const int64_t n_begin, const int64_t n_end, const int nkb) {
     const AugParams& ap = p.ap;
@@ -717,16 +736,18 @@ __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, u
             int t = R.t0 + j, b = R.b0;
             if (t >= T) { t -= T; ++b; }
             bool zx = !in;
-            if (MODE == 2 && in && ap.t_start && ap.mask_len > 0) {
+            if (!XS && MODE == 2 && in && ap.t_start && ap.mask_len > 0) {
                 const int s0 = __ldg(ap.t_start + b);
                 zx = (t >= s0 && t < s0 + ap.mask_len);
             }
             if (in) {
-                R.x[2 * j] = __ldg(reinterpret_cast<const float4*>(src + j * DAD_D));
-                R.x[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(src + j * DAD_D + 128));
+                if (!XS) {
+                    R.x[2 * j] = __ldg(reinterpret_cast<const float4*>(src + j * DAD_D));
+                    R.x[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(src + j * DAD_D + 128));
+                }
                 R.w[j] = __ldg(p.bits + (n0 + j) * DAD_HW + (lane >> 2));
             } else {
-                R.x[2 * j] = R.x[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!XS) R.x[2 * j] = R.x[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 R.w[j] = 0u;
             }
             const bool on = in && !(p.pad && p.pad[n0 + j]);
@@ -778,8 +799,8 @@ __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, u
             tc::sts128(st + BOFF_AHI + off, gh);
             tc::sts128(st + BOFF_ALO + off, gl);
         }
-        // ---- B operand: aug(x) rows -> fp16 hi/lo (scaled by TC_XS)
-        if (MODE != 0) {
+        // ---- B operand: aug(x) rows -> fp16 hi/lo (scaled by TC_XS); with the operand cache (XS) the TMA warp loads it instead
+        if (!XS && MODE != 0) {
 #pragma unroll
             for (int rp = 0; rp < 2; ++rp) {
 #pragma unroll
@@ -811,7 +832,7 @@ __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, u
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < (XS ? 0 : 4); ++j) {
             const uint32_t r7 = r7b + (uint32_t)j;
             const uint32_t roff = xoff0 + r7 * 128u + ((xc ^ r7) << 4);
 #pragma unroll
@@ -849,7 +870,8 @@ __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, u
     }
 }
 
-__global__ void __launch_bounds__(BWD_THREADS, 1) k_enc_bwd_tc(BwdParams p) {
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+k_enc_bwd_tc(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo, BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BOFF_BARS);
@@ -867,7 +889,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_enc_bwd_tc(BwdParams p) {
 
     if (warp == 1 && lane == 0) {
         *progress = 0;
-        for (int s = 0; s < BWD_STAGES; ++s) { tc::mbar_init(&full[s], N_CONV_WARPS); tc::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < BWD_STAGES; ++s) { tc::mbar_init(&full[s], N_CONV_WARPS + (p.use_xs ? 1 : 0)); tc::mbar_init(&empty[s], 1); }
         tc::mbar_init(tfull, 1);
         tc::fence_barrier_init();
     }
@@ -880,7 +902,28 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_enc_bwd_tc(BwdParams p) {
     tc::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 1) {
+    if (warp == 0) {
+        // ===================== TMA producer (operand cache -> B operand) =====================
+        // one box = 32 frames x 64 d-columns (128-byte rows, SWIZZLE_128B) = exactly one MN-major 64-column chunk of the stage;
+        // frames beyond N are zero-filled by the tensor map
+        tc::reg_dec<40>();
+        if (p.use_xs && lane == 0) {
+            tc::prefetch_tmap(&tm_xhi);
+            tc::prefetch_tmap(&tm_xlo);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const uint32_t s = kb % BWD_STAGES, ph = (kb / BWD_STAGES) & 1;
+                tc::mbar_wait(&empty[s], ph ^ 1);
+                tc::mbar_arrive_expect_tx(&full[s], 2 * BOP_BYTES);
+                const int row = (int)(n_begin + (int64_t)kb * BWD_BK);
+                uint8_t* st = smem + s * BSTAGE_BYTES;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    tc::tma_load_2d(st + BOFF_BHI + c * MN_LBO, &tm_xhi, &full[s], dslice * 256 + c * 64, row);
+                    tc::tma_load_2d(st + BOFF_BLO + c * MN_LBO, &tm_xlo, &full[s], dslice * 256 + c * 64, row);
+                }
+            }
+        }
+    } else if (warp == 1) {
         // ===================== MMA issuer =====================
         tc::reg_dec<40>();
         constexpr uint32_t idesc = tc::make_idesc_f16(128, DAD_H, 1, 1);  // A and B both MN-major
@@ -912,13 +955,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_enc_bwd_tc(BwdParams p) {
         // ===================== converters =====================
         tc::reg_inc<200>();  // 128 x 40 (control) + 256 x 200 (converters: three 39-register landing sets) + 128 x 64 (epilogue) <= 64 K
         const int cw = warp - CONV_WARP0;
-        const int variant = p.ap.mode == 0 ? 0 : (p.ap.mode * 2 - 1 + (p.ap.noise_src == 1 ? 1 : 0));
+        const int variant = p.use_xs ? 5 : (p.ap.mode == 0 ? 0 : (p.ap.mode * 2 - 1 + (p.ap.noise_src == 1 ? 1 : 0)));
         switch (variant) {
-            case 0: bwd_convert<0, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 1: bwd_convert<1, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 2: bwd_convert<1, true>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 3: bwd_convert<2, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
-            default: bwd_convert<2, true>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 0: bwd_convert<0, false, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 1: bwd_convert<1, false, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 2: bwd_convert<1, true, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 3: bwd_convert<2, false, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 4: bwd_convert<2, true, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
+            default: bwd_convert<0, false, true>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;  // A operand only
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: TMEM -> split-K partial dW =====================
@@ -951,7 +995,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_enc_bwd_tc(BwdParams p) {
             }
         }
     } else {
-        tc::reg_dec<40>();  // warps 0, 2, 3: same warpgroup as the MMA warp
+        tc::reg_dec<40>();  // warps 2, 3: same warpgroup as the TMA / MMA warps
     }
     tc::tcgen05_fence_before();
     __syncthreads();
@@ -984,8 +1028,9 @@ static BwdCarve bwd_carve(int64_t B) {
 }
 size_t enc_bwd_tc_ws_bytes(int64_t B, int64_t) { return bwd_carve(B).total; }
 
-int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, const uint32_t* bits, const float* g_emb, const float* lens,
-                      float* dWp, float* dbp, int splits, void* ws, size_t ws_bytes, int64_t B, int64_t T, cudaStream_t st) {
+int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, const uint32_t* bits, const void* xs_hi, const void* xs_lo,
+                      const float* g_emb, const float* lens, float* dWp, float* dbp, int splits, void* ws, size_t ws_bytes, int64_t B, int64_t T,
+                      cudaStream_t st) {
     const BwdCarve cv = bwd_carve(B);
     if (ws_bytes < cv.total) return dad_set_error(DAD_ERR_WS, "encoder_bwd(tc): workspace too small");
     if (T < 32) return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_bwd: the tcgen05 path needs T >= 32 (got %lld); use DAD_GEMM_FP32", (long long)T);
@@ -1009,7 +1054,19 @@ int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, c
     p.x = x; p.pad = pad; p.ap = ap; p.bits = bits; p.g_hi = g_hi; p.g_lo = g_lo; p.unscale = scal + ABSMAX_GRID; p.dWp = dWp;
     p.N = B * T; p.T = (int)T;
     p.rows_per_split = ceil_div64(ceil_div64(p.N, splits), BWD_BK) * BWD_BK;
-    k_enc_bwd_tc<<<dim3(DAD_D / 256, splits), BWD_THREADS, BWD_SMEM, st>>>(p);
+    CUtensorMap tm_hi, tm_lo;
+    memset(&tm_hi, 0, sizeof(tm_hi));
+    memset(&tm_lo, 0, sizeof(tm_lo));
+    p.use_xs = (xs_hi && xs_lo) ? 1 : 0;
+    if (p.use_xs) {
+        if ((reinterpret_cast<uintptr_t>(xs_hi) | reinterpret_cast<uintptr_t>(xs_lo)) & 15u)
+            return dad_set_error(DAD_ERR_ARG, "encoder_bwd: xs_hi/xs_lo must be 16-byte aligned (TMA)");
+        int rc = make_tmap_f16(&tm_hi, xs_hi, (uint64_t)p.N, DAD_D, BWD_BK);
+        if (rc) return rc;
+        rc = make_tmap_f16(&tm_lo, xs_lo, (uint64_t)p.N, DAD_D, BWD_BK);
+        if (rc) return rc;
+    }
+    k_enc_bwd_tc<<<dim3(DAD_D / 256, splits), BWD_THREADS, BWD_SMEM, st>>>(tm_hi, tm_lo, p);
     DAD_CHECK_LAUNCH("k_enc_bwd_tc");
     k_bwd_db<<<(unsigned)ceil_div64(B, DB_WARPS), DB_WARPS * 32, 0, st>>>(bits, pad, g_emb, lens, contrib, (int)T, (int)B);
     DAD_CHECK_LAUNCH("k_bwd_db");

@@ -81,7 +81,7 @@ class StepScalars:
 
 class DADStepEngine:
     def __init__(self, cfg, B_local, T, device=None, dataset="iemocap", world=1, rank=0, process_group=None, gemm_mode=None,
-                 use_graph=True, seed=42, noise_mode="philox"):
+                 use_graph=True, seed=42, noise_mode="philox", operand_cache="strong"):
         _lib.require_device()
         self.cfg, self.dataset = cfg, dataset
         self.B, self.T = int(B_local), int(T)
@@ -95,6 +95,11 @@ class DADStepEngine:
         if noise_mode not in ("philox", "supplied"):
             raise DadError("noise_mode must be 'philox' or 'supplied'")
         self.noise_mode = noise_mode
+        if operand_cache not in ("none", "strong", "both"):
+            raise DadError("operand_cache must be 'none', 'strong' or 'both'")
+        if self.gemm_mode != GEMM_TC:
+            operand_cache = "none"
+        self.operand_cache = operand_cache
         B, T, dev = self.B, self.T, self.dev
         Bg = B * self.world
         self.Bg = Bg
@@ -133,6 +138,10 @@ class DADStepEngine:
         self.emb_teacher = z(B, D_HID)
         self.bits_clean = torch.zeros(B * T, D_HID // 32, dtype=torch.int32, device=dev)
         self.bits_strong = torch.zeros(B * T, D_HID // 32, dtype=torch.int32, device=dev)
+        # operand cache: fp16 hi/lo split of the augmented input, written by the student forwards and TMA-loaded by the backward
+        f16 = lambda: torch.zeros(2, B * T, D_IN, dtype=torch.float16, device=dev)
+        self.xs_strong = f16() if operand_cache in ("strong", "both") else None
+        self.xs_clean = f16() if operand_cache == "both" else None
         self.lens_clean, self.lens_noisy, self.lens_scratch = z(B), z(B), z(B)
         self.dz_clean, self.probs, self.logq = z(B, N_CLS), z(B, N_CLS), z(B, N_CLS)
         self.n_head = lib().dad_head_grid(B)
@@ -236,20 +245,23 @@ class DADStepEngine:
                         t_start=self.t_start if (sc.mask_ratio > 0 and L > 0) else None, mask_len=L, seed=self.seed, stream=2,
                         step_ptr=self.step_count.data_ptr())
 
-    def _enc_fwd(self, x, pad, teacher, aug, emb_ptr, bits, lens, s):
+    def _enc_fwd(self, x, pad, teacher, aug, emb_ptr, bits, lens, s, xs=None):
         flat = self.t if teacher else self.p
         hi, lo = (self.hi_lo[2], self.hi_lo[3]) if teacher else (self.hi_lo[0], self.hi_lo[1])
         check(lib().dad_encoder_fwd(x.data_ptr(), pad.data_ptr(), flat.data_ptr() + OFF_W * 4, flat.data_ptr() + OFF_B * 4,
                                     hi.data_ptr(), lo.data_ptr(), C.byref(aug) if aug is not None else None, emb_ptr,
-                                    bits.data_ptr() if bits is not None else None, lens.data_ptr(), self.enc_ws.data_ptr(),
+                                    bits.data_ptr() if bits is not None else None,
+                                    xs[0].data_ptr() if xs is not None else None, xs[1].data_ptr() if xs is not None else None,
+                                    lens.data_ptr(), self.enc_ws.data_ptr(),
                                     self.enc_ws.numel(), self.B, self.T, self.gemm_mode, s))
-        self.launches_per_step += 1
+        self.launches_per_step += 2 if self.gemm_mode == GEMM_TC else 1
 
-    def _enc_bwd(self, x, pad, aug, bits, g, lens, slot, s):
+    def _enc_bwd(self, x, pad, aug, bits, g, lens, slot, s, xs=None):
         check(lib().dad_encoder_bwd(x.data_ptr(), pad.data_ptr(), C.byref(aug) if aug is not None else None, bits.data_ptr(),
+                                    xs[0].data_ptr() if xs is not None else None, xs[1].data_ptr() if xs is not None else None,
                                     g.data_ptr(), lens.data_ptr(), self.dWp[slot].data_ptr(), self.dbp[slot].data_ptr(), self.S,
                                     self.bwd_ws.data_ptr(), self.bwd_ws.numel(), self.B, self.T, self.gemm_mode, s))
-        self.launches_per_step += 1
+        self.launches_per_step += 5 if self.gemm_mode == GEMM_TC else 1
 
     def _enqueue(self, sc):
         """Enqueue one full step on the current stream (eager or under graph capture)."""
@@ -272,12 +284,12 @@ class DADStepEngine:
                                  self.t_start.data_ptr() if noisy else None, T, Lm, s))
             self.launches_per_step += 1
         # ---- forwards (I/train.py:399, 409, 439)
-        self._enc_fwd(self.x_clean, self.pad_clean, False, None, emb_clean_ptr, self.bits_clean, self.lens_clean, s)
+        self._enc_fwd(self.x_clean, self.pad_clean, False, None, emb_clean_ptr, self.bits_clean, self.lens_clean, s, xs=self.xs_clean)
         aug_w = aug_s = None
         if noisy:
             aug_w, aug_s = self._aug(1, sc), self._aug(2, sc)
             self._enc_fwd(self.x_noisy, self.pad_noisy, True, aug_w, self.emb_teacher.data_ptr(), None, self.lens_scratch, s)
-            self._enc_fwd(self.x_noisy, self.pad_noisy, False, aug_s, emb_strong_ptr, self.bits_strong, self.lens_noisy, s)
+            self._enc_fwd(self.x_noisy, self.pad_noisy, False, aug_s, emb_strong_ptr, self.bits_strong, self.lens_noisy, s, xs=self.xs_strong)
         # ---- heads
         hf = HeadFwdArgs()
         hf.pack, hf.rank, hf.B_local, hf.noisy, hf.use_entropy = pk, self.rank, B, int(noisy), int(sc.use_entropy)
@@ -329,9 +341,9 @@ class DADStepEngine:
         else:
             self.g_ext[NPARAM + 2:NPARAM + 3].zero_()
         # ---- backward of the two student encoder calls (I/train.py:486)
-        self._enc_bwd(self.x_clean, self.pad_clean, None, self.bits_clean, self.g_clean, self.lens_clean, 0, s)
+        self._enc_bwd(self.x_clean, self.pad_clean, None, self.bits_clean, self.g_clean, self.lens_clean, 0, s, xs=self.xs_clean)
         if noisy:
-            self._enc_bwd(self.x_noisy, self.pad_noisy, aug_s, self.bits_strong, self.g_strong, self.lens_noisy, 1, s)
+            self._enc_bwd(self.x_noisy, self.pad_noisy, aug_s, self.bits_strong, self.g_strong, self.lens_noisy, 1, s, xs=self.xs_strong)
         check(L.dad_grad_reduce(self.dWp[0].data_ptr(), self.dbp[0].data_ptr(), self.S,
                                 self.dWp[1].data_ptr() if noisy else None, self.dbp[1].data_ptr() if noisy else None, self.S,
                                 hb.dWc, hb.dbc, self.g_ext.data_ptr(), s))

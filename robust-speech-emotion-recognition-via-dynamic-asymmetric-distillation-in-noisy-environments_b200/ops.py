@@ -63,8 +63,9 @@ def augment(x, sigma, noise=None, seed=None, stream=0, feat_keep=None, t_start=N
     return out if x.dim() == 3 else out[0]
 
 
-def encoder_pool_fwd(x, pad, W, b, aug=None, gemm_mode=None, want_bits=True, W_hi=None, W_lo=None, emb_out=None):
-    """emb[B,256] = masked-mean_t relu(W aug(x) + b)  (I/model.py:18-41).  Returns (emb, relu_bits|None, lens)."""
+def encoder_pool_fwd(x, pad, W, b, aug=None, gemm_mode=None, want_bits=True, W_hi=None, W_lo=None, emb_out=None, xs=None):
+    """emb[B,256] = masked-mean_t relu(W aug(x) + b)  (I/model.py:18-41).  Returns (emb, relu_bits|None, lens).
+    xs = (xs_hi, xs_lo): optional fp16 [B*T,768] operand-cache buffers filled for encoder_pool_bwd (tcgen05 mode only)."""
     _lib.require_device()
     if x.dim() != 3 or x.shape[-1] != D_IN:
         raise DadError(f"encoder: expected x [B,T,{D_IN}], got {tuple(x.shape)}")
@@ -84,13 +85,16 @@ def encoder_pool_fwd(x, pad, W, b, aug=None, gemm_mode=None, want_bits=True, W_h
     ws = _zeros_ws(nb, dev, "enc_fwd")
     check(lib().dad_encoder_fwd(ptr(x, torch.float32, "x"), ptr(pad8), ptr(W.contiguous(), torch.float32, "W"),
                                 ptr(b.contiguous(), torch.float32, "b"), ptr(W_hi), ptr(W_lo),
-                                C.byref(aug) if aug is not None else None, ptr(emb), ptr(bits), ptr(lens), ptr(ws), ws.numel(),
+                                C.byref(aug) if aug is not None else None, ptr(emb), ptr(bits),
+                                ptr(xs[0], torch.float16, "xs_hi") if xs is not None else None,
+                                ptr(xs[1], torch.float16, "xs_lo") if xs is not None else None, ptr(lens), ptr(ws), ws.numel(),
                                 B, T, mode, stream_ptr()))
     return emb, bits, lens
 
 
-def encoder_pool_bwd(x, pad, bits, g_emb, lens, aug=None, gemm_mode=None):
-    """(dW[256,768], db[256]) of encoder_pool_fwd given dL/d emb (autograd of I/model.py:28-39; no dX is needed)."""
+def encoder_pool_bwd(x, pad, bits, g_emb, lens, aug=None, gemm_mode=None, xs=None):
+    """(dW[256,768], db[256]) of encoder_pool_fwd given dL/d emb (autograd of I/model.py:28-39; no dX is needed).
+    xs = the operand cache filled by encoder_pool_fwd (then x / aug are not read)."""
     _lib.require_device()
     x = x.contiguous()
     B, T, _ = x.shape
@@ -103,7 +107,9 @@ def encoder_pool_bwd(x, pad, bits, g_emb, lens, aug=None, gemm_mode=None):
     nb = lib().dad_encoder_bwd_workspace_bytes(B, T, mode)
     ws = _zeros_ws(nb, dev, "enc_bwd")
     check(lib().dad_encoder_bwd(ptr(x, torch.float32, "x"), ptr(pad8), C.byref(aug) if aug is not None else None,
-                                ptr(bits), ptr(g_emb.contiguous(), torch.float32, "g_emb"), ptr(lens, torch.float32, "lens"),
+                                ptr(bits), ptr(xs[0], torch.float16, "xs_hi") if xs is not None else None,
+                                ptr(xs[1], torch.float16, "xs_lo") if xs is not None else None,
+                                ptr(g_emb.contiguous(), torch.float32, "g_emb"), ptr(lens, torch.float32, "lens"),
                                 ptr(dWp), ptr(dbp), S, ptr(ws), ws.numel(), B, T, mode, stream_ptr()))
     g = torch.empty(NPARAM, dtype=torch.float32, device=dev)
     zc = torch.zeros(4 * D_HID + 4, dtype=torch.float32, device=dev)

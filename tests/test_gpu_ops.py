@@ -24,7 +24,7 @@ def _inputs(B, T, seed, variable=True):
 def test_library_loaded_and_device_ok():
     from dad_b200 import _lib
     _lib.require_device()
-    assert _lib.lib().dad_abi_version() == 1
+    assert _lib.lib().dad_abi_version() == 2
 
 
 @pytest.mark.parametrize("B,T", [(6, 20), (3, 7), (2, 200), (1, 1)])
@@ -134,6 +134,38 @@ def test_encoder_forward_backward_vs_oracle(mode, B, T, aug):
     tolW = 2e-5 if mode == "fp32" else 1e-4
     assert float((dW.cpu() - W.grad).abs().max()) <= tolW * sW + 1e-7, (float((dW.cpu() - W.grad).abs().max()), sW)
     assert float((db.cpu() - b.grad).abs().max()) <= tolW * sb + 1e-7
+
+
+@pytest.mark.parametrize("B,T,aug", [(4, 64, 0), (5, 200, 2), (3, 97, 1), (2, 33, 2), (37, 41, 2)])
+def test_operand_cache_backward_is_bit_identical(B, T, aug):
+    """tcgen05 mode: the backward fed by TMA from the forward's fp16 hi/lo operand cache == the backward that re-reads,
+    re-augments and re-splits x (same operand values -> same dW partials, bit for bit); emb / bits are unaffected."""
+    from dad_b200 import _lib, ops
+    c, n, rng = _inputs(B, T, 777 + B * 1000 + T)
+    st = pretrained_state()
+    W, b = st["student_encoder.pre_net.weight"].cuda(), st["student_encoder.pre_net.bias"].cuda()
+    x, pad = n["net_input"]["feats"].cuda(), n["net_input"]["padding_mask"].cuda()
+    L = int(T * 0.1)
+    a = None
+    if aug == 1:
+        noise_d = rng["n_weak"].cuda()
+        a = _lib.make_aug(1, noise=noise_d, sigma=0.01)
+    elif aug == 2:
+        keep_d, ts_d, noise_d = (rng["feat_keep_u"] > 0.1).float().cuda(), rng["t_start"].to(torch.int32).cuda(), rng["n_strong"].cuda()
+        a = _lib.make_aug(2, noise=noise_d, sigma=0.05, feat_keep=keep_d, t_start=ts_d if L > 0 else None, mask_len=L)
+    g_emb = torch.randn(B, 256, generator=torch.Generator().manual_seed(11)).cuda()
+    emb0, bits0, lens0 = ops.encoder_pool_fwd(x, pad, W, b, aug=a, gemm_mode=_lib.GEMM_TC)
+    dW0, db0 = ops.encoder_pool_bwd(x, pad, bits0, g_emb, lens0, aug=a, gemm_mode=_lib.GEMM_TC)
+    xs = torch.full((2, B * T, 768), float("nan"), dtype=torch.float16, device="cuda")
+    emb1, bits1, lens1 = ops.encoder_pool_fwd(x, pad, W, b, aug=a, gemm_mode=_lib.GEMM_TC, xs=(xs[0], xs[1]))
+    assert torch.equal(emb0, emb1) and torch.equal(bits0, bits1)
+    assert not torch.isnan(xs.float()).any()  # every frame row of the cache was written
+    dW1, db1 = ops.encoder_pool_bwd(x, pad, bits1, g_emb, lens1, aug=None, gemm_mode=_lib.GEMM_TC, xs=(xs[0], xs[1]))
+    assert torch.equal(dW0, dW1) and torch.equal(db0, db1)
+    # the cache holds the augmented view itself: hi + lo == 8 * aug(x) to ~2^-21
+    if aug == 0:
+        rec = (xs[0].float() + xs[1].float()) / 8.0
+        assert float((rec.view(B, T, 768) - x).abs().max()) <= 2e-6 * float(x.abs().max())
 
 
 def test_encoder_rejects_bad_arguments():
