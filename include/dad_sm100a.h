@@ -106,6 +106,9 @@ typedef struct dad_head_fwd_args {
     float label_smoothing, inv_B_global;
     float *dz_clean, *probs, *logq;        /* out [B_local,C]: dCE/dlogits (/B_global), teacher probs, student log-probs */
     float* ce_part;                        /* out [dad_head_grid(B_local)] per-CTA CE sums */
+    int32_t n_clean, n_noisy;              /* real samples among the B_local clean / noisy slots (the rest is padding of a ragged
+                                              batch: label := -1, pred := -1, no loss, no gradient, never in a quantile or class);
+                                              inv_B_global must be 1 / (global number of REAL clean samples) */
 } dad_head_fwd_args;
 int32_t dad_head_grid(int32_t B_local);
 int dad_head_fwd(const dad_head_fwd_args* a, void* stream);
@@ -126,6 +129,8 @@ typedef struct dad_dacp_args {
     int64_t* epoch_cnt;                    /* [C] */
 } dad_dacp_args;
 int dad_dacp_mask(const dad_dacp_args* a, void* stream);
+/* DACPManager.calculate_certainty_scores (I/utils.py:400-428) as a stand-alone op: probs [B,C] -> scores [B] f32, preds [B] i32 */
+int dad_certainty_scores(const float* probs, int32_t B, int32_t use_entropy, float* scores, int32_t* preds, void* stream);
 
 /* ---- KD + head backward (I/train.py:444-447 and autograd through I/model.py:62-63) ---------------------------- */
 typedef struct dad_head_bwd_args {

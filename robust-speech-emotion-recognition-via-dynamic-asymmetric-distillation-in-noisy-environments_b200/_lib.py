@@ -20,7 +20,7 @@ EXPORTS = (
     "dad_encoder_fwd", "dad_encoder_bwd_splits", "dad_encoder_bwd", "dad_encoder_bwd_workspace_bytes",
     "dad_pack_rank_words", "dad_head_grid", "dad_head_fwd", "dad_dacp_mask", "dad_head_bwd",
     "dad_ecda_workspace_bytes", "dad_ecda", "dad_grad_reduce", "dad_grad_norm", "dad_adam_ema", "dad_ema",
-    "dad_split_f16", "dad_step_rng",
+    "dad_split_f16", "dad_step_rng", "dad_certainty_scores",
 )
 
 
@@ -43,7 +43,8 @@ class HeadFwdArgs(C.Structure):
                 ("emb_teacher", C.c_void_p), ("Wc", C.c_void_p), ("bc", C.c_void_p), ("tWc", C.c_void_p), ("tbc", C.c_void_p),
                 ("keep_clean", C.c_void_p), ("keep_strong", C.c_void_p), ("drop_scale", C.c_float),
                 ("label_smoothing", C.c_float), ("inv_B_global", C.c_float),
-                ("dz_clean", C.c_void_p), ("probs", C.c_void_p), ("logq", C.c_void_p), ("ce_part", C.c_void_p)]
+                ("dz_clean", C.c_void_p), ("probs", C.c_void_p), ("logq", C.c_void_p), ("ce_part", C.c_void_p),
+                ("n_clean", C.c_int32), ("n_noisy", C.c_int32)]
 
 
 class DacpArgs(C.Structure):
@@ -106,6 +107,7 @@ def lib():
     L.dad_adam_ema.argtypes = [vp, vp, vp, vp, vp, vp, f32, f32, f32, i32, vp, vp, vp, vp, vp, vp, vp, f32, f32, vp]
     L.dad_ema.argtypes = [vp, vp, f32, f32, i64, vp]
     L.dad_split_f16.argtypes = [vp, vp, vp, i64, vp]
+    L.dad_certainty_scores.argtypes = [vp, i32, i32, vp, vp, vp]
     L.dad_step_rng.argtypes = [C.c_uint64, vp, vp, vp, i64, f32, vp, f32, vp, i64, i32, vp]
     if L.dad_abi_version() != 2:
         raise DadError("libdad_sm100a.so ABI version mismatch")

@@ -26,6 +26,7 @@ int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, c
                       cudaStream_t st);
 int launch_head_fwd(const HeadFwdArgs& a, cudaStream_t st);
 int head_grid(int B_local);
+int launch_certainty(const float* probs, int B, int use_entropy, float* scores, int* preds, cudaStream_t st);
 int launch_dacp(DacpArgs a, cudaStream_t st);
 int launch_head_bwd(const HeadBwdArgs& a, cudaStream_t st);
 size_t ecda_pairs_smem_bytes();
@@ -180,7 +181,15 @@ int dad_head_fwd(const dad_head_fwd_args* a, void* stream) {
     DAD_REQUIRE(a->B_local == a->pack.B_local && a->rank >= 0 && a->rank < a->pack.world, "head_fwd: rank/B_local inconsistent with pack");
     DAD_REQUIRE(a->Wc && a->bc && a->dz_clean && a->ce_part, "head_fwd: null pointer");
     DAD_REQUIRE(!a->noisy || (a->emb_teacher && a->tWc && a->tbc && a->probs && a->logq), "head_fwd: noisy path needs teacher tensors");
+    DAD_REQUIRE(a->n_clean >= 0 && a->n_clean <= a->B_local && a->n_noisy >= 0 && a->n_noisy <= a->B_local, "head_fwd: n_clean / n_noisy out of range");
     return launch_head_fwd(*a, (cudaStream_t)stream);
+}
+
+int dad_certainty_scores(const float* probs, int32_t B, int32_t use_entropy, float* scores, int32_t* preds, void* stream) {
+    DAD_REQUIRE(B >= 0, "certainty_scores: negative size");
+    if (B == 0) return DAD_OK;
+    DAD_REQUIRE(probs && aligned16(probs) && scores && preds, "certainty_scores: null/unaligned pointer");
+    return launch_certainty(probs, B, use_entropy, scores, preds, (cudaStream_t)stream);
 }
 
 int dad_dacp_mask(const dad_dacp_args* a, void* stream) {

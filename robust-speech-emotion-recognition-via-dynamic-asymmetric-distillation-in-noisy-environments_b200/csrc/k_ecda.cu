@@ -34,7 +34,9 @@ __device__ __forceinline__ int row_slot(const EcdaArgs& a, int r, int Bg, float&
     if (r < Bg) {
         omega = 1.f;
         z = pack_emb_clean(a.pack, r);
-        return a.class_aware ? pack_label(a.pack, r) : 0;
+        const int y = pack_label(a.pack, r);
+        if (y < 0) return -1;  // null sample (padding of a ragged batch)
+        return a.class_aware ? y : 0;
     }
     const int gi = r - Bg;
     z = pack_emb_strong(a.pack, gi);

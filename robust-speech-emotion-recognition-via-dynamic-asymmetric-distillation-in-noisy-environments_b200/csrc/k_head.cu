@@ -47,7 +47,37 @@ __device__ __forceinline__ void softmax4(const float (&z)[DAD_C], float (&p)[DAD
     for (int c = 0; c < DAD_C; ++c) p[c] = e[c] / s;
 }
 
+// DACPManager.calculate_certainty_scores (I/utils.py:400-428): max prob, argmax, optional entropy weighting
+__device__ __forceinline__ void certainty4(const float (&p)[DAD_C], int use_entropy, float& score, int& pred) {
+    float maxp = p[0];
+    pred = 0;
+#pragma unroll
+    for (int c = 1; c < DAD_C; ++c)
+        if (p[c] > maxp) { maxp = p[c]; pred = c; }
+    score = maxp;
+    if (use_entropy) {
+        float ent = 0.f;
+#pragma unroll
+        for (int c = 0; c < DAD_C; ++c) ent -= p[c] * log2f(p[c] + 1e-8f);
+        score = maxp * (1.f - ent / 2.0f);  // log2(4) = 2
+    }
+}
+
 }  // namespace
+
+// stand-alone certainty scores for the op-level API (DACPManager.calculate_certainty_scores): one thread per sample
+__global__ void __launch_bounds__(256) k_certainty(const float* __restrict__ probs, int B, int use_entropy, float* __restrict__ scores,
+                                                   int* __restrict__ preds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float4 q = *reinterpret_cast<const float4*>(probs + (int64_t)i * DAD_C);
+    const float p[DAD_C] = {q.x, q.y, q.z, q.w};
+    float score;
+    int pred;
+    certainty4(p, use_entropy, score, pred);
+    scores[i] = score;
+    preds[i] = pred;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // k_head_fwd: per local sample.  mode bit0: clean head (CE), bit1: noisy heads (teacher probs/score + student log q)
@@ -74,7 +104,10 @@ __global__ void __launch_bounds__(HD_THREADS) k_head_fwd(HeadFwdArgs a) {
             const Logits4 z = head_gemv(u, a.Wc, a.bc, lane);
             float lp[DAD_C];
             log_softmax4(z.z, lp);
-            const int y = pack_label(a.pack, gi);
+            // samples i >= n_clean are padding ("null" samples of a ragged last batch): label := -1, no CE, zero gradient
+            const bool real = i < a.n_clean;
+            const int y = real ? pack_label(a.pack, gi) : -1;
+            if (!real && lane == 0) pack_label(a.pack, gi) = -1;
             const float eps = a.label_smoothing;
             float nll = 0.f, smooth = 0.f;
 #pragma unroll
@@ -82,10 +115,10 @@ __global__ void __launch_bounds__(HD_THREADS) k_head_fwd(HeadFwdArgs a) {
                 smooth -= lp[c];
                 if (c == y) nll = -lp[c];
             }
-            ce_i = (1.f - eps) * nll + eps * (smooth / DAD_C);
+            ce_i = real ? (1.f - eps) * nll + eps * (smooth / DAD_C) : 0.f;
             if (lane < DAD_C) {
                 const float p = expf(lp[lane]);
-                a.dz_clean[i * DAD_C + lane] = (p - (1.f - eps) * (lane == y ? 1.f : 0.f) - eps / DAD_C) * a.inv_B_global;
+                a.dz_clean[i * DAD_C + lane] = real ? (p - (1.f - eps) * (lane == y ? 1.f : 0.f) - eps / DAD_C) * a.inv_B_global : 0.f;
             }
         }
         if (a.noisy) {
@@ -94,18 +127,10 @@ __global__ void __launch_bounds__(HD_THREADS) k_head_fwd(HeadFwdArgs a) {
             const Logits4 zt = head_gemv(u, a.tWc, a.tbc, lane);
             float p[DAD_C];
             softmax4(zt.z, p);
-            float maxp = p[0];
-            int pred = 0;
-#pragma unroll
-            for (int c = 1; c < DAD_C; ++c)
-                if (p[c] > maxp) { maxp = p[c]; pred = c; }
-            float score = maxp;
-            if (a.use_entropy) {
-                float ent = 0.f;
-#pragma unroll
-                for (int c = 0; c < DAD_C; ++c) ent -= p[c] * log2f(p[c] + 1e-8f);
-                score = maxp * (1.f - ent / 2.0f);  // log2(4) = 2
-            }
+            float score;
+            int pred;
+            certainty4(p, a.use_entropy, score, pred);
+            if (i >= a.n_noisy) { score = 0.f; pred = -1; }  // null sample: no pseudo-label, never masked in, not in the quantiles
             // ---- strong student head (I/train.py:439-440)
             load8(pack_emb_strong(a.pack, gi) + lane * 8, u);
             if (a.keep_strong) {
@@ -163,8 +188,10 @@ __global__ void __launch_bounds__(1024) k_dacp(DacpArgs a) {
             unsigned long long k = ~0ull;
             if (i < Bg) {
                 const int c = pack_pred(a.pack, i);
-                k = ((unsigned long long)c << 32) | f2sortable(pack_score(a.pack, i));
-                atomicAdd(&s_cnt[c], 1);
+                if (c >= 0) {  // pred < 0: null sample (sorts to the end with the padding keys)
+                    k = ((unsigned long long)c << 32) | f2sortable(pack_score(a.pack, i));
+                    atomicAdd(&s_cnt[c], 1);
+                }
             }
             keys[i] = k;
         }
@@ -218,10 +245,10 @@ __global__ void __launch_bounds__(1024) k_dacp(DacpArgs a) {
     for (int i = tid; i < Bg; i += nt) {
         const int c = pack_pred(a.pack, i);
         const float s = pack_score(a.pack, i);
-        const int m = s >= s_thr[c];
+        const int m = c >= 0 && s >= s_thr[c < 0 ? 0 : c];
         a.mask[i] = (uint8_t)m;
         local += m;
-        if (a.use_dacp) atomicAdd(&s_sum[c], (double)s);  // per-class epoch accumulators (utils.py:503-505); sum order-insensitive in fp64 at this scale
+        if (a.use_dacp && c >= 0) atomicAdd(&s_sum[c], (double)s);  // per-class epoch accumulators (utils.py:503-505); sum order-insensitive in fp64 at this scale
     }
     local = (int)warp_sum((float)local);
     if ((tid & 31) == 0) atomicAdd(&s_nmask, local);
@@ -390,6 +417,13 @@ int launch_head_fwd(const HeadFwdArgs& a, cudaStream_t st) {
     return DAD_OK;
 }
 int head_grid(int B_local) { return ceil_div(B_local, HD_THREADS / 32); }
+
+int launch_certainty(const float* probs, int B, int use_entropy, float* scores, int* preds, cudaStream_t st) {
+    if (B == 0) return DAD_OK;
+    k_certainty<<<ceil_div(B, 256), 256, 0, st>>>(probs, B, use_entropy, scores, preds);
+    DAD_CHECK_LAUNCH("k_certainty");
+    return DAD_OK;
+}
 
 int launch_dacp(DacpArgs a, cudaStream_t st) {
     const int Bg = a.pack.B_local * a.pack.world;

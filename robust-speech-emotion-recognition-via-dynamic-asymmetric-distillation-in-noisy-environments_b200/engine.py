@@ -12,7 +12,13 @@ Data layout in HBM (all fp32 unless noted; N = B_local*T):
     flat params x5    [197892]    student, teacher, Adam m, Adam v, grad (+8 loss words)      the all-reduce payload = grad
     dW split-K partials [S,256,768] x2
 Under data parallelism (world > 1): one packed all-gather after the forwards, one all-reduce of the flat grad;
-DACP runs redundantly on the global batch, ECDA rows are sharded by owner rank (see csrc/k_ecda.cu)."""
+DACP runs redundantly on the global batch, ECDA rows are sharded by owner rank (see csrc/k_ecda.cu).
+
+Shapes.  The engine is built for a CAPACITY (B_local, T); every step may use any batch (B_clean, T_clean), (B_noisy, T_noisy)
+within it -- the reference's loaders pad each batch to ITS OWN longest utterance (I/dataload_clean.py:177-193), clean and noisy
+batches have different T, and the last batch of an epoch is ragged.  All buffers are flat allocations viewed at the step's
+shape (so captured CUDA graphs, keyed by shape, stay valid); when the two batch sizes differ the smaller one is padded with
+"null" samples that the kernels ignore (label / pseudo-label -1: no loss, no gradient, not in any quantile or class)."""
 import ctypes as C
 import math
 
@@ -84,12 +90,13 @@ class DADStepEngine:
                  use_graph=True, seed=42, noise_mode="philox", operand_cache="strong"):
         _lib.require_device()
         self.cfg, self.dataset = cfg, dataset
-        self.B, self.T = int(B_local), int(T)
+        self.Bcap, self.Tcap = int(B_local), int(T)
+        self.B, self.Tc, self.Tn = self.Bcap, self.Tcap, self.Tcap      # current step shape (set_inputs / set_shape)
+        self.n_clean = self.n_noisy = self.Bcap                          # real samples among the B slots
         self.world, self.rank, self.pg = int(world), int(rank), process_group
+        self.n_clean_global = self.Bcap * self.world
         self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.gemm_mode = GEMM_FP32 if gemm_mode is None else gemm_mode
-        if self.gemm_mode == GEMM_TC and self.T < 32:
-            raise DadError("tcgen05 encoder path needs T >= 32; use gemm_mode=GEMM_FP32")
         self.use_graph = use_graph
         self.seed = int(seed)
         if noise_mode not in ("philox", "supplied"):
@@ -100,9 +107,8 @@ class DADStepEngine:
         if self.gemm_mode != GEMM_TC:
             operand_cache = "none"
         self.operand_cache = operand_cache
-        B, T, dev = self.B, self.T, self.dev
+        B, T, dev = self.Bcap, self.Tcap, self.dev
         Bg = B * self.world
-        self.Bg = Bg
         f32 = dict(dtype=torch.float32, device=dev)
         z = lambda *s, **k: torch.zeros(*s, **({**f32, **k}))
         # ---- parameters and optimiser state (flat)
@@ -120,50 +126,108 @@ class DADStepEngine:
         self.anchors = torch.full((N_CLS,), 0.05, **f32)
         self.epoch_sum = torch.zeros(N_CLS, dtype=torch.float64, device=dev)
         self.epoch_cnt = torch.zeros(N_CLS, dtype=torch.int64, device=dev)
-        # ---- inputs (static buffers)
-        self.x_clean, self.x_noisy = z(B, T, D_IN), z(B, T, D_IN)
-        self.pad_clean = torch.zeros(B, T, dtype=torch.uint8, device=dev)
-        self.pad_noisy = torch.zeros(B, T, dtype=torch.uint8, device=dev)
-        self.keep_clean, self.keep_strong = torch.ones(B, D_HID, **f32), torch.ones(B, D_HID, **f32)
+        # ---- inputs (static flat buffers, viewed at the step's shape)
+        self._xc, self._xn = z(B * T * D_IN), z(B * T * D_IN)
+        self._pc = torch.zeros(B * T, dtype=torch.uint8, device=dev)
+        self._pn = torch.zeros(B * T, dtype=torch.uint8, device=dev)
+        self._keep_c, self._keep_s = torch.ones(B * D_HID, **f32), torch.ones(B * D_HID, **f32)
         self.feat_keep = torch.ones(D_IN, **f32)
-        self.t_start = torch.zeros(B, dtype=torch.int32, device=dev)
-        self.n_weak = self.n_strong = None
+        self._t_start = torch.zeros(B, dtype=torch.int32, device=dev)
+        self._nw = self._ns = None
         if noise_mode == "supplied":
-            self.n_weak, self.n_strong = z(B, T, D_IN), z(B, T, D_IN)
+            self._nw, self._ns = z(B * T * D_IN), z(B * T * D_IN)
         # ---- activations / exchange
-        rw = _lib.pack_rank_words(B)
-        self.pack = z(self.world * rw)
-        self.pack_i32 = self.pack.view(torch.int32)
-        self._rw = rw
-        self.emb_teacher = z(B, D_HID)
-        self.bits_clean = torch.zeros(B * T, D_HID // 32, dtype=torch.int32, device=dev)
-        self.bits_strong = torch.zeros(B * T, D_HID // 32, dtype=torch.int32, device=dev)
+        self._pack = z(self.world * _lib.pack_rank_words(B))
+        self._emb_t = z(B * D_HID)
+        self._bits_c = torch.zeros(B * T * (D_HID // 32), dtype=torch.int32, device=dev)
+        self._bits_s = torch.zeros(B * T * (D_HID // 32), dtype=torch.int32, device=dev)
         # operand cache: fp16 hi/lo split of the augmented input, written by the student forwards and TMA-loaded by the backward
-        f16 = lambda: torch.zeros(2, B * T, D_IN, dtype=torch.float16, device=dev)
-        self.xs_strong = f16() if operand_cache in ("strong", "both") else None
-        self.xs_clean = f16() if operand_cache == "both" else None
+        f16 = lambda: torch.zeros(2, B * T * D_IN, dtype=torch.float16, device=dev)
+        self._xs_s = f16() if operand_cache in ("strong", "both") else None
+        self._xs_c = f16() if operand_cache == "both" else None
         self.lens_clean, self.lens_noisy, self.lens_scratch = z(B), z(B), z(B)
-        self.dz_clean, self.probs, self.logq = z(B, N_CLS), z(B, N_CLS), z(B, N_CLS)
-        self.n_head = lib().dad_head_grid(B)
-        self.ce_part = z(self.n_head)
-        self.mask = torch.zeros(Bg, dtype=torch.uint8, device=dev)
+        self._dz, self._probs, self._logq = z(B * N_CLS), z(B * N_CLS), z(B * N_CLS)
+        self.ce_part = z(lib().dad_head_grid(B))
+        self._mask = torch.zeros(Bg, dtype=torch.uint8, device=dev)
         self.nmask = torch.zeros(1, dtype=torch.int32, device=dev)
         self.out_w, self.out_thr = torch.ones(N_CLS, **f32), z(N_CLS)
-        self.g_clean, self.g_strong = z(B, D_HID), z(B, D_HID)
+        self._g_c, self._g_s = z(B * D_HID), z(B * D_HID)
         self.dWc_dbc = z(N_CLS * D_HID + N_CLS)
-        self.head_part = z(self.n_head * (N_CLS * D_HID + N_CLS + 1))
+        self.head_part = z(lib().dad_head_grid(B) * (N_CLS * D_HID + N_CLS + 1))
         self.counters = torch.zeros(16, dtype=torch.int32, device=dev)
         self.norm_part = torch.zeros(128, dtype=torch.float64, device=dev)
         self.ecda_ws = torch.zeros(lib().dad_ecda_workspace_bytes(B, self.world), dtype=torch.uint8, device=dev)
-        nb = max(lib().dad_encoder_fwd_workspace_bytes(B, T, self.gemm_mode), 256)
+        modes = (GEMM_FP32, self.gemm_mode)  # frames-per-batch < 32 fall back to the exact-fp32 CUDA-core kernels
+        nb = max(max(lib().dad_encoder_fwd_workspace_bytes(B, T, m) for m in modes), 256)
         self.enc_ws = torch.zeros(nb, dtype=torch.uint8, device=dev)
-        self.bwd_ws = torch.zeros(max(lib().dad_encoder_bwd_workspace_bytes(B, T, self.gemm_mode), 256), dtype=torch.uint8, device=dev)
-        self.S = lib().dad_encoder_bwd_splits(B, T, self.gemm_mode)
-        self.dWp = z(2, self.S, D_HID * D_IN)
-        self.dbp = z(2, self.S, D_HID)
+        self.bwd_ws = torch.zeros(max(max(lib().dad_encoder_bwd_workspace_bytes(B, T, m) for m in modes), 256), dtype=torch.uint8, device=dev)
+        s_max = max(lib().dad_encoder_bwd_splits(B, T, m) for m in modes)
+        self._dWp = z(2, s_max * D_HID * D_IN)
+        self._dbp = z(2, s_max * D_HID)
         self._graphs = {}
+        self.max_graphs = 64
         self._scalars = None
         self.launches_per_step = 0
+
+    # ------------------------------------------------------------------ shape and views
+    def set_shape(self, B=None, T_clean=None, T_noisy=None, n_clean=None, n_noisy=None, n_clean_global=None):
+        """Shape of the next step(s): B slots per domain (<= capacity), padded lengths of the clean / noisy batch, and how many of
+        the B slots hold real samples.  n_clean_global = real clean samples over ALL ranks (CE is their mean)."""
+        B = self.Bcap if B is None else int(B)
+        Tc = self.Tcap if T_clean is None else int(T_clean)
+        Tn = Tc if T_noisy is None else int(T_noisy)
+        if not (1 <= B <= self.Bcap and 1 <= Tc <= self.Tcap and 1 <= Tn <= self.Tcap):
+            raise DadError(f"batch shape B={B}, T_clean={Tc}, T_noisy={Tn} exceeds the engine capacity ({self.Bcap}, {self.Tcap})")
+        if self.world > 1 and B != self.Bcap:
+            raise DadError("under data parallelism every rank uses B = capacity slots (pad with null samples: n_clean / n_noisy)")
+        self.B, self.Tc, self.Tn = B, Tc, Tn
+        self.n_clean = B if n_clean is None else int(n_clean)
+        self.n_noisy = B if n_noisy is None else int(n_noisy)
+        if not (0 <= self.n_clean <= B and 0 <= self.n_noisy <= B):
+            raise DadError("n_clean / n_noisy must lie in [0, B]")
+        self.n_clean_global = self.n_clean * self.world if n_clean_global is None else int(n_clean_global)
+
+    @property
+    def Bg(self):
+        return self.B * self.world
+
+    @property
+    def T(self):
+        return self.Tc
+
+    def _v(self, flat, *shape):
+        n = 1
+        for d in shape:
+            n *= d
+        return flat[:n].view(*shape)
+
+    x_clean = property(lambda self: self._v(self._xc, self.B, self.Tc, D_IN))
+    x_noisy = property(lambda self: self._v(self._xn, self.B, self.Tn, D_IN))
+    pad_clean = property(lambda self: self._v(self._pc, self.B, self.Tc))
+    pad_noisy = property(lambda self: self._v(self._pn, self.B, self.Tn))
+    keep_clean = property(lambda self: self._v(self._keep_c, self.B, D_HID))
+    keep_strong = property(lambda self: self._v(self._keep_s, self.B, D_HID))
+    t_start = property(lambda self: self._v(self._t_start, self.B))
+    n_weak = property(lambda self: None if self._nw is None else self._v(self._nw, self.B, self.Tn, D_IN))
+    n_strong = property(lambda self: None if self._ns is None else self._v(self._ns, self.B, self.Tn, D_IN))
+    pack = property(lambda self: self._v(self._pack, self.world * _lib.pack_rank_words(self.B)))
+    pack_i32 = property(lambda self: self.pack.view(torch.int32))
+    _rw = property(lambda self: _lib.pack_rank_words(self.B))
+    emb_teacher = property(lambda self: self._v(self._emb_t, self.B, D_HID))
+    bits_clean = property(lambda self: self._v(self._bits_c, self.B * self.Tc, D_HID // 32))
+    bits_strong = property(lambda self: self._v(self._bits_s, self.B * self.Tn, D_HID // 32))
+    xs_clean = property(lambda self: None if self._xs_c is None else self._xs_c[:, :self.B * self.Tc * D_IN])
+    xs_strong = property(lambda self: None if self._xs_s is None else self._xs_s[:, :self.B * self.Tn * D_IN])
+    dz_clean = property(lambda self: self._v(self._dz, self.B, N_CLS))
+    probs = property(lambda self: self._v(self._probs, self.B, N_CLS))
+    logq = property(lambda self: self._v(self._logq, self.B, N_CLS))
+    mask = property(lambda self: self._v(self._mask, self.B * self.world))
+    g_clean = property(lambda self: self._v(self._g_c, self.B, D_HID))
+    g_strong = property(lambda self: self._v(self._g_s, self.B, D_HID))
+    n_head = property(lambda self: lib().dad_head_grid(self.B))
+
+    def _mode(self, T):
+        return self.gemm_mode if (self.gemm_mode != GEMM_TC or T >= 32) else GEMM_FP32
 
     # ------------------------------------------------------------------ parameters
     def views(self, flat):
@@ -203,30 +267,54 @@ class DADStepEngine:
         self.lr.fill_(float(lr))
 
     # ------------------------------------------------------------------ inputs
-    def set_inputs(self, clean_batch, noisy_batch=None, rng=None):
-        """Copy one (clean, noisy) batch pair -- reference collator layout (I/dataload_clean.py:177-193) -- and, in the
-        supplied-noise mode, the step's RNG draws into the static device buffers."""
-        B, T = self.B, self.T
+    def set_inputs(self, clean_batch, noisy_batch=None, rng=None, n_clean_global=None):
+        """Copy one (clean, noisy) batch pair -- reference collator layout (I/dataload_clean.py:177-193; the CASIA / EMODB noisy
+        collator has no 'labels' key, C/dataload_casia_noisy.py:72-107) -- and, in the supplied-noise mode, the step's RNG draws
+         into the static device buffers.  The step shape follows the batches: B = max(B_clean, B_noisy),
+        T_clean / T_noisy = their padded lengths; the shorter batch is padded with null samples."""
         xc = clean_batch["net_input"]["feats"]
-        if tuple(xc.shape) != (B, T, D_IN):
-            raise DadError(f"clean feats {tuple(xc.shape)} != {(B, T, D_IN)} (engine is shape-specialised)")
-        self.x_clean.copy_(xc, non_blocking=True)
-        self.pad_clean.copy_(clean_batch["net_input"]["padding_mask"], non_blocking=True)
+        xn = noisy_batch["net_input"]["feats"] if noisy_batch is not None else None
+        if xc.dim() != 3 or xc.shape[2] != D_IN or (xn is not None and (xn.dim() != 3 or xn.shape[2] != D_IN)):
+            raise DadError(f"feats must be [B,T,{D_IN}]")
+        Bc, Tc = int(xc.shape[0]), int(xc.shape[1])
+        Bn, Tn = (int(xn.shape[0]), int(xn.shape[1])) if xn is not None else (Bc, self.Tn if self.Tn <= self.Tcap else Tc)
+        B = self.Bcap if self.world > 1 else max(Bc, Bn)
+        self.set_shape(B, Tc, Tn, n_clean=Bc, n_noisy=Bn, n_clean_global=n_clean_global)
+
+        def put(dst, src, n):
+            dst[:n].copy_(src, non_blocking=True)
+            if n < dst.shape[0]:
+                dst[n:].zero_()
+
+        put(self.x_clean, xc, Bc)
+        pm = clean_batch["net_input"].get("padding_mask")
+        if pm is None:
+            self.pad_clean.zero_()
+        else:
+            put(self.pad_clean, pm, Bc)
+        if Bc < B:
+            self.pad_clean[Bc:].fill_(1)
         lab = _lib.pack_global_views(self.pack, B, self.world)["label"][self.rank]
-        lab.copy_(clean_batch["labels"], non_blocking=True)
-        if noisy_batch is not None:
-            self.x_noisy.copy_(noisy_batch["net_input"]["feats"], non_blocking=True)
-            self.pad_noisy.copy_(noisy_batch["net_input"]["padding_mask"], non_blocking=True)
+        put(lab, clean_batch["labels"], Bc)
+        if xn is not None:
+            put(self.x_noisy, xn, Bn)
+            pm = noisy_batch["net_input"].get("padding_mask")
+            if pm is None:
+                self.pad_noisy.zero_()
+            else:
+                put(self.pad_noisy, pm, Bn)
+            if Bn < B:
+                self.pad_noisy[Bn:].fill_(1)
         if rng is not None:
             if self.noise_mode != "supplied":
                 raise DadError("rng inputs given but the engine was built with noise_mode='philox'")
             drop_p = float(getattr(self.cfg, "DROPOUT_RATE"))
-            self.keep_clean.copy_(rng["drop_clean"], non_blocking=True)
-            self.keep_strong.copy_(rng["drop_strong"], non_blocking=True)
-            self.n_weak.copy_(rng["n_weak"], non_blocking=True)
-            self.n_strong.copy_(rng["n_strong"], non_blocking=True)
+            put(self.keep_clean, rng["drop_clean"], Bc)
+            put(self.keep_strong, rng["drop_strong"], Bn)
+            put(self.n_weak, rng["n_weak"], Bn)
+            put(self.n_strong, rng["n_strong"], Bn)
             self.feat_keep.copy_((rng["feat_keep_u"] > drop_p).float(), non_blocking=True)
-            self.t_start.copy_(rng["t_start"], non_blocking=True)
+            put(self.t_start, rng["t_start"], Bn)
 
     # ------------------------------------------------------------------ the step
     def _pack_struct(self):
@@ -235,7 +323,7 @@ class DADStepEngine:
     def _aug(self, mode, sc):
         if mode == 0:
             return None
-        L = int(self.T * sc.mask_ratio)
+        L = int(self.Tn * sc.mask_ratio)
         supplied = self.noise_mode == "supplied"
         if mode == 1:
             return make_aug(1, noise=self.n_weak if supplied else None, sigma=sc.weak_std, seed=self.seed, stream=1,
@@ -248,33 +336,43 @@ class DADStepEngine:
     def _enc_fwd(self, x, pad, teacher, aug, emb_ptr, bits, lens, s, xs=None):
         flat = self.t if teacher else self.p
         hi, lo = (self.hi_lo[2], self.hi_lo[3]) if teacher else (self.hi_lo[0], self.hi_lo[1])
+        B, T = int(x.shape[0]), int(x.shape[1])
+        mode = self._mode(T)
+        if mode != GEMM_TC:
+            xs = None
         check(lib().dad_encoder_fwd(x.data_ptr(), pad.data_ptr(), flat.data_ptr() + OFF_W * 4, flat.data_ptr() + OFF_B * 4,
                                     hi.data_ptr(), lo.data_ptr(), C.byref(aug) if aug is not None else None, emb_ptr,
                                     bits.data_ptr() if bits is not None else None,
                                     xs[0].data_ptr() if xs is not None else None, xs[1].data_ptr() if xs is not None else None,
-                                    lens.data_ptr(), self.enc_ws.data_ptr(),
-                                    self.enc_ws.numel(), self.B, self.T, self.gemm_mode, s))
-        self.launches_per_step += 2 if self.gemm_mode == GEMM_TC else 1
+                                    lens.data_ptr(), self.enc_ws.data_ptr(), self.enc_ws.numel(), B, T, mode, s))
+        self.launches_per_step += 2 if mode == GEMM_TC else 1
 
     def _enc_bwd(self, x, pad, aug, bits, g, lens, slot, s, xs=None):
+        """-> number of split-K partials written to self._dWp[slot] / self._dbp[slot]"""
+        B, T = int(x.shape[0]), int(x.shape[1])
+        mode = self._mode(T)
+        if mode != GEMM_TC:
+            xs = None
+        S = lib().dad_encoder_bwd_splits(B, T, mode)
         check(lib().dad_encoder_bwd(x.data_ptr(), pad.data_ptr(), C.byref(aug) if aug is not None else None, bits.data_ptr(),
                                     xs[0].data_ptr() if xs is not None else None, xs[1].data_ptr() if xs is not None else None,
-                                    g.data_ptr(), lens.data_ptr(), self.dWp[slot].data_ptr(), self.dbp[slot].data_ptr(), self.S,
-                                    self.bwd_ws.data_ptr(), self.bwd_ws.numel(), self.B, self.T, self.gemm_mode, s))
-        self.launches_per_step += 5 if self.gemm_mode == GEMM_TC else 1
+                                    g.data_ptr(), lens.data_ptr(), self._dWp[slot].data_ptr(), self._dbp[slot].data_ptr(), S,
+                                    self.bwd_ws.data_ptr(), self.bwd_ws.numel(), B, T, mode, s))
+        self.launches_per_step += 5 if mode == GEMM_TC else 1
+        return S
 
     def _enqueue(self, sc):
         """Enqueue one full step on the current stream (eager or under graph capture)."""
         L = lib()
         s = _lib.stream_ptr()
-        B, T = self.B, self.T
+        B, T = self.B, self.Tn
         self.launches_per_step = 0
         pk = self._pack_struct()
         rbase = self.pack.data_ptr() + self.rank * self._rw * 4
         emb_clean_ptr, emb_strong_ptr = rbase, rbase + B * D_HID * 4
         noisy = not sc.warmup
         philox = self.noise_mode == "philox"
-        inv_Bg = _f32(1.0 / self.Bg)
+        inv_Bg = _f32(1.0 / max(self.n_clean_global, 1))
         drop = sc.drop_p > 0
         if philox and (drop or noisy):
             Lm = int(T * sc.mask_ratio)
@@ -301,6 +399,7 @@ class DADStepEngine:
         hf.drop_scale, hf.label_smoothing, hf.inv_B_global = sc.drop_scale, sc.label_smoothing, inv_Bg
         hf.dz_clean, hf.probs, hf.logq, hf.ce_part = (self.dz_clean.data_ptr(), self.probs.data_ptr(), self.logq.data_ptr(),
                                                       self.ce_part.data_ptr())
+        hf.n_clean, hf.n_noisy = self.n_clean, self.n_noisy
         check(L.dad_head_fwd(C.byref(hf), s))
         self.launches_per_step += 1
         if self.world > 1:
@@ -341,11 +440,12 @@ class DADStepEngine:
         else:
             self.g_ext[NPARAM + 2:NPARAM + 3].zero_()
         # ---- backward of the two student encoder calls (I/train.py:486)
-        self._enc_bwd(self.x_clean, self.pad_clean, None, self.bits_clean, self.g_clean, self.lens_clean, 0, s, xs=self.xs_clean)
+        S0 = self._enc_bwd(self.x_clean, self.pad_clean, None, self.bits_clean, self.g_clean, self.lens_clean, 0, s, xs=self.xs_clean)
+        S1 = 0
         if noisy:
-            self._enc_bwd(self.x_noisy, self.pad_noisy, aug_s, self.bits_strong, self.g_strong, self.lens_noisy, 1, s, xs=self.xs_strong)
-        check(L.dad_grad_reduce(self.dWp[0].data_ptr(), self.dbp[0].data_ptr(), self.S,
-                                self.dWp[1].data_ptr() if noisy else None, self.dbp[1].data_ptr() if noisy else None, self.S,
+            S1 = self._enc_bwd(self.x_noisy, self.pad_noisy, aug_s, self.bits_strong, self.g_strong, self.lens_noisy, 1, s, xs=self.xs_strong)
+        check(L.dad_grad_reduce(self._dWp[0].data_ptr(), self._dbp[0].data_ptr(), S0,
+                                self._dWp[1].data_ptr() if noisy else None, self._dbp[1].data_ptr() if noisy else None, S1,
                                 hb.dWc, hb.dbc, self.g_ext.data_ptr(), s))
         self.launches_per_step += 1
         if self.world > 1:
@@ -373,7 +473,7 @@ class DADStepEngine:
         if not self.use_graph:
             self._enqueue(sc)
             return
-        key = sc.key()
+        key = (self.B, self.Tc, self.Tn, self.n_clean, self.n_noisy, self.n_clean_global) + sc.key()
         ent = self._graphs.get(key)
         if ent is None:
             # warm-up run on a side stream (sets func attributes, NCCL lazy init), then capture
@@ -389,7 +489,7 @@ class DADStepEngine:
             with torch.cuda.graph(g):
                 self._enqueue(sc)
             ent = (g, self.launches_per_step)
-            if len(self._graphs) > 8:
+            if len(self._graphs) > self.max_graphs:
                 self._graphs.clear()
             self._graphs[key] = ent
         ent[0].replay()

@@ -208,3 +208,90 @@ def test_autograd_module_path_matches_oracle():
     gW = model.student_encoder.pre_net.weight.grad.cpu()
     assert float((gW - W.grad).abs().max()) <= 1e-4 * float(W.grad.abs().max())
     assert model.teacher_encoder.pre_net.weight.grad is None
+
+
+# ------------------------------------------------------------------------------------------------ op-level classes (dad_b200.utils)
+def test_data_augmentation_class_semantics():
+    """utils.DataAugmentation keeps the reference's semantics (I/utils.py:317-375): weak = x + N(0, 0.01^2); strong zeroes one
+    shared set of feature columns (no rescale) and one span of int(T*0.1) frames per sample; 2-D and 3-D inputs."""
+    from dad_b200.utils import DataAugmentation
+    torch.manual_seed(0)
+    aug = DataAugmentation()
+    x = torch.randn(6, 50, 768, device="cuda")
+    w = aug.weak_augment(x)
+    assert w.shape == x.shape and abs(float((w - x).std()) - 0.01) < 5e-4
+    s = aug.strong_augment(x)
+    zero_cols = (s == 0).all(dim=0).all(dim=0)               # feature columns dropped for the whole batch
+    assert 30 <= int(zero_cols.sum()) <= 130                 # ~10 % of 768
+    live = s[:, :, ~zero_cols]
+    zero_rows = (live == 0).all(dim=2)                       # [B,T]
+    assert torch.equal(zero_rows.sum(dim=1).cpu(), torch.full((6,), 5))  # int(50 * 0.1) frames per sample
+    for b in range(6):                                        # contiguous span
+        idx = zero_rows[b].nonzero().flatten()
+        assert int(idx[-1] - idx[0]) == 4
+    keep_rows = ~zero_rows
+    d = (s - x)[:, :, ~zero_cols][keep_rows]
+    assert abs(float(d.std()) - 0.05) < 2e-3
+    s2 = aug.strong_augment(x[0])
+    assert s2.shape == x[0].shape
+
+
+def test_dacp_manager_matches_oracle_over_steps():
+    from dad_b200 import config as cfg
+    from dad_b200.utils import DACPManager
+    from oracle import dad_oracle as O
+    hp = O.HParams.from_cfg(cfg)
+    st = O.DACPState.fresh(4)
+    mgr = DACPManager(4, cfg.EPOCHS, "cuda")
+    anchors = torch.tensor([0.05, 0.3, 0.1, 0.0])
+    g = torch.Generator().manual_seed(5)
+    for step in range(12):
+        B = 64 if step % 3 else 7
+        probs = torch.softmax(3.0 * torch.randn(B, 4, generator=g), dim=1)
+        if step == 4:
+            probs[:, 2] = 0; probs = probs / probs.sum(1, keepdim=True)   # an empty predicted class -> threshold falls back to theta
+        s_ref, p_ref = O.certainty_scores(probs, True)
+        s_got, p_got = DACPManager.calculate_certainty_scores(probs.cuda())
+        assert torch.equal(p_got.cpu(), p_ref) and torch.allclose(s_got.cpu(), s_ref, rtol=2e-6, atol=1e-7)
+        epoch = 40 + step
+        m_ref, sc_ref, w_ref = O.dacp_mask(st, probs, epoch, anchors, hp)
+        m_got, sc_got, w_got = mgr.calculate_mask(probs.cuda(), epoch, anchors.cuda())
+        near = (sc_ref - st.ema_thr[p_ref]).abs() < 1e-6        # samples within an ulp of the threshold may legitimately flip
+        assert torch.equal(m_got.cpu()[~near], m_ref[~near])
+        assert torch.allclose(mgr.ema_thresholds.cpu(), st.ema_thr, rtol=0, atol=1e-6)
+        assert torch.allclose(w_got.cpu(), w_ref, rtol=1e-6, atol=1e-7)
+        if step % 4 == 3:
+            O.dacp_epoch_update(st, hp)
+            mgr.update_class_quality_scores_epoch(mgr.batch_scores_per_class)
+            assert torch.allclose(mgr.class_quality_scores.cpu(), st.quality, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("class_aware", [True, False])
+def test_ecda_loss_module_forward_backward_vs_oracle(class_aware):
+    from dad_b200.utils import ECDALoss, use_config
+    from oracle import dad_oracle as O
+    from helpers import cfg_for
+    cfg = cfg_for("iemocap", {"USE_CLASS_AWARE_MMD": class_aware})
+    use_config(cfg)
+    try:
+        hp = O.HParams.from_cfg(cfg)
+        g = torch.Generator().manual_seed(21)
+        B = 48
+        mu = torch.randn(4, 256, generator=g)
+        yc, yn = torch.randint(0, 4, (B,), generator=g), torch.randint(0, 4, (B,), generator=g)
+        clean = (mu[yc] + 0.5 * torch.randn(B, 256, generator=g)).requires_grad_(True)
+        noisy = (mu[yn] + 0.7 * torch.randn(B, 256, generator=g)).requires_grad_(True)
+        mask = torch.rand(B, generator=g) > 0.3
+        scores = torch.rand(B, generator=g)
+        w = torch.rand(4, generator=g)
+        ref = O.ecda_loss(clean, noisy, yc, yn, mask, scores, w, hp)
+        ref.backward()
+        c2, n2 = clean.detach().cuda().requires_grad_(True), noisy.detach().cuda().requires_grad_(True)
+        got = ECDALoss()(c2, n2, yc.cuda(), yn.cuda(), mask.cuda(), scores.cuda(), w.cuda())
+        (2.0 * got).backward()
+        assert abs(float(got) - float(ref)) <= 1e-4 * max(abs(float(ref)), 1e-3), (float(got), float(ref))
+        for a, b in ((c2.grad, clean.grad), (n2.grad, noisy.grad)):
+            assert float((a.cpu() - 2.0 * b).abs().max()) <= 2e-4 * float(b.abs().max()) + 1e-7
+    finally:
+        from dad_b200 import config
+        use_config(config)

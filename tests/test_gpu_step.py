@@ -236,3 +236,39 @@ def test_philox_mode_runs_and_is_deterministic():
     assert torch.equal(outs[0][0], outs[1][0])
     l = outs[0][1]
     assert l["supervised_ce_loss"] > 0 and l["total_loss"] == l["total_loss"]  # finite
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+@pytest.mark.parametrize("Bc,Tc,Bn,Tn", [(13, 40, 16, 50), (16, 64, 9, 33), (5, 20, 5, 48)])
+def test_ragged_batches_and_capacity_engine(mode, Bc, Tc, Bn, Tn):
+    """The reference pads every batch to its own longest utterance and its last batch is ragged (I/dataload_clean.py:177-193,
+    I/train.py:479-483): clean and noisy batches of DIFFERENT size and padded length, run on an engine built for a larger
+    capacity, must reproduce the oracle step on exactly those batches (null-sample padding is invisible)."""
+    from dad_b200 import synth
+    orc, cfg, hp = make_oracle("iemocap")
+    from dad_b200 import _lib
+    from dad_b200.engine import DADStepEngine
+    gm = {"fp32": _lib.GEMM_FP32, "tc": _lib.GEMM_TC}[mode]
+    eng = DADStepEngine(cfg, 16, 64, gemm_mode=gm, use_graph=True, noise_mode="supplied")
+    for k, epoch in enumerate((5, 41, 42)):
+        orc.lr = O.cosine_lr(hp.LEARNING_RATE, epoch, hp.EPOCHS)
+        c, _ = synth.make_batches(Bc, Tc, 7100 + k, variable_len=True)
+        _, n = synth.make_batches(Bn, Tn, 7200 + k, variable_len=True)
+        rc, rn = synth.make_rng_inputs(Bc, Tc, 7300 + k), synth.make_rng_inputs(Bn, Tn, 7400 + k)
+        rng = {"drop_clean": rc["drop_clean"], "n_weak": rn["n_weak"], "n_strong": rn["n_strong"], "feat_keep_u": rn["feat_keep_u"],
+               "t_start": rn["t_start"], "drop_strong": rn["drop_strong"]}
+        push_oracle_state(eng, orc)
+        eng.set_inputs(_to_dev(c), _to_dev(n), {kk: v.cuda() for kk, v in rng.items()})
+        eng.step(epoch)
+        ref = orc.step(c, n, epoch, rng)
+        got = eng.losses()
+        for key in LOSS_KEYS:
+            assert abs(got[key] - ref[key]) <= 1e-4 * max(abs(ref[key]), 1e-3), (mode, k, key, got[key], ref[key])
+        if epoch >= hp.WARMUP_EPOCHS:
+            B = max(Bc, Bn)
+            assert torch.equal(eng.mask.cpu().bool()[:Bn], orc.last["mask"]) and not eng.mask.cpu()[Bn:].any()
+            assert float((eng.ema_thr.cpu() - orc.dacp.ema_thr).abs().max()) <= 1e-6
+        g_orc = torch.cat([orc.p[key].grad.reshape(-1) for key in O.PARAM_KEYS])
+        well = g_orc.abs() >= 1e-6
+        p_orc = torch.cat([orc.p[key].detach().reshape(-1) for key in O.PARAM_KEYS])
+        assert float((eng.p.cpu() - p_orc).abs()[well].max()) <= 1e-5, (mode, k, "weights")
