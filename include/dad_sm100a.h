@@ -166,6 +166,22 @@ typedef struct dad_ecda_args {
 size_t dad_ecda_workspace_bytes(int32_t B_local, int32_t world);
 int dad_ecda(const dad_ecda_args* a, void* stream);
 
+/* ---- supervised contrastive loss (NOT in the reference any more: removed upstream, C/utils.py:377-378; old ctor
+ * C/train_CASIA.py:396 temperature=0.1).  SupCon over L2-normalised embeddings of {clean samples} U {masked-in noisy samples with
+ * their pseudo-labels}, forward + backward; parity unpinned (checked against the oracle's own restatement).  Default weight 0. */
+typedef struct dad_scl_args {
+    dad_pack pack;
+    int32_t rank, noisy;                   /* noisy 0: clean members only (warm-up) */
+    const uint8_t* mask;                   /* [B_global] (noisy != 0) */
+    float temperature, w_scl;
+    float *g_clean, *g_strong;             /* [B_local,H] accumulated: += w_scl * dSCL/d emb for the rows this rank owns */
+    float* loss_out;                       /* out [3] = this rank's share of the (unweighted) SCL loss */
+    void* ws;
+    size_t ws_bytes;
+} dad_scl_args;
+size_t dad_scl_workspace_bytes(int32_t B_local, int32_t world);
+int dad_scl(const dad_scl_args* a, void* stream);
+
 /* ---- optimiser tail (I/train.py:487-492; I/model.py:211-223) --------------------------------------------------- */
 /* g[DAD_NPARAM] = fixed-order sum of the encoder split-K partials (up to two backward launches) ++ head grads */
 int dad_grad_reduce(const float* dW_part0, const float* db_part0, int32_t splits0, const float* dW_part1,
@@ -174,11 +190,12 @@ int dad_grad_reduce(const float* dW_part0, const float* db_part0, int32_t splits
 int dad_grad_norm(const float* g, double* part_ws /*[128]*/, uint32_t* counter, int64_t* step, const double* lr,
                   float* scal, float max_norm, void* stream);
 /* clip -> Adam (betas .9/.999, eps 1e-8, coupled L2 wd) -> EMA teacher (do_ema) -> fp16 hi/lo splits of W, teacher W (nullable).
- * loss_src (nullable) = [CE, KD, ECDA] of this step: loss_last[4] = {total, CE, KD, ECDA}, loss_acc[5] += {.., 1}
- * (device-side replacement of the per-step .item() reads of I/train.py:494-495; total = CE + w_kd KD + w_ecda ECDA). */
+ * loss_src (nullable) = [CE, KD, ECDA, SCL] of this step: loss_last[5] = {total, CE, KD, ECDA, SCL},
+ * loss_acc[6] += {total, CE, KD, ECDA, 1, SCL}  (device-side replacement of the per-step .item() reads of I/train.py:494-495;
+ * total = CE + w_kd KD + w_ecda ECDA + w_scl SCL). */
 int dad_adam_ema(float* p, float* t, float* m, float* v, const float* g, const float* scal, float wd, float ema_m,
                  float ema_1m, int32_t do_ema, void* s_hi, void* s_lo, void* t_hi, void* t_lo, const float* loss_src,
-                 float* loss_last, double* loss_acc, float w_kd, float w_ecda, void* stream);
+                 float* loss_last, double* loss_acc, float w_kd, float w_ecda, float w_scl, void* stream);
 /* SSRLModel.update_teacher_ema on a flat buffer: t = t*m + s*(1-m) (two muls + add, no FMA) */
 int dad_ema(float* t, const float* s, float ema_m, float ema_1m, int64_t n, void* stream);
 /* fp16 hi/lo split of an fp32 encoder weight matrix: hi = fp16(256 w), lo = fp16(256 w - hi) (saturating) */

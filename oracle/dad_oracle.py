@@ -425,7 +425,13 @@ class OracleStepper:
             use_ecda = hp.USE_ECDA or self.dataset == "emodb"
             if use_ecda and w_ecda > 0:
                 ecda = ecda_loss(emb_c, emb_s, yc, probs.argmax(dim=1), mask_arg, scores, wce, hp)
-        out.update(consistency_loss=kd, ecda_loss=ecda, total_loss=ce + w_kd * kd + w_ecda * ecda)
+        total = ce + w_kd * kd + w_ecda * ecda
+        if hp.TARGET_SCL_WEIGHT > 0 and epoch >= hp.SCL_START_EPOCH:  # optional term, absent upstream (parity unpinned)
+            scl = scl_loss(torch.cat([emb_c, emb_s]), torch.cat([yc, probs.argmax(dim=1)]),
+                           torch.cat([torch.ones_like(yc, dtype=torch.bool), mask_f.bool()]), temperature=0.1)
+            out["scl_loss"] = scl
+            total = total + hp.TARGET_SCL_WEIGHT * scl
+        out.update(consistency_loss=kd, ecda_loss=ecda, total_loss=total)
         self.last = dict(probs=probs, mask=mask_f.bool(), scores=scores, pred=probs.argmax(1), emb_clean=emb_c.detach(),
                          emb_strong=emb_s.detach(), weak=weak, strong=strong, wce=wce)
         return out

@@ -20,7 +20,7 @@ EXPORTS = (
     "dad_encoder_fwd", "dad_encoder_bwd_splits", "dad_encoder_bwd", "dad_encoder_bwd_workspace_bytes",
     "dad_pack_rank_words", "dad_head_grid", "dad_head_fwd", "dad_dacp_mask", "dad_head_bwd",
     "dad_ecda_workspace_bytes", "dad_ecda", "dad_grad_reduce", "dad_grad_norm", "dad_adam_ema", "dad_ema",
-    "dad_split_f16", "dad_step_rng", "dad_certainty_scores",
+    "dad_split_f16", "dad_step_rng", "dad_certainty_scores", "dad_scl_workspace_bytes", "dad_scl",
 )
 
 
@@ -71,6 +71,12 @@ class EcdaArgs(C.Structure):
                 ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
 
 
+class SclArgs(C.Structure):
+    _fields_ = [("pack", Pack), ("rank", C.c_int32), ("noisy", C.c_int32), ("mask", C.c_void_p), ("temperature", C.c_float),
+                ("w_scl", C.c_float), ("g_clean", C.c_void_p), ("g_strong", C.c_void_p), ("loss_out", C.c_void_p),
+                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
+
 _lib = None
 
 
@@ -85,7 +91,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     L.dad_last_error.restype = C.c_char_p
     L.dad_abi_version.restype = C.c_int
-    for name in ("dad_encoder_fwd_workspace_bytes", "dad_encoder_bwd_workspace_bytes", "dad_ecda_workspace_bytes"):
+    for name in ("dad_encoder_fwd_workspace_bytes", "dad_encoder_bwd_workspace_bytes", "dad_ecda_workspace_bytes", "dad_scl_workspace_bytes"):
         getattr(L, name).restype = C.c_size_t
     L.dad_pack_rank_words.restype = C.c_int64
     L.dad_encoder_fwd_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int32]
@@ -102,9 +108,11 @@ def lib():
     L.dad_dacp_mask.argtypes = [C.POINTER(DacpArgs), vp]
     L.dad_head_bwd.argtypes = [C.POINTER(HeadBwdArgs), vp]
     L.dad_ecda.argtypes = [C.POINTER(EcdaArgs), vp]
+    L.dad_scl_workspace_bytes.argtypes = [i32, i32]
+    L.dad_scl.argtypes = [C.POINTER(SclArgs), vp]
     L.dad_grad_reduce.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp, vp]
     L.dad_grad_norm.argtypes = [vp, vp, vp, vp, vp, vp, f32, vp]
-    L.dad_adam_ema.argtypes = [vp, vp, vp, vp, vp, vp, f32, f32, f32, i32, vp, vp, vp, vp, vp, vp, vp, f32, f32, vp]
+    L.dad_adam_ema.argtypes = [vp, vp, vp, vp, vp, vp, f32, f32, f32, i32, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, vp]
     L.dad_ema.argtypes = [vp, vp, f32, f32, i64, vp]
     L.dad_split_f16.argtypes = [vp, vp, vp, i64, vp]
     L.dad_certainty_scores.argtypes = [vp, i32, i32, vp, vp, vp]

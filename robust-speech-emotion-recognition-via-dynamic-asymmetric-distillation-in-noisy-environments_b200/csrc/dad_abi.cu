@@ -33,6 +33,7 @@ size_t ecda_pairs_smem_bytes();
 int ecda_prep_grid(int B_global);
 int ecda_max_tiles(int B_local);
 int launch_ecda(const EcdaArgs& a, cudaStream_t st);
+int launch_scl(const SclArgs& a, cudaStream_t st);
 int launch_grad_reduce(const GradReduceArgs& a, cudaStream_t st);
 int launch_grad_norm(const NormArgs& a, cudaStream_t st);
 int launch_adam_ema(const AdamArgs& a, cudaStream_t st);
@@ -212,6 +213,42 @@ int dad_head_bwd(const dad_head_bwd_args* a, void* stream) {
     return launch_head_bwd(*a, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------- SCL
+struct SclCarve { size_t F, nrm, cls, lse, invp, row_loss, cnt, total; };
+static SclCarve scl_carve(int B_local, int world) {
+    const size_t R = (size_t)2 * B_local * world;
+    SclCarve c;
+    size_t o = 0;
+    c.cnt = o; o = align_up(o + DAD_C * sizeof(int), 256);
+    c.F = o; o = align_up(o + R * DAD_H * sizeof(float), 256);
+    c.nrm = o; o = align_up(o + R * sizeof(float), 256);
+    c.cls = o; o = align_up(o + R * sizeof(int), 256);
+    c.lse = o; o = align_up(o + R * sizeof(float), 256);
+    c.invp = o; o = align_up(o + R * sizeof(float), 256);
+    c.row_loss = o; o = align_up(o + R * sizeof(float), 256);
+    c.total = o;
+    return c;
+}
+size_t dad_scl_workspace_bytes(int32_t B_local, int32_t world) { return scl_carve(B_local, world).total; }
+
+int dad_scl(const dad_scl_args* a, void* stream) {
+    DAD_REQUIRE(a, "scl: null args");
+    int rc = check_pack(a->pack, "scl");
+    if (rc) return rc;
+    DAD_REQUIRE(a->rank >= 0 && a->rank < a->pack.world, "scl: bad rank");
+    DAD_REQUIRE(a->g_clean && a->g_strong && a->loss_out && (!a->noisy || a->mask), "scl: null pointer");
+    DAD_REQUIRE(a->temperature > 0.f, "scl: temperature must be > 0");
+    const SclCarve c = scl_carve(a->pack.B_local, a->pack.world);
+    if (!a->ws || a->ws_bytes < c.total) return dad_set_error(DAD_ERR_WS, "scl: workspace %zu < %zu bytes", a->ws_bytes, c.total);
+    char* w = reinterpret_cast<char*>(a->ws);
+    SclArgs k;
+    k.pack = a->pack; k.rank = a->rank; k.noisy = a->noisy; k.mask = a->mask; k.inv_tau = 1.0f / a->temperature; k.w_scl = a->w_scl;
+    k.g_clean = a->g_clean; k.g_strong = a->g_strong; k.loss_out = a->loss_out;
+    k.F = (float*)(w + c.F); k.nrm = (float*)(w + c.nrm); k.cls = (int*)(w + c.cls); k.lse = (float*)(w + c.lse);
+    k.invp = (float*)(w + c.invp); k.row_loss = (float*)(w + c.row_loss); k.cnt = (int*)(w + c.cnt);
+    return launch_scl(k, (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------- ECDA
 struct EcdaCarve { size_t part_vec, part_sc, part_cnt, stats, lists, tiles, mu_t, rep_grad, tile_sums, counter, total; };
 static EcdaCarve ecda_carve(int B_local, int world) {
@@ -276,14 +313,14 @@ int dad_grad_norm(const float* g, double* part_ws, uint32_t* counter, int64_t* s
 
 int dad_adam_ema(float* p, float* t, float* m, float* v, const float* g, const float* scal, float wd, float ema_m, float ema_1m,
                  int32_t do_ema, void* s_hi, void* s_lo, void* t_hi, void* t_lo, const float* loss_src, float* loss_last,
-                 double* loss_acc, float w_kd, float w_ecda, void* stream) {
+                 double* loss_acc, float w_kd, float w_ecda, float w_scl, void* stream) {
     DAD_REQUIRE(p && t && m && v && g && scal, "adam_ema: null pointer");
     DAD_REQUIRE((!s_hi) == (!s_lo) && (!s_hi) == (!t_hi) && (!s_hi) == (!t_lo), "adam_ema: bf16 split outputs must be all set or all null");
     AdamArgs a;
     a.p = p; a.t = t; a.m = m; a.v = v; a.g = g; a.scal = scal; a.wd = wd; a.ema_m = ema_m; a.ema_1m = ema_1m; a.do_ema = do_ema;
     a.s_hi = s_hi; a.s_lo = s_lo; a.t_hi = t_hi; a.t_lo = t_lo;
     DAD_REQUIRE(!loss_src || (loss_last && loss_acc), "adam_ema: loss_src needs loss_last and loss_acc");
-    a.loss_src = loss_src; a.loss_last = loss_last; a.loss_acc = loss_acc; a.w_kd = w_kd; a.w_ecda = w_ecda;
+    a.loss_src = loss_src; a.loss_last = loss_last; a.loss_acc = loss_acc; a.w_kd = w_kd; a.w_ecda = w_ecda; a.w_scl = w_scl;
     return launch_adam_ema(a, (cudaStream_t)stream);
 }
 

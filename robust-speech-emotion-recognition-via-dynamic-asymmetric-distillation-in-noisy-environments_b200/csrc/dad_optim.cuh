@@ -26,8 +26,8 @@ struct AdamArgs {
     float wd, ema_m, ema_1m;  // weight decay; fl32(momentum), fl32(1-momentum)
     int do_ema;            // 0 during warm-up (I/train.py:491)
     void *s_hi, *s_lo, *t_hi, *t_lo;  // [H*D] fp16 splits of W / teacher W (nullable)
-    const float* loss_src;  // [3] CE, KD, ECDA of this step (global sums), nullable
-    float* loss_last;       // [4] total, CE, KD, ECDA of this step
-    double* loss_acc;       // [5] running sums (total, CE, KD, ECDA, steps) since the host last cleared them
-    float w_kd, w_ecda;
+    const float* loss_src;  // [4] CE, KD, ECDA, SCL of this step (global sums), nullable
+    float* loss_last;       // [5] total, CE, KD, ECDA, SCL of this step
+    double* loss_acc;       // [6] running sums (total, CE, KD, ECDA, steps, SCL) since the host last cleared them
+    float w_kd, w_ecda, w_scl;
 };

@@ -62,3 +62,21 @@ struct EcdaArgs {
     unsigned* counter;      // [2] zero-initialised, self-resetting
     int max_tiles, prep_grid;
 };
+
+// supervised contrastive loss (csrc/k_scl.cu)
+struct SclArgs {
+    dad_pack pack;
+    int rank, noisy;
+    const uint8_t* mask;   // [Bg] (noisy != 0)
+    float inv_tau, w_scl;
+    float *g_clean, *g_strong;  // [B_local, H] accumulated
+    float* loss_out;       // [3] := this rank's share of the (unweighted) loss
+    float* F;              // [2Bg, H] normalised embeddings (0 for non-members)
+    float* nrm;            // [2Bg]
+    int* cls;              // [2Bg] class or -1
+    float* lse;            // [2Bg]
+    float* invp;           // [2Bg] 1/|P(i)| for valid anchors else 0
+    float* row_loss;       // [2Bg]
+    int* cnt;              // [DAD_C] members per class (zeroed by the launcher)
+};
+

@@ -86,10 +86,11 @@ __global__ void __launch_bounds__(OPT_THREADS) k_adam_ema(AdamArgs a) {
     const int e = blockIdx.x * OPT_THREADS + threadIdx.x;
     if (e >= NP) return;
     if (e == 0 && a.loss_src) {  // device-side loss bookkeeping: no per-step host sync (replaces the .item() calls of I/train.py:494-495)
-        const float ce = a.loss_src[0], kd = a.loss_src[1], ec = a.loss_src[2];
-        const float tot = ce + a.w_kd * kd + a.w_ecda * ec;  // I/train.py:462-466
-        a.loss_last[0] = tot; a.loss_last[1] = ce; a.loss_last[2] = kd; a.loss_last[3] = ec;
-        a.loss_acc[0] += tot; a.loss_acc[1] += ce; a.loss_acc[2] += kd; a.loss_acc[3] += ec; a.loss_acc[4] += 1.0;
+        const float ce = a.loss_src[0], kd = a.loss_src[1], ec = a.loss_src[2], sc = a.loss_src[3];
+        float tot = ce + a.w_kd * kd + a.w_ecda * ec;  // I/train.py:462-466
+        if (a.w_scl != 0.f) tot += a.w_scl * sc;       // optional SCL term (absent upstream; weight 0 by default)
+        a.loss_last[0] = tot; a.loss_last[1] = ce; a.loss_last[2] = kd; a.loss_last[3] = ec; a.loss_last[4] = sc;
+        a.loss_acc[0] += tot; a.loss_acc[1] += ce; a.loss_acc[2] += kd; a.loss_acc[3] += ec; a.loss_acc[4] += 1.0; a.loss_acc[5] += sc;
     }
     const float coef = a.scal[1], step_size = a.scal[2], bc2s = a.scal[3];
     float p = a.p[e];

@@ -27,7 +27,7 @@ import torch
 
 from . import _lib
 from ._lib import (D_HID, D_IN, GEMM_FP32, GEMM_TC, N_CLS, NPARAM, OFF_B, OFF_BC, OFF_W, OFF_WC, Aug, DacpArgs, DadError,
-                   EcdaArgs, HeadBwdArgs, HeadFwdArgs, Pack, check, lib, make_aug, ptr)
+                   EcdaArgs, HeadBwdArgs, HeadFwdArgs, Pack, SclArgs, check, lib, make_aug, ptr)
 
 PARAM_KEYS = ("encoder.pre_net.weight", "encoder.pre_net.bias", "classifier.fc_layer.weight", "classifier.fc_layer.bias")
 _SLICES = ((OFF_W, OFF_B, (D_HID, D_IN)), (OFF_B, OFF_WC, (D_HID,)), (OFF_WC, OFF_BC, (N_CLS, D_HID)), (OFF_BC, NPARAM, (N_CLS,)))
@@ -58,6 +58,9 @@ class StepScalars:
                 if epoch >= g("ECDA_START_EPOCH") else 0.0
         emodb = dataset == "emodb"  # E/train_emodb.py:418-437 has no USE_DACP / USE_ECDA switches
         iemocap = dataset == "iemocap"  # only I/utils.py honours USE_ENTROPY_IN_SCORE / USE_CLASS_AWARE_MMD
+        # optional supervised-contrastive term (absent upstream: weight 0 / start epoch 5001 by default -> never active)
+        self.w_scl = float(g("TARGET_SCL_WEIGHT", 0.0)) if (not self.warmup and epoch >= g("SCL_START_EPOCH", 10 ** 9)) else 0.0
+        self.scl_temperature = _f32(g("SCL_TEMPERATURE", 0.1))
         self.use_dacp = True if emodb else bool(g("USE_DACP", True))
         self.use_ecda = (True if emodb else bool(g("USE_ECDA", True))) and self.w_ecda > 0
         self.use_entropy = (bool(g("USE_ENTROPY_IN_SCORE", True)) if iemocap else True) if self.use_dacp else False
@@ -118,8 +121,8 @@ class DADStepEngine:
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self.lr = torch.zeros(1, dtype=torch.float64, device=dev)
         self.scal = z(8)
-        self.loss_last = z(4)
-        self.loss_acc = torch.zeros(5, dtype=torch.float64, device=dev)
+        self.loss_last = z(5)
+        self.loss_acc = torch.zeros(6, dtype=torch.float64, device=dev)
         # ---- DACP state (I/utils.py:391-395)
         self.quality = torch.full((N_CLS,), 0.5, **f32)
         self.ema_thr = torch.full((N_CLS,), 0.5, **f32)
@@ -157,6 +160,7 @@ class DADStepEngine:
         self.counters = torch.zeros(16, dtype=torch.int32, device=dev)
         self.norm_part = torch.zeros(128, dtype=torch.float64, device=dev)
         self.ecda_ws = torch.zeros(lib().dad_ecda_workspace_bytes(B, self.world), dtype=torch.uint8, device=dev)
+        self.scl_ws = None  # allocated on first use (the SCL term is off by default)
         modes = (GEMM_FP32, self.gemm_mode)  # frames-per-batch < 32 fall back to the exact-fp32 CUDA-core kernels
         nb = max(max(lib().dad_encoder_fwd_workspace_bytes(B, T, m) for m in modes), 256)
         self.enc_ws = torch.zeros(nb, dtype=torch.uint8, device=dev)
@@ -439,6 +443,18 @@ class DADStepEngine:
             self.launches_per_step += 2
         else:
             self.g_ext[NPARAM + 2:NPARAM + 3].zero_()
+        if noisy and sc.w_scl > 0:
+            if self.scl_ws is None:
+                self.scl_ws = torch.zeros(lib().dad_scl_workspace_bytes(self.Bcap, self.world), dtype=torch.uint8, device=self.dev)
+            sa = SclArgs()
+            sa.pack, sa.rank, sa.noisy, sa.mask = pk, self.rank, 1, self.mask.data_ptr()
+            sa.temperature, sa.w_scl = sc.scl_temperature, _f32(sc.w_scl)
+            sa.g_clean, sa.g_strong, sa.loss_out = hb.g_clean, hb.g_strong, hb.loss_out
+            sa.ws, sa.ws_bytes = self.scl_ws.data_ptr(), self.scl_ws.numel()
+            check(L.dad_scl(C.byref(sa), s))
+            self.launches_per_step += 4
+        else:
+            self.g_ext[NPARAM + 3:NPARAM + 4].zero_()
         # ---- backward of the two student encoder calls (I/train.py:486)
         S0 = self._enc_bwd(self.x_clean, self.pad_clean, None, self.bits_clean, self.g_clean, self.lens_clean, 0, s, xs=self.xs_clean)
         S1 = 0
@@ -460,7 +476,7 @@ class DADStepEngine:
                              self.hi_lo[0].data_ptr() if tc else None, self.hi_lo[1].data_ptr() if tc else None,
                              self.hi_lo[2].data_ptr() if tc else None, self.hi_lo[3].data_ptr() if tc else None,
                              self.g_ext.data_ptr() + NPARAM * 4, self.loss_last.data_ptr(), self.loss_acc.data_ptr(),
-                             _f32(sc.w_kd), _f32(sc.w_ecda), s))
+                             _f32(sc.w_kd), _f32(sc.w_ecda), _f32(sc.w_scl), s))
         self.launches_per_step += 2
 
     def scalars(self, epoch):
@@ -514,14 +530,15 @@ class DADStepEngine:
     def losses(self):
         """Loss dict of the last step (one D2H read; the reference does one .item() per loss per step)."""
         v = self.loss_last.tolist()
-        return {"total_loss": v[0], "supervised_ce_loss": v[1], "consistency_loss": v[2], "ecda_loss": v[3]}
+        return {"total_loss": v[0], "supervised_ce_loss": v[1], "consistency_loss": v[2], "ecda_loss": v[3], "scl_loss": v[4]}
 
     def pop_epoch_losses(self):
         """Mean losses since the last call (train_epoch's return value, I/train.py:520) and reset."""
         a = self.loss_acc.tolist()
         self.loss_acc.zero_()
         n = max(a[4], 1.0)
-        return {"total_loss": a[0] / n, "supervised_ce_loss": a[1] / n, "consistency_loss": a[2] / n, "ecda_loss": a[3] / n}
+        return {"total_loss": a[0] / n, "supervised_ce_loss": a[1] / n, "consistency_loss": a[2] / n, "ecda_loss": a[3] / n,
+                "scl_loss": a[5] / n}
 
     def end_epoch(self, epoch):
         """DACPManager.update_class_quality_scores_epoch (I/utils.py:430-447) from the device accumulators."""

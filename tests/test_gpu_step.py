@@ -272,3 +272,34 @@ def test_ragged_batches_and_capacity_engine(mode, Bc, Tc, Bn, Tn):
         well = g_orc.abs() >= 1e-6
         p_orc = torch.cat([orc.p[key].detach().reshape(-1) for key in O.PARAM_KEYS])
         assert float((eng.p.cpu() - p_orc).abs()[well].max()) <= 1e-5, (mode, k, "weights")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+def test_optional_scl_term_vs_oracle(mode):
+    """SCL is absent upstream (parity unpinned): the kernel is checked against the oracle's own SupCon restatement, inside the
+    full step (loss value, total loss, and the updated weights, i.e. its gradient through both student encoder calls)."""
+    over = {"TARGET_SCL_WEIGHT": 0.2, "SCL_START_EPOCH": 35}
+    orc, cfg, hp = make_oracle("iemocap", over)
+    from dad_b200 import _lib
+    from dad_b200.engine import DADStepEngine
+    gm = {"fp32": _lib.GEMM_FP32, "tc": _lib.GEMM_TC}[mode]
+    B, T = 24, 40
+    eng = DADStepEngine(cfg, B, T, gemm_mode=gm, use_graph=False, noise_mode="supplied")
+    meta = {"B": B, "T": T, "seed": 8800, "snr_db": 10.0, "variable_len": True}
+    for k, epoch in enumerate((33, 40, 41, 42)):  # 33: post warm-up but before SCL_START_EPOCH -> term inactive
+        orc.lr = O.cosine_lr(hp.LEARNING_RATE, epoch, hp.EPOCHS)
+        c, n, rng = step_inputs(meta, k, cfg)
+        push_oracle_state(eng, orc)
+        eng.set_inputs(_to_dev(c), _to_dev(n), {kk: v.cuda() for kk, v in rng.items()})
+        eng.step(epoch)
+        ref = orc.step(c, n, epoch, rng)
+        got = eng.losses()
+        assert (epoch < 35) == ("scl_loss" not in ref)
+        for key in LOSS_KEYS + (("scl_loss",) if "scl_loss" in ref else ()):
+            assert abs(got[key] - ref[key]) <= 1e-4 * max(abs(ref[key]), 1e-3), (mode, k, key, got[key], ref[key])
+        if epoch < 35:
+            assert got["scl_loss"] == 0.0
+        g_orc = torch.cat([orc.p[key].grad.reshape(-1) for key in O.PARAM_KEYS])
+        well = g_orc.abs() >= 1e-6
+        p_orc = torch.cat([orc.p[key].detach().reshape(-1) for key in O.PARAM_KEYS])
+        assert float((eng.p.cpu() - p_orc).abs()[well].max()) <= 1e-5, (mode, k, "weights")

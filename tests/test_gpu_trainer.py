@@ -1,0 +1,88 @@
+"""GPU (-m gpu): the trainer surface of the reference end to end on synthetic stand-in data."""
+import glob
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+FAST = dict(EPOCHS=6, WARMUP_EPOCHS=2, ECDA_START_EPOCH=2, WEIGHT_RAMP_EPOCHS=2, BATCH_SIZE=32, VALIDATION_INTERVAL=1,
+            LEARNING_RATE=5e-3, PATIENCE=50)
+
+
+def _patch(monkeypatch, cfg, extra=None):
+    for k, v in {**FAST, **(extra or {})}.items():
+        monkeypatch.setattr(cfg, k, v, raising=False)
+
+
+def test_iemocap_trainer_end_to_end(monkeypatch, tmp_path):
+    from dad_b200 import config as cfg
+    from dad_b200.train import IEMOCAPCrossDomainTrainer
+    monkeypatch.chdir(tmp_path)
+    _patch(monkeypatch, cfg)
+    torch.manual_seed(0)
+    tr = IEMOCAPCrossDomainTrainer(fold=1, experiment_name="unit/test", loaders=IEMOCAPCrossDomainTrainer.synthetic_loaders(1, utt_per_session=64),
+                                   require_pretrained=False)
+    # reference surface
+    for attr in ("model", "optimizer", "scheduler", "dacp_manager", "ecda_criterion", "augmenter", "training_history", "calibrated_anchors",
+                 "clean_train_loader", "noisy_student_loader", "noisy_val_loader", "results_dir", "noise_info"):
+        assert hasattr(tr, attr), attr
+    assert tr.calibrated_anchors.shape == (4,)
+    assert tr.dacp_manager.ema_thresholds.data_ptr() == tr.engine.ema_thr.data_ptr()
+    out = tr.train_step(next(iter(tr.clean_train_loader)), next(iter(tr.noisy_student_loader)), 3)
+    assert set(out) == {"total_loss", "supervised_ce_loss", "consistency_loss", "ecda_loss"} and all(v.dim() == 0 for v in out.values())
+    res = tr.train()
+    assert set(res) == {"best_noisy_weighted_acc", "results_dir"} and "unittest" in res["results_dir"]
+    assert res["best_noisy_weighted_acc"] > 50.0, res  # 4 separable synthetic classes: far above the 25 % chance level
+    rep = sorted(glob.glob(os.path.join(res["results_dir"], "reports", "BEST_detailed_results_epoch_*.json")))
+    assert rep
+    summ = json.load(open(rep[-1]))["summary"]
+    assert summ["noisy"]["w_acc"].endswith("%") and float(summ["noisy"]["w_acc"].rstrip("%")) >= 0  # parsed by I/run_granular_ablations.py:62-67
+    ck = torch.load(os.path.join(res["results_dir"], "models", "iemocap_cross_domain_best.pth"), weights_only=False)
+    assert {"epoch", "model_state_dict", "optimizer_state_dict", "clean_results", "noisy_results"} <= set(ck)
+    assert set(ck["model_state_dict"]) == {f"{r}_{m}" for r in ("student", "teacher") for m in
+                                           ("encoder.pre_net.weight", "encoder.pre_net.bias", "classifier.fc_layer.weight", "classifier.fc_layer.bias")}
+    hist = json.load(open(os.path.join(res["results_dir"], "reports", "training_history.json")))
+    assert len(hist["total_loss"]) == cfg.EPOCHS and len(hist["dacp_ema_thresholds"]) == cfg.EPOCHS - cfg.WARMUP_EPOCHS
+    assert hist["consistency_loss"][0] == 0.0 and hist["supervised_ce_loss"][-1] < hist["supervised_ce_loss"][0]
+    assert os.path.exists(os.path.join(res["results_dir"], "reports", "FINAL_test_set_results.json"))
+    # resume: state (weights, Adam moments, DACP thresholds) comes back from the checkpoint
+    tr2 = IEMOCAPCrossDomainTrainer(fold=1, loaders=IEMOCAPCrossDomainTrainer.synthetic_loaders(1, utt_per_session=64), require_pretrained=False)
+    tr2.load_checkpoint(os.path.join(res["results_dir"], "models", "iemocap_cross_domain_best.pth"))
+    assert torch.equal(tr2.engine.state_dict()["student_encoder.pre_net.weight"], ck["model_state_dict"]["student_encoder.pre_net.weight"].cuda())
+    assert torch.equal(tr2.engine.ema_thr.cpu(), ck["dacp_state"]["ema_thresholds"])
+
+
+@pytest.mark.parametrize("which", ["casia", "emodb"])
+def test_speaker_fold_trainers(monkeypatch, tmp_path, which):
+    monkeypatch.chdir(tmp_path)
+    if which == "casia":
+        from dad_b200 import config_casia as cfg
+        from dad_b200.train_CASIA import FixedCASIACrossDomainTrainer as T
+    else:
+        from dad_b200 import config_emodb as cfg
+        from dad_b200.train_emodb import FixedEMODBCrossDomainTrainer as T
+    _patch(monkeypatch, cfg, {"EPOCHS": 8})
+    tr = T(fold=3, loaders=T.synthetic_loaders(3, utt_per_speaker=48), require_pretrained=False)
+    hist = [tr.train_epoch(epoch) for epoch in range(8)]
+    avg = hist[-1]
+    assert set(avg) == {"total_loss", "supervised_ce_loss", "consistency_loss", "ecda_loss", "scl_loss"} and avg["scl_loss"] == 0.0
+    assert all(h["consistency_loss"] == 0.0 and h["ecda_loss"] == 0.0 for h in hist[:2])  # warm-up: CE only (I/train.py:402-403)
+    assert any(h["consistency_loss"] > 0.0 for h in hist[2:])
+    if which == "casia":
+        assert all(h["ecda_loss"] == 0.0 for h in hist)  # C/config_casia.py: USE_ECDA = False by default
+    else:
+        assert any(h["ecda_loss"] != 0.0 for h in hist[3:])  # E/train_emodb.py has no USE_ECDA switch
+    r = tr.validate(tr.noisy_val_loader, "Noisy")
+    assert 0.0 <= r["weighted_accuracy"] <= 100.0 and r["confusion_matrix"].shape == (4, 4)
+
+
+def test_cli_fold_argument(monkeypatch, tmp_path):
+    from dad_b200 import config as cfg
+    from dad_b200 import train
+    monkeypatch.chdir(tmp_path)
+    _patch(monkeypatch, cfg, {"EPOCHS": 3})
+    res = train.main(["--fold", "2", "--synthetic", "--epochs", "3"])
+    assert res is not None and os.path.basename(res["results_dir"]) == "fold_2"
