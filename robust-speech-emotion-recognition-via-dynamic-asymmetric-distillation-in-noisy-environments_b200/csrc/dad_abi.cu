@@ -32,6 +32,7 @@ int launch_head_bwd(const HeadBwdArgs& a, cudaStream_t st);
 size_t ecda_pairs_smem_bytes();
 int ecda_prep_grid(int B_global);
 int ecda_max_tiles(int B_local);
+int ecda_col_splits(int B_local);
 int launch_ecda(const EcdaArgs& a, cudaStream_t st);
 int launch_scl(const SclArgs& a, cudaStream_t st);
 int launch_grad_reduce(const GradReduceArgs& a, cudaStream_t st);
@@ -250,9 +251,9 @@ int dad_scl(const dad_scl_args* a, void* stream) {
 }
 
 // ---------------------------------------------------------------- ECDA
-struct EcdaCarve { size_t part_vec, part_sc, part_cnt, stats, lists, tiles, mu_t, rep_grad, tile_sums, counter, total; };
+struct EcdaCarve { size_t part_vec, part_sc, part_cnt, stats, lists, tiles, mu_t, mu_all, rep_grad, tile_sums, part_acc, part_rowp, counter, total; };
 static EcdaCarve ecda_carve(int B_local, int world) {
-    const int Bg = B_local * world, G = ecda_prep_grid(Bg), MT = ecda_max_tiles(B_local);
+    const int Bg = B_local * world, G = ecda_prep_grid(Bg), MT = ecda_max_tiles(B_local), Q = ecda_col_splits(B_local);
     EcdaCarve c;
     size_t o = 0;
     c.counter = o; o = align_up(o + 2 * sizeof(unsigned), 256);
@@ -264,7 +265,10 @@ static EcdaCarve ecda_carve(int B_local, int world) {
     c.tiles = o; o = align_up(o + (size_t)MT * sizeof(EcdaTile), 256);
     c.mu_t = o; o = align_up(o + (size_t)ECDA_MAXC * DAD_H * sizeof(float), 256);
     c.rep_grad = o; o = align_up(o + (size_t)ECDA_MAXC * DAD_H * sizeof(float), 256);
-    c.tile_sums = o; o = align_up(o + (size_t)MT * 3 * sizeof(float), 256);
+    c.mu_all = o; o = align_up(o + (size_t)ECDA_MAXC * DAD_H * sizeof(float), 256);
+    c.tile_sums = o; o = align_up(o + (size_t)MT * Q * 3 * sizeof(float), 256);
+    c.part_acc = o; o = align_up(o + (size_t)MT * Q * ECDA_TR * DAD_H * sizeof(float), 256);
+    c.part_rowp = o; o = align_up(o + (size_t)MT * Q * ECDA_TR * sizeof(float), 256);
     c.total = o;
     return c;
 }
@@ -286,7 +290,9 @@ int dad_ecda(const dad_ecda_args* a, void* stream) {
     k.stats = (EcdaStats*)(w + c.stats); k.lists = (int*)(w + c.lists); k.tiles = (EcdaTile*)(w + c.tiles);
     k.mu_t = (float*)(w + c.mu_t); k.rep_grad = (float*)(w + c.rep_grad); k.tile_sums = (float*)(w + c.tile_sums);
     k.g_clean = a->g_clean; k.g_strong = a->g_strong; k.loss_out = a->loss_out; k.counter = (unsigned*)(w + c.counter);
+    k.mu_all = (float*)(w + c.mu_all); k.part_acc = (float*)(w + c.part_acc); k.part_rowp = (float*)(w + c.part_rowp);
     k.max_tiles = ecda_max_tiles(a->pack.B_local);
+    k.col_splits = ecda_col_splits(a->pack.B_local);
     k.prep_grid = ecda_prep_grid(a->pack.B_local * a->pack.world);
     return launch_ecda(k, (cudaStream_t)stream);
 }

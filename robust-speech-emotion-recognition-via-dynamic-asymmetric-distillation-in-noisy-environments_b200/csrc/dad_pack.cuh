@@ -25,7 +25,7 @@ typedef dad_dacp_args DacpArgs;
 typedef dad_head_bwd_args HeadBwdArgs;
 
 // ---- ECDA
-constexpr int ECDA_TR = 32;  // rows (members of one class) per CTA tile
+constexpr int ECDA_TR = 64;  // rows (members of one class) per CTA tile
 constexpr int ECDA_MAXC = 4;
 struct EcdaTile { int cls, row_begin, row_count, feasible; };
 
@@ -56,11 +56,14 @@ struct EcdaArgs {
     EcdaTile* tiles;        // [max_tiles]
     float* mu_t;            // [4][256] noisy centroids
     float* rep_grad;        // [4][256] rho * d rep / d z_i for noisy members of class c
-    float* tile_sums;       // [max_tiles][3]
+    float* mu_all;          // [4][256] mean of ALL members (clean + masked noisy) of class c: the centring point of k_ecda_pairs
+    float* tile_sums;       // [max_tiles * col_splits][3]
+    float* part_acc;        // [max_tiles * col_splits][64][256] per-CTA partial sum_j P_ij z'_j
+    float* part_rowp;       // [max_tiles * col_splits][64]      per-CTA partial sum_j P_ij
     float *g_clean, *g_strong;  // [B_local,256], accumulated (+=)
     float* loss_out;        // [2] = ecda loss share, [3] = full-batch ecda loss when world == 1
     unsigned* counter;      // [2] zero-initialised, self-resetting
-    int max_tiles, prep_grid;
+    int max_tiles, prep_grid, col_splits;
 };
 
 // supervised contrastive loss (csrc/k_scl.cu)

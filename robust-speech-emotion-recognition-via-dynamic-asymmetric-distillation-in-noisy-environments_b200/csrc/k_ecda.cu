@@ -6,18 +6,15 @@
 //                partial sums; the last CTA reduces them in fixed order (fp64) into class statistics (counts,
 //                bandwidths via the centred closed form  sum_ij|zi-zj|^2 = 2n sum_i|zi-m|^2, centroids, compactness,
 //                repulsion + its gradient, attention), builds the per-class member lists and the row-tile table.
-//  k_ecda_pairs: one CTA per 32-row tile of one class; loops over all members of the class (32 columns at a
-//                time, staged in shared memory): L2 by direct differences (as the reference), sum of 5 Gaussians,
-//                weighted block sums (loss) and P = coef*K' (gradient); each row is owned by exactly one CTA, so
-//                d/dz rows are accumulated in registers and added to g without atomics.  Under data parallelism a
-//                rank launches tiles only for the rows it owns (its local clean / noisy samples).
+//  k_ecda_pairs: one CTA per (64-row tile of one class, column split): two register-tiled SIMT GEMMs on class-centred
+//                embeddings (Gram form of the squared distances, then P z) -- see the comment above the kernel.  Under data
+//                parallelism a rank launches tiles only for the rows it owns (its local clean / noisy samples).
 #include "dad_common.cuh"
 #include "dad_pack.cuh"
 
 namespace {
 
 constexpr int EP_THREADS = 256;
-constexpr int ZS = DAD_H + 4;  // padded smem row stride (floats): conflict-free float4 access (see k_ecda_pairs)
 
 __device__ __forceinline__ double block_sum_d(double v, double* s_red) {
     v = warp_sum_d(v);
@@ -172,6 +169,7 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_prep(EcdaArgs a) {
             st->comp[c] = (float)(comp > 0.0 ? comp : 0.0);
         }
         a.mu_t[c * DAD_H + tid] = (float)mu[c];
+        a.mu_all[c * DAD_H + tid] = (float)m;
     }
     __syncthreads();
     for (int c = 0; c < NC; ++c)
@@ -279,30 +277,57 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_prep(EcdaArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(EP_THREADS) k_ecda_pairs(EcdaArgs a) {
+// ---------------------------------------------------------------------------------------------------------------------
+// k_ecda_pairs: one CTA per (64-row tile of one class, column split q).  The class's members are processed 64 columns at a
+// time as two register-tiled SIMT GEMMs on class-CENTRED embeddings z' = z - mean_c (centring removes the cancellation of the
+// Gram form: |z'| is of the order of the pair distances themselves):
+//   phase A  dot_ij = z'_i . z'_j  (thread = 4x4 outputs),  L2_ij = |z'_i|^2 + |z'_j|^2 - 2 dot_ij  (exactly 0 on the diagonal),
+//            K = sum_r exp(-L2/beta_r), K' = sum_r exp(-L2/beta_r)/beta_r -> weighted block sums (loss) and P_ij = coef K'
+//   phase B  accZ_i += sum_j P_ij z'_j,  rowP_i += sum_j P_ij            (thread = 8 rows x 8 features)
+// so that d/dz_i = rowP_i z'_i - accZ_i  (= sum_j P_ij (z_i - z_j), I/utils.py:537 differentiated).  Each CTA writes its partial
+// (accZ, rowP, sums) to the workspace; k_ecda_fold then folds the Q partials of a row tile in fixed q order, adds the
+// compactness / repulsion gradients and accumulates into g -- every gradient row has exactly one writer, no float atomics,
+// bit-reproducible.  The column split gives ~2 CTAs per SM on one GPU and keeps all SMs busy when a rank owns only 1/8 of the rows.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int PT = ECDA_TR;          // 64: rows per tile = columns per chunk
+constexpr int PZS = DAD_H + 4;       // padded row stride of the staged embeddings (floats): conflict-free float4 rows
+constexpr int PPS = PT + 4;          // padded row stride of P
+}
+
+__global__ void __launch_bounds__(EP_THREADS, 1) k_ecda_pairs(EcdaArgs a) {
     extern __shared__ __align__(16) float smem[];
-    float* zi = smem;                      // [32][ZS]
-    float* zj = zi + ECDA_TR * ZS;         // [32][ZS]
-    float* Pm = zj + ECDA_TR * ZS;         // [32][33]
-    float* wi = Pm + ECDA_TR * 33;         // [32] omega_i
-    float* wj = wi + ECDA_TR;              // [32] omega_j
-    int* ri = reinterpret_cast<int*>(wj + ECDA_TR);  // [32] row ids
-    int* dj = ri + ECDA_TR;                // [32] column domain (0 clean, 1 noisy, -1 invalid)
+    float* zi = smem;                       // [64][PZS]  centred row tile
+    float* zj = zi + PT * PZS;              // [64][PZS]  centred column chunk
+    float* Pm = zj + PT * PZS;              // [64][PPS]
+    float* mu = Pm + PT * PPS;              // [256] class mean
+    float* ni = mu + DAD_H;                 // [64] |z'_i|^2
+    float* nj = ni + PT;                    // [64]
+    float* wi = nj + PT;                    // [64] omega_i
+    float* wj = wi + PT;                    // [64]
+    int* ri = reinterpret_cast<int*>(wj + PT);  // [64] row ids (-1 = padding)
+    int* pj = ri + PT;                      // [64] list position of column j (-1 = padding)
+    int* dj = pj + PT;                      // [64] column domain (0 clean, 1 noisy)
     __shared__ float s_red[3][EP_THREADS / 32];
-    __shared__ int s_last;
+    __shared__ int s_flag;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const EcdaStats* st = a.stats;
     const int Bg = a.pack.B_local * a.pack.world;
     const int n_tiles = st->n_tiles;
+    const int Q = a.col_splits;
+    const int tile_id = blockIdx.x / Q, q = blockIdx.x - tile_id * Q;
     float sums[3] = {0.f, 0.f, 0.f};
 
-    if ((int)blockIdx.x < n_tiles) {
-        const EcdaTile t = a.tiles[blockIdx.x];
+    if (tile_id < n_tiles) {
+        const EcdaTile t = a.tiles[tile_id];
         const int c = t.cls;
         const int off = st->list_off[c], ns = st->n_s[c], n = ns + st->n_t[c];
         const int dom_i = (t.row_begin - off) >= ns ? 1 : 0;
-        // ---- stage the row tile
-        if (tid < ECDA_TR) {
+        float* part_acc = a.part_acc + (int64_t)blockIdx.x * PT * DAD_H;
+        float* part_rowp = a.part_rowp + (int64_t)blockIdx.x * PT;
+        // ---- stage the class mean and the (centred) row tile
+        mu[tid] = a.mu_all[c * DAD_H + tid];
+        if (tid < PT) {
             int r = -1;
             float om = 0.f;
             if (tid < t.row_count) {
@@ -313,124 +338,156 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_pairs(EcdaArgs a) {
             wi[tid] = om;
         }
         __syncthreads();
-        for (int e = tid; e < ECDA_TR * (DAD_H / 4); e += EP_THREADS) {
-            const int row = e / (DAD_H / 4), q = e - row * (DAD_H / 4);
-            const int r = ri[row];
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r >= 0) v = *reinterpret_cast<const float4*>((r < Bg ? pack_emb_clean(a.pack, r) : pack_emb_strong(a.pack, r - Bg)) + q * 4);
-            *reinterpret_cast<float4*>(zi + row * ZS + q * 4) = v;
-        }
+        auto stage = [&](float* dst, float* nsq, const int* rows_or_null, int list_base, int count) {
+            // 8 warps x 8 rows; lane owns features lane*4..+3 and 128+lane*4..+3
+#pragma unroll 2
+            for (int rr = 0; rr < 8; ++rr) {
+                const int row = warp * 8 + rr;
+                int r = -1;
+                if (rows_or_null) r = rows_or_null[row];
+                else if (row < count) r = a.lists[list_base + row];
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (r >= 0) {
+                    const float* z = r < Bg ? pack_emb_clean(a.pack, r) : pack_emb_strong(a.pack, r - Bg);
+                    v0 = *reinterpret_cast<const float4*>(z + lane * 4);
+                    v1 = *reinterpret_cast<const float4*>(z + 128 + lane * 4);
+                    const float4 m0 = *reinterpret_cast<const float4*>(mu + lane * 4), m1 = *reinterpret_cast<const float4*>(mu + 128 + lane * 4);
+                    v0.x -= m0.x; v0.y -= m0.y; v0.z -= m0.z; v0.w -= m0.w;
+                    v1.x -= m1.x; v1.y -= m1.y; v1.z -= m1.z; v1.w -= m1.w;
+                }
+                *reinterpret_cast<float4*>(dst + row * PZS + lane * 4) = v0;
+                *reinterpret_cast<float4*>(dst + row * PZS + 128 + lane * 4) = v1;
+                float s2 = v0.x * v0.x;
+                s2 = fmaf(v0.y, v0.y, s2); s2 = fmaf(v0.z, v0.z, s2); s2 = fmaf(v0.w, v0.w, s2);
+                s2 = fmaf(v1.x, v1.x, s2); s2 = fmaf(v1.y, v1.y, s2); s2 = fmaf(v1.z, v1.z, s2); s2 = fmaf(v1.w, v1.w, s2);
+                s2 = warp_sum(s2);
+                if (lane == 0) nsq[row] = s2;
+            }
+        };
+        stage(zi, ni, ri, 0, 0);
         __syncthreads();
-        // phase-B ownership: rows warp*4..+3, features lane+32m
-        float ziv[4][8], acc[4][8];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int m = 0; m < 8; ++m) { ziv[r][m] = zi[(warp * 4 + r) * ZS + lane + 32 * m]; acc[r][m] = 0.f; }
 
+        // phase-B accumulators: rows warp*8 + r, features lane*4 + (f&3) + 128*(f>>2)
+        float acc[8][8], rowp[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            rowp[r] = 0.f;
+#pragma unroll
+            for (int f = 0; f < 8; ++f) acc[r][f] = 0.f;
+        }
         if (t.feasible) {
             const float ib0 = st->inv_beta[c][0], ib1 = st->inv_beta[c][1], ib2 = st->inv_beta[c][2], ib3 = st->inv_beta[c][3], ib4 = st->inv_beta[c][4];
             const float css = st->c_ss[c], ctt = st->c_tt[c], cst = st->c_st[c];
             const float gscale = -4.f * st->att[c] * a.w_ecda;
-            const int ti = tid >> 3, tj = tid & 7;  // phase A: row ti, columns tj + 8m
-            for (int j0 = 0; j0 < n; j0 += ECDA_TR) {
-                __syncthreads();  // previous iteration's readers of zj / Pm are done
-                if (tid < ECDA_TR) {
-                    int d = -1;
+            const int ty = tid >> 4, tx = tid & 15;  // phase A: rows ty + 16a, columns tx + 16b
+            const int n_chunks = ceil_div(n, PT), per = ceil_div(n_chunks, Q);
+            const int ch0 = q * per, ch1 = min(n_chunks, ch0 + per);
+            for (int ch = ch0; ch < ch1; ++ch) {
+                const int j0 = ch * PT;
+                __syncthreads();  // previous chunk's readers of zj / Pm are done
+                if (tid < PT) {
+                    int pos = -1, d = 0;
                     float om = 0.f;
                     if (j0 + tid < n) {
-                        const int r = a.lists[off + j0 + tid];
+                        pos = off + j0 + tid;
+                        const int r = a.lists[pos];
                         d = (r >= Bg) ? 1 : 0;
                         om = (d && a.class_aware) ? pack_score(a.pack, r - Bg) : 1.f;
                     }
-                    dj[tid] = d;
-                    wj[tid] = om;
+                    pj[tid] = pos; dj[tid] = d; wj[tid] = om;
                 }
-                for (int e = tid; e < ECDA_TR * (DAD_H / 4); e += EP_THREADS) {
-                    const int row = e / (DAD_H / 4), q = e - row * (DAD_H / 4);
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (j0 + row < n) {
-                        const int r = a.lists[off + j0 + row];
-                        v = *reinterpret_cast<const float4*>((r < Bg ? pack_emb_clean(a.pack, r) : pack_emb_strong(a.pack, r - Bg)) + q * 4);
-                    }
-                    *reinterpret_cast<float4*>(zj + row * ZS + q * 4) = v;
-                }
+                stage(zj, nj, nullptr, off + j0, n - j0);
                 __syncthreads();
-                // ---- phase A: squared distances by direct differences (I/utils.py:537), kernels, P
-                float l2[4] = {0.f, 0.f, 0.f, 0.f};
-                const float* zrow = zi + ti * ZS;
-#pragma unroll 4
-                for (int h = 0; h < DAD_H; h += 4) {
-                    const float4 x = *reinterpret_cast<const float4*>(zrow + h);
+                // ---- phase A: 4x4 dot products per thread over the 256 features
+                float d[4][4];
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        const float4 y = *reinterpret_cast<const float4*>(zj + (tj + 8 * m) * ZS + h);
-                        float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
-                        l2[m] = fmaf(d0, d0, l2[m]); l2[m] = fmaf(d1, d1, l2[m]); l2[m] = fmaf(d2, d2, l2[m]); l2[m] = fmaf(d3, d3, l2[m]);
-                    }
-                }
-                const bool i_ok = ti < t.row_count;
-                const float om_i = wi[ti];
+                for (int x = 0; x < 4; ++x)
 #pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    const int j = tj + 8 * m;
-                    const int d = dj[j];
-                    float p = 0.f;
-                    if (i_ok && d >= 0) {
-                        const float e0 = expf(-l2[m] * ib0), e1 = expf(-l2[m] * ib1), e2 = expf(-l2[m] * ib2), e3 = expf(-l2[m] * ib3), e4 = expf(-l2[m] * ib4);
-                        const float K = e0 + e1 + e2 + e3 + e4;
-                        const float Kp = e0 * ib0 + e1 * ib1 + e2 * ib2 + e3 * ib3 + e4 * ib4;
-                        const float ww = om_i * wj[j];
-                        float s;
-                        if (dom_i == 0 && d == 0) { sums[0] += ww * K; s = css; }
-                        else if (dom_i == 1 && d == 1) { sums[1] += ww * K; s = ctt; }
-                        else { if (dom_i == 0) sums[2] += ww * K; s = -cst; }
-                        p = gscale * s * ww * Kp;
-                    }
-                    Pm[ti * 33 + j] = p;
-                }
-                __syncthreads();
-                // ---- phase B: g_i += sum_j P_ij (z_i - z_j)
+                    for (int y = 0; y < 4; ++y) d[x][y] = 0.f;
 #pragma unroll 2
-                for (int j = 0; j < ECDA_TR; ++j) {
-                    float zjv[8];
+                for (int h = 0; h < DAD_H; h += 4) {
+                    float4 xi[4], xj[4];
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) zjv[m] = zj[j * ZS + lane + 32 * m];
+                    for (int x = 0; x < 4; ++x) xi[x] = *reinterpret_cast<const float4*>(zi + (ty + 16 * x) * PZS + h);
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float p = Pm[(warp * 4 + r) * 33 + j];
+                    for (int y = 0; y < 4; ++y) xj[y] = *reinterpret_cast<const float4*>(zj + (tx + 16 * y) * PZS + h);
 #pragma unroll
-                        for (int m = 0; m < 8; ++m) acc[r][m] = fmaf(p, ziv[r][m] - zjv[m], acc[r][m]);
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            d[x][y] = fmaf(xi[x].x, xj[y].x, d[x][y]); d[x][y] = fmaf(xi[x].y, xj[y].y, d[x][y]);
+                            d[x][y] = fmaf(xi[x].z, xj[y].z, d[x][y]); d[x][y] = fmaf(xi[x].w, xj[y].w, d[x][y]);
+                        }
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int i = ty + 16 * x;
+                    const bool i_ok = i < t.row_count;
+                    const float om_i = wi[i], nii = ni[i];
+                    const int pos_i = t.row_begin + i;
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        const int j = tx + 16 * y;
+                        const int pos = pj[j];
+                        float p = 0.f;
+                        if (i_ok && pos >= 0) {
+                            const bool diag = pos == pos_i;
+                            const float l2 = diag ? 0.f : fmaxf(nii + nj[j] - 2.f * d[x][y], 0.f);
+                            const float e0 = expf(-l2 * ib0), e1 = expf(-l2 * ib1), e2 = expf(-l2 * ib2), e3 = expf(-l2 * ib3), e4 = expf(-l2 * ib4);
+                            const float K = e0 + e1 + e2 + e3 + e4;
+                            const float Kp = e0 * ib0 + e1 * ib1 + e2 * ib2 + e3 * ib3 + e4 * ib4;
+                            const float ww = om_i * wj[j];
+                            const int dd = dj[j];
+                            float sblk;
+                            if (dom_i == 0 && dd == 0) { sums[0] += ww * K; sblk = css; }
+                            else if (dom_i == 1 && dd == 1) { sums[1] += ww * K; sblk = ctt; }
+                            else { if (dom_i == 0) sums[2] += ww * K; sblk = -cst; }
+                            p = diag ? 0.f : gscale * sblk * ww * Kp;  // (z_i - z_i) = 0: the diagonal carries no gradient
+                        }
+                        Pm[i * PPS + j] = p;
+                    }
+                }
+                __syncthreads();
+                // ---- phase B: accZ_i += sum_j P_ij z'_j, rowP_i += sum_j P_ij   (rows warp*8.., 8 features per lane)
+#pragma unroll 1
+                for (int j = 0; j < PT; j += 4) {
+                    float4 pr[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) pr[r] = *reinterpret_cast<const float4*>(Pm + (warp * 8 + r) * PPS + j);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const float4 z0 = *reinterpret_cast<const float4*>(zj + (j + jj) * PZS + lane * 4);
+                        const float4 z1 = *reinterpret_cast<const float4*>(zj + (j + jj) * PZS + 128 + lane * 4);
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            const float p = jj == 0 ? pr[r].x : jj == 1 ? pr[r].y : jj == 2 ? pr[r].z : pr[r].w;
+                            rowp[r] += p;
+                            acc[r][0] = fmaf(p, z0.x, acc[r][0]); acc[r][1] = fmaf(p, z0.y, acc[r][1]);
+                            acc[r][2] = fmaf(p, z0.z, acc[r][2]); acc[r][3] = fmaf(p, z0.w, acc[r][3]);
+                            acc[r][4] = fmaf(p, z1.x, acc[r][4]); acc[r][5] = fmaf(p, z1.y, acc[r][5]);
+                            acc[r][6] = fmaf(p, z1.z, acc[r][6]); acc[r][7] = fmaf(p, z1.w, acc[r][7]);
+                        }
                     }
                 }
             }
         }
-        // ---- compactness + repulsion gradients (noisy rows), then accumulate into g
-        const float comp_k = (t.feasible && dom_i) ? a.w_ecda * st->att[c] * a.gamma_comp * 2.f / (float)st->n_t[c] : 0.f;
+        // ---- this CTA's partial -> workspace
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int row = warp * 4 + r;
-            const int rid = ri[row];
-            if (rid < 0) continue;
-            const int gi = rid < Bg ? rid : rid - Bg;
-            float* g = (rid < Bg ? a.g_clean : a.g_strong) + (int64_t)(gi - a.rank * a.pack.B_local) * DAD_H;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int h = lane + 32 * m;
-                float v = acc[r][m];
-                if (dom_i && a.class_aware) v += comp_k * (ziv[r][m] - a.mu_t[c * DAD_H + h]) + a.w_ecda * a.rep_grad[c * DAD_H + h];
-                g[h] += v;
-            }
+        for (int r = 0; r < 8; ++r) {
+            const int row = warp * 8 + r;
+            *reinterpret_cast<float4*>(part_acc + row * DAD_H + lane * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+            *reinterpret_cast<float4*>(part_acc + row * DAD_H + 128 + lane * 4) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+            if (lane == 0) part_rowp[row] = rowp[r];
         }
     }
-    // ---- tile partial sums -> fixed-order loss assembly by the last CTA
+    // ---- per-CTA loss partial sums -> fixed-order loss assembly by the last CTA of the grid
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float v = warp_sum(sums[k]);
         if (lane == 0) s_red[k][warp] = v;
     }
     __syncthreads();
-    if (tid < 3 && (int)blockIdx.x < a.max_tiles) {
+    if (tid < 3) {
         float v = 0.f;
         for (int w = 0; w < EP_THREADS / 32; ++w) v += s_red[tid][w];
         a.tile_sums[blockIdx.x * 3 + tid] = v;
@@ -439,19 +496,19 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_pairs(EcdaArgs a) {
     __syncthreads();
     if (tid == 0) {
         const unsigned prev = atomicAdd(&a.counter[1], 1u);
-        s_last = (prev == gridDim.x - 1u);
+        s_flag = (prev == gridDim.x - 1u);
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_flag) return;
     __threadfence();
-    // per-class block sums over this rank's tiles: thread-strided partials, then a fixed-order cross-thread sum
     float cs[ECDA_MAXC][3];
 #pragma unroll
     for (int c = 0; c < ECDA_MAXC; ++c) cs[c][0] = cs[c][1] = cs[c][2] = 0.f;
-    for (int tl = tid; tl < n_tiles; tl += EP_THREADS) {
+    for (int e = tid; e < n_tiles * Q; e += EP_THREADS) {
+        const int tl = e / Q;
         const int c = a.tiles[tl].cls;
         if (!a.tiles[tl].feasible) continue;
-        const float v0 = __ldcg(&a.tile_sums[tl * 3 + 0]), v1 = __ldcg(&a.tile_sums[tl * 3 + 1]), v2 = __ldcg(&a.tile_sums[tl * 3 + 2]);
+        const float v0 = __ldcg(&a.tile_sums[e * 3 + 0]), v1 = __ldcg(&a.tile_sums[e * 3 + 1]), v2 = __ldcg(&a.tile_sums[e * 3 + 2]);
 #pragma unroll
         for (int cc = 0; cc < ECDA_MAXC; ++cc)
             if (cc == c) { cs[cc][0] += v0; cs[cc][1] += v1; cs[cc][2] += v2; }
@@ -485,7 +542,48 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_pairs(EcdaArgs a) {
     a.loss_out[2] = loss;  // this rank's share; shares sum to the global-batch ECDA loss
 }
 
-size_t ecda_pairs_smem_bytes() { return (size_t)(2 * ECDA_TR * ZS + ECDA_TR * 33 + 2 * ECDA_TR) * sizeof(float) + 2 * ECDA_TR * sizeof(int); }
+// k_ecda_fold: one CTA per row tile: folds the Q column-split partials of k_ecda_pairs in fixed q order, adds the compactness
+// and repulsion gradients of the noisy rows and accumulates into g (each gradient row has exactly one writer: deterministic).
+__global__ void __launch_bounds__(EP_THREADS) k_ecda_fold(EcdaArgs a) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const EcdaStats* st = a.stats;
+    const int tile_id = blockIdx.x;
+    if (tile_id >= st->n_tiles) return;
+    const int Bg = a.pack.B_local * a.pack.world, Q = a.col_splits;
+    const EcdaTile t = a.tiles[tile_id];
+    const int c = t.cls;
+    const int dom_i = (t.row_begin - st->list_off[c]) >= st->n_s[c] ? 1 : 0;
+    const float comp_k = (t.feasible && dom_i) ? a.w_ecda * st->att[c] * a.gamma_comp * 2.f / (float)st->n_t[c] : 0.f;
+#pragma unroll 1
+    for (int r = 0; r < 8; ++r) {
+        const int row = warp * 8 + r;
+        if (row >= t.row_count) continue;
+        const int rid = a.lists[t.row_begin + row];
+        float g8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float rp = 0.f;
+        if (t.feasible) {
+            for (int qq = 0; qq < Q; ++qq) {
+                const float* pa = a.part_acc + ((int64_t)(tile_id * Q + qq) * PT + row) * DAD_H;
+                const float4 u0 = *reinterpret_cast<const float4*>(pa + lane * 4), u1 = *reinterpret_cast<const float4*>(pa + 128 + lane * 4);
+                g8[0] += u0.x; g8[1] += u0.y; g8[2] += u0.z; g8[3] += u0.w; g8[4] += u1.x; g8[5] += u1.y; g8[6] += u1.z; g8[7] += u1.w;
+                rp += a.part_rowp[(int64_t)(tile_id * Q + qq) * PT + row];
+            }
+        }
+        const int gi = rid < Bg ? rid : rid - Bg;
+        const float* z = rid < Bg ? pack_emb_clean(a.pack, rid) : pack_emb_strong(a.pack, rid - Bg);
+        float* g = (rid < Bg ? a.g_clean : a.g_strong) + (int64_t)(gi - a.rank * a.pack.B_local) * DAD_H;
+#pragma unroll
+        for (int f = 0; f < 8; ++f) {
+            const int h = lane * 4 + (f & 3) + 128 * (f >> 2);
+            const float zr = z[h];
+            float v = rp * (zr - a.mu_all[c * DAD_H + h]) - g8[f];  // sum_j P_ij (z_i - z_j) on the centred rows
+            if (dom_i && a.class_aware) v += comp_k * (zr - a.mu_t[c * DAD_H + h]) + a.w_ecda * a.rep_grad[c * DAD_H + h];
+            g[h] += v;
+        }
+    }
+}
+
+size_t ecda_pairs_smem_bytes() { return (size_t)(2 * PT * PZS + PT * PPS + DAD_H + 4 * PT) * sizeof(float) + 3 * PT * sizeof(int); }
 int ecda_prep_grid(int B_global) {
     // rows per CTA <= 256 (k_ecda_prep classifies its chunk with one thread per row); aim at ~16 rows per CTA
     int g = ceil_div(2 * B_global, 16);
@@ -495,6 +593,12 @@ int ecda_prep_grid(int B_global) {
     return g < 1 ? 1 : g;
 }
 int ecda_max_tiles(int B_local) { return ceil_div(2 * B_local, ECDA_TR) + 2 * ECDA_MAXC; }
+// column splits per row tile: ~2 CTAs per SM over the whole grid, at most 16 (a class of the global batch has ~Bg/2 members)
+int ecda_col_splits(int B_local) {
+    const int tiles = ecda_max_tiles(B_local);
+    int q = ceil_div(2 * 148, tiles);
+    return q < 1 ? 1 : (q > 16 ? 16 : q);
+}
 
 int launch_ecda(const EcdaArgs& a, cudaStream_t st) {
     static bool attr_set = false;
@@ -504,7 +608,9 @@ int launch_ecda(const EcdaArgs& a, cudaStream_t st) {
     }
     k_ecda_prep<<<a.prep_grid, EP_THREADS, 0, st>>>(a);
     DAD_CHECK_LAUNCH("k_ecda_prep");
-    k_ecda_pairs<<<a.max_tiles, EP_THREADS, ecda_pairs_smem_bytes(), st>>>(a);
+    k_ecda_pairs<<<a.max_tiles * a.col_splits, EP_THREADS, ecda_pairs_smem_bytes(), st>>>(a);
     DAD_CHECK_LAUNCH("k_ecda_pairs");
+    k_ecda_fold<<<a.max_tiles, EP_THREADS, 0, st>>>(a);
+    DAD_CHECK_LAUNCH("k_ecda_fold");
     return DAD_OK;
 }

@@ -64,7 +64,8 @@ def test_speaker_fold_trainers(monkeypatch, tmp_path, which):
     else:
         from dad_b200 import config_emodb as cfg
         from dad_b200.train_emodb import FixedEMODBCrossDomainTrainer as T
-    _patch(monkeypatch, cfg, {"EPOCHS": 8})
+    # the fixed-threshold branch (CASIA default) needs a confident teacher; without pretrained weights lower the bar for the test
+    _patch(monkeypatch, cfg, {"EPOCHS": 8, "FIXED_CONFIDENCE_THRESHOLD": 0.26})
     tr = T(fold=3, loaders=T.synthetic_loaders(3, utt_per_speaker=48), require_pretrained=False)
     hist = [tr.train_epoch(epoch) for epoch in range(8)]
     avg = hist[-1]
