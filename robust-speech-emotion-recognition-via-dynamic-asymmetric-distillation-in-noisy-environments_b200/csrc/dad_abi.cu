@@ -251,7 +251,7 @@ int dad_scl(const dad_scl_args* a, void* stream) {
 }
 
 // ---------------------------------------------------------------- ECDA
-struct EcdaCarve { size_t part_vec, part_sc, part_cnt, stats, lists, tiles, mu_t, mu_all, rep_grad, tile_sums, part_acc, part_rowp, counter, total; };
+struct EcdaCarve { size_t part_vec, part_sc, part_cnt, stats, lists, tiles, mu_t, mu_all, rep_grad, tile_sums, part_acc, part_rowp, slot_of, counter, total; };
 static EcdaCarve ecda_carve(int B_local, int world) {
     const int Bg = B_local * world, G = ecda_prep_grid(Bg), MT = ecda_max_tiles(B_local), Q = ecda_col_splits(B_local);
     EcdaCarve c;
@@ -262,6 +262,7 @@ static EcdaCarve ecda_carve(int B_local, int world) {
     c.part_cnt = o; o = align_up(o + (size_t)G * 8 * sizeof(int), 256);
     c.stats = o; o = align_up(o + sizeof(EcdaStats), 256);
     c.lists = o; o = align_up(o + (size_t)2 * Bg * sizeof(int), 256);
+    c.slot_of = o; o = align_up(o + (size_t)2 * Bg, 256);
     c.tiles = o; o = align_up(o + (size_t)MT * sizeof(EcdaTile), 256);
     c.mu_t = o; o = align_up(o + (size_t)ECDA_MAXC * DAD_H * sizeof(float), 256);
     c.rep_grad = o; o = align_up(o + (size_t)ECDA_MAXC * DAD_H * sizeof(float), 256);
@@ -290,6 +291,7 @@ int dad_ecda(const dad_ecda_args* a, void* stream) {
     k.stats = (EcdaStats*)(w + c.stats); k.lists = (int*)(w + c.lists); k.tiles = (EcdaTile*)(w + c.tiles);
     k.mu_t = (float*)(w + c.mu_t); k.rep_grad = (float*)(w + c.rep_grad); k.tile_sums = (float*)(w + c.tile_sums);
     k.g_clean = a->g_clean; k.g_strong = a->g_strong; k.loss_out = a->loss_out; k.counter = (unsigned*)(w + c.counter);
+    k.slot_of = (uint8_t*)(w + c.slot_of);
     k.mu_all = (float*)(w + c.mu_all); k.part_acc = (float*)(w + c.part_acc); k.part_rowp = (float*)(w + c.part_rowp);
     k.max_tiles = ecda_max_tiles(a->pack.B_local);
     k.col_splits = ecda_col_splits(a->pack.B_local);

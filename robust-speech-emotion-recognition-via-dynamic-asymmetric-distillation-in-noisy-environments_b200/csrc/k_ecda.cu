@@ -42,15 +42,6 @@ __device__ __forceinline__ int row_slot(const EcdaArgs& a, int r, int Bg, float&
     return 4 + (a.class_aware ? pack_pred(a.pack, gi) : 0);
 }
 
-__device__ __forceinline__ int list_lower_bound(const int* lists, int lo, int hi, int key) {
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldcg(lists + mid) < key) lo = mid + 1;
-        else hi = mid;
-    }
-    return lo;
-}
-
 }  // namespace
 
 __global__ void __launch_bounds__(EP_THREADS) k_ecda_prep(EcdaArgs a) {
@@ -80,6 +71,7 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_prep(EcdaArgs a) {
             const float* z;
             s_slot[tid] = row_slot(a, r0 + tid, Bg, om, z);
             s_om[tid] = om;
+            a.slot_of[r0 + tid] = (uint8_t)(s_slot[tid] < 0 ? 255 : s_slot[tid]);  // for the ordered scatter of phase 3
         }
         __syncthreads();
         for (int r = r0; r < r1; ++r) {
@@ -120,22 +112,35 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_prep(EcdaArgs a) {
         if (tid == 0) { st->n_tiles = 0; st->any_feasible = 0; st->rep = 0.f; st->rho = 0.f; }
         return;
     }
+    // fixed-order sums of the G per-CTA partials.  The order is "g mod 8 lanes, then lane 0..7": eight INDEPENDENT accumulators
+    // keep eight L2 loads in flight (a single running sum made this one CTA latency-bound: ~0.2 ms at global batch 4096 while
+    // the rest of the GPU idled) and the result is still bit-reproducible.
     double tv[8];
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < 8; ++s) {
-        double t = 0.0;
-        for (int g = 0; g < G; ++g) t += (double)__ldcg(&a.part_vec[((int64_t)g * 8 + s) * DAD_H + tid]);
-        tv[s] = t;
+        double t8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        int g = 0;
+        for (; g + 8 <= G; g += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t8[u] += (double)__ldcg(&a.part_vec[((int64_t)(g + u) * 8 + s) * DAD_H + tid]);
+        }
+        for (int u = 0; g < G; ++g, ++u) t8[u] += (double)__ldcg(&a.part_vec[((int64_t)g * 8 + s) * DAD_H + tid]);
+        tv[s] = ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
     }
-    if (tid < 8) {
+    {
+        // scalar partials: warp w reduces slot w (8 warps, 8 slots), lanes stride over g, fixed-order shuffle tree
+        const int w8 = tid >> 5, l = tid & 31;
         double q = 0.0, w = 0.0;
         int c = 0;
-        for (int g = 0; g < G; ++g) {
-            q += __ldcg(&a.part_sc[((int64_t)g * 8 + tid) * 2 + 0]);
-            w += __ldcg(&a.part_sc[((int64_t)g * 8 + tid) * 2 + 1]);
-            c += __ldcg(&a.part_cnt[g * 8 + tid]);
+        for (int g = l; g < G; g += 32) {
+            q += __ldcg(&a.part_sc[((int64_t)g * 8 + w8) * 2 + 0]);
+            w += __ldcg(&a.part_sc[((int64_t)g * 8 + w8) * 2 + 1]);
+            c += __ldcg(&a.part_cnt[g * 8 + w8]);
         }
-        s_sq[tid] = q; s_ws[tid] = w; s_cnt[tid] = c;
+        q = warp_sum_d(q); w = warp_sum_d(w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (l == 0) { s_sq[w8] = q; s_ws[w8] = w; s_cnt[w8] = c; }
     }
     __syncthreads();
     const int NC = a.class_aware ? ECDA_MAXC : 1;
@@ -212,22 +217,27 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_prep(EcdaArgs a) {
         st->any_feasible = any;
     }
     // ---------------- phase 3: ordered member lists (per class: clean ascending, then noisy ascending)
+    // All row slots were published by phase 1; one coalesced pass brings them into shared memory (every load in flight at
+    // once), so the ordered scatter below touches no global memory on its critical path.  (The first version re-derived each
+    // slot from the pack inside the loop -- 32 dependent global round trips -- and then binary-searched the lists it had just
+    // written with L2-latency probes from one thread: together ~0.15 ms of a single CTA at global batch 4096.)
+    extern __shared__ uint8_t s_sl[];  // [R]
+    __shared__ int s_lt_lo[8], s_lt_hi[8];
     if (tid < 8) {
         const int c = tid & 3, dom = tid >> 2;
         int off = 0;
         for (int cc = 0; cc < c; ++cc) off += s_cnt[cc] + s_cnt[4 + cc];
         s_off[tid] = off + (dom ? s_cnt[c] : 0);
+        s_lt_lo[tid] = 0; s_lt_hi[tid] = 0;
     }
+    for (int r = tid; r < R; r += EP_THREADS) s_sl[r] = __ldcg(a.slot_of + r);
     __syncthreads();
+    const int own_lo = a.rank * a.pack.B_local, own_hi = own_lo + a.pack.B_local;
     const int warp = tid >> 5, lane = tid & 31;
     for (int base = 0; base < R; base += EP_THREADS) {
         const int r = base + tid;
         int slot = -1;
-        if (r < R) {
-            float om;
-            const float* z;
-            slot = row_slot(a, r, Bg, om, z);
-        }
+        if (r < R) { const int v = s_sl[r]; slot = v == 255 ? -1 : v; }
         unsigned myballot = 0;
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
@@ -240,6 +250,10 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_prep(EcdaArgs a) {
             int pos = s_off[slot] + __popc(myballot & ((1u << lane) - 1u));
             for (int w = 0; w < warp; ++w) pos += s_wc[w][slot];
             a.lists[pos] = r;
+            // members of this slot that precede the rows this rank owns / precede the end of them (lists are ascending)
+            const int id = slot >= 4 ? r - Bg : r;
+            if (id < own_lo) atomicAdd(&s_lt_lo[slot], 1);
+            if (id < own_hi) atomicAdd(&s_lt_hi[slot], 1);
         }
         __syncthreads();
         if (tid < 8) {
@@ -253,19 +267,15 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_prep(EcdaArgs a) {
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const int lo = a.rank * a.pack.B_local, hi = lo + a.pack.B_local;
         int nt_ = 0;
         for (int c = 0; c < NC; ++c) {
-            const int off = st->list_off[c], ns = s_cnt[c], ntc = s_cnt[4 + c];
+            const int off = st->list_off[c], ns = s_cnt[c];
             const bool feas = st->feasible[c] != 0;
             for (int dom = 0; dom < 2; ++dom) {
                 if (dom == 0 && !feas) continue;                              // clean rows only matter through the MMD
                 if (dom == 1 && !feas && !(a.class_aware && nvalid > 1)) continue;  // noisy rows: MMD/comp or repulsion
-                const int b0 = off + (dom ? ns : 0), cntd = dom ? ntc : ns;
-                const int shift = dom ? Bg : 0;
-                // [first,last): members owned by this rank (lists are ascending) -> two lower bounds
-                const int first = list_lower_bound(a.lists, b0, b0 + cntd, lo + shift);
-                const int last = list_lower_bound(a.lists, b0, b0 + cntd, hi + shift);
+                const int b0 = off + (dom ? ns : 0);
+                const int first = b0 + s_lt_lo[dom * 4 + c], last = b0 + s_lt_hi[dom * 4 + c];
                 for (int p = first; p < last && nt_ < a.max_tiles; p += ECDA_TR) {
                     EcdaTile t;
                     t.cls = c; t.row_begin = p; t.row_count = min(ECDA_TR, last - p); t.feasible = feas ? 1 : 0;
@@ -606,7 +616,13 @@ int launch_ecda(const EcdaArgs& a, cudaStream_t st) {
         cudaFuncSetAttribute(k_ecda_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ecda_pairs_smem_bytes());
         attr_set = true;
     }
-    k_ecda_prep<<<a.prep_grid, EP_THREADS, 0, st>>>(a);
+    const size_t prep_smem = (size_t)2 * a.pack.B_local * a.pack.world;  // row slots, one byte each (last CTA)
+    if (prep_smem > 160 * 1024) return dad_set_error(DAD_ERR_UNSUPPORTED, "ecda: global batch too large for the single-CTA list builder");
+    if (prep_smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_ecda_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "ecda: cannot opt in to shared memory: %s", cudaGetErrorString(e));
+    }
+    k_ecda_prep<<<a.prep_grid, EP_THREADS, prep_smem, st>>>(a);
     DAD_CHECK_LAUNCH("k_ecda_prep");
     k_ecda_pairs<<<a.max_tiles * a.col_splits, EP_THREADS, ecda_pairs_smem_bytes(), st>>>(a);
     DAD_CHECK_LAUNCH("k_ecda_pairs");

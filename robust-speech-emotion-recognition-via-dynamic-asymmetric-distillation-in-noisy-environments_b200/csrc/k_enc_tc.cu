@@ -21,6 +21,7 @@
 #include "tc_ptx.cuh"
 #include <cuda_fp16.h>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -45,6 +46,8 @@ struct FwdParams {
     AugParams ap;
     float* part;        // [num_groups][2][256]
     uint32_t* bits;     // [N][8] or null
+    int dbg;            // DAD_TC_DBG timing experiments (never set in production): 1 = one product instead of three, 2 = W k-blocks
+                        //   TMA-loaded for the first STAGES iterations only (stale weights afterwards): isolates MMA time / smem fill traffic
     int cache;          // operand cache on: every A tile (the fp16 hi/lo split of the augmented, scaled input) is also TMA-stored from
                         //   shared memory to xs_hi / xs_lo [N][768] for the backward kernel (tm_xhi / tm_xlo), at no converter cost
     int64_t N;
@@ -254,6 +257,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     tc::mbar_wait(&empty[s], ph ^ 1);
+                    if ((p.dbg & 2) && it >= STAGES) { tc::mbar_arrive(&full[s]); continue; }
                     tc::mbar_arrive_expect_tx(&full[s], 2 * W_BYTES);
                     tc::tma_load_2d(smem + s * STAGE_BYTES + OFF_WHI, &tm_whi, &full[s], kb * BK, 0);
                     tc::tma_load_2d(smem + s * STAGE_BYTES + OFF_WLO, &tm_wlo, &full[s], kb * BK, 0);
@@ -277,6 +281,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
                     const uint32_t base = tc::smem_u32(smem + s * STAGE_BYTES);
 #pragma unroll
                     for (int prod = 0; prod < 3; ++prod) {
+                        if ((p.dbg & 1) && prod > 0) break;
                         const uint32_t a_off = (prod == 2) ? OFF_ALO : OFF_AHI;  // hi*hi, hi*lo, lo*hi
                         const uint32_t b_off = (prod == 1) ? OFF_WLO : OFF_WHI;
 #pragma unroll
@@ -501,6 +506,11 @@ int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W_hi, cons
     }
     FwdParams p;
     p.x = x; p.pad = pad; p.bias = bias; p.ap = ap; p.part = reinterpret_cast<float*>(ws); p.bits = bits;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("DAD_TC_DBG"); dbg = e ? atoi(e) : 0; }
+        p.dbg = dbg;
+    }
     p.cache = (xs_hi && xs_lo) ? 1 : 0;
     CUtensorMap tm_xhi, tm_xlo;
     memset(&tm_xhi, 0, sizeof(tm_xhi));

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(HD_THREADS) k_head_fwd(HeadFwdArgs a) {
 
 // ---------------------------------------------------------------------------------------------------------
 // k_dacp: one CTA over the GLOBAL batch (after the all-gather under data parallelism).
-// Bitonic sort of (class, score) keys in shared memory -> per-class linear-interpolated quantiles
+// MSB-first radix select over sortable score keys in shared memory -> per-class linear-interpolated quantiles
 // (torch.quantile semantics), EMA thresholds (state, in place), mask, per-class epoch accumulators.
 // Reference: I/utils.py:449-507; fixed-threshold branch I/train.py:417-420.
 // ---------------------------------------------------------------------------------------------------------
@@ -172,11 +172,14 @@ __device__ __forceinline__ float sortable2f(uint32_t k) {
 }
 
 __global__ void __launch_bounds__(1024) k_dacp(DacpArgs a) {
-    extern __shared__ unsigned long long keys[];  // npow2 entries
+    extern __shared__ uint32_t keys[];  // [Bg] sortable score keys (class in s_cls)
     __shared__ int s_cnt[DAD_C];
     __shared__ float s_thr[DAD_C];
     __shared__ int s_nmask;
     __shared__ double s_sum[DAD_C];
+    __shared__ int s_hist[2 * DAD_C][256];   // radix-select histograms: target = class * 2 + {lo, hi}
+    __shared__ uint32_t s_prefix[2 * DAD_C]; // key bits fixed so far
+    __shared__ int s_rank[2 * DAD_C];        // remaining 0-based rank inside the prefix bucket (-1: class empty)
     const int tid = threadIdx.x, nt = blockDim.x;
     const int Bg = a.pack.B_local * a.pack.world;
     if (tid < DAD_C) { s_cnt[tid] = 0; s_sum[tid] = 0.0; }
@@ -184,34 +187,75 @@ __global__ void __launch_bounds__(1024) k_dacp(DacpArgs a) {
     __syncthreads();
 
     if (a.use_dacp) {
-        for (int i = tid; i < a.npow2_; i += nt) {
-            unsigned long long k = ~0ull;
-            if (i < Bg) {
-                const int c = pack_pred(a.pack, i);
-                if (c >= 0) {  // pred < 0: null sample (sorts to the end with the padding keys)
-                    k = ((unsigned long long)c << 32) | f2sortable(pack_score(a.pack, i));
-                    atomicAdd(&s_cnt[c], 1);
-                }
-            }
-            keys[i] = k;
+        // The per-class quantile needs two order statistics per class (torch.quantile, linear interpolation): an MSB-first
+        // radix SELECT over the 32-bit sortable keys -- 4 passes of 8 bits, 8 targets at once -- instead of a full sort
+        // (the bitonic sort of the global batch was ~95 us of a single CTA per step, a fixed cost on every data-parallel rank).
+        uint8_t* s_cls = reinterpret_cast<uint8_t*>(keys + Bg);
+        for (int i = tid; i < Bg; i += nt) {
+            const int c = pack_pred(a.pack, i);
+            keys[i] = f2sortable(pack_score(a.pack, i));
+            s_cls[i] = (uint8_t)(c < 0 ? 255 : c);  // 255: null sample
+            if (c >= 0) atomicAdd(&s_cnt[c], 1);
         }
         __syncthreads();
-        for (int k = 2; k <= a.npow2_; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < a.npow2_; i += nt) {
-                    const int ixj = i ^ j;
-                    if (ixj > i) {
-                        const unsigned long long x = keys[i], y = keys[ixj];
-                        const bool up = (i & k) == 0;
-                        if ((x > y) == up) { keys[i] = y; keys[ixj] = x; }
-                    }
-                }
-                __syncthreads();
+        if (tid < 2 * DAD_C) {
+            const int c = tid >> 1, n = s_cnt[c];
+            int rank = -1;
+            if (n > 0) {  // pos = q*(n-1); lo = floor, hi = ceil
+                const float pos = a.gamma * (float)(n - 1);
+                rank = (tid & 1) ? (int)ceilf(pos) : (int)floorf(pos);
             }
+            s_rank[tid] = rank;
+            s_prefix[tid] = 0u;
+        }
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            for (int e = tid; e < 2 * DAD_C * 256; e += nt) (&s_hist[0][0])[e] = 0;
+            __syncthreads();
+            // scores cluster in a few exponent buckets, so the first passes would hammer two or three bins with 32-way
+            // conflicting shared-memory atomics: lanes with the same (target, digit) are merged first (match.any)
+            for (int i0 = 0; i0 < Bg; i0 += nt) {  // warp-uniform trip count
+                const int i = i0 + tid;
+                const int c = i < Bg ? s_cls[i] : 255;
+                const uint32_t k = i < Bg ? keys[i] : 0u;
+                const uint32_t hi_bits = pass == 0 ? 0u : (k >> (shift + 8));
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    const int t = (c == 255 ? 0 : c) * 2 + w;
+                    const bool on = c != 255 && s_rank[t] >= 0 && (pass == 0 || hi_bits == (s_prefix[t] >> (shift + 8)));
+                    const uint32_t id = on ? ((uint32_t)t << 8) | ((k >> shift) & 0xFFu) : 0xFFFFFFFFu;
+                    const unsigned peers = __match_any_sync(0xffffffffu, id);
+                    if (on && (tid & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[t][(k >> shift) & 0xFFu], __popc(peers));
+                }
+            }
+            __syncthreads();
+            // one warp per target: find the bin holding the rank (lane = 8 consecutive bins, exclusive warp scan)
+            const int warp = tid >> 5, lane = tid & 31;
+            if (warp < 2 * DAD_C && s_rank[warp] >= 0) {
+                int h[8], tot = 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { h[u] = s_hist[warp][lane * 8 + u]; tot += h[u]; }
+                int incl = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int excl = incl - tot, rank = s_rank[warp];
+                if (rank >= excl && rank < incl) {  // exactly one lane
+                    int r = rank - excl, bin = 0;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (r >= 0 && r < h[u]) { bin = u; s_rank[warp] = r; r = -1; }
+                        else if (r >= 0) r -= h[u];
+                    }
+                    s_prefix[warp] |= (uint32_t)(lane * 8 + bin) << shift;
+                }
+            }
+            __syncthreads();
+        }
         if (tid < DAD_C) {
             const int c = tid;
-            int start = 0;
-            for (int cc = 0; cc < c; ++cc) start += s_cnt[cc];
             const int n = s_cnt[c];
             // class weights W_c = sigmoid(K (Q_c - mean Q))  (utils.py:466-470)
             const float q0 = a.quality[0], q1 = a.quality[1], q2 = a.quality[2], q3 = a.quality[3];
@@ -221,10 +265,9 @@ __global__ void __launch_bounds__(1024) k_dacp(DacpArgs a) {
             float tau;
             if (n > 0) {  // torch.quantile(linear): pos = q*(n-1); lerp(sorted[floor], sorted[ceil], frac)
                 const float pos = a.gamma * (float)(n - 1);
-                const float lo = floorf(pos), hi = ceilf(pos);
-                const float wgt = pos - lo;
-                const float vlo = sortable2f((uint32_t)keys[start + (int)lo]);
-                const float vhi = sortable2f((uint32_t)keys[start + (int)hi]);
+                const float wgt = pos - floorf(pos);
+                const float vlo = sortable2f(s_prefix[2 * c]);
+                const float vhi = sortable2f(s_prefix[2 * c + 1]);
                 const float diff = vhi - vlo;
                 tau = (wgt < 0.5f) ? vlo + wgt * diff : vhi - diff * (1.0f - wgt);
             } else {
@@ -427,17 +470,16 @@ int launch_certainty(const float* probs, int B, int use_entropy, float* scores, 
 
 int launch_dacp(DacpArgs a, cudaStream_t st) {
     const int Bg = a.pack.B_local * a.pack.world;
-    int np2 = 32;
-    while (np2 < Bg) np2 <<= 1;
-    a.npow2_ = np2;
-    const size_t smem = (size_t)np2 * sizeof(unsigned long long);
-    if (smem > 200 * 1024) return dad_set_error(DAD_ERR_UNSUPPORTED, "dacp: global batch %d too large for the single-CTA sort", Bg);
+    a.npow2_ = 0;
+    const size_t smem = (size_t)Bg * (sizeof(uint32_t) + 1) + 16;  // sortable keys + class bytes
+    if (smem > 180 * 1024) return dad_set_error(DAD_ERR_UNSUPPORTED, "dacp: global batch %d too large for the single-CTA select", Bg);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_dacp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_dacp, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
         attr_set = true;
     }
-    int threads = np2 / 2 < 1024 ? (np2 / 2 < 128 ? 128 : np2 / 2) : 1024;
+    int threads = 256;
+    while (threads < 1024 && threads * 4 < Bg) threads <<= 1;
     k_dacp<<<1, threads, smem, st>>>(a);
     DAD_CHECK_LAUNCH("k_dacp");
     return DAD_OK;
