@@ -258,8 +258,16 @@ def run_ours(args):
     share = {"encoder_fwd": kern["encoder_fwd"]["ms"] + kern["encoder_fwd_weak"]["ms"] + kern["encoder_fwd_strong"]["ms"],
              "encoder_bwd": kern["encoder_bwd"]["ms"] + kern["encoder_bwd_strong"]["ms"]}
     dom = max(share, key=share.get)
+    # dram__bytes_read + dram__bytes_write of one launch of the dominant kernel, from the committed `ncu --set full` capture of this
+    # workload at this per-GPU batch (profiles/traffic.json; null when no capture matches)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{args.workload}:B{B}:T{T}:{args.operand_cache}", {}).get(dom)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": kern[dom]["GBps"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "frac": kern[dom]["GBps"] / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": B * T * D_IN * 4, "kernels": kern,
                 "step": {"algorithmic_bytes": BYTES_PER_PAIR_T * T * B, "algorithmic_flops": FLOPS_PER_PAIR_T * T * B,
                          "hbm_roofline_ms": BYTES_PER_PAIR_T * T * B / (peaks["hbm_gbs"] * 1e6),

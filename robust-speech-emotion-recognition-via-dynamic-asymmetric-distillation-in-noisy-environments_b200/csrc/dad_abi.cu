@@ -251,7 +251,7 @@ int dad_scl(const dad_scl_args* a, void* stream) {
 }
 
 // ---------------------------------------------------------------- ECDA
-struct EcdaCarve { size_t part_vec, part_sc, part_cnt, stats, lists, tiles, mu_t, mu_all, rep_grad, tile_sums, part_acc, part_rowp, slot_of, counter, total; };
+struct EcdaCarve { size_t part_vec, part_sc, part_cnt, stats, lists, tiles, mu_t, mu_all, rep_grad, tile_sums, part_acc, part_rowp, slot_of, red_vec, red_sc, red_cnt, counter, total; };
 static EcdaCarve ecda_carve(int B_local, int world) {
     const int Bg = B_local * world, G = ecda_prep_grid(Bg), MT = ecda_max_tiles(B_local), Q = ecda_col_splits(B_local);
     EcdaCarve c;
@@ -263,6 +263,9 @@ static EcdaCarve ecda_carve(int B_local, int world) {
     c.stats = o; o = align_up(o + sizeof(EcdaStats), 256);
     c.lists = o; o = align_up(o + (size_t)2 * Bg * sizeof(int), 256);
     c.slot_of = o; o = align_up(o + (size_t)2 * Bg, 256);
+    c.red_vec = o; o = align_up(o + (size_t)8 * DAD_H * sizeof(double), 256);
+    c.red_sc = o; o = align_up(o + (size_t)16 * sizeof(double), 256);
+    c.red_cnt = o; o = align_up(o + (size_t)8 * sizeof(int), 256);
     c.tiles = o; o = align_up(o + (size_t)MT * sizeof(EcdaTile), 256);
     c.mu_t = o; o = align_up(o + (size_t)ECDA_MAXC * DAD_H * sizeof(float), 256);
     c.rep_grad = o; o = align_up(o + (size_t)ECDA_MAXC * DAD_H * sizeof(float), 256);
@@ -292,6 +295,7 @@ int dad_ecda(const dad_ecda_args* a, void* stream) {
     k.mu_t = (float*)(w + c.mu_t); k.rep_grad = (float*)(w + c.rep_grad); k.tile_sums = (float*)(w + c.tile_sums);
     k.g_clean = a->g_clean; k.g_strong = a->g_strong; k.loss_out = a->loss_out; k.counter = (unsigned*)(w + c.counter);
     k.slot_of = (uint8_t*)(w + c.slot_of);
+    k.red_vec = (double*)(w + c.red_vec); k.red_sc = (double*)(w + c.red_sc); k.red_cnt = (int*)(w + c.red_cnt);
     k.mu_all = (float*)(w + c.mu_all); k.part_acc = (float*)(w + c.part_acc); k.part_rowp = (float*)(w + c.part_rowp);
     k.max_tiles = ecda_max_tiles(a->pack.B_local);
     k.col_splits = ecda_col_splits(a->pack.B_local);

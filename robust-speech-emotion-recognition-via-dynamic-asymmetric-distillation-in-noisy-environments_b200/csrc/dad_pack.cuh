@@ -56,6 +56,9 @@ struct EcdaArgs {
     EcdaTile* tiles;        // [max_tiles]
     float* mu_t;            // [4][256] noisy centroids
     float* rep_grad;        // [4][256] rho * d rep / d z_i for noisy members of class c
+    double* red_vec;        // [8][256] slot sums over all rows (k_ecda_reduce)
+    double* red_sc;         // [8][2]
+    int* red_cnt;           // [8]
     uint8_t* slot_of;       // [2*B_global] slot (dom*4 + class) of every row, 255 = not a member
     float* mu_all;          // [4][256] mean of ALL members (clean + masked noisy) of class c: the centring point of k_ecda_pairs
     float* tile_sums;       // [max_tiles * col_splits][3]

@@ -3,9 +3,10 @@
 // Reference: I/utils.py:510-652 (ECDALoss._gaussian_kernel / forward), gate I/train.py:444,450.
 //
 //  k_ecda_prep : grid over the 2*B_global rows (clean rows then noisy rows of the pack) -> per-(domain,class)
-//                partial sums; the last CTA reduces them in fixed order (fp64) into class statistics (counts,
-//                bandwidths via the centred closed form  sum_ij|zi-zj|^2 = 2n sum_i|zi-m|^2, centroids, compactness,
-//                repulsion + its gradient, attention), builds the per-class member lists and the row-tile table.
+//                partial sums;  k_ecda_reduce (8 CTAs, one per slot) folds them in fixed order (fp64);  k_ecda_stats
+//                (one CTA) turns them into class statistics (counts, bandwidths via the centred closed form
+//                sum_ij|zi-zj|^2 = 2n sum_i|zi-m|^2, centroids, compactness, repulsion + its gradient, attention) and
+//                builds the per-class member lists and the row-tile table.
 //  k_ecda_pairs: one CTA per (64-row tile of one class, column split): two register-tiled SIMT GEMMs on class-centred
 //                embeddings (Gram form of the squared distances, then P z) -- see the comment above the kernel.  Under data
 //                parallelism a rank launches tiles only for the rows it owns (its local clean / noisy samples).
@@ -46,10 +47,6 @@ __device__ __forceinline__ int row_slot(const EcdaArgs& a, int r, int Bg, float&
 
 __global__ void __launch_bounds__(EP_THREADS) k_ecda_prep(EcdaArgs a) {
     __shared__ double s_red[EP_THREADS / 32];
-    __shared__ int s_last;
-    __shared__ int s_cnt[8], s_off[8], s_wc[EP_THREADS / 32][8];
-    __shared__ double s_sq[8], s_ws[8];
-    __shared__ float s_dist[ECDA_MAXC][ECDA_MAXC];
     __shared__ int s_slot[EP_THREADS];
     __shared__ float s_om[EP_THREADS];
     const int tid = threadIdx.x, G = gridDim.x;
@@ -95,53 +92,65 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_prep(EcdaArgs a) {
             a.part_cnt[blockIdx.x * 8 + s] = cnt[s];
         }
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned prev = atomicAdd(&a.counter[0], 1u);
-        s_last = (prev == (unsigned)G - 1u);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+}
 
-    // ---------------- phase 2 (last CTA): class statistics
-    EcdaStats* st = a.stats;
-    if (tid == 0) { a.counter[0] = 0u; st->active = active ? 1 : 0; }
-    if (!active) {
-        if (tid == 0) { st->n_tiles = 0; st->any_feasible = 0; st->rep = 0.f; st->rho = 0.f; }
-        return;
-    }
-    // fixed-order sums of the G per-CTA partials.  The order is "g mod 8 lanes, then lane 0..7": eight INDEPENDENT accumulators
-    // keep eight L2 loads in flight (a single running sum made this one CTA latency-bound: ~0.2 ms at global batch 4096 while
-    // the rest of the GPU idled) and the result is still bit-reproducible.
-    double tv[8];
-#pragma unroll 1
-    for (int s = 0; s < 8; ++s) {
-        double t8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        int g = 0;
-        for (; g + 8 <= G; g += 8) {
+// k_ecda_reduce: folds the G per-CTA partials of every slot in a fixed order.  Eight independent accumulators per thread keep
+// eight L2 loads in flight; 32 CTAs (slot x feature quarter) work in parallel (as the tail of one "last CTA" this
+// reduction alone was >0.1 ms at global batch 4096 -- a fixed cost on every data-parallel rank).
+__global__ void __launch_bounds__(EP_THREADS) k_ecda_reduce(EcdaArgs a, int G) {
+    // grid = 8 slots x 4 feature quarters; thread (f = tid & 63, part = tid >> 6) sums the part-th quarter of the g range
+    // (8 loads in flight), the four quarters are then combined in fixed order through shared memory
+    __shared__ double s_part[4][64];
+    const int tid = threadIdx.x, s = blockIdx.x >> 2, f = (blockIdx.x & 3) * 64 + (tid & 63), part = tid >> 6;
+    const int per = ceil_div(G, 4), g0 = part * per, g1 = min(G, g0 + per);
+    double t8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int g = g0;
+    for (; g + 8 <= g1; g += 8) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) t8[u] += (double)__ldcg(&a.part_vec[((int64_t)(g + u) * 8 + s) * DAD_H + tid]);
-        }
-        for (int u = 0; g < G; ++g, ++u) t8[u] += (double)__ldcg(&a.part_vec[((int64_t)g * 8 + s) * DAD_H + tid]);
-        tv[s] = ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
+        for (int u = 0; u < 8; ++u) t8[u] += (double)a.part_vec[((int64_t)(g + u) * 8 + s) * DAD_H + f];
     }
-    {
-        // scalar partials: warp w reduces slot w (8 warps, 8 slots), lanes stride over g, fixed-order shuffle tree
-        const int w8 = tid >> 5, l = tid & 31;
+    for (int u = 0; g < g1; ++g, ++u) t8[u] += (double)a.part_vec[((int64_t)g * 8 + s) * DAD_H + f];
+    s_part[part][tid & 63] = ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
+    __syncthreads();
+    if (tid < 64) a.red_vec[s * DAD_H + f] = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+    if ((blockIdx.x & 3) == 0 && tid >= 64 && tid < 96) {  // scalar partials (one warp of the slot's first CTA)
+        const int l = tid - 64;
         double q = 0.0, w = 0.0;
         int c = 0;
-        for (int g = l; g < G; g += 32) {
-            q += __ldcg(&a.part_sc[((int64_t)g * 8 + w8) * 2 + 0]);
-            w += __ldcg(&a.part_sc[((int64_t)g * 8 + w8) * 2 + 1]);
-            c += __ldcg(&a.part_cnt[g * 8 + w8]);
+        for (int gg = l; gg < G; gg += 32) {
+            q += a.part_sc[((int64_t)gg * 8 + s) * 2 + 0];
+            w += a.part_sc[((int64_t)gg * 8 + s) * 2 + 1];
+            c += a.part_cnt[gg * 8 + s];
         }
         q = warp_sum_d(q); w = warp_sum_d(w);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (l == 0) { s_sq[w8] = q; s_ws[w8] = w; s_cnt[w8] = c; }
+        if (l == 0) { a.red_sc[s * 2 + 0] = q; a.red_sc[s * 2 + 1] = w; a.red_cnt[s] = c; }
     }
+}
+
+// k_ecda_stats (one CTA): class statistics, ordered member lists, row-tile table
+__global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
+    __shared__ double s_red[EP_THREADS / 32];
+    __shared__ int s_cnt[8], s_off[8], s_wc[EP_THREADS / 32][8];
+    __shared__ double s_sq[8], s_ws[8];
+    __shared__ float s_dist[ECDA_MAXC][ECDA_MAXC];
+    const int tid = threadIdx.x;
+    const int Bg = a.pack.B_local * a.pack.world;
+    const int R = 2 * Bg;
+    const bool active = a.nmask[0] > 1;
+
+    // ---------------- phase 2: class statistics
+    EcdaStats* st = a.stats;
+    if (tid == 0) st->active = active ? 1 : 0;
+    if (!active) {
+        if (tid == 0) { st->n_tiles = 0; st->any_feasible = 0; st->rep = 0.f; st->rho = 0.f; }
+        return;
+    }
+    double tv[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) tv[s] = a.red_vec[s * DAD_H + tid];
+    if (tid < 8) { s_sq[tid] = a.red_sc[tid * 2 + 0]; s_ws[tid] = a.red_sc[tid * 2 + 1]; s_cnt[tid] = a.red_cnt[tid]; }
     __syncthreads();
     const int NC = a.class_aware ? ECDA_MAXC : 1;
     float wmean = 0.f;
@@ -616,14 +625,18 @@ int launch_ecda(const EcdaArgs& a, cudaStream_t st) {
         cudaFuncSetAttribute(k_ecda_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ecda_pairs_smem_bytes());
         attr_set = true;
     }
-    const size_t prep_smem = (size_t)2 * a.pack.B_local * a.pack.world;  // row slots, one byte each (last CTA)
-    if (prep_smem > 160 * 1024) return dad_set_error(DAD_ERR_UNSUPPORTED, "ecda: global batch too large for the single-CTA list builder");
-    if (prep_smem > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_ecda_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    const size_t stats_smem = (size_t)2 * a.pack.B_local * a.pack.world;  // row slots, one byte each
+    if (stats_smem > 160 * 1024) return dad_set_error(DAD_ERR_UNSUPPORTED, "ecda: global batch too large for the single-CTA list builder");
+    if (stats_smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_ecda_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "ecda: cannot opt in to shared memory: %s", cudaGetErrorString(e));
     }
-    k_ecda_prep<<<a.prep_grid, EP_THREADS, prep_smem, st>>>(a);
+    k_ecda_prep<<<a.prep_grid, EP_THREADS, 0, st>>>(a);
     DAD_CHECK_LAUNCH("k_ecda_prep");
+    k_ecda_reduce<<<32, EP_THREADS, 0, st>>>(a, a.prep_grid);
+    DAD_CHECK_LAUNCH("k_ecda_reduce");
+    k_ecda_stats<<<1, EP_THREADS, stats_smem, st>>>(a);
+    DAD_CHECK_LAUNCH("k_ecda_stats");
     k_ecda_pairs<<<a.max_tiles * a.col_splits, EP_THREADS, ecda_pairs_smem_bytes(), st>>>(a);
     DAD_CHECK_LAUNCH("k_ecda_pairs");
     k_ecda_fold<<<a.max_tiles, EP_THREADS, 0, st>>>(a);

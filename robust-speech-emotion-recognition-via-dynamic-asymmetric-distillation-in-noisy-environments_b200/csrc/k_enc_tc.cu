@@ -397,7 +397,10 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
             tc::bulk_wait0();
         }
     } else {
-        tc::reg_dec<40>();  // warp 2: same warpgroup as the TMA / MMA / store warps
+        // warp 2 (TMEM allocator).  Negative result kept for the record: bulk L2 prefetch (cp.async.bulk.prefetch.L2) of this
+        // CTA's next x tile from here made the kernel 25 % SLOWER (0.875 -> 1.105 ms at B=4096): the prefetches compete with the
+        // demand loads for the same HBM bandwidth instead of hiding their latency.
+        tc::reg_dec<40>();
     }
     tc::tcgen05_fence_before();
     __syncthreads();

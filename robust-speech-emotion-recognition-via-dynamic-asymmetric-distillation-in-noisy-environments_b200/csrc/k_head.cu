@@ -191,11 +191,19 @@ __global__ void __launch_bounds__(1024) k_dacp(DacpArgs a) {
         // radix SELECT over the 32-bit sortable keys -- 4 passes of 8 bits, 8 targets at once -- instead of a full sort
         // (the bitonic sort of the global batch was ~95 us of a single CTA per step, a fixed cost on every data-parallel rank).
         uint8_t* s_cls = reinterpret_cast<uint8_t*>(keys + Bg);
-        for (int i = tid; i < Bg; i += nt) {
-            const int c = pack_pred(a.pack, i);
-            keys[i] = f2sortable(pack_score(a.pack, i));
-            s_cls[i] = (uint8_t)(c < 0 ? 255 : c);  // 255: null sample
-            if (c >= 0) atomicAdd(&s_cnt[c], 1);
+        for (int i0 = 0; i0 < Bg; i0 += nt) {  // warp-uniform trip count: class counts are merged per warp (ballot) before
+            const int i = i0 + tid;             // touching the 4 shared counters (4096 same-address atomics took ~20 us)
+            int c = -1;
+            if (i < Bg) {
+                c = pack_pred(a.pack, i);
+                keys[i] = f2sortable(pack_score(a.pack, i));
+                s_cls[i] = (uint8_t)(c < 0 ? 255 : c);  // 255: null sample
+            }
+#pragma unroll
+            for (int cc = 0; cc < DAD_C; ++cc) {
+                const unsigned b = __ballot_sync(0xffffffffu, c == cc);
+                if ((tid & 31) == 0 && b) atomicAdd(&s_cnt[cc], __popc(b));
+            }
         }
         __syncthreads();
         if (tid < 2 * DAD_C) {
@@ -285,13 +293,26 @@ __global__ void __launch_bounds__(1024) k_dacp(DacpArgs a) {
     }
     __syncthreads();
     int local = 0;
-    for (int i = tid; i < Bg; i += nt) {
-        const int c = pack_pred(a.pack, i);
-        const float s = pack_score(a.pack, i);
-        const int m = c >= 0 && s >= s_thr[c < 0 ? 0 : c];
-        a.mask[i] = (uint8_t)m;
-        local += m;
-        if (a.use_dacp && c >= 0) atomicAdd(&s_sum[c], (double)s);  // per-class epoch accumulators (utils.py:503-505); sum order-insensitive in fp64 at this scale
+    for (int i0 = 0; i0 < Bg; i0 += nt) {  // warp-uniform trip count
+        const int i = i0 + tid;
+        int c = -1;
+        float s = 0.f;
+        if (i < Bg) {
+            c = pack_pred(a.pack, i);
+            s = pack_score(a.pack, i);
+            const int m = c >= 0 && s >= s_thr[c < 0 ? 0 : c];
+            a.mask[i] = (uint8_t)m;
+            local += m;
+        }
+        if (a.use_dacp) {
+            // per-class epoch accumulators (utils.py:503-505): warp sums first, then one shared fp64 add per warp and class
+            // (fp64 sums of <= 2^24 fp32 scores in [2^-20, 1] are exact, so the order of the adds cannot change the result)
+#pragma unroll
+            for (int cc = 0; cc < DAD_C; ++cc) {
+                const double v = warp_sum_d(c == cc ? (double)s : 0.0);
+                if ((tid & 31) == 0 && v != 0.0) atomicAdd(&s_sum[cc], v);
+            }
+        }
     }
     local = (int)warp_sum((float)local);
     if ((tid & 31) == 0) atomicAdd(&s_nmask, local);
