@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="data-parallel exchange: NVLink peer-memory pushes or NCCL")
     ap.add_argument("--operand-cache", default="strong", choices=["none", "strong", "both"],
                     help="which student forwards write the fp16 hi/lo operand cache that feeds the dW kernels by TMA")
     ap.add_argument("--pretrain-steps", type=int, default=30, help="CE-only steps before the timed region (SURVEY 8d); lower it under ncu")
@@ -55,35 +56,65 @@ def workload(name, world):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs (B200_PROFILING.md)."""
+    """Samples SM clock + throttle reasons of one GPU while the timed region runs (B200_PROFILING.md "clocks line").
+    NVML (nvidia-ml-py) gives a sample every ~5 ms; nvidia-smi is the fallback (one sample per ~100 ms)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.stop_flag = index, False
+        self.sm, self.sm_max, self.reasons, self.source = [], None, set(), "nvidia-smi"
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            c = [t.strip() for t in out.split(",")]
+            if c[0].replace(".", "").isdigit():
+                self.sm.append(float(c[0]))
+            self.sm_max = float(c[1])
+            self.reasons.update(n for i, n in enumerate(self.NAMES) if c[2 + i] == "Active")
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.004 if self.nvml is not None else 0.1)
 
     def summary(self):
         self.stop_flag = True
         self.join(timeout=6)
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == "Active" for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"], "samples": 0, "source": self.source}
+        return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.sm_max,
+                "reasons": [n for n in self.NAMES if n in self.reasons], "samples": len(self.sm), "source": self.source}
 
 
 def measured_peaks():
@@ -184,7 +215,7 @@ def run_ours(args):
     B = Bg // world
     gm = _lib.GEMM_TC if args.gemm == "tc" else _lib.GEMM_FP32
     eng = DADStepEngine(cfg, B, T, device=dev, world=world, rank=rank, process_group=pg, gemm_mode=gm, use_graph=not args.no_graph,
-                        noise_mode="philox", seed=42, operand_cache=args.operand_cache)
+                        noise_mode="philox", seed=42, operand_cache=args.operand_cache, exchange=args.exchange)
     eng.load_state_dict(synth.init_state(42))
     clean, noisy = device_batches(B, T, 1234 + rank, dev)
     eng.set_inputs(clean, noisy)
@@ -311,7 +342,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
             "dtype": "f32 (scaled fp16 hi/lo split, 3 tcgen05 products per GEMM, fp32 accumulate)" if args.gemm == "tc" else "f32", "data": "synthetic",
             "config": {"workload": wl["label"], "global_batch": Bg, "per_gpu_batch": B, "T": T, "parallelism": f"dp{world}",
-                       "noise": "in-kernel Philox", "cuda_graph": not args.no_graph, "operand_cache": eng.operand_cache,
+                       "noise": "in-kernel Philox", "cuda_graph": not args.no_graph, "operand_cache": eng.operand_cache, "exchange": eng.exchange,
                        "l2": "inputs >> L2 (126 MB)" if not small else "L2 flushed (256 MB write) between individually timed steps"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "losses_last_step": losses,

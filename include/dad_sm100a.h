@@ -29,6 +29,7 @@ extern "C" {
 #define DAD_D 768
 #define DAD_H 256
 #define DAD_C 4
+#define DAD_MAX_WORLD 16  /* ranks of one NVLink domain served by the peer-memory exchange */
 #define DAD_NPARAM 197892 /* flat parameter buffer: [W 256x768 | b 256 | Wc 4x256 | bc 4] */
 
 /* GEMM arithmetic of the encoder kernels */
@@ -36,6 +37,7 @@ extern "C" {
 #define DAD_GEMM_TC_F16X3 1  /* tcgen05 (5th-gen tensor core, TMEM accumulators): power-of-two scaled fp16 hi/lo split, 3 products, fp32 accumulate */
 
 int dad_abi_version(void);
+int dad_max_world(void); /* DAD_MAX_WORLD */
 const char* dad_last_error(void);
 /* 0 when the current CUDA device is compute capability 10.x, else an error */
 int dad_device_check(void);
@@ -181,6 +183,21 @@ typedef struct dad_scl_args {
 } dad_scl_args;
 size_t dad_scl_workspace_bytes(int32_t B_local, int32_t world);
 int dad_scl(const dad_scl_args* a, void* stream);
+
+/* ---- data-parallel exchange over NVLink peer memory (replaces the NCCL all-gather / all-reduce of the step) ----
+ * Every rank owns one symmetric, peer-mapped exchange buffer with the same layout; `peers[r]` (HOST array of `world` device
+ * pointers) is rank r's buffer as mapped into this process (e.g. torch symmetric-memory buffer_ptrs).  All three ops are
+ * stream-ordered, never synchronise the host and are CUDA-graph capturable.
+ *   dad_peer_push     copy `bytes` (multiple of 4) from `src_local` to offset `dst_offset` of every peer's buffer
+ *                     (own buffer too when include_self)
+ *   dad_peer_barrier  all ranks' earlier pushes are complete and visible; `flag_offset` = byte offset of a zero-initialised
+ *                     array of `world` u32 inside the exchange buffer, `local_seq` = zero-initialised device counter private to
+ *                     this rank.  Every rank must call its barriers in the same order.
+ *   dad_grad_sum_ranks  out[e] = sum over r = 0..world-1 of stage[r][e]  (fixed order: identical result on every rank) */
+int dad_peer_push(const void* src_local, void* const* peers, int32_t world, int32_t self_rank, int32_t include_self,
+                  size_t dst_offset, size_t bytes, void* stream);
+int dad_peer_barrier(void* const* peers, int32_t world, int32_t rank, size_t flag_offset, uint32_t* local_seq, void* stream);
+int dad_grad_sum_ranks(const float* stage, int32_t world, int64_t n, float* out, void* stream);
 
 /* ---- optimiser tail (I/train.py:487-492; I/model.py:211-223) --------------------------------------------------- */
 /* g[DAD_NPARAM] = fixed-order sum of the encoder split-K partials (up to two backward launches) ++ head grads */

@@ -35,6 +35,9 @@ int ecda_max_tiles(int B_local);
 int ecda_col_splits(int B_local);
 int launch_ecda(const EcdaArgs& a, cudaStream_t st);
 int launch_scl(const SclArgs& a, cudaStream_t st);
+int launch_peer_push(const void* src, void* const* peers, int world, int self_rank, int include_self, size_t dst_off, size_t bytes, cudaStream_t st);
+int launch_peer_barrier(void* const* peers, int world, int rank, size_t flag_off, unsigned* local_seq, cudaStream_t st);
+int launch_grad_sum_ranks(const float* stage, int world, int64_t n, float* out, cudaStream_t st);
 int launch_grad_reduce(const GradReduceArgs& a, cudaStream_t st);
 int launch_grad_norm(const NormArgs& a, cudaStream_t st);
 int launch_adam_ema(const AdamArgs& a, cudaStream_t st);
@@ -68,6 +71,7 @@ static int check_aug(const dad_aug* a, bool need) {
 extern "C" {
 
 int dad_abi_version(void) { return DAD_ABI_VERSION; }
+int dad_max_world(void) { return DAD_MAX_WORLD; }
 const char* dad_last_error(void) { return g_err; }
 
 int dad_device_check(void) {
@@ -212,6 +216,34 @@ int dad_head_bwd(const dad_head_bwd_args* a, void* stream) {
     DAD_REQUIRE(!a->noisy || (a->probs && a->logq && a->mask && a->nmask && a->g_strong), "head_bwd: noisy path needs probs/logq/mask");
     DAD_REQUIRE(a->n_ce_part == head_grid(a->B_local), "head_bwd: n_ce_part must equal dad_head_grid(B_local)");
     return launch_head_bwd(*a, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- peer-memory exchange
+static int check_peers(void* const* peers, int32_t world, const char* who) {
+    DAD_REQUIRE(peers && world >= 1 && world <= DAD_MAX_WORLD, "%s: world must be in [1, %d]", who, DAD_MAX_WORLD);
+    for (int r = 0; r < world; ++r) DAD_REQUIRE(peers[r] && aligned16(peers[r]), "%s: peers[%d] null or unaligned", who, r);
+    return DAD_OK;
+}
+int dad_peer_push(const void* src_local, void* const* peers, int32_t world, int32_t self_rank, int32_t include_self, size_t dst_offset,
+                  size_t bytes, void* stream) {
+    int rc = check_peers(peers, world, "peer_push");
+    if (rc) return rc;
+    DAD_REQUIRE(src_local && (reinterpret_cast<uintptr_t>(src_local) & 3) == 0 && (dst_offset & 3) == 0 && (bytes & 3) == 0,
+                "peer_push: src / offset / bytes must be multiples of 4 (16-byte alignment enables the vector path)");
+    DAD_REQUIRE(self_rank >= 0 && self_rank < world, "peer_push: bad rank");
+    if (bytes == 0) return DAD_OK;
+    return launch_peer_push(src_local, peers, world, self_rank, include_self, dst_offset, bytes, (cudaStream_t)stream);
+}
+int dad_peer_barrier(void* const* peers, int32_t world, int32_t rank, size_t flag_offset, uint32_t* local_seq, void* stream) {
+    int rc = check_peers(peers, world, "peer_barrier");
+    if (rc) return rc;
+    DAD_REQUIRE(rank >= 0 && rank < world && local_seq && (flag_offset & 3) == 0, "peer_barrier: bad rank / counter / offset");
+    return launch_peer_barrier(peers, world, rank, flag_offset, local_seq, (cudaStream_t)stream);
+}
+int dad_grad_sum_ranks(const float* stage, int32_t world, int64_t n, float* out, void* stream) {
+    DAD_REQUIRE(stage && out && world >= 1 && n >= 0, "grad_sum_ranks: bad arguments");
+    if (n == 0) return DAD_OK;
+    return launch_grad_sum_ranks(stage, world, n, out, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------- SCL

@@ -566,17 +566,16 @@ __global__ void __launch_bounds__(EP_THREADS, 1) k_ecda_pairs(EcdaArgs a) {
 __global__ void __launch_bounds__(EP_THREADS) k_ecda_fold(EcdaArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const EcdaStats* st = a.stats;
-    const int tile_id = blockIdx.x;
-    if (tile_id >= st->n_tiles) return;
+    const int tile_id = blockIdx.x;  // blockIdx.y = which 8 rows of the tile (one row per warp: Q dependent loads per row,
+    if (tile_id >= st->n_tiles) return;  // so the fold is latency-bound and wants many independent rows in flight)
     const int Bg = a.pack.B_local * a.pack.world, Q = a.col_splits;
     const EcdaTile t = a.tiles[tile_id];
     const int c = t.cls;
     const int dom_i = (t.row_begin - st->list_off[c]) >= st->n_s[c] ? 1 : 0;
     const float comp_k = (t.feasible && dom_i) ? a.w_ecda * st->att[c] * a.gamma_comp * 2.f / (float)st->n_t[c] : 0.f;
-#pragma unroll 1
-    for (int r = 0; r < 8; ++r) {
-        const int row = warp * 8 + r;
-        if (row >= t.row_count) continue;
+    {
+        const int row = blockIdx.y * 8 + warp;
+        if (row >= t.row_count) return;
         const int rid = a.lists[t.row_begin + row];
         float g8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float rp = 0.f;
@@ -612,10 +611,11 @@ int ecda_prep_grid(int B_global) {
     return g < 1 ? 1 : g;
 }
 int ecda_max_tiles(int B_local) { return ceil_div(2 * B_local, ECDA_TR) + 2 * ECDA_MAXC; }
-// column splits per row tile: ~2 CTAs per SM over the whole grid, at most 16 (a class of the global batch has ~Bg/2 members)
+// column splits per row tile: the kernel runs one CTA per SM (152 KB of shared memory), so the grid should be ONE wave:
+// Q = floor(148 / row tiles this rank can own), at most 16.  (Q = 13 over 24 tiles = 2.1 waves cost 2x at 1/8 of the rows.)
 int ecda_col_splits(int B_local) {
-    const int tiles = ecda_max_tiles(B_local);
-    int q = ceil_div(2 * 148, tiles);
+    const int tiles = ceil_div(2 * B_local, ECDA_TR);
+    int q = 148 / (tiles < 1 ? 1 : tiles);
     return q < 1 ? 1 : (q > 16 ? 16 : q);
 }
 
@@ -639,7 +639,7 @@ int launch_ecda(const EcdaArgs& a, cudaStream_t st) {
     DAD_CHECK_LAUNCH("k_ecda_stats");
     k_ecda_pairs<<<a.max_tiles * a.col_splits, EP_THREADS, ecda_pairs_smem_bytes(), st>>>(a);
     DAD_CHECK_LAUNCH("k_ecda_pairs");
-    k_ecda_fold<<<a.max_tiles, EP_THREADS, 0, st>>>(a);
+    k_ecda_fold<<<dim3(a.max_tiles, ECDA_TR / 8), EP_THREADS, 0, st>>>(a);
     DAD_CHECK_LAUNCH("k_ecda_fold");
     return DAD_OK;
 }

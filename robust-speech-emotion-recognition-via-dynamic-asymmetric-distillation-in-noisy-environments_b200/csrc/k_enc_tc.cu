@@ -638,13 +638,20 @@ __global__ void __launch_bounds__(DB_WARPS * 32) k_bwd_db(const uint32_t* __rest
 #pragma unroll
     for (int k = 0; k < 16; ++k) c[k] = 0u;
     const int64_t n0 = (int64_t)b * T;
-#pragma unroll 2
-    for (int t = q; t < T; t += 4) {
-        const int64_t n = n0 + t;
-        uint32_t word = __ldg(bits + n * DAD_HW + w);  // a warp reads 4 frames x 32 B = 128 contiguous bytes
-        if (pad && pad[n]) word = 0u;
+    // 8 independent loads in flight per lane (one utterance = T/4 frames per lane: a plain loop was one L2 latency per frame)
+    for (int t0 = q; t0 < T; t0 += 32) {
+        uint32_t wd[8];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) c[k] += (word >> k) & 0x00010001u;
+        for (int u = 0; u < 8; ++u) {
+            const int t = t0 + 4 * u;
+            const int64_t n = n0 + t;
+            wd[u] = t < T ? __ldg(bits + n * DAD_HW + w) : 0u;  // a warp reads 4 frames x 32 B = 128 contiguous bytes
+            if (pad && t < T && pad[n]) wd[u] = 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) c[k] += (wd[u] >> k) & 0x00010001u;
     }
 #pragma unroll
     for (int k = 0; k < 16; ++k) {

@@ -90,7 +90,7 @@ class StepScalars:
 
 class DADStepEngine:
     def __init__(self, cfg, B_local, T, device=None, dataset="iemocap", world=1, rank=0, process_group=None, gemm_mode=None,
-                 use_graph=True, seed=42, noise_mode="philox", operand_cache="strong"):
+                 use_graph=True, seed=42, noise_mode="philox", operand_cache="strong", exchange="auto"):
         _lib.require_device()
         self.cfg, self.dataset = cfg, dataset
         self.Bcap, self.Tcap = int(B_local), int(T)
@@ -141,6 +141,24 @@ class DADStepEngine:
             self._nw, self._ns = z(B * T * D_IN), z(B * T * D_IN)
         # ---- activations / exchange
         self._pack = z(self.world * _lib.pack_rank_words(B))
+        # data-parallel exchange: "p2p" = pushes over NVLink peer memory + flag barriers (csrc/k_peer.cu), "nccl" = all_gather +
+        # all_reduce; "auto" tries p2p (torch symmetric memory provides the peer mappings) and falls back to NCCL with a warning
+        self.exchange = "none"
+        if self.world > 1:
+            if B % 4:
+                raise DadError("data parallelism needs a per-rank batch that is a multiple of 4 (16-byte aligned pack segments)")
+            self.exchange = "nccl"
+            if exchange in ("auto", "p2p"):
+                try:
+                    self._setup_peer_exchange()
+                    self.exchange = "p2p"
+                except Exception as e:  # noqa: BLE001
+                    if exchange == "p2p":
+                        raise
+                    import warnings
+                    warnings.warn(f"peer-memory exchange unavailable ({e}); using NCCL collectives")
+            elif exchange != "nccl":
+                raise DadError("exchange must be 'auto', 'p2p' or 'nccl'")
         self._emb_t = z(B * D_HID)
         self._bits_c = torch.zeros(B * T * (D_HID // 32), dtype=torch.int32, device=dev)
         self._bits_s = torch.zeros(B * T * (D_HID // 32), dtype=torch.int32, device=dev)
@@ -172,6 +190,41 @@ class DADStepEngine:
         self.max_graphs = 64
         self._scalars = None
         self.launches_per_step = 0
+
+    FLAG_WORDS = 64
+
+    def _setup_peer_exchange(self):
+        """One symmetric buffer per rank: [flags 64 u32 | pack world*rw f32 | grad stage world*(NPARAM+8) f32] (k_peer.cu)."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        if self.world > lib().dad_max_world():
+            raise DadError("world size beyond DAD_MAX_WORLD")
+        n_pack = self.world * _lib.pack_rank_words(self.Bcap)
+        n_pack_al = (n_pack + 3) // 4 * 4
+        total = self.FLAG_WORDS + n_pack_al + self.world * (NPARAM + 8)
+        group = self.pg if self.pg is not None else dist.group.WORLD
+        try:  # needed by older torch releases, a deprecated no-op in newer ones
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:  # noqa: BLE001
+            pass
+        sym = symm.empty(total, dtype=torch.float32, device=self.dev)
+        sym.zero_()
+        hdl = symm.rendezvous(sym, group)
+        self._sym, self._sym_hdl = sym, hdl
+        self._peer_ptrs = (C.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+        self._pack = sym[self.FLAG_WORDS:self.FLAG_WORDS + n_pack]
+        self._stage = sym[self.FLAG_WORDS + n_pack_al:]
+        self._pack_off, self._stage_off = self.FLAG_WORDS * 4, (self.FLAG_WORDS + n_pack_al) * 4
+        self._peer_seq = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=self.pg)  # every rank has zeroed its flags before anyone signals
+
+    def _peer_barrier(self, s):
+        check(lib().dad_peer_barrier(self._peer_ptrs, self.world, self.rank, 0, self._peer_seq.data_ptr(), s))
+        self.launches_per_step += 1
 
     # ------------------------------------------------------------------ shape and views
     def set_shape(self, B=None, T_clean=None, T_noisy=None, n_clean=None, n_noisy=None, n_clean_global=None):
@@ -406,7 +459,14 @@ class DADStepEngine:
         hf.n_clean, hf.n_noisy = self.n_clean, self.n_noisy
         check(L.dad_head_fwd(C.byref(hf), s))
         self.launches_per_step += 1
-        if self.world > 1:
+        if self.exchange == "p2p":
+            # pack all-gather: push this rank's segment into every peer's pack, then the flag barrier
+            rwb = self._rw * 4
+            check(L.dad_peer_push(self.pack.data_ptr() + self.rank * rwb, self._peer_ptrs, self.world, self.rank, 0,
+                                  self._pack_off + self.rank * rwb, rwb, s))
+            self.launches_per_step += 1
+            self._peer_barrier(s)
+        elif self.world > 1:
             import torch.distributed as dist
             dist.all_gather_into_tensor(self.pack, self.pack[self.rank * self._rw:(self.rank + 1) * self._rw], group=self.pg)
         if noisy:
@@ -464,7 +524,15 @@ class DADStepEngine:
                                 self._dWp[1].data_ptr() if noisy else None, self._dbp[1].data_ptr() if noisy else None, S1,
                                 hb.dWc, hb.dbc, self.g_ext.data_ptr(), s))
         self.launches_per_step += 1
-        if self.world > 1:
+        if self.exchange == "p2p":
+            # gradient all-reduce: push the local gradient (+ loss shares) into slot [rank] of every rank's stage, barrier,
+            # then every rank sums the slots in rank order (identical bits everywhere)
+            nb = (NPARAM + 8) * 4
+            check(L.dad_peer_push(self.g_ext.data_ptr(), self._peer_ptrs, self.world, self.rank, 1, self._stage_off + self.rank * nb, nb, s))
+            self._peer_barrier(s)
+            check(L.dad_grad_sum_ranks(self._stage.data_ptr(), self.world, NPARAM + 8, self.g_ext.data_ptr(), s))
+            self.launches_per_step += 2
+        elif self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.g_ext, group=self.pg)
         # ---- clip + Adam + EMA (I/train.py:487-492)

@@ -178,7 +178,8 @@ def run_gpu(args):
     cfg = cfg_for("iemocap")
     gm = _lib.GEMM_TC if args.gemm == "tc" else _lib.GEMM_FP32
     dp = DADStepEngine(cfg, B, T, device=dev, world=world, rank=rank, process_group=dist.group.WORLD, gemm_mode=gm,
-                       use_graph=args.graph, noise_mode="supplied")
+                       use_graph=args.graph, noise_mode="supplied", exchange=args.exchange)
+    assert dp.exchange == args.exchange, (dp.exchange, args.exchange)
     one = DADStepEngine(cfg, Bg, T, device=dev, gemm_mode=gm, use_graph=False, noise_mode="supplied")
     st = pretrained_state()
     dp.load_state_dict(st); one.load_state_dict(st)
@@ -219,7 +220,7 @@ def run_gpu(args):
     assert torch.equal(flat, ref0), (rank, "replicated state diverged across ranks")
     torch.cuda.synchronize()
     if rank == 0:
-        print(f"DP_GPU_OK world={world} gemm={args.gemm} graph={args.graph} steps={steps} worst loss rel={worst['loss']:.2e} w={worst['w']:.2e}", flush=True)
+        print(f"DP_GPU_OK world={world} gemm={args.gemm} graph={args.graph} exchange={dp.exchange} steps={steps} worst loss rel={worst['loss']:.2e} w={worst['w']:.2e}", flush=True)
     dp.close(); one.close()
     DADStepEngine.shutdown_process_group()
 
@@ -232,5 +233,6 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--gemm", default="fp32")
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"])
     a = ap.parse_args()
     run_cpu(a) if a.mode == "cpu" else run_gpu(a)

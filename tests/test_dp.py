@@ -50,9 +50,10 @@ def test_dp_protocol_world2_gloo():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("gemm,graph", [("fp32", False), ("tc", True)])
-def test_dp_engine_world2_nccl(gemm, graph):
+@pytest.mark.parametrize("gemm,graph,exchange", [("fp32", False, "nccl"), ("tc", True, "nccl"), ("fp32", False, "p2p"), ("tc", True, "p2p")])
+def test_dp_engine_world2(gemm, graph, exchange):
+    """world 2 == world 1 on the global batch, with the NCCL collectives and with the NVLink peer-memory exchange (k_peer.cu)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    r = _torchrun(2, ["--mode", "gpu", "--B", "8", "--T", "40", "--steps", "5", "--gemm", gemm] + (["--graph"] if graph else []))
+    r = _torchrun(2, ["--mode", "gpu", "--B", "8", "--T", "40", "--steps", "5", "--gemm", gemm, "--exchange", exchange] + (["--graph"] if graph else []))
     assert r.returncode == 0 and "DP_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
