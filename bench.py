@@ -65,7 +65,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag = index, False
-        self.sm, self.sm_max, self.reasons, self.source = [], None, set(), "nvidia-smi"
+        self.sm, self.sm_max, self.reasons, self.source, self.mask = [], None, set(), "nvidia-smi", 0
         self.nvml = None
         try:
             import pynvml
@@ -83,6 +83,7 @@ class ClockSampler(threading.Thread):
         self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
         r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
             else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        self.mask |= int(r)
         for name, bit in (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4)):
             if r & bit:
                 self.reasons.add(name)
@@ -114,7 +115,8 @@ class ClockSampler(threading.Thread):
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"], "samples": 0, "source": self.source}
         return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.sm_max,
-                "reasons": [n for n in self.NAMES if n in self.reasons], "samples": len(self.sm), "source": self.source}
+                "reasons": [n for n in self.NAMES if n in self.reasons], "samples": len(self.sm), "source": self.source,
+                "nvml_reasons_mask": hex(self.mask)}
 
 
 def measured_peaks():
@@ -352,8 +354,26 @@ def run_ours(args):
         DADStepEngine.shutdown_process_group()
 
 
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner from C) write to fd 1, so fd 1 is pointed at
+    stderr for the rest of the process and the JSON goes to a private duplicate of the original stdout."""
+    global print
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(keep, "w")
+    import builtins
+
+    def _print(*args, **kw):
+        kw.setdefault("file", out)
+        builtins.print(*args, **kw)
+        kw["file"].flush()
+    print = _print
+
+
 if __name__ == "__main__":
     a = parse()
+    _claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
