@@ -87,3 +87,45 @@ def test_cli_fold_argument(monkeypatch, tmp_path):
     _patch(monkeypatch, cfg, {"EPOCHS": 3})
     res = train.main(["--fold", "2", "--synthetic", "--epochs", "3"])
     assert res is not None and os.path.basename(res["results_dir"]) == "fold_2"
+
+
+@pytest.mark.parametrize("snr_db", [0.0, 5.0, 10.0, 20.0])
+def test_casia_fold_sweep_step_parity(snr_db):
+    """BASELINE configs[2]: CASIA 4-fold sweep x SNR {0,5,10,20} dB.  For every fold the first (clean, noisy) training batch pair of
+    the CASIA data layer goes through one full-stack step of the engine (supplied noise) and of the oracle: losses, mask and
+    updated weights agree at the north-star tolerances for every fold / SNR (CASIA cfg with DACP + ECDA switched on, and the
+    default fixed-threshold configuration on fold 0)."""
+    from dad_b200 import _lib, dataload, synth
+    from dad_b200.engine import DADStepEngine
+    from helpers import make_oracle, oracle_step_adopting_ties, push_oracle_state
+    from oracle import dad_oracle as O
+    names = [f"spk_{i}" for i in range(4)]
+    fs_c, fs_n = dataload.synthetic_feature_sets(4, 24, t_min=40, t_max=64, snr_db=snr_db, seed=int(snr_db) + 3, group_names=names)
+    ld = {"angry": 0, "happy": 1, "neutral": 2, "sad": 3}
+    for fold in range(4):
+        for over in ({"USE_DACP": True, "USE_ECDA": True},) + (({},) if fold == 0 else ()):
+            orc, cfg, hp = make_oracle("casia", over)
+            tr, _, _, _, _ = dataload.create_speaker_isolated_loaders(None, 16, fold, ld, noisy=False, feature_set=fs_c)
+            st, _, _, _ = dataload.create_speaker_isolated_loaders(None, 16, fold, ld, noisy=True, feature_set=fs_n)
+            c, n = next(iter(tr)), next(iter(st))
+            Bc, Tc = c["net_input"]["feats"].shape[:2]
+            Bn, Tn = n["net_input"]["feats"].shape[:2]
+            rc, rn = synth.make_rng_inputs(Bc, Tc, 31 + fold), synth.make_rng_inputs(Bn, Tn, 47 + fold)
+            rng = {"drop_clean": rc["drop_clean"], "n_weak": rn["n_weak"], "n_strong": rn["n_strong"], "feat_keep_u": rn["feat_keep_u"],
+                   "t_start": rn["t_start"], "drop_strong": rn["drop_strong"]}
+            eng = DADStepEngine(cfg, 16, 64, dataset="casia", gemm_mode=_lib.GEMM_TC, use_graph=False, noise_mode="supplied")
+            epoch = 45
+            orc.lr = O.cosine_lr(hp.LEARNING_RATE, epoch, hp.EPOCHS)
+            push_oracle_state(eng, orc)
+            dev = lambda b: {"net_input": {k: v.cuda() for k, v in b["net_input"].items()}, "labels": (b["labels"] if b.get("labels") is not None else torch.zeros(0)).cuda()}
+            nb = {"net_input": {k: v.cuda() for k, v in n["net_input"].items()}}
+            eng.set_inputs(dev(c), nb, {k: v.cuda() for k, v in rng.items()})
+            eng.step(epoch)
+            ref, _ = oracle_step_adopting_ties(orc, eng, c, n, epoch, rng, "tc")
+            got = eng.losses()
+            for key in ("total_loss", "supervised_ce_loss", "consistency_loss", "ecda_loss"):
+                assert abs(got[key] - ref[key]) <= 1e-4 * max(abs(ref[key]), 1e-3), (snr_db, fold, over, key, got[key], ref[key])
+            assert torch.equal(eng.mask.cpu().bool()[:Bn], orc.last["mask"])
+            g_orc = torch.cat([orc.p[k].grad.reshape(-1) for k in O.PARAM_KEYS])
+            p_orc = torch.cat([orc.p[k].detach().reshape(-1) for k in O.PARAM_KEYS])
+            assert float((eng.p.cpu() - p_orc).abs()[g_orc.abs() >= 1e-6].max()) <= 1e-5, (snr_db, fold, over)

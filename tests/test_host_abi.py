@@ -1,0 +1,96 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dad_sm100a.h declares, the host-side schedule / config mirror
+matches the reference, and nothing falls back to the CPU."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+import dad_b200  # noqa: F401
+from dad_b200 import _lib, config, config_casia, config_emodb
+from dad_b200.engine import StepScalars
+from helpers import GOLDEN, cfg_for
+from oracle import dad_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "dad_sm100a.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(?:int|size_t|int32_t|int64_t|const char\*)\s+(dad_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared()
+    assert len(names) >= 25 and "dad_encoder_fwd" in names and "dad_peer_push" in names
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert set(_lib.EXPORTS) <= set(names), sorted(set(_lib.EXPORTS) - set(names))
+    assert _lib.lib().dad_abi_version() == 2 and _lib.lib().dad_max_world() == 16
+    assert _lib.lib().dad_pack_rank_words(7) == 7 * (2 * 256 + 3)
+
+
+def test_no_cpu_fallback():
+    from dad_b200 import ops
+    from dad_b200.engine import DADStepEngine
+    if torch.cuda.is_available():
+        pytest.skip("this check is about hosts without a GPU")
+    with pytest.raises(_lib.DadError):
+        ops.encoder_pool_fwd(torch.zeros(2, 4, 768), None, torch.zeros(256, 768), torch.zeros(256))
+    with pytest.raises(_lib.DadError):
+        ops.augment(torch.zeros(2, 4, 768), 0.01, seed=1)
+    with pytest.raises(_lib.DadError):
+        DADStepEngine(config, 4, 32)
+    from dad_b200.train import IEMOCAPCrossDomainTrainer
+    with pytest.raises(_lib.DadError):
+        IEMOCAPCrossDomainTrainer(fold=0, loaders=lambda bs: None, require_pretrained=False)
+
+
+@pytest.mark.parametrize("dataset", ["iemocap", "casia", "emodb"])
+def test_step_scalars_follow_the_reference_schedule(dataset):
+    cfg = cfg_for(dataset)
+    hp = O.HParams.from_cfg(cfg)
+    for epoch in (0, 5, 29, 30, 31, 45, 60, 90, 499):
+        sc = StepScalars(cfg, epoch, dataset)
+        w_kd, w_ecda = O.loss_weights(epoch, hp)  # I/train.py:380-395
+        assert sc.warmup == (epoch < cfg.WARMUP_EPOCHS) and sc.w_kd == w_kd and sc.w_ecda == w_ecda
+        g = cfg.DACP_QUANTILE_START + (cfg.DACP_QUANTILE_END - cfg.DACP_QUANTILE_START) * (epoch / cfg.EPOCHS)
+        assert abs(sc.gamma - g) < 1e-7 and sc.w_scl == 0.0
+    sc = StepScalars(cfg, 60, dataset)
+    if dataset == "emodb":   # E/train_emodb.py:418-437 has no USE_DACP / USE_ECDA switches
+        assert sc.use_dacp and sc.use_ecda
+    elif dataset == "casia":  # C/config_casia.py defaults
+        assert not sc.use_dacp and not sc.use_ecda
+    else:
+        assert sc.use_dacp and sc.use_ecda and sc.use_entropy and sc.class_aware
+    over = cfg_for(dataset, {"USE_ENTROPY_IN_SCORE": False, "USE_CLASS_AWARE_MMD": False, "USE_DACP": True})
+    sc = StepScalars(over, 60, dataset)  # only I/utils.py honours these two switches
+    assert sc.use_entropy == (dataset != "iemocap") and sc.class_aware == (dataset != "iemocap")
+
+
+def test_config_modules_keep_the_reference_field_names_and_values():
+    golden = json.load(open(os.path.join(GOLDEN, "config_fields.json")))
+    for tag, mod in (("iemocap", config), ("casia", config_casia), ("emodb", config_emodb)):
+        for name, want in golden[tag].items():
+            assert hasattr(mod, name), (tag, name)
+            if want != "<non-scalar or path>" and name not in ("DEVICE",):
+                got = getattr(mod, name)
+                assert got == want, (tag, name, got, want)
+        for fn in ("validate_config", "print_config", "setup_environment"):
+            assert callable(getattr(mod, fn))
+
+
+def test_runner_style_override_is_seen_live():
+    """The ablation runners setattr on the config module after import (I/run_granular_ablations.py:25-44): the step reads live."""
+    old = config.USE_ECDA
+    try:
+        config.USE_ECDA = False
+        assert not StepScalars(config, 60, "iemocap").use_ecda
+        config.USE_ECDA = True
+        assert StepScalars(config, 60, "iemocap").use_ecda
+    finally:
+        config.USE_ECDA = old

@@ -32,7 +32,7 @@ for kn in kernels:
     except StopIteration:
         continue
     hd = rws[h]; ix = {k: i for i, k in enumerate(hd)}
-    data = [r for r in rws[h + 1:] if len(r) == len(hd)]
+    data = [r for r in rws[h + 1:] if len(r) == len(hd) and r[0].startswith("0x")]  # several launches: headers repeat
     stalls = [k for k in hd if k.startswith("stall_") and "Not Issued" not in k]
     tot = sum(int(r[ix["# Samples"]]) for r in data)
     ex = sum(int(r[ix["Instructions Executed"]]) for r in data)
