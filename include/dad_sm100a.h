@@ -66,6 +66,12 @@ int dad_step_rng(uint64_t seed, const int64_t* step_ptr, float* keep_clean, floa
 /* replaces DataAugmentation.weak_augment / strong_augment (I/utils.py:328-375): out[B,T,D] = aug(x) */
 int dad_augment(const float* x, float* out, const dad_aug* aug, int64_t B, int64_t T, void* stream);
 
+/* device-side batch assembly: the reference collator (I/dataload_clean.py:177-193) over a split whose
+ * features stay resident in HBM.  feats [sum T, D] f32; offsets [B] i64 (first row of each utterance), sizes [B] i32 (frames);
+ * out: x [B,T,D] zero-padded, pad [B,T] uint8 (1 = padded frame; nullable).  T >= max(sizes). */
+int dad_gather_pad(const float* feats, const int64_t* offsets, const int32_t* sizes, float* x, uint8_t* pad, int64_t B,
+                   int64_t T, void* stream);
+
 /* ---- encoder (I/model.py:18-41 Emotion2VecEncoder.forward) and its autograd backward ------------------------- */
 size_t dad_encoder_fwd_workspace_bytes(int64_t B, int64_t T, int32_t gemm_mode);
 /* emb[B,H] = masked-mean_t relu(W aug(x)[b,t,:] + bias).  pad: [B,T] uint8, 1 = padded frame, NULL = none.

@@ -37,6 +37,7 @@ _COMMON = dict(
     PRINT_MODEL_INFO=True, DEBUG_MODE=False, VERBOSE_LOGGING=True,
     # B200 additions (not in the reference): kernel arithmetic + noise source of the fused step
     DAD_GEMM_MODE=os.environ.get("DAD_GEMM", "tc"), DAD_USE_CUDA_GRAPH=True,
+    DAD_DEVICE_DATA=True,  # keep each split's features resident in HBM and assemble batches on the device (dataload.DeviceUtteranceLoader)
 )
 
 

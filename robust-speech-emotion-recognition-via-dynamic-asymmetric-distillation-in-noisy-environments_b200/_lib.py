@@ -21,7 +21,7 @@ EXPORTS = (
     "dad_pack_rank_words", "dad_head_grid", "dad_head_fwd", "dad_dacp_mask", "dad_head_bwd",
     "dad_ecda_workspace_bytes", "dad_ecda", "dad_grad_reduce", "dad_grad_norm", "dad_adam_ema", "dad_ema",
     "dad_split_f16", "dad_step_rng", "dad_certainty_scores", "dad_scl_workspace_bytes", "dad_scl",
-    "dad_peer_push", "dad_peer_barrier", "dad_grad_sum_ranks", "dad_max_world",
+    "dad_peer_push", "dad_peer_barrier", "dad_grad_sum_ranks", "dad_max_world", "dad_gather_pad",
 )
 
 
@@ -114,6 +114,7 @@ def lib():
     L.dad_peer_push.argtypes = [vp, C.POINTER(vp), i32, i32, i32, C.c_size_t, C.c_size_t, vp]
     L.dad_peer_barrier.argtypes = [C.POINTER(vp), i32, i32, C.c_size_t, vp, vp]
     L.dad_grad_sum_ranks.argtypes = [vp, i32, i64, vp, vp]
+    L.dad_gather_pad.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp]
     L.dad_grad_reduce.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp, vp]
     L.dad_grad_norm.argtypes = [vp, vp, vp, vp, vp, vp, f32, vp]
     L.dad_adam_ema.argtypes = [vp, vp, vp, vp, vp, vp, f32, f32, f32, i32, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, vp]

@@ -35,6 +35,8 @@ int ecda_max_tiles(int B_local);
 int ecda_col_splits(int B_local);
 int launch_ecda(const EcdaArgs& a, cudaStream_t st);
 int launch_scl(const SclArgs& a, cudaStream_t st);
+int launch_gather_pad(const float* feats, const int64_t* offsets, const int32_t* sizes, float* x, uint8_t* pad, int64_t B, int64_t T, int64_t D,
+                      cudaStream_t st);
 int launch_peer_push(const void* src, void* const* peers, int world, int self_rank, int include_self, size_t dst_off, size_t bytes, cudaStream_t st);
 int launch_peer_barrier(void* const* peers, int world, int rank, size_t flag_off, unsigned* local_seq, cudaStream_t st);
 int launch_grad_sum_ranks(const float* stage, int world, int64_t n, float* out, cudaStream_t st);
@@ -216,6 +218,13 @@ int dad_head_bwd(const dad_head_bwd_args* a, void* stream) {
     DAD_REQUIRE(!a->noisy || (a->probs && a->logq && a->mask && a->nmask && a->g_strong), "head_bwd: noisy path needs probs/logq/mask");
     DAD_REQUIRE(a->n_ce_part == head_grid(a->B_local), "head_bwd: n_ce_part must equal dad_head_grid(B_local)");
     return launch_head_bwd(*a, (cudaStream_t)stream);
+}
+
+int dad_gather_pad(const float* feats, const int64_t* offsets, const int32_t* sizes, float* x, uint8_t* pad, int64_t B, int64_t T, void* stream) {
+    DAD_REQUIRE(B >= 0 && T >= 0, "gather_pad: negative size");
+    if (B == 0 || T == 0) return DAD_OK;
+    DAD_REQUIRE(feats && aligned16(feats) && offsets && sizes && x && aligned16(x), "gather_pad: null/unaligned pointer");
+    return launch_gather_pad(feats, offsets, sizes, x, pad, B, T, DAD_D, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------- peer-memory exchange

@@ -46,6 +46,35 @@ int launch_augment(const float* x, float* out, const AugParams& ap, int64_t B, i
     return DAD_OK;
 }
 
+// Device-side batch assembly (the reference's collator, I/dataload_clean.py:177-193, as one HBM-bound pass):
+// utterance b of the batch = rows [offsets[b], offsets[b] + sizes[b]) of the split's resident [sum T, D] feature array; the output is
+// the zero-padded [B, T, D] batch and its padding mask (1 = pad).  One float4 per thread, grid-stride, fully coalesced.
+__global__ void __launch_bounds__(256) k_gather_pad(const float* __restrict__ feats, const int64_t* __restrict__ offsets, const int32_t* __restrict__ sizes,
+                                                    float* __restrict__ x, uint8_t* __restrict__ pad, int64_t n_vec, int T, int D) {
+    const int dv = D >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / dv;  // b*T + t
+        const int d4 = (int)(i - row * dv);
+        const int b = (int)(row / T), t = (int)(row - (int64_t)b * T);
+        const bool valid = t < __ldg(sizes + b);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) v = __ldg(reinterpret_cast<const float4*>(feats + (__ldg(offsets + b) + t) * (int64_t)D) + d4);
+        reinterpret_cast<float4*>(x)[i] = v;
+        if (d4 == 0 && pad) pad[row] = valid ? 0 : 1;
+    }
+}
+
+int launch_gather_pad(const float* feats, const int64_t* offsets, const int32_t* sizes, float* x, uint8_t* pad, int64_t B, int64_t T, int64_t D,
+                      cudaStream_t st) {
+    const int64_t n_vec = B * T * D / 4;
+    if (n_vec == 0) return DAD_OK;
+    int64_t blocks = ceil_div64(n_vec, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_gather_pad<<<(unsigned)blocks, 256, 0, st>>>(feats, offsets, sizes, x, pad, n_vec, (int)T, (int)D);
+    DAD_CHECK_LAUNCH("k_gather_pad");
+    return DAD_OK;
+}
+
 // Per-step draws of the throughput mode (dropout keep masks, feature keep mask, temporal span starts).
 __global__ void __launch_bounds__(256) k_step_rng(unsigned long long seed, const int64_t* step_ptr, float* keep_clean, float* keep_strong,
                                                   int64_t n_keep, float p_drop, float* feat_keep, float feat_rate, int32_t* t_start,

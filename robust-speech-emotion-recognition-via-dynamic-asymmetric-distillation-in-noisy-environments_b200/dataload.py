@@ -141,43 +141,72 @@ class UtteranceLoader:
             yield self.collate(order[s:s + self.batch_size])
 
 
-def _split_loaders(fs, train_idx, val_idx, test_idx, batch_size, noisy, with_id):
-    mk = lambda idx, shuffle, labels: UtteranceLoader(fs, idx, batch_size, shuffle, use_labels=labels, with_id=with_id)
+class DeviceUtteranceLoader(UtteranceLoader):
+    """Same interface, but the split's features live in HBM and every batch is assembled ON the device by one gather kernel
+    (csrc/k_aug.cu k_gather_pad): no per-sample Python loop, no pageable host->device copy per step
+    (I/dataload_clean.py:170-193, I/train.py:398,405).  An IEMOCAP training fold is ~2.2 GB of the 180 GB."""
+
+    def __init__(self, fs, indices, batch_size, shuffle, use_labels=True, with_id=True, generator=None, device=None):
+        super().__init__(fs, indices, batch_size, shuffle, use_labels, with_id, generator)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.feats_dev = self.feats.to(self.device, non_blocking=True)
+        self.offsets_dev = self.offsets.to(self.device)
+        self.sizes_dev = self.sizes.to(torch.int32).to(self.device)
+        self.labels_dev = self.labels.to(self.device)
+
+    def collate(self, ids):
+        from . import ops
+        T = int(self.sizes[ids].max())  # host copy of the lengths: no device sync
+        ids_dev = ids.to(self.device, non_blocking=True)
+        feats, pad = ops.gather_pad(self.feats_dev, self.offsets_dev[ids_dev], self.sizes_dev[ids_dev], T=T)
+        batch = {"net_input": {"feats": feats, "padding_mask": pad}}
+        if self.with_id:
+            batch["id"] = ids.clone()
+        if self.use_labels:
+            batch["labels"] = self.labels_dev[ids_dev]
+        elif self.with_id:
+            batch["labels"] = None
+        return batch
+
+
+def _split_loaders(fs, train_idx, val_idx, test_idx, batch_size, noisy, with_id, device=None):
+    cls = UtteranceLoader if device is None else (lambda *a, **k: DeviceUtteranceLoader(*a, device=device, **k))
+    mk = lambda idx, shuffle, labels: cls(fs, idx, batch_size, shuffle, use_labels=labels, with_id=with_id)
     if noisy:  # student + teacher train loaders are two independently shuffled views of the same unlabeled split
         return mk(train_idx, True, False), mk(train_idx, True, False), mk(val_idx, False, True), mk(test_idx, False, True)
     return mk(train_idx, True, True), mk(val_idx, False, True), mk(test_idx, False, True)
 
 
 # ------------------------------------------------------------------------------------------------ reference entry points
-def get_cv_dataloaders(data_path, batch_size, fold_id=1, label_dict=None, feature_set=None):
+def get_cv_dataloaders(data_path, batch_size, fold_id=1, label_dict=None, feature_set=None, device=None):
     """IEMOCAP clean: -> (train_loader, val_loader, test_loader, class_names, num_classes).  I/dataload_clean.py:222-295."""
     from . import config as cfg
     label_dict = label_dict or cfg.LABEL_DICT
     fs = feature_set if feature_set is not None else load_iemocap_set(data_path, label_dict)
     tr, va, te = iemocap_fold_sessions(fold_id)
     g = fs.groups.astype(np.int64)
-    loaders = _split_loaders(fs, np.where(np.isin(g, tr))[0], np.where(g == va)[0], np.where(g == te)[0], batch_size, False, True)
+    loaders = _split_loaders(fs, np.where(np.isin(g, tr))[0], np.where(g == va)[0], np.where(g == te)[0], batch_size, False, True, device)
     return (*loaders, list(label_dict.keys()), len(label_dict))
 
 
-def get_cv_dataloaders_noisy(data_path, batch_size, fold_id=1, label_dict=None, feature_set=None):
+def get_cv_dataloaders_noisy(data_path, batch_size, fold_id=1, label_dict=None, feature_set=None, device=None):
     """IEMOCAP noisy: -> (student_loader, teacher_loader, val_loader, test_loader).  I/dataload_noisy.py:159-245."""
     from . import config as cfg
     label_dict = label_dict or cfg.LABEL_DICT
     fs = feature_set if feature_set is not None else load_iemocap_set(data_path, label_dict)
     tr, va, te = iemocap_fold_sessions(fold_id)
     g = fs.groups.astype(np.int64)
-    return _split_loaders(fs, np.where(np.isin(g, tr))[0], np.where(g == va)[0], np.where(g == te)[0], batch_size, True, True)
+    return _split_loaders(fs, np.where(np.isin(g, tr))[0], np.where(g == va)[0], np.where(g == te)[0], batch_size, True, True, device)
 
 
-def create_speaker_isolated_loaders(feat_path, batch_size, fold, label_dict, noisy, emodb=False, feature_set=None):
+def create_speaker_isolated_loaders(feat_path, batch_size, fold, label_dict, noisy, emodb=False, feature_set=None, device=None):
     """CASIA (4 folds) / EMODB (10 folds): clean -> (train, val, test, num_classes, class_names); noisy -> (student, teacher,
     val, test).  C/dataload_casia_clean.py:70-160, C/dataload_casia_noisy.py:160-315, E/dataload_emodb_noisy.py:191-376."""
     fs = feature_set if feature_set is not None else load_speaker_set(feat_path, label_dict)
     ids, train, val, test = speaker_fold(fs.groups, fold, emodb=emodb)
     tr_idx, va_idx, te_idx = np.where(np.isin(ids, train))[0], np.where(ids == val)[0], np.where(ids == test)[0]
     assert not (set(train) & {val, test}) and val != test, "speaker leak between splits"  # E/dataload_emodb_noisy.py:253-255
-    loaders = _split_loaders(fs, tr_idx, va_idx, te_idx, batch_size, noisy, with_id=not noisy)
+    loaders = _split_loaders(fs, tr_idx, va_idx, te_idx, batch_size, noisy, with_id=not noisy, device=device)
     if noisy:
         return loaders
     return (*loaders, len(label_dict), list(label_dict.keys()))

@@ -117,6 +117,20 @@ def encoder_pool_bwd(x, pad, bits, g_emb, lens, aug=None, gemm_mode=None, xs=Non
     return g[:_lib.OFF_B].view(D_HID, D_IN), g[_lib.OFF_B:_lib.OFF_WC]
 
 
+def gather_pad(feats, offsets, sizes, T=None, x_out=None, pad_out=None):
+    """Device-side collate (I/dataload_clean.py:177-193): utterances (offsets, sizes) of a resident [sum T, 768] feature array ->
+    zero-padded x [B,T,768] and padding mask [B,T] (bool, True = pad).  offsets int64, sizes int32, all on the device."""
+    _lib.require_device()
+    B = int(offsets.numel())
+    if T is None:
+        T = int(sizes.max()) if B else 0
+    x = x_out if x_out is not None else torch.empty(B, T, D_IN, dtype=torch.float32, device=feats.device)
+    pad = pad_out if pad_out is not None else torch.empty(B, T, dtype=torch.uint8, device=feats.device)
+    check(lib().dad_gather_pad(ptr(feats, torch.float32, "feats"), ptr(offsets, torch.int64, "offsets"), ptr(sizes, torch.int32, "sizes"),
+                               ptr(x, torch.float32, "x"), ptr(pad, torch.uint8, "pad"), B, T, stream_ptr()))
+    return x, pad.view(torch.bool)
+
+
 def ema_(teacher_flat, student_flat, momentum):
     """In-place t = t*m + s*(1-m) with the reference's rounding (I/model.py:211-223)."""
     _lib.require_device()

@@ -13,18 +13,19 @@ class IEMOCAPCrossDomainTrainer(CrossDomainTrainer):
 
     def _make_loaders(self, batch_size):
         fold_id = self.fold + 1
-        clean = dataload.get_cv_dataloaders(cfg.CLEAN_DATA_DIR, batch_size, fold_id=fold_id, label_dict=cfg.LABEL_DICT)
-        noisy = dataload.get_cv_dataloaders_noisy(cfg.NOISY_DATA_DIR, batch_size, fold_id=fold_id, label_dict=cfg.LABEL_DICT)
+        dev = self._data_device()
+        clean = dataload.get_cv_dataloaders(cfg.CLEAN_DATA_DIR, batch_size, fold_id=fold_id, label_dict=cfg.LABEL_DICT, device=dev)
+        noisy = dataload.get_cv_dataloaders_noisy(cfg.NOISY_DATA_DIR, batch_size, fold_id=fold_id, label_dict=cfg.LABEL_DICT, device=dev)
         return clean, noisy
 
     @classmethod
-    def synthetic_loaders(cls, fold, utt_per_session=96, seed=0):
+    def synthetic_loaders(cls, fold, utt_per_session=96, seed=0, device=None):
         """Loader factory over synthetic stand-in features with IEMOCAP's 5-session structure (offline runs / tests)."""
         fs_c, fs_n = dataload.synthetic_feature_sets(5, utt_per_session, seed=seed)
 
         def make(batch_size):
-            return (dataload.get_cv_dataloaders(None, batch_size, fold + 1, cfg.LABEL_DICT, feature_set=fs_c),
-                    dataload.get_cv_dataloaders_noisy(None, batch_size, fold + 1, cfg.LABEL_DICT, feature_set=fs_n))
+            return (dataload.get_cv_dataloaders(None, batch_size, fold + 1, cfg.LABEL_DICT, feature_set=fs_c, device=device),
+                    dataload.get_cv_dataloaders_noisy(None, batch_size, fold + 1, cfg.LABEL_DICT, feature_set=fs_n, device=device))
         return make
 
 

@@ -17,21 +17,23 @@ class FixedCASIACrossDomainTrainer(CrossDomainTrainer):
         super().__init__(fold=fold, experiment_name=experiment_name, **kw)
 
     def _make_loaders(self, batch_size):
+        dev = self._data_device()
         tr, va, te, ncls, names = dataload.create_speaker_isolated_loaders(self.cfg.CLEAN_FEAT_PATH, batch_size, self.fold,
-                                                                          self.cfg.LABEL_DICT, noisy=False, emodb=self.EMODB)
+                                                                          self.cfg.LABEL_DICT, noisy=False, emodb=self.EMODB, device=dev)
         noisy = dataload.create_speaker_isolated_loaders(self.cfg.NOISY_FEAT_PATH, batch_size, self.fold, self.cfg.LABEL_DICT,
-                                                         noisy=True, emodb=self.EMODB)
+                                                         noisy=True, emodb=self.EMODB, device=dev)
         return (tr, va, te, names, ncls), noisy
 
     @classmethod
-    def synthetic_loaders(cls, fold, utt_per_speaker=96, seed=0):
+    def synthetic_loaders(cls, fold, utt_per_speaker=96, seed=0, device=None):
         names = [f"spk_{i:02d}" for i in range(cls.N_FOLDS_TOTAL)]
         fs_c, fs_n = dataload.synthetic_feature_sets(cls.N_FOLDS_TOTAL, utt_per_speaker, seed=seed, group_names=names)
         ld = cls.cfg.LABEL_DICT
 
         def make(batch_size):
-            tr, va, te, ncls, cn = dataload.create_speaker_isolated_loaders(None, batch_size, fold, ld, False, cls.EMODB, feature_set=fs_c)
-            return (tr, va, te, cn, ncls), dataload.create_speaker_isolated_loaders(None, batch_size, fold, ld, True, cls.EMODB, feature_set=fs_n)
+            tr, va, te, ncls, cn = dataload.create_speaker_isolated_loaders(None, batch_size, fold, ld, False, cls.EMODB, feature_set=fs_c, device=device)
+            return (tr, va, te, cn, ncls), dataload.create_speaker_isolated_loaders(None, batch_size, fold, ld, True, cls.EMODB, feature_set=fs_n,
+                                                                                   device=device)
         return make
 
 

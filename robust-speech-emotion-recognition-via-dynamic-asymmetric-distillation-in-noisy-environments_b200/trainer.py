@@ -180,6 +180,10 @@ class CrossDomainTrainer:
         """-> ((clean_train, clean_val, clean_test, class_names, num_classes), (student, teacher, noisy_val, noisy_test))"""
         raise NotImplementedError
 
+    def _data_device(self):
+        """Device the loaders keep the splits on (None = pinned host memory + one H2D copy per batch)."""
+        return self.device if getattr(self.cfg, "DAD_DEVICE_DATA", True) else None
+
     def _setup_dataloaders(self):
         clean, noisy = self._loaders(self.cfg.BATCH_SIZE) if self._loaders is not None else self._make_loaders(self.cfg.BATCH_SIZE)
         self.clean_train_loader, self.clean_val_loader, self.clean_test_loader, self.class_names, self.num_classes = clean
@@ -343,7 +347,7 @@ class CrossDomainTrainer:
                 feats, mask = self._batch_to_device(batch)
                 preds.append(self.model.predict(feats, mask, use_teacher=use_teacher).argmax(dim=1))
                 labels.append(batch["labels"])
-        return torch.cat(preds).cpu().numpy(), torch.cat(labels).numpy()
+        return torch.cat(preds).cpu().numpy(), torch.cat(labels).cpu().numpy()
 
     def validate(self, data_loader, domain_name="unknown"):
         """Accuracy, balanced ('weighted') accuracy, F1s, per-class stats, confusion matrix (I/train.py:522-564)."""
@@ -515,7 +519,8 @@ def run_main(trainer_cls, default_fold, argv=None):
     if args.epochs is not None:
         cfg.EPOCHS = args.epochs
     fold = default_fold if args.fold is None else args.fold - 1
-    loaders = trainer_cls.synthetic_loaders(fold) if args.synthetic else None
+    dev = "cuda" if (getattr(cfg, "DAD_DEVICE_DATA", True) and torch.cuda.is_available()) else None
+    loaders = trainer_cls.synthetic_loaders(fold, device=dev) if args.synthetic else None
     try:
         trainer = trainer_cls(fold=fold, experiment_name=args.experiment_name, loaders=loaders, require_pretrained=not args.synthetic)
         res = trainer.train()

@@ -295,3 +295,20 @@ def test_ecda_loss_module_forward_backward_vs_oracle(class_aware):
     finally:
         from dad_b200 import config
         use_config(config)
+
+
+def test_device_batch_assembly_equals_host_collator():
+    """dad_gather_pad (device-side collate) == the host collator == the reference layout, bit for bit."""
+    from dad_b200 import dataload
+    fs, _ = dataload.synthetic_feature_sets(5, 7, t_min=3, t_max=41, seed=5)
+    idx = list(range(len(fs)))
+    host = dataload.UtteranceLoader(fs, idx, 6, shuffle=False)
+    dev = dataload.DeviceUtteranceLoader(fs, idx, 6, shuffle=False, device="cuda")
+    n = 0
+    for hb, db in zip(host, dev):
+        assert db["net_input"]["feats"].is_cuda and db["net_input"]["padding_mask"].dtype == torch.bool
+        assert torch.equal(db["net_input"]["feats"].cpu(), hb["net_input"]["feats"])
+        assert torch.equal(db["net_input"]["padding_mask"].cpu(), hb["net_input"]["padding_mask"])
+        assert torch.equal(db["labels"].cpu(), hb["labels"]) and torch.equal(db["id"], hb["id"])
+        n += 1
+    assert n == len(host) == 6

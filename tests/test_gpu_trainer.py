@@ -23,8 +23,10 @@ def test_iemocap_trainer_end_to_end(monkeypatch, tmp_path):
     monkeypatch.chdir(tmp_path)
     _patch(monkeypatch, cfg)
     torch.manual_seed(0)
-    tr = IEMOCAPCrossDomainTrainer(fold=1, experiment_name="unit/test", loaders=IEMOCAPCrossDomainTrainer.synthetic_loaders(1, utt_per_session=64),
+    tr = IEMOCAPCrossDomainTrainer(fold=1, experiment_name="unit/test",
+                                   loaders=IEMOCAPCrossDomainTrainer.synthetic_loaders(1, utt_per_session=64, device="cuda"),  # HBM-resident splits
                                    require_pretrained=False)
+    assert next(iter(tr.clean_train_loader))["net_input"]["feats"].is_cuda
     # reference surface
     for attr in ("model", "optimizer", "scheduler", "dacp_manager", "ecda_criterion", "augmenter", "training_history", "calibrated_anchors",
                  "clean_train_loader", "noisy_student_loader", "noisy_val_loader", "results_dir", "noise_info"):
@@ -129,3 +131,38 @@ def test_casia_fold_sweep_step_parity(snr_db):
             g_orc = torch.cat([orc.p[k].grad.reshape(-1) for k in O.PARAM_KEYS])
             p_orc = torch.cat([orc.p[k].detach().reshape(-1) for k in O.PARAM_KEYS])
             assert float((eng.p.cpu() - p_orc).abs()[g_orc.abs() >= 1e-6].max()) <= 1e-5, (snr_db, fold, over)
+
+
+def test_stage1_pretrainer_feeds_stage2(tmp_path, monkeypatch):
+    """stage-1 supervised pre-training on the same kernels writes the `pre_net/post_net` checkpoint that
+    stage 2 loads (I/model.py:143-198), and its step equals the oracle's plain-CE Adam step."""
+    from dad_b200 import config as cfg
+    from dad_b200 import dataload, synth
+    from dad_b200.model import SSRLModel
+    from dad_b200.pretrain import CleanPretrainer, stage1_cfg
+    from helpers import push_oracle_state
+    from oracle import dad_oracle as O
+    fs_c, _ = dataload.synthetic_feature_sets(5, 40, t_min=40, t_max=80, seed=11)
+    tr, va, te, _, _ = dataload.get_cv_dataloaders(None, 32, 1, cfg.LABEL_DICT, feature_set=fs_c, device="cuda")
+    pt = CleanPretrainer(cfg, tr, va, capacity_T=80, BATCH_SIZE=32, LEARNING_RATE=2e-3)
+    # one step against the oracle (no dropout, no smoothing, no clipping, wd 1e-5)
+    hp = O.HParams.from_cfg(stage1_cfg(cfg, BATCH_SIZE=32, LEARNING_RATE=2e-3))
+    orc = O.OracleStepper(synth.init_state(42), hp, lr=2e-3)
+    batch = next(iter(tr))
+    host = {"net_input": {k: v.cpu() for k, v in batch["net_input"].items()}, "labels": batch["labels"].cpu()}
+    push_oracle_state(pt.engine, orc)
+    pt.engine.set_lr(2e-3)
+    pt.engine.set_inputs(batch, None)
+    pt.engine.step(0)
+    B = host["labels"].numel()
+    ref = orc.step(host, None, 0, {"drop_clean": torch.ones(B, 256)})
+    assert abs(pt.engine.losses()["supervised_ce_loss"] - ref["supervised_ce_loss"]) <= 1e-4 * ref["supervised_ce_loss"]
+    g = torch.cat([orc.p[k].grad.reshape(-1) for k in O.PARAM_KEYS])
+    p = torch.cat([orc.p[k].detach().reshape(-1) for k in O.PARAM_KEYS])
+    assert float((pt.engine.p.cpu() - p).abs()[g.abs() >= 1e-6].max()) <= 1e-5
+    hist = pt.train(epochs=6, ckpt_path=str(tmp_path / "best_model_fold_1.ckpt"))
+    assert hist[-1]["train_loss"] < hist[0]["train_loss"] and pt.best_acc > 0.5
+    model = SSRLModel(cfg).cuda()
+    model.load_complete_pretrained_weights(str(tmp_path / "best_model_fold_1.ckpt"))
+    assert torch.equal(model.student_encoder.pre_net.weight.detach().cpu(), pt.best_state["pre_net.weight"])
+    assert torch.equal(model.student_classifier.fc_layer.bias.detach().cpu(), pt.best_state["post_net.bias"])
