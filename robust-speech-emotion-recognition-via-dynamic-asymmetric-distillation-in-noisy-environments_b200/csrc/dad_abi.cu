@@ -33,6 +33,7 @@ size_t ecda_pairs_smem_bytes();
 int ecda_prep_grid(int B_global);
 int ecda_max_tiles(int B_local);
 int ecda_col_splits(int B_local);
+int ecda_max_gram_items(int B_local, int world);
 int launch_ecda(const EcdaArgs& a, cudaStream_t st);
 int launch_scl(const SclArgs& a, cudaStream_t st);
 int launch_gather_pad(const float* feats, const int64_t* offsets, const int32_t* sizes, float* x, uint8_t* pad, int64_t B, int64_t T, int64_t D,
@@ -292,7 +293,7 @@ int dad_scl(const dad_scl_args* a, void* stream) {
 }
 
 // ---------------------------------------------------------------- ECDA
-struct EcdaCarve { size_t part_vec, part_sc, part_cnt, stats, lists, tiles, mu_t, mu_all, rep_grad, tile_sums, part_acc, part_rowp, slot_of, red_vec, red_sc, red_cnt, counter, total; };
+struct EcdaCarve { size_t part_vec, part_sc, part_cnt, stats, lists, tiles, mu_t, mu_all, rep_grad, tile_sums, part_acc, part_rowp, slot_of, red_vec, red_sc, red_cnt, z_hi, z_lo, G, gram_items, counter, total; };
 static EcdaCarve ecda_carve(int B_local, int world) {
     const int Bg = B_local * world, G = ecda_prep_grid(Bg), MT = ecda_max_tiles(B_local), Q = ecda_col_splits(B_local);
     EcdaCarve c;
@@ -307,6 +308,10 @@ static EcdaCarve ecda_carve(int B_local, int world) {
     c.red_vec = o; o = align_up(o + (size_t)8 * DAD_H * sizeof(double), 256);
     c.red_sc = o; o = align_up(o + (size_t)16 * sizeof(double), 256);
     c.red_cnt = o; o = align_up(o + (size_t)8 * sizeof(int), 256);
+    c.z_hi = o; o = align_up(o + (size_t)2 * Bg * DAD_H * sizeof(unsigned short), 1024);
+    c.z_lo = o; o = align_up(o + (size_t)2 * Bg * DAD_H * sizeof(unsigned short), 1024);
+    c.gram_items = o; o = align_up(o + (size_t)ecda_max_gram_items(B_local, world) * sizeof(GramItem), 256);
+    c.G = o; o = align_up(o + (size_t)(2 * B_local + 8 * 128) * (size_t)align_up((size_t)2 * Bg, 256) * sizeof(float), 256);
     c.tiles = o; o = align_up(o + (size_t)MT * sizeof(EcdaTile), 256);
     c.mu_t = o; o = align_up(o + (size_t)ECDA_MAXC * DAD_H * sizeof(float), 256);
     c.rep_grad = o; o = align_up(o + (size_t)ECDA_MAXC * DAD_H * sizeof(float), 256);
@@ -336,6 +341,9 @@ int dad_ecda(const dad_ecda_args* a, void* stream) {
     k.mu_t = (float*)(w + c.mu_t); k.rep_grad = (float*)(w + c.rep_grad); k.tile_sums = (float*)(w + c.tile_sums);
     k.g_clean = a->g_clean; k.g_strong = a->g_strong; k.loss_out = a->loss_out; k.counter = (unsigned*)(w + c.counter);
     k.slot_of = (uint8_t*)(w + c.slot_of);
+    k.z_hi = (unsigned short*)(w + c.z_hi); k.z_lo = (unsigned short*)(w + c.z_lo); k.G = (float*)(w + c.G);
+    k.ldg = (long long)align_up((size_t)2 * a->pack.B_local * a->pack.world, 256);
+    k.gram_items = (GramItem*)(w + c.gram_items); k.max_gram_items = ecda_max_gram_items(a->pack.B_local, a->pack.world);
     k.red_vec = (double*)(w + c.red_vec); k.red_sc = (double*)(w + c.red_sc); k.red_cnt = (int*)(w + c.red_cnt);
     k.mu_all = (float*)(w + c.mu_all); k.part_acc = (float*)(w + c.part_acc); k.part_rowp = (float*)(w + c.part_rowp);
     k.max_tiles = ecda_max_tiles(a->pack.B_local);

@@ -27,7 +27,9 @@ typedef dad_head_bwd_args HeadBwdArgs;
 // ---- ECDA
 constexpr int ECDA_TR = 64;  // rows (members of one class) per CTA tile
 constexpr int ECDA_MAXC = 4;
-struct EcdaTile { int cls, row_begin, row_count, feasible; };
+constexpr float ECDA_ZS = 256.0f;  // power-of-two scale of the centred embeddings before the fp16 hi/lo split (k_gram_tc.cu)
+struct EcdaTile { int cls, row_begin, row_count, feasible, g_row, pad_[3]; };  // g_row: first row of this tile in the Gram buffer
+struct GramItem { int a_row, b_row, g_row, g_col; };  // 128 list rows from a_row  x  256 list rows from b_row -> G[g_row.., g_col..]
 
 struct EcdaStats {  // written by k_ecda_prep's last CTA, read by k_ecda_pairs
     int n_s[ECDA_MAXC], n_t[ECDA_MAXC], feasible[ECDA_MAXC], list_off[ECDA_MAXC];
@@ -38,6 +40,7 @@ struct EcdaStats {  // written by k_ecda_prep's last CTA, read by k_ecda_pairs
     float rep;                                                // repulsion loss (<= 0)
     float rho;                                                // delta * sum_{feasible} a_c
     int n_tiles, any_feasible, n_classes, active;
+    int n_gram_items, pad_[3];
 };
 
 struct EcdaArgs {
@@ -60,6 +63,12 @@ struct EcdaArgs {
     double* red_sc;         // [8][2]
     int* red_cnt;           // [8]
     uint8_t* slot_of;       // [2*B_global] slot (dom*4 + class) of every row, 255 = not a member
+    unsigned short* z_hi;   // [2*B_global][256] fp16 hi / lo split of the scaled, class-centred member embeddings, in list order
+    unsigned short* z_lo;
+    float* G;               // [2*B_local + 8*128][ldg] Gram rows of the member rows this rank owns (k_gram_tc)
+    long long ldg;
+    GramItem* gram_items;   // [max_gram_items]
+    int max_gram_items;
     float* mu_all;          // [4][256] mean of ALL members (clean + masked noisy) of class c: the centring point of k_ecda_pairs
     float* tile_sums;       // [max_tiles * col_splits][3]
     float* part_acc;        // [max_tiles * col_splits][64][256] per-CTA partial sum_j P_ij z'_j

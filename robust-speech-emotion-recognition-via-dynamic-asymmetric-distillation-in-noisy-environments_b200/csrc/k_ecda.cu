@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
     EcdaStats* st = a.stats;
     if (tid == 0) st->active = active ? 1 : 0;
     if (!active) {
-        if (tid == 0) { st->n_tiles = 0; st->any_feasible = 0; st->rep = 0.f; st->rho = 0.f; }
+        if (tid == 0) { st->n_tiles = 0; st->n_gram_items = 0; st->any_feasible = 0; st->rep = 0.f; st->rho = 0.f; }
         return;
     }
     double tv[8];
@@ -276,9 +276,9 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        int nt_ = 0;
+        int nt_ = 0, ng_ = 0, g_rows = 0;
         for (int c = 0; c < NC; ++c) {
-            const int off = st->list_off[c], ns = s_cnt[c];
+            const int off = st->list_off[c], ns = s_cnt[c], n_c = s_cnt[c] + s_cnt[4 + c];
             const bool feas = st->feasible[c] != 0;
             for (int dom = 0; dom < 2; ++dom) {
                 if (dom == 0 && !feas) continue;                              // clean rows only matter through the MMD
@@ -288,11 +288,22 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
                 for (int p = first; p < last && nt_ < a.max_tiles; p += ECDA_TR) {
                     EcdaTile t;
                     t.cls = c; t.row_begin = p; t.row_count = min(ECDA_TR, last - p); t.feasible = feas ? 1 : 0;
+                    t.g_row = g_rows + (p - first);
                     a.tiles[nt_++] = t;
+                }
+                if (feas) {  // Gram work items: 128-row blocks of this segment x 256-column blocks of the class (k_gram_tc)
+                    for (int p = first; p < last; p += 128)
+                        for (int cb = 0; cb < n_c && ng_ < a.max_gram_items; cb += 256) {
+                            GramItem gi;
+                            gi.a_row = p; gi.b_row = off + cb; gi.g_row = g_rows + (p - first); gi.g_col = cb;
+                            a.gram_items[ng_++] = gi;
+                        }
+                    g_rows += ((last - first + 127) / 128) * 128;
                 }
             }
         }
         st->n_tiles = nt_;
+        st->n_gram_items = ng_;
     }
 }
 
@@ -300,7 +311,8 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
 // k_ecda_pairs: one CTA per (64-row tile of one class, column split q).  The class's members are processed 64 columns at a
 // time as two register-tiled SIMT GEMMs on class-CENTRED embeddings z' = z - mean_c (centring removes the cancellation of the
 // Gram form: |z'| is of the order of the pair distances themselves):
-//   phase A  dot_ij = z'_i . z'_j  (thread = 4x4 outputs),  L2_ij = |z'_i|^2 + |z'_j|^2 - 2 dot_ij  (exactly 0 on the diagonal),
+//   phase A  dot_ij = z'_i . z'_j  read from the tcgen05 Gram G (k_gram_tc.cu; thread = 4x4 outputs),
+//            L2_ij = |z'_i|^2 + |z'_j|^2 - 2 dot_ij  (exactly 0 on the diagonal),
 //            K = sum_r exp(-L2/beta_r), K' = sum_r exp(-L2/beta_r)/beta_r -> weighted block sums (loss) and P_ij = coef K'
 //   phase B  accZ_i += sum_j P_ij z'_j,  rowP_i += sum_j P_ij            (thread = 8 rows x 8 features)
 // so that d/dz_i = rowP_i z'_i - accZ_i  (= sum_j P_ij (z_i - z_j), I/utils.py:537 differentiated).  Each CTA writes its partial
@@ -417,26 +429,13 @@ __global__ void __launch_bounds__(EP_THREADS, 1) k_ecda_pairs(EcdaArgs a) {
                 }
                 stage(zj, nj, nullptr, off + j0, n - j0);
                 __syncthreads();
-                // ---- phase A: 4x4 dot products per thread over the 256 features
+                // ---- phase A: the 4x4 dot products of this thread come from the tensor-core Gram (k_gram_tc; L2-resident)
                 float d[4][4];
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
+                for (int x = 0; x < 4; ++x) {
+                    const float* grow = a.G + (int64_t)(t.g_row + ty + 16 * x) * a.ldg + j0 + tx;
 #pragma unroll
-                    for (int y = 0; y < 4; ++y) d[x][y] = 0.f;
-#pragma unroll 2
-                for (int h = 0; h < DAD_H; h += 4) {
-                    float4 xi[4], xj[4];
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) xi[x] = *reinterpret_cast<const float4*>(zi + (ty + 16 * x) * PZS + h);
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) xj[y] = *reinterpret_cast<const float4*>(zj + (tx + 16 * y) * PZS + h);
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) {
-                            d[x][y] = fmaf(xi[x].x, xj[y].x, d[x][y]); d[x][y] = fmaf(xi[x].y, xj[y].y, d[x][y]);
-                            d[x][y] = fmaf(xi[x].z, xj[y].z, d[x][y]); d[x][y] = fmaf(xi[x].w, xj[y].w, d[x][y]);
-                        }
+                    for (int y = 0; y < 4; ++y) d[x][y] = __ldcg(grow + 16 * y);
                 }
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
@@ -601,6 +600,8 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_fold(EcdaArgs a) {
     }
 }
 
+int launch_ecda_gram(const EcdaArgs& a, cudaStream_t st);  // k_gram_tc.cu
+int ecda_max_gram_items(int B_local, int world) { return (ceil_div(2 * B_local, 128) + 8) * (ceil_div(2 * B_local * world, 256) + 1); }
 size_t ecda_pairs_smem_bytes() { return (size_t)(2 * PT * PZS + PT * PPS + DAD_H + 4 * PT) * sizeof(float) + 3 * PT * sizeof(int); }
 int ecda_prep_grid(int B_global) {
     // rows per CTA <= 256 (k_ecda_prep classifies its chunk with one thread per row); aim at ~16 rows per CTA
@@ -637,6 +638,8 @@ int launch_ecda(const EcdaArgs& a, cudaStream_t st) {
     DAD_CHECK_LAUNCH("k_ecda_reduce");
     k_ecda_stats<<<1, EP_THREADS, stats_smem, st>>>(a);
     DAD_CHECK_LAUNCH("k_ecda_stats");
+    int rc = launch_ecda_gram(a, st);
+    if (rc) return rc;
     k_ecda_pairs<<<a.max_tiles * a.col_splits, EP_THREADS, ecda_pairs_smem_bytes(), st>>>(a);
     DAD_CHECK_LAUNCH("k_ecda_pairs");
     k_ecda_fold<<<dim3(a.max_tiles, ECDA_TR / 8), EP_THREADS, 0, st>>>(a);
