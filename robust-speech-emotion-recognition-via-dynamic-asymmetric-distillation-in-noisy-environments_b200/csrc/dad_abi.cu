@@ -32,8 +32,8 @@ int launch_head_bwd(const HeadBwdArgs& a, cudaStream_t st);
 size_t ecda_pairs_smem_bytes();
 int ecda_prep_grid(int B_global);
 int ecda_max_tiles(int B_local);
-int ecda_col_splits(int B_local);
 int ecda_max_gram_items(int B_local, int world);
+int ecda_max_pz_items(int B_local);
 int launch_ecda(const EcdaArgs& a, cudaStream_t st);
 int launch_scl(const SclArgs& a, cudaStream_t st);
 int launch_gather_pad(const float* feats, const int64_t* offsets, const int32_t* sizes, float* x, uint8_t* pad, int64_t B, int64_t T, int64_t D,
@@ -293,9 +293,11 @@ int dad_scl(const dad_scl_args* a, void* stream) {
 }
 
 // ---------------------------------------------------------------- ECDA
-struct EcdaCarve { size_t part_vec, part_sc, part_cnt, stats, lists, tiles, mu_t, mu_all, rep_grad, tile_sums, part_acc, part_rowp, slot_of, red_vec, red_sc, red_cnt, z_hi, z_lo, G, gram_items, counter, total; };
+struct EcdaCarve { size_t part_vec, part_sc, part_cnt, stats, lists, tiles, mu_t, mu_all, rep_grad, slot_of, red_vec, red_sc, red_cnt, z_hi, z_lo, G, gram_items,
+                   p_hi, p_lo, rowp_part, accz, item_sums, pos_nsq, pos_om, pos_dom, pz_items, counter, total; };
 static EcdaCarve ecda_carve(int B_local, int world) {
-    const int Bg = B_local * world, G = ecda_prep_grid(Bg), MT = ecda_max_tiles(B_local), Q = ecda_col_splits(B_local);
+    const int Bg = B_local * world, G = ecda_prep_grid(Bg), MT = ecda_max_tiles(B_local);
+    const size_t g_rows = (size_t)2 * B_local + 8 * 128, ldg = align_up((size_t)2 * Bg, 256);
     EcdaCarve c;
     size_t o = 0;
     c.counter = o; o = align_up(o + 2 * sizeof(unsigned), 256);
@@ -311,14 +313,20 @@ static EcdaCarve ecda_carve(int B_local, int world) {
     c.z_hi = o; o = align_up(o + (size_t)2 * Bg * DAD_H * sizeof(unsigned short), 1024);
     c.z_lo = o; o = align_up(o + (size_t)2 * Bg * DAD_H * sizeof(unsigned short), 1024);
     c.gram_items = o; o = align_up(o + (size_t)ecda_max_gram_items(B_local, world) * sizeof(GramItem), 256);
-    c.G = o; o = align_up(o + (size_t)(2 * B_local + 8 * 128) * (size_t)align_up((size_t)2 * Bg, 256) * sizeof(float), 256);
+    c.G = o; o = align_up(o + g_rows * ldg * sizeof(float), 1024);
+    c.p_hi = o; o = align_up(o + g_rows * ldg * sizeof(unsigned short), 1024);
+    c.p_lo = o; o = align_up(o + g_rows * ldg * sizeof(unsigned short), 1024);
+    c.rowp_part = o; o = align_up(o + (ldg / 256) * g_rows * sizeof(float), 256);
+    c.accz = o; o = align_up(o + g_rows * DAD_H * sizeof(float), 256);
+    c.item_sums = o; o = align_up(o + (size_t)ecda_max_gram_items(B_local, world) * 3 * sizeof(float), 256);
+    c.pos_nsq = o; o = align_up(o + (size_t)2 * Bg * sizeof(float), 256);
+    c.pos_om = o; o = align_up(o + (size_t)2 * Bg * sizeof(float), 256);
+    c.pos_dom = o; o = align_up(o + (size_t)2 * Bg * sizeof(int), 256);
+    c.pz_items = o; o = align_up(o + (size_t)ecda_max_pz_items(B_local) * sizeof(PzItem), 256);
     c.tiles = o; o = align_up(o + (size_t)MT * sizeof(EcdaTile), 256);
     c.mu_t = o; o = align_up(o + (size_t)ECDA_MAXC * DAD_H * sizeof(float), 256);
     c.rep_grad = o; o = align_up(o + (size_t)ECDA_MAXC * DAD_H * sizeof(float), 256);
     c.mu_all = o; o = align_up(o + (size_t)ECDA_MAXC * DAD_H * sizeof(float), 256);
-    c.tile_sums = o; o = align_up(o + (size_t)MT * Q * 3 * sizeof(float), 256);
-    c.part_acc = o; o = align_up(o + (size_t)MT * Q * ECDA_TR * DAD_H * sizeof(float), 256);
-    c.part_rowp = o; o = align_up(o + (size_t)MT * Q * ECDA_TR * sizeof(float), 256);
     c.total = o;
     return c;
 }
@@ -338,16 +346,19 @@ int dad_ecda(const dad_ecda_args* a, void* stream) {
     k.lambda_cls = a->lambda_cls; k.gamma_comp = a->gamma_comp; k.delta_rep = a->delta_rep; k.w_ecda = a->w_ecda;
     k.part_vec = (float*)(w + c.part_vec); k.part_sc = (double*)(w + c.part_sc); k.part_cnt = (int*)(w + c.part_cnt);
     k.stats = (EcdaStats*)(w + c.stats); k.lists = (int*)(w + c.lists); k.tiles = (EcdaTile*)(w + c.tiles);
-    k.mu_t = (float*)(w + c.mu_t); k.rep_grad = (float*)(w + c.rep_grad); k.tile_sums = (float*)(w + c.tile_sums);
+    k.mu_t = (float*)(w + c.mu_t); k.rep_grad = (float*)(w + c.rep_grad);
     k.g_clean = a->g_clean; k.g_strong = a->g_strong; k.loss_out = a->loss_out; k.counter = (unsigned*)(w + c.counter);
     k.slot_of = (uint8_t*)(w + c.slot_of);
     k.z_hi = (unsigned short*)(w + c.z_hi); k.z_lo = (unsigned short*)(w + c.z_lo); k.G = (float*)(w + c.G);
     k.ldg = (long long)align_up((size_t)2 * a->pack.B_local * a->pack.world, 256);
     k.gram_items = (GramItem*)(w + c.gram_items); k.max_gram_items = ecda_max_gram_items(a->pack.B_local, a->pack.world);
     k.red_vec = (double*)(w + c.red_vec); k.red_sc = (double*)(w + c.red_sc); k.red_cnt = (int*)(w + c.red_cnt);
-    k.mu_all = (float*)(w + c.mu_all); k.part_acc = (float*)(w + c.part_acc); k.part_rowp = (float*)(w + c.part_rowp);
+    k.mu_all = (float*)(w + c.mu_all);
+    k.p_hi = (unsigned short*)(w + c.p_hi); k.p_lo = (unsigned short*)(w + c.p_lo); k.rowp_part = (float*)(w + c.rowp_part);
+    k.accz = (float*)(w + c.accz); k.item_sums = (float*)(w + c.item_sums); k.pos_nsq = (float*)(w + c.pos_nsq);
+    k.pos_om = (float*)(w + c.pos_om); k.pos_dom = (int*)(w + c.pos_dom); k.pz_items = (PzItem*)(w + c.pz_items);
+    k.max_pz_items = ecda_max_pz_items(a->pack.B_local); k.g_rows_alloc = 2 * a->pack.B_local + 8 * 128;
     k.max_tiles = ecda_max_tiles(a->pack.B_local);
-    k.col_splits = ecda_col_splits(a->pack.B_local);
     k.prep_grid = ecda_prep_grid(a->pack.B_local * a->pack.world);
     return launch_ecda(k, (cudaStream_t)stream);
 }

@@ -29,7 +29,9 @@ constexpr int ECDA_TR = 64;  // rows (members of one class) per CTA tile
 constexpr int ECDA_MAXC = 4;
 constexpr float ECDA_ZS = 256.0f;  // power-of-two scale of the centred embeddings before the fp16 hi/lo split (k_gram_tc.cu)
 struct EcdaTile { int cls, row_begin, row_count, feasible, g_row, pad_[3]; };  // g_row: first row of this tile in the Gram buffer
-struct GramItem { int a_row, b_row, g_row, g_col; };  // 128 list rows from a_row  x  256 list rows from b_row -> G[g_row.., g_col..]
+// 128 list rows from a_row (n_rows valid) x 256 list rows from b_row (columns g_col.. of the class's n_cols members) -> G[g_row.., g_col..]
+struct GramItem { int a_row, b_row, g_row, g_col, n_rows, n_cols, cls, pad_; };
+struct PzItem { int g_row, b_row, n_kb, cls; };  // (P Z') block: P rows g_row..+127, Z' rows from b_row, n_kb k-blocks of 64 members
 
 struct EcdaStats {  // written by k_ecda_prep's last CTA, read by k_ecda_pairs
     int n_s[ECDA_MAXC], n_t[ECDA_MAXC], feasible[ECDA_MAXC], list_off[ECDA_MAXC];
@@ -40,7 +42,8 @@ struct EcdaStats {  // written by k_ecda_prep's last CTA, read by k_ecda_pairs
     float rep;                                                // repulsion loss (<= 0)
     float rho;                                                // delta * sum_{feasible} a_c
     int n_tiles, any_feasible, n_classes, active;
-    int n_gram_items, pad_[3];
+    int n_gram_items, n_pz_items, pad_[2];
+    float p_scale[ECDA_MAXC];                                 // power-of-two scale of P before its fp16 split
 };
 
 struct EcdaArgs {
@@ -69,14 +72,21 @@ struct EcdaArgs {
     long long ldg;
     GramItem* gram_items;   // [max_gram_items]
     int max_gram_items;
+    unsigned short* p_hi;   // [g_rows_alloc][ldg] fp16 hi / lo split of the scaled gradient weights P (k_ecda_p)
+    unsigned short* p_lo;
+    float* rowp_part;       // [ldg/256][g_rows_alloc] row sums of (scaled) P per 256-column block
+    float* accz;            // [g_rows_alloc][256] (scaled) P Z' (k_pz_tc)
+    float* item_sums;       // [max_gram_items][3] weighted block sums of K per Gram item
+    float* pos_nsq;         // [2*B_global] |z'|^2, omega, domain of every list position (k_ecda_pack)
+    float* pos_om;
+    int* pos_dom;
+    PzItem* pz_items;       // [max_pz_items]
+    int max_pz_items, g_rows_alloc;
     float* mu_all;          // [4][256] mean of ALL members (clean + masked noisy) of class c: the centring point of k_ecda_pairs
-    float* tile_sums;       // [max_tiles * col_splits][3]
-    float* part_acc;        // [max_tiles * col_splits][64][256] per-CTA partial sum_j P_ij z'_j
-    float* part_rowp;       // [max_tiles * col_splits][64]      per-CTA partial sum_j P_ij
     float *g_clean, *g_strong;  // [B_local,256], accumulated (+=)
     float* loss_out;        // [2] = ecda loss share, [3] = full-batch ecda loss when world == 1
     unsigned* counter;      // [2] zero-initialised, self-resetting
-    int max_tiles, prep_grid, col_splits;
+    int max_tiles, prep_grid;
 };
 
 // supervised contrastive loss (csrc/k_scl.cu)

@@ -7,11 +7,13 @@
 //                (one CTA) turns them into class statistics (counts, bandwidths via the centred closed form
 //                sum_ij|zi-zj|^2 = 2n sum_i|zi-m|^2, centroids, compactness, repulsion + its gradient, attention) and
 //                builds the per-class member lists and the row-tile table.
-//  k_ecda_pairs: one CTA per (64-row tile of one class, column split): two register-tiled SIMT GEMMs on class-centred
-//                embeddings (Gram form of the squared distances, then P z) -- see the comment above the kernel.  Under data
-//                parallelism a rank launches tiles only for the rows it owns (its local clean / noisy samples).
+//  k_ecda_pack + k_gram_tc (k_gram_tc.cu): class-centred embeddings -> fp16 hi/lo, Gram G = Z' Z'^T on tcgen05 (rows this rank owns)
+//  k_ecda_p    : elementwise over G: distances, 5 Gaussians, weighted block sums (loss) and the gradient weights P (fp16 hi/lo)
+//  k_pz_tc     (k_gram_tc.cu): P Z' on tcgen05;   k_ecda_fold: d/dz rows;   k_ecda_loss: fixed-order loss assembly.
+//                Under data parallelism a rank works only on the member rows it owns (its local clean / noisy samples).
 #include "dad_common.cuh"
 #include "dad_pack.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
     EcdaStats* st = a.stats;
     if (tid == 0) st->active = active ? 1 : 0;
     if (!active) {
-        if (tid == 0) { st->n_tiles = 0; st->n_gram_items = 0; st->any_feasible = 0; st->rep = 0.f; st->rho = 0.f; }
+        if (tid == 0) { st->n_tiles = 0; st->n_gram_items = 0; st->n_pz_items = 0; st->any_feasible = 0; st->rep = 0.f; st->rho = 0.f; }
         return;
     }
     double tv[8];
@@ -179,6 +181,22 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
             st->c_st[c] = (float)(1.0 / ((double)ns * wt + 1e-8));
             const float att = a.class_aware ? expf(a.lambda_cls * (wmean - a.w_class[c])) : 1.f;  // utils.py:598-599
             st->att[c] = att;
+            // power-of-two operand scale of this class's gradient weights P = coef K' before their fp16 hi/lo split (k_ecda_p):
+            // |P| <= 4 att w_ecda max(c_ss, c_tt, c_st) sum_r 1/beta_r (scores <= 1, exp <= 1); the largest value lands below 2^13
+            {
+                float cmax = fmaxf(st->c_ss[c], fmaxf(st->c_tt[c], st->c_st[c]));
+                float sb = 0.f;
+                for (int r = 0; r < 5; ++r) sb += st->inv_beta[c][r];
+                const float pmax = 4.f * att * fabsf(a.w_ecda) * cmax * sb;
+                float sc = 1.0f;
+                if (pmax > 0.f && pmax < 3.0e38f) {
+                    int e = (int)((__float_as_uint(pmax) >> 23) & 0xFFu) - 127;  // floor(log2 pmax)
+                    int se = 12 - e;
+                    se = se > 100 ? 100 : (se < -100 ? -100 : se);
+                    sc = __uint_as_float((uint32_t)(127 + se) << 23);
+                }
+                st->p_scale[c] = sc;
+            }
             double comp = nt > 0 ? s_sq[4 + c] / (double)nt - mu2 : 0.0;  // mean |z - mu|^2
             st->comp[c] = (float)(comp > 0.0 ? comp : 0.0);
         }
@@ -276,7 +294,7 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        int nt_ = 0, ng_ = 0, g_rows = 0;
+        int nt_ = 0, ng_ = 0, np_ = 0, g_rows = 0;
         for (int c = 0; c < NC; ++c) {
             const int off = st->list_off[c], ns = s_cnt[c], n_c = s_cnt[c] + s_cnt[4 + c];
             const bool feas = st->feasible[c] != 0;
@@ -296,242 +314,130 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
                         for (int cb = 0; cb < n_c && ng_ < a.max_gram_items; cb += 256) {
                             GramItem gi;
                             gi.a_row = p; gi.b_row = off + cb; gi.g_row = g_rows + (p - first); gi.g_col = cb;
+                            gi.n_rows = min(128, last - p); gi.n_cols = n_c; gi.cls = c; gi.pad_ = 0;
                             a.gram_items[ng_++] = gi;
                         }
+                    for (int p = first; p < last && np_ < a.max_pz_items; p += 128) {
+                        PzItem pi;
+                        pi.g_row = g_rows + (p - first); pi.b_row = off; pi.n_kb = (n_c + 63) / 64; pi.cls = c;
+                        a.pz_items[np_++] = pi;
+                    }
                     g_rows += ((last - first + 127) / 128) * 128;
                 }
             }
         }
         st->n_tiles = nt_;
         st->n_gram_items = ng_;
+        st->n_pz_items = np_;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// k_ecda_pairs: one CTA per (64-row tile of one class, column split q).  The class's members are processed 64 columns at a
-// time as two register-tiled SIMT GEMMs on class-CENTRED embeddings z' = z - mean_c (centring removes the cancellation of the
-// Gram form: |z'| is of the order of the pair distances themselves):
-//   phase A  dot_ij = z'_i . z'_j  read from the tcgen05 Gram G (k_gram_tc.cu; thread = 4x4 outputs),
-//            L2_ij = |z'_i|^2 + |z'_j|^2 - 2 dot_ij  (exactly 0 on the diagonal),
-//            K = sum_r exp(-L2/beta_r), K' = sum_r exp(-L2/beta_r)/beta_r -> weighted block sums (loss) and P_ij = coef K'
-//   phase B  accZ_i += sum_j P_ij z'_j,  rowP_i += sum_j P_ij            (thread = 8 rows x 8 features)
-// so that d/dz_i = rowP_i z'_i - accZ_i  (= sum_j P_ij (z_i - z_j), I/utils.py:537 differentiated).  Each CTA writes its partial
-// (accZ, rowP, sums) to the workspace; k_ecda_fold then folds the Q partials of a row tile in fixed q order, adds the
-// compactness / repulsion gradients and accumulates into g -- every gradient row has exactly one writer, no float atomics,
-// bit-reproducible.  The column split gives ~2 CTAs per SM on one GPU and keeps all SMs busy when a rank owns only 1/8 of the rows.
+// k_ecda_p: elementwise pass over the tensor-core Gram G -- one CTA per Gram work item (128 owned rows x 256 members of the class):
+//   L2_ij = |z'_i|^2 + |z'_j|^2 - 2 G_ij (exactly 0 on the diagonal),  K = sum_r exp(-L2/beta_r),  K' = sum_r exp(-L2/beta_r)/beta_r
+//   -> weighted block sums of K (the three MMD terms, I/utils.py:546-563) and P_ij = coef * K' (the gradient weights), written as a
+//      per-class power-of-two scaled fp16 hi/lo split for the second tensor-core GEMM (k_pz_tc: sum_j P_ij z'_j), plus the row sums
+//      of P per column block.  Warp = 16 of the 128 rows, lane = 8 consecutive columns: 32-byte G loads, 16-byte P stores.
+// Deterministic: per-item sums and per-(column block, row) partial row sums are folded in fixed order by k_ecda_fold / k_ecda_loss.
 // ---------------------------------------------------------------------------------------------------------------------
-namespace {
-constexpr int PT = ECDA_TR;          // 64: rows per tile = columns per chunk
-constexpr int PZS = DAD_H + 4;       // padded row stride of the staged embeddings (floats): conflict-free float4 rows
-constexpr int PPS = PT + 4;          // padded row stride of P
-}
-
-__global__ void __launch_bounds__(EP_THREADS, 1) k_ecda_pairs(EcdaArgs a) {
-    extern __shared__ __align__(16) float smem[];
-    float* zi = smem;                       // [64][PZS]  centred row tile
-    float* zj = zi + PT * PZS;              // [64][PZS]  centred column chunk
-    float* Pm = zj + PT * PZS;              // [64][PPS]
-    float* mu = Pm + PT * PPS;              // [256] class mean
-    float* ni = mu + DAD_H;                 // [64] |z'_i|^2
-    float* nj = ni + PT;                    // [64]
-    float* wi = nj + PT;                    // [64] omega_i
-    float* wj = wi + PT;                    // [64]
-    int* ri = reinterpret_cast<int*>(wj + PT);  // [64] row ids (-1 = padding)
-    int* pj = ri + PT;                      // [64] list position of column j (-1 = padding)
-    int* dj = pj + PT;                      // [64] column domain (0 clean, 1 noisy)
+__global__ void __launch_bounds__(EP_THREADS) k_ecda_p(EcdaArgs a) {
     __shared__ float s_red[3][EP_THREADS / 32];
-    __shared__ int s_flag;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const EcdaStats* st = a.stats;
-    const int Bg = a.pack.B_local * a.pack.world;
-    const int n_tiles = st->n_tiles;
-    const int Q = a.col_splits;
-    const int tile_id = blockIdx.x / Q, q = blockIdx.x - tile_id * Q;
     float sums[3] = {0.f, 0.f, 0.f};
-
-    if (tile_id < n_tiles) {
-        const EcdaTile t = a.tiles[tile_id];
-        const int c = t.cls;
-        const int off = st->list_off[c], ns = st->n_s[c], n = ns + st->n_t[c];
-        const int dom_i = (t.row_begin - off) >= ns ? 1 : 0;
-        float* part_acc = a.part_acc + (int64_t)blockIdx.x * PT * DAD_H;
-        float* part_rowp = a.part_rowp + (int64_t)blockIdx.x * PT;
-        // ---- stage the class mean and the (centred) row tile
-        mu[tid] = a.mu_all[c * DAD_H + tid];
-        if (tid < PT) {
-            int r = -1;
-            float om = 0.f;
-            if (tid < t.row_count) {
-                r = a.lists[t.row_begin + tid];
-                om = (dom_i && a.class_aware) ? pack_score(a.pack, r - Bg) : 1.f;
-            }
-            ri[tid] = r;
-            wi[tid] = om;
+    const int n_items = st->n_gram_items;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const GramItem gi = a.gram_items[w];
+        const int c = gi.cls;
+        const float ib0 = st->inv_beta[c][0], ib1 = st->inv_beta[c][1], ib2 = st->inv_beta[c][2], ib3 = st->inv_beta[c][3], ib4 = st->inv_beta[c][4];
+        const float css = st->c_ss[c], ctt = st->c_tt[c], cst = st->c_st[c];
+        const float pcoef = -4.f * st->att[c] * a.w_ecda * st->p_scale[c];  // gradient weight scale x the fp16 operand scale of this class
+        // this lane's 8 columns
+        float njv[8], wjv[8];
+        int dj[8];
+        bool jok[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int col = lane * 8 + u;
+            jok[u] = gi.g_col + col < gi.n_cols;
+            const int pos = gi.b_row + col;
+            njv[u] = jok[u] ? a.pos_nsq[pos] : 0.f;
+            wjv[u] = jok[u] ? a.pos_om[pos] : 0.f;
+            dj[u] = jok[u] ? a.pos_dom[pos] : 0;
         }
-        __syncthreads();
-        auto stage = [&](float* dst, float* nsq, const int* rows_or_null, int list_base, int count) {
-            // 8 warps x 8 rows; lane owns features lane*4..+3 and 128+lane*4..+3
+        sums[0] = sums[1] = sums[2] = 0.f;
 #pragma unroll 2
-            for (int rr = 0; rr < 8; ++rr) {
-                const int row = warp * 8 + rr;
-                int r = -1;
-                if (rows_or_null) r = rows_or_null[row];
-                else if (row < count) r = a.lists[list_base + row];
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                if (r >= 0) {
-                    const float* z = r < Bg ? pack_emb_clean(a.pack, r) : pack_emb_strong(a.pack, r - Bg);
-                    v0 = *reinterpret_cast<const float4*>(z + lane * 4);
-                    v1 = *reinterpret_cast<const float4*>(z + 128 + lane * 4);
-                    const float4 m0 = *reinterpret_cast<const float4*>(mu + lane * 4), m1 = *reinterpret_cast<const float4*>(mu + 128 + lane * 4);
-                    v0.x -= m0.x; v0.y -= m0.y; v0.z -= m0.z; v0.w -= m0.w;
-                    v1.x -= m1.x; v1.y -= m1.y; v1.z -= m1.z; v1.w -= m1.w;
-                }
-                *reinterpret_cast<float4*>(dst + row * PZS + lane * 4) = v0;
-                *reinterpret_cast<float4*>(dst + row * PZS + 128 + lane * 4) = v1;
-                float s2 = v0.x * v0.x;
-                s2 = fmaf(v0.y, v0.y, s2); s2 = fmaf(v0.z, v0.z, s2); s2 = fmaf(v0.w, v0.w, s2);
-                s2 = fmaf(v1.x, v1.x, s2); s2 = fmaf(v1.y, v1.y, s2); s2 = fmaf(v1.z, v1.z, s2); s2 = fmaf(v1.w, v1.w, s2);
-                s2 = warp_sum(s2);
-                if (lane == 0) nsq[row] = s2;
+        for (int rr = 0; rr < 16; ++rr) {
+            const int r = warp * 16 + rr;
+            const bool iok = r < gi.n_rows;
+            const int pos_i = gi.a_row + r;
+            const float nii = iok ? a.pos_nsq[pos_i] : 0.f, om_i = iok ? a.pos_om[pos_i] : 0.f;
+            const int dom_i = iok ? a.pos_dom[pos_i] : 0;
+            const int64_t base = (int64_t)(gi.g_row + r) * a.ldg + gi.g_col + lane * 8;
+            float gv[8];
+            if (iok) {
+                const float4 g0 = __ldcg(reinterpret_cast<const float4*>(a.G + base)), g1 = __ldcg(reinterpret_cast<const float4*>(a.G + base + 4));
+                gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w; gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
             }
-        };
-        stage(zi, ni, ri, 0, 0);
+            float pv[8], rowp = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                float p = 0.f;
+                if (iok && jok[u]) {
+                    const bool diag = pos_i == gi.b_row + lane * 8 + u;
+                    const float l2 = diag ? 0.f : fmaxf(nii + njv[u] - 2.f * gv[u], 0.f);
+                    const float e0 = expf(-l2 * ib0), e1 = expf(-l2 * ib1), e2 = expf(-l2 * ib2), e3 = expf(-l2 * ib3), e4 = expf(-l2 * ib4);
+                    const float K = e0 + e1 + e2 + e3 + e4;
+                    const float Kp = e0 * ib0 + e1 * ib1 + e2 * ib2 + e3 * ib3 + e4 * ib4;
+                    const float ww = om_i * wjv[u];
+                    float sblk;
+                    if (dom_i == 0 && dj[u] == 0) { sums[0] += ww * K; sblk = css; }
+                    else if (dom_i == 1 && dj[u] == 1) { sums[1] += ww * K; sblk = ctt; }
+                    else { if (dom_i == 0) sums[2] += ww * K; sblk = -cst; }
+                    p = diag ? 0.f : pcoef * sblk * ww * Kp;  // (z_i - z_i) = 0: the diagonal carries no gradient
+                }
+                pv[u] = p;
+                rowp += p;
+            }
+            uint32_t h[4], l[4];
+            tc::split2_f16(pv[0], pv[1], h[0], l[0]); tc::split2_f16(pv[2], pv[3], h[1], l[1]);
+            tc::split2_f16(pv[4], pv[5], h[2], l[2]); tc::split2_f16(pv[6], pv[7], h[3], l[3]);
+            *reinterpret_cast<uint4*>(a.p_hi + base) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(a.p_lo + base) = make_uint4(l[0], l[1], l[2], l[3]);
+            rowp = warp_sum(rowp);
+            if (lane == 0) a.rowp_part[(int64_t)(gi.g_col >> 8) * a.g_rows_alloc + gi.g_row + r] = rowp;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float v = warp_sum(sums[k]);
+            if (lane == 0) s_red[k][warp] = v;
+        }
         __syncthreads();
+        if (tid < 3) {
+            float v = 0.f;
+            for (int ww = 0; ww < EP_THREADS / 32; ++ww) v += s_red[tid][ww];
+            a.item_sums[w * 3 + tid] = v;
+        }
+        __syncthreads();
+    }
+}
 
-        // phase-B accumulators: rows warp*8 + r, features lane*4 + (f&3) + 128*(f>>2)
-        float acc[8][8], rowp[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            rowp[r] = 0.f;
-#pragma unroll
-            for (int f = 0; f < 8; ++f) acc[r][f] = 0.f;
-        }
-        if (t.feasible) {
-            const float ib0 = st->inv_beta[c][0], ib1 = st->inv_beta[c][1], ib2 = st->inv_beta[c][2], ib3 = st->inv_beta[c][3], ib4 = st->inv_beta[c][4];
-            const float css = st->c_ss[c], ctt = st->c_tt[c], cst = st->c_st[c];
-            const float gscale = -4.f * st->att[c] * a.w_ecda;
-            const int ty = tid >> 4, tx = tid & 15;  // phase A: rows ty + 16a, columns tx + 16b
-            const int n_chunks = ceil_div(n, PT), per = ceil_div(n_chunks, Q);
-            const int ch0 = q * per, ch1 = min(n_chunks, ch0 + per);
-            for (int ch = ch0; ch < ch1; ++ch) {
-                const int j0 = ch * PT;
-                __syncthreads();  // previous chunk's readers of zj / Pm are done
-                if (tid < PT) {
-                    int pos = -1, d = 0;
-                    float om = 0.f;
-                    if (j0 + tid < n) {
-                        pos = off + j0 + tid;
-                        const int r = a.lists[pos];
-                        d = (r >= Bg) ? 1 : 0;
-                        om = (d && a.class_aware) ? pack_score(a.pack, r - Bg) : 1.f;
-                    }
-                    pj[tid] = pos; dj[tid] = d; wj[tid] = om;
-                }
-                stage(zj, nj, nullptr, off + j0, n - j0);
-                __syncthreads();
-                // ---- phase A: the 4x4 dot products of this thread come from the tensor-core Gram (k_gram_tc; L2-resident)
-                float d[4][4];
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    const float* grow = a.G + (int64_t)(t.g_row + ty + 16 * x) * a.ldg + j0 + tx;
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) d[x][y] = __ldcg(grow + 16 * y);
-                }
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    const int i = ty + 16 * x;
-                    const bool i_ok = i < t.row_count;
-                    const float om_i = wi[i], nii = ni[i];
-                    const int pos_i = t.row_begin + i;
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        const int j = tx + 16 * y;
-                        const int pos = pj[j];
-                        float p = 0.f;
-                        if (i_ok && pos >= 0) {
-                            const bool diag = pos == pos_i;
-                            const float l2 = diag ? 0.f : fmaxf(nii + nj[j] - 2.f * d[x][y], 0.f);
-                            const float e0 = expf(-l2 * ib0), e1 = expf(-l2 * ib1), e2 = expf(-l2 * ib2), e3 = expf(-l2 * ib3), e4 = expf(-l2 * ib4);
-                            const float K = e0 + e1 + e2 + e3 + e4;
-                            const float Kp = e0 * ib0 + e1 * ib1 + e2 * ib2 + e3 * ib3 + e4 * ib4;
-                            const float ww = om_i * wj[j];
-                            const int dd = dj[j];
-                            float sblk;
-                            if (dom_i == 0 && dd == 0) { sums[0] += ww * K; sblk = css; }
-                            else if (dom_i == 1 && dd == 1) { sums[1] += ww * K; sblk = ctt; }
-                            else { if (dom_i == 0) sums[2] += ww * K; sblk = -cst; }
-                            p = diag ? 0.f : gscale * sblk * ww * Kp;  // (z_i - z_i) = 0: the diagonal carries no gradient
-                        }
-                        Pm[i * PPS + j] = p;
-                    }
-                }
-                __syncthreads();
-                // ---- phase B: accZ_i += sum_j P_ij z'_j, rowP_i += sum_j P_ij   (rows warp*8.., 8 features per lane)
-#pragma unroll 1
-                for (int j = 0; j < PT; j += 4) {
-                    float4 pr[8];
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) pr[r] = *reinterpret_cast<const float4*>(Pm + (warp * 8 + r) * PPS + j);
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const float4 z0 = *reinterpret_cast<const float4*>(zj + (j + jj) * PZS + lane * 4);
-                        const float4 z1 = *reinterpret_cast<const float4*>(zj + (j + jj) * PZS + 128 + lane * 4);
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            const float p = jj == 0 ? pr[r].x : jj == 1 ? pr[r].y : jj == 2 ? pr[r].z : pr[r].w;
-                            rowp[r] += p;
-                            acc[r][0] = fmaf(p, z0.x, acc[r][0]); acc[r][1] = fmaf(p, z0.y, acc[r][1]);
-                            acc[r][2] = fmaf(p, z0.z, acc[r][2]); acc[r][3] = fmaf(p, z0.w, acc[r][3]);
-                            acc[r][4] = fmaf(p, z1.x, acc[r][4]); acc[r][5] = fmaf(p, z1.y, acc[r][5]);
-                            acc[r][6] = fmaf(p, z1.z, acc[r][6]); acc[r][7] = fmaf(p, z1.w, acc[r][7]);
-                        }
-                    }
-                }
-            }
-        }
-        // ---- this CTA's partial -> workspace
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int row = warp * 8 + r;
-            *reinterpret_cast<float4*>(part_acc + row * DAD_H + lane * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-            *reinterpret_cast<float4*>(part_acc + row * DAD_H + 128 + lane * 4) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
-            if (lane == 0) part_rowp[row] = rowp[r];
-        }
-    }
-    // ---- per-CTA loss partial sums -> fixed-order loss assembly by the last CTA of the grid
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float v = warp_sum(sums[k]);
-        if (lane == 0) s_red[k][warp] = v;
-    }
-    __syncthreads();
-    if (tid < 3) {
-        float v = 0.f;
-        for (int w = 0; w < EP_THREADS / 32; ++w) v += s_red[tid][w];
-        a.tile_sums[blockIdx.x * 3 + tid] = v;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned prev = atomicAdd(&a.counter[1], 1u);
-        s_flag = (prev == gridDim.x - 1u);
-    }
-    __syncthreads();
-    if (!s_flag) return;
-    __threadfence();
+// k_ecda_loss (one CTA): per-class block sums over this rank's Gram items in fixed order -> this rank's share of the ECDA loss
+__global__ void __launch_bounds__(EP_THREADS) k_ecda_loss(EcdaArgs a) {
+    __shared__ float s_cs[ECDA_MAXC * 3][EP_THREADS / 32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const EcdaStats* st = a.stats;
+    const int n_items = st->n_gram_items;
     float cs[ECDA_MAXC][3];
 #pragma unroll
     for (int c = 0; c < ECDA_MAXC; ++c) cs[c][0] = cs[c][1] = cs[c][2] = 0.f;
-    for (int e = tid; e < n_tiles * Q; e += EP_THREADS) {
-        const int tl = e / Q;
-        const int c = a.tiles[tl].cls;
-        if (!a.tiles[tl].feasible) continue;
-        const float v0 = __ldcg(&a.tile_sums[e * 3 + 0]), v1 = __ldcg(&a.tile_sums[e * 3 + 1]), v2 = __ldcg(&a.tile_sums[e * 3 + 2]);
+    for (int e = tid; e < n_items; e += EP_THREADS) {
+        const int c = a.gram_items[e].cls;
+        const float v0 = a.item_sums[e * 3 + 0], v1 = a.item_sums[e * 3 + 1], v2 = a.item_sums[e * 3 + 2];
 #pragma unroll
         for (int cc = 0; cc < ECDA_MAXC; ++cc)
             if (cc == c) { cs[cc][0] += v0; cs[cc][1] += v1; cs[cc][2] += v2; }
     }
-    __shared__ float s_cs[ECDA_MAXC * 3][EP_THREADS / 32];
 #pragma unroll
     for (int c = 0; c < ECDA_MAXC; ++c)
 #pragma unroll
@@ -541,7 +447,6 @@ __global__ void __launch_bounds__(EP_THREADS, 1) k_ecda_pairs(EcdaArgs a) {
         }
     __syncthreads();
     if (tid != 0) return;
-    a.counter[1] = 0u;
     float loss = 0.f;
     if (st->active) {
         for (int c = 0; c < st->n_classes; ++c) {
@@ -560,49 +465,51 @@ __global__ void __launch_bounds__(EP_THREADS, 1) k_ecda_pairs(EcdaArgs a) {
     a.loss_out[2] = loss;  // this rank's share; shares sum to the global-batch ECDA loss
 }
 
-// k_ecda_fold: one CTA per row tile: folds the Q column-split partials of k_ecda_pairs in fixed q order, adds the compactness
-// and repulsion gradients of the noisy rows and accumulates into g (each gradient row has exactly one writer: deterministic).
+// k_ecda_fold: one warp per owned member row: d/dz_i = rowP_i z'_i - (P Z')_i  (= sum_j P_ij (z_i - z_j), I/utils.py:537 differentiated;
+// (P Z') from k_pz_tc, rowP folded over the column blocks in fixed order) + the compactness and repulsion gradients of the noisy
+// rows, accumulated into g.  Every gradient row has exactly one writer: no float atomics, bit-reproducible.
 __global__ void __launch_bounds__(EP_THREADS) k_ecda_fold(EcdaArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const EcdaStats* st = a.stats;
-    const int tile_id = blockIdx.x;  // blockIdx.y = which 8 rows of the tile (one row per warp: Q dependent loads per row,
-    if (tile_id >= st->n_tiles) return;  // so the fold is latency-bound and wants many independent rows in flight)
-    const int Bg = a.pack.B_local * a.pack.world, Q = a.col_splits;
+    const int tile_id = blockIdx.x;
+    if (tile_id >= st->n_tiles) return;
+    const int Bg = a.pack.B_local * a.pack.world;
     const EcdaTile t = a.tiles[tile_id];
     const int c = t.cls;
     const int dom_i = (t.row_begin - st->list_off[c]) >= st->n_s[c] ? 1 : 0;
     const float comp_k = (t.feasible && dom_i) ? a.w_ecda * st->att[c] * a.gamma_comp * 2.f / (float)st->n_t[c] : 0.f;
-    {
-        const int row = blockIdx.y * 8 + warp;
-        if (row >= t.row_count) return;
-        const int rid = a.lists[t.row_begin + row];
-        float g8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        float rp = 0.f;
-        if (t.feasible) {
-            for (int qq = 0; qq < Q; ++qq) {
-                const float* pa = a.part_acc + ((int64_t)(tile_id * Q + qq) * PT + row) * DAD_H;
-                const float4 u0 = *reinterpret_cast<const float4*>(pa + lane * 4), u1 = *reinterpret_cast<const float4*>(pa + 128 + lane * 4);
-                g8[0] += u0.x; g8[1] += u0.y; g8[2] += u0.z; g8[3] += u0.w; g8[4] += u1.x; g8[5] += u1.y; g8[6] += u1.z; g8[7] += u1.w;
-                rp += a.part_rowp[(int64_t)(tile_id * Q + qq) * PT + row];
-            }
-        }
-        const int gi = rid < Bg ? rid : rid - Bg;
-        const float* z = rid < Bg ? pack_emb_clean(a.pack, rid) : pack_emb_strong(a.pack, rid - Bg);
-        float* g = (rid < Bg ? a.g_clean : a.g_strong) + (int64_t)(gi - a.rank * a.pack.B_local) * DAD_H;
+    const int row = blockIdx.y * 8 + warp;
+    if (row >= t.row_count) return;
+    const int rid = a.lists[t.row_begin + row];
+    float g8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float rp = 0.f;
+    if (t.feasible) {
+        const float unscale = 1.0f / st->p_scale[c];
+        const int n_cb = (st->n_s[c] + st->n_t[c] + 255) >> 8;
+        for (int cb = 0; cb < n_cb; ++cb) rp += a.rowp_part[(int64_t)cb * a.g_rows_alloc + t.g_row + row];
+        rp *= unscale;
+        const float* pa = a.accz + (int64_t)(t.g_row + row) * DAD_H;
+        const float4 u0 = *reinterpret_cast<const float4*>(pa + lane * 4), u1 = *reinterpret_cast<const float4*>(pa + 128 + lane * 4);
+        g8[0] = u0.x * unscale; g8[1] = u0.y * unscale; g8[2] = u0.z * unscale; g8[3] = u0.w * unscale;
+        g8[4] = u1.x * unscale; g8[5] = u1.y * unscale; g8[6] = u1.z * unscale; g8[7] = u1.w * unscale;
+    }
+    const int gi = rid < Bg ? rid : rid - Bg;
+    const float* z = rid < Bg ? pack_emb_clean(a.pack, rid) : pack_emb_strong(a.pack, rid - Bg);
+    float* g = (rid < Bg ? a.g_clean : a.g_strong) + (int64_t)(gi - a.rank * a.pack.B_local) * DAD_H;
 #pragma unroll
-        for (int f = 0; f < 8; ++f) {
-            const int h = lane * 4 + (f & 3) + 128 * (f >> 2);
-            const float zr = z[h];
-            float v = rp * (zr - a.mu_all[c * DAD_H + h]) - g8[f];  // sum_j P_ij (z_i - z_j) on the centred rows
-            if (dom_i && a.class_aware) v += comp_k * (zr - a.mu_t[c * DAD_H + h]) + a.w_ecda * a.rep_grad[c * DAD_H + h];
-            g[h] += v;
-        }
+    for (int f = 0; f < 8; ++f) {
+        const int h = lane * 4 + (f & 3) + 128 * (f >> 2);
+        const float zr = z[h];
+        float v = rp * (zr - a.mu_all[c * DAD_H + h]) - g8[f];
+        if (dom_i && a.class_aware) v += comp_k * (zr - a.mu_t[c * DAD_H + h]) + a.w_ecda * a.rep_grad[c * DAD_H + h];
+        g[h] += v;
     }
 }
 
-int launch_ecda_gram(const EcdaArgs& a, cudaStream_t st);  // k_gram_tc.cu
+int launch_ecda_gram(const EcdaArgs& a, cudaStream_t st);  // k_gram_tc.cu: pack + Gram GEMM
+int launch_ecda_pz(const EcdaArgs& a, cudaStream_t st);    // k_gram_tc.cu: (P Z') GEMM
 int ecda_max_gram_items(int B_local, int world) { return (ceil_div(2 * B_local, 128) + 8) * (ceil_div(2 * B_local * world, 256) + 1); }
-size_t ecda_pairs_smem_bytes() { return (size_t)(2 * PT * PZS + PT * PPS + DAD_H + 4 * PT) * sizeof(float) + 3 * PT * sizeof(int); }
+int ecda_max_pz_items(int B_local) { return ceil_div(2 * B_local, 128) + 8; }
 int ecda_prep_grid(int B_global) {
     // rows per CTA <= 256 (k_ecda_prep classifies its chunk with one thread per row); aim at ~16 rows per CTA
     int g = ceil_div(2 * B_global, 16);
@@ -612,20 +519,8 @@ int ecda_prep_grid(int B_global) {
     return g < 1 ? 1 : g;
 }
 int ecda_max_tiles(int B_local) { return ceil_div(2 * B_local, ECDA_TR) + 2 * ECDA_MAXC; }
-// column splits per row tile: the kernel runs one CTA per SM (152 KB of shared memory), so the grid should be ONE wave:
-// Q = floor(148 / row tiles this rank can own), at most 16.  (Q = 13 over 24 tiles = 2.1 waves cost 2x at 1/8 of the rows.)
-int ecda_col_splits(int B_local) {
-    const int tiles = ceil_div(2 * B_local, ECDA_TR);
-    int q = 148 / (tiles < 1 ? 1 : tiles);
-    return q < 1 ? 1 : (q > 16 ? 16 : q);
-}
 
 int launch_ecda(const EcdaArgs& a, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_ecda_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ecda_pairs_smem_bytes());
-        attr_set = true;
-    }
     const size_t stats_smem = (size_t)2 * a.pack.B_local * a.pack.world;  // row slots, one byte each
     if (stats_smem > 160 * 1024) return dad_set_error(DAD_ERR_UNSUPPORTED, "ecda: global batch too large for the single-CTA list builder");
     if (stats_smem > 40 * 1024) {
@@ -638,11 +533,16 @@ int launch_ecda(const EcdaArgs& a, cudaStream_t st) {
     DAD_CHECK_LAUNCH("k_ecda_reduce");
     k_ecda_stats<<<1, EP_THREADS, stats_smem, st>>>(a);
     DAD_CHECK_LAUNCH("k_ecda_stats");
-    int rc = launch_ecda_gram(a, st);
+    int rc = launch_ecda_gram(a, st);  // z' -> fp16 hi/lo, G = Z' Z'^T on tcgen05
     if (rc) return rc;
-    k_ecda_pairs<<<a.max_tiles * a.col_splits, EP_THREADS, ecda_pairs_smem_bytes(), st>>>(a);
-    DAD_CHECK_LAUNCH("k_ecda_pairs");
+    const int pg = a.max_gram_items < 4 * 148 ? a.max_gram_items : 4 * 148;
+    k_ecda_p<<<pg < 1 ? 1 : pg, EP_THREADS, 0, st>>>(a);
+    DAD_CHECK_LAUNCH("k_ecda_p");
+    rc = launch_ecda_pz(a, st);        // (P Z') on tcgen05
+    if (rc) return rc;
     k_ecda_fold<<<dim3(a.max_tiles, ECDA_TR / 8), EP_THREADS, 0, st>>>(a);
     DAD_CHECK_LAUNCH("k_ecda_fold");
+    k_ecda_loss<<<1, EP_THREADS, 0, st>>>(a);
+    DAD_CHECK_LAUNCH("k_ecda_loss");
     return DAD_OK;
 }

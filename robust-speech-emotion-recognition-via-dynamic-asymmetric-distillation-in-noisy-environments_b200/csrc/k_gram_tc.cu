@@ -145,6 +145,131 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ CUt
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_pz_tc: the second ECDA GEMM, (P Z')[i][h] = sum_j P_ij z'_j[h], on tcgen05.  A = P rows (K-major: the member index j is the
+// contiguous axis of P), B = Z' rows [j][h] = MN-major (h contiguous), so neither operand is transposed in memory -- the same
+// operand-major trick as the encoder backward (k_enc_tc.cu).  One work item = 128 owned rows x all 256 features, K = the class's
+// members in k-blocks of 64; P columns beyond the class are zeros (k_ecda_p writes whole 256-column blocks), so ragged class
+// sizes need no tail handling.  Same warp roles / barriers / f16x3 products as k_gram_tc.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GRAM_THREADS, 1)
+k_pz_tc(const __grid_constant__ CUtensorMap tm_ph, const __grid_constant__ CUtensorMap tm_pl, const __grid_constant__ CUtensorMap tm_zh,
+        const __grid_constant__ CUtensorMap tm_zl, const PzItem* __restrict__ items, const int* __restrict__ n_items_ptr, float* __restrict__ accz) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GOFF_BARS);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + 2;
+    uint64_t* tfull = bars + 4;
+    uint64_t* tempty = bars + 6;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = *n_items_ptr;
+    constexpr uint32_t B_CHUNK = GBK * 128;  // 8 KB: one 64-feature chunk of a 64-member k-block (MN-major B)
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tm_ph); tc::prefetch_tmap(&tm_pl); tc::prefetch_tmap(&tm_zh); tc::prefetch_tmap(&tm_zl);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < GSTAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], 4); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) {
+        tc::tmem_alloc(tmem_ptr, 512);
+        tc::tmem_relinquish();
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+                const PzItem pi = items[w];
+                for (int kb = 0; kb < pi.n_kb; ++kb, ++it) {
+                    const uint32_t s = it % GSTAGES, ph = (it / GSTAGES) & 1;
+                    tc::mbar_wait(&empty[s], ph ^ 1);
+                    tc::mbar_arrive_expect_tx(&full[s], GSTAGE);
+                    uint8_t* st = smem + s * GSTAGE;
+                    tc::tma_load_2d(st + GOFF_AHI, &tm_ph, &full[s], kb * GBK, pi.g_row);
+                    tc::tma_load_2d(st + GOFF_ALO, &tm_pl, &full[s], kb * GBK, pi.g_row);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        tc::tma_load_2d(st + GOFF_BHI + c * B_CHUNK, &tm_zh, &full[s], c * 64, pi.b_row + kb * GBK);
+                        tc::tma_load_2d(st + GOFF_BLO + c * B_CHUNK, &tm_zl, &full[s], c * 64, pi.b_row + kb * GBK);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = tc::make_idesc_f16(GBM, GBN, 0, 1);  // A K-major, B MN-major
+        uint32_t it = 0, ti = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++ti) {
+            const int n_kb = items[w].n_kb;
+            const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
+            tc::mbar_wait(&tempty[acc], tph ^ 1);
+            tc::tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * GBN;
+            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const uint32_t s = it % GSTAGES, ph = (it / GSTAGES) & 1;
+                tc::mbar_wait(&full[s], ph);
+                tc::tcgen05_fence_after();
+                if (lane == 0) {
+                    const uint32_t base = tc::smem_u32(smem + s * GSTAGE);
+#pragma unroll
+                    for (int prod = 0; prod < 3; ++prod) {
+                        const uint32_t a_off = (prod == 2) ? GOFF_ALO : GOFF_AHI;
+                        const uint32_t b_off = (prod == 1) ? GOFF_BLO : GOFF_BHI;
+#pragma unroll
+                        for (int k = 0; k < GBK / 16; ++k) {
+                            const uint64_t ad = tc::make_smem_desc(base + a_off + k * 32, 16, 1024);
+                            const uint64_t bd = tc::make_smem_desc(base + b_off + k * 2048, B_CHUNK, 1024);  // LBO = chunk pitch, SBO = 8-member group
+                            tc::umma_f16(d_tmem, ad, bd, idesc, (kb | prod | k) != 0);
+                        }
+                    }
+                    tc::umma_commit(&empty[s]);
+                    if (kb == n_kb - 1) tc::umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        uint32_t ti = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++ti) {
+            const PzItem pi = items[w];
+            const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
+            tc::mbar_wait(&tfull[acc], tph);
+            tc::tcgen05_fence_after();
+            float* row = accz + (int64_t)(pi.g_row + q * 32 + lane) * DAD_H;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * GBN;
+            constexpr float unscale = 1.0f / ECDA_ZS;  // the P scale (per class) is removed by k_ecda_fold
+#pragma unroll 1
+            for (int c = 0; c < GBN / 32; ++c) {
+                uint32_t r[32];
+                tc::tmem_ld_32x32(taddr + c * 32, r);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(row + c * 32 + j) = make_float4(__uint_as_float(r[j]) * unscale, __uint_as_float(r[j + 1]) * unscale,
+                                                                                __uint_as_float(r[j + 2]) * unscale, __uint_as_float(r[j + 3]) * unscale);
+            }
+            tc::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc::tcgen05_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // Z_hi / Z_lo rows in LIST ORDER (class by class, clean members then noisy members): z' = z - mean of the row's class, scaled 2^8
 __global__ void __launch_bounds__(256) k_ecda_pack(EcdaArgs a) {
     const EcdaStats* st = a.stats;
@@ -162,6 +287,19 @@ __global__ void __launch_bounds__(256) k_ecda_pack(EcdaArgs a) {
     const float* z = r < Bg ? pack_emb_clean(a.pack, r) : pack_emb_strong(a.pack, r - Bg);
     const float4 v0 = *reinterpret_cast<const float4*>(z + lane * 8), v1 = *reinterpret_cast<const float4*>(z + lane * 8 + 4);
     const float4 m0 = *reinterpret_cast<const float4*>(a.mu_all + c * DAD_H + lane * 8), m1 = *reinterpret_cast<const float4*>(a.mu_all + c * DAD_H + lane * 8 + 4);
+    {
+        const float d[8] = {v0.x - m0.x, v0.y - m0.y, v0.z - m0.z, v0.w - m0.w, v1.x - m1.x, v1.y - m1.y, v1.z - m1.z, v1.w - m1.w};
+        float s2 = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s2 = fmaf(d[u], d[u], s2);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+            const int dom = r >= Bg ? 1 : 0;
+            a.pos_nsq[pos] = s2;
+            a.pos_om[pos] = (dom && a.class_aware) ? pack_score(a.pack, r - Bg) : 1.f;
+            a.pos_dom[pos] = dom;
+        }
+    }
     uint32_t h[4], l[4];
     tc::split2_f16((v0.x - m0.x) * ECDA_ZS, (v0.y - m0.y) * ECDA_ZS, h[0], l[0]);
     tc::split2_f16((v0.z - m0.z) * ECDA_ZS, (v0.w - m0.w) * ECDA_ZS, h[1], l[1]);
@@ -193,5 +331,26 @@ int launch_ecda_gram(const EcdaArgs& a, cudaStream_t st) {
     if (grid < 1) grid = 1;
     k_gram_tc<<<grid, GRAM_THREADS, GRAM_SMEM, st>>>(ah, al, bh, bl, a.gram_items, &a.stats->n_gram_items, a.G, a.ldg);
     DAD_CHECK_LAUNCH("k_gram_tc");
+    return DAD_OK;
+}
+
+int launch_ecda_pz(const EcdaArgs& a, cudaStream_t st) {
+    const int R = 2 * a.pack.B_local * a.pack.world;
+    CUtensorMap ph, pl, zh, zl;
+    int rc = make_tmap_f16(&ph, a.p_hi, (uint64_t)a.g_rows_alloc, (uint64_t)a.ldg, GBM);
+    if (!rc) rc = make_tmap_f16(&pl, a.p_lo, (uint64_t)a.g_rows_alloc, (uint64_t)a.ldg, GBM);
+    if (!rc) rc = make_tmap_f16(&zh, a.z_hi, (uint64_t)R, DAD_H, GBK);
+    if (!rc) rc = make_tmap_f16(&zl, a.z_lo, (uint64_t)R, DAD_H, GBK);
+    if (rc) return rc;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_pz_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM);
+        if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "ecda pz: cannot opt in to %u B shared memory: %s", GRAM_SMEM, cudaGetErrorString(e));
+        attr = true;
+    }
+    int grid = a.max_pz_items < sm_count() ? a.max_pz_items : sm_count();
+    if (grid < 1) grid = 1;
+    k_pz_tc<<<grid, GRAM_THREADS, GRAM_SMEM, st>>>(ph, pl, zh, zl, a.pz_items, &a.stats->n_pz_items, a.accz);
+    DAD_CHECK_LAUNCH("k_pz_tc");
     return DAD_OK;
 }

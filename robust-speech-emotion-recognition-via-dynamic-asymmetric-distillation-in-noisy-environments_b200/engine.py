@@ -500,7 +500,7 @@ class DADStepEngine:
             ea.g_clean, ea.g_strong, ea.loss_out = hb.g_clean, hb.g_strong, hb.loss_out
             ea.ws, ea.ws_bytes = self.ecda_ws.data_ptr(), self.ecda_ws.numel()
             check(L.dad_ecda(C.byref(ea), s))
-            self.launches_per_step += 7
+            self.launches_per_step += 9
         else:
             self.g_ext[NPARAM + 2:NPARAM + 3].zero_()
         if noisy and sc.w_scl > 0:
