@@ -29,7 +29,6 @@ int head_grid(int B_local);
 int launch_certainty(const float* probs, int B, int use_entropy, float* scores, int* preds, cudaStream_t st);
 int launch_dacp(DacpArgs a, cudaStream_t st);
 int launch_head_bwd(const HeadBwdArgs& a, cudaStream_t st);
-size_t ecda_pairs_smem_bytes();
 int ecda_prep_grid(int B_global);
 int ecda_max_tiles(int B_local);
 int ecda_max_gram_items(int B_local, int world);

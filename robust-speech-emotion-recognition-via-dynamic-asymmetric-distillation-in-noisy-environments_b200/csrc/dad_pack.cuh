@@ -33,7 +33,7 @@ struct EcdaTile { int cls, row_begin, row_count, feasible, g_row, pad_[3]; };  /
 struct GramItem { int a_row, b_row, g_row, g_col, n_rows, n_cols, cls, pad_; };
 struct PzItem { int g_row, b_row, n_kb, cls; };  // (P Z') block: P rows g_row..+127, Z' rows from b_row, n_kb k-blocks of 64 members
 
-struct EcdaStats {  // written by k_ecda_prep's last CTA, read by k_ecda_pairs
+struct EcdaStats {  // written by k_ecda_stats, read by the Gram / P / fold / loss kernels
     int n_s[ECDA_MAXC], n_t[ECDA_MAXC], feasible[ECDA_MAXC], list_off[ECDA_MAXC];
     float inv_beta[ECDA_MAXC][5];                             // 1/(bw*2^r + 1e-8)
     float c_ss[ECDA_MAXC], c_tt[ECDA_MAXC], c_st[ECDA_MAXC];  // 1/(D_ss+1e-8), 1/(D_tt+1e-8), 1/(D_st+1e-8)
@@ -82,7 +82,7 @@ struct EcdaArgs {
     int* pos_dom;
     PzItem* pz_items;       // [max_pz_items]
     int max_pz_items, g_rows_alloc;
-    float* mu_all;          // [4][256] mean of ALL members (clean + masked noisy) of class c: the centring point of k_ecda_pairs
+    float* mu_all;          // [4][256] mean of ALL members (clean + masked noisy) of class c: the centring point of the Gram (k_ecda_pack)
     float *g_clean, *g_strong;  // [B_local,256], accumulated (+=)
     float* loss_out;        // [2] = ecda loss share, [3] = full-batch ecda loss when world == 1
     unsigned* counter;      // [2] zero-initialised, self-resetting

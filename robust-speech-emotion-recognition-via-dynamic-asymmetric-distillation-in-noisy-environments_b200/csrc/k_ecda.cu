@@ -290,45 +290,69 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
         }
         __syncthreads();
     }
-    // ---------------- phase 4: row tiles for the rows this rank owns
+    // ---------------- phase 4: work tables for the rows this rank owns (fold tiles of 64 rows, Gram items, (P Z') items)
+    // Thread 0 lays out the <= 8 (class, domain) segments (first / last owned position, bases into G and into the tables); then
+    // all threads emit the entries in parallel (a serial loop over ~700 entries cost 30 us of this single CTA).
     __threadfence();
     __syncthreads();
+    __shared__ int sg_first[8], sg_last[8], sg_grow[8], sg_tile0[8], sg_item0[8], sg_pz0[8], sg_feas[8], sg_on[8], s_tot[3];
     if (tid == 0) {
         int nt_ = 0, ng_ = 0, np_ = 0, g_rows = 0;
-        for (int c = 0; c < NC; ++c) {
+        for (int sgi = 0; sgi < 8; ++sgi) {
+            const int c = sgi >> 1, dom = sgi & 1;
+            sg_on[sgi] = 0;
+            if (c >= NC) continue;
             const int off = st->list_off[c], ns = s_cnt[c], n_c = s_cnt[c] + s_cnt[4 + c];
             const bool feas = st->feasible[c] != 0;
-            for (int dom = 0; dom < 2; ++dom) {
-                if (dom == 0 && !feas) continue;                              // clean rows only matter through the MMD
-                if (dom == 1 && !feas && !(a.class_aware && nvalid > 1)) continue;  // noisy rows: MMD/comp or repulsion
-                const int b0 = off + (dom ? ns : 0);
-                const int first = b0 + s_lt_lo[dom * 4 + c], last = b0 + s_lt_hi[dom * 4 + c];
-                for (int p = first; p < last && nt_ < a.max_tiles; p += ECDA_TR) {
-                    EcdaTile t;
-                    t.cls = c; t.row_begin = p; t.row_count = min(ECDA_TR, last - p); t.feasible = feas ? 1 : 0;
-                    t.g_row = g_rows + (p - first);
-                    a.tiles[nt_++] = t;
-                }
-                if (feas) {  // Gram work items: 128-row blocks of this segment x 256-column blocks of the class (k_gram_tc)
-                    for (int p = first; p < last; p += 128)
-                        for (int cb = 0; cb < n_c && ng_ < a.max_gram_items; cb += 256) {
-                            GramItem gi;
-                            gi.a_row = p; gi.b_row = off + cb; gi.g_row = g_rows + (p - first); gi.g_col = cb;
-                            gi.n_rows = min(128, last - p); gi.n_cols = n_c; gi.cls = c; gi.pad_ = 0;
-                            a.gram_items[ng_++] = gi;
-                        }
-                    for (int p = first; p < last && np_ < a.max_pz_items; p += 128) {
-                        PzItem pi;
-                        pi.g_row = g_rows + (p - first); pi.b_row = off; pi.n_kb = (n_c + 63) / 64; pi.cls = c;
-                        a.pz_items[np_++] = pi;
-                    }
-                    g_rows += ((last - first + 127) / 128) * 128;
-                }
+            if (dom == 0 && !feas) continue;                              // clean rows only matter through the MMD
+            if (dom == 1 && !feas && !(a.class_aware && nvalid > 1)) continue;  // noisy rows: MMD/comp or repulsion
+            const int b0 = off + (dom ? ns : 0);
+            const int first = b0 + s_lt_lo[dom * 4 + c], last = b0 + s_lt_hi[dom * 4 + c];
+            int ntl = (last - first + ECDA_TR - 1) / ECDA_TR;
+            if (nt_ + ntl > a.max_tiles) ntl = a.max_tiles - nt_;
+            sg_on[sgi] = 1; sg_first[sgi] = first; sg_last[sgi] = last; sg_grow[sgi] = g_rows; sg_feas[sgi] = feas ? 1 : 0;
+            sg_tile0[sgi] = nt_; sg_item0[sgi] = ng_; sg_pz0[sgi] = np_;
+            nt_ += ntl;
+            if (feas) {
+                const int rb = (last - first + 127) / 128, cbs = (n_c + 255) / 256;
+                ng_ += rb * cbs; np_ += rb;
+                g_rows += rb * 128;
             }
         }
-        st->n_tiles = nt_;
-        st->n_gram_items = ng_;
-        st->n_pz_items = np_;
+        if (ng_ > a.max_gram_items || np_ > a.max_pz_items) { ng_ = 0; np_ = 0; }  // cannot happen (tables are sized for the worst case)
+        s_tot[0] = nt_; s_tot[1] = ng_; s_tot[2] = np_;
+        st->n_tiles = nt_; st->n_gram_items = ng_; st->n_pz_items = np_;
+    }
+    __syncthreads();
+    for (int sgi = 0; sgi < 8; ++sgi) {
+        if (!sg_on[sgi]) continue;
+        const int c = sgi >> 1;
+        const int off = st->list_off[c], n_c = s_cnt[c] + s_cnt[4 + c];
+        const int first = sg_first[sgi], last = sg_last[sgi], grow = sg_grow[sgi], feas = sg_feas[sgi];
+        const int ntl = min((last - first + ECDA_TR - 1) / ECDA_TR, a.max_tiles - sg_tile0[sgi]);
+        for (int i = tid; i < ntl; i += EP_THREADS) {
+            const int p = first + i * ECDA_TR;
+            EcdaTile t;
+            t.cls = c; t.row_begin = p; t.row_count = min(ECDA_TR, last - p); t.feasible = feas; t.g_row = grow + (p - first);
+            t.pad_[0] = t.pad_[1] = t.pad_[2] = 0;
+            a.tiles[sg_tile0[sgi] + i] = t;
+        }
+        if (feas && s_tot[1] > 0) {
+            const int rb = (last - first + 127) / 128, cbs = (n_c + 255) / 256;
+            for (int i = tid; i < rb * cbs; i += EP_THREADS) {
+                const int r = i / cbs, cb = i - r * cbs;
+                const int p = first + r * 128;
+                GramItem gi;
+                gi.a_row = p; gi.b_row = off + cb * 256; gi.g_row = grow + r * 128; gi.g_col = cb * 256;
+                gi.n_rows = min(128, last - p); gi.n_cols = n_c; gi.cls = c; gi.pad_ = 0;
+                a.gram_items[sg_item0[sgi] + i] = gi;
+            }
+            for (int i = tid; i < rb; i += EP_THREADS) {
+                PzItem pi;
+                pi.g_row = grow + i * 128; pi.b_row = off; pi.n_kb = (n_c + 63) / 64; pi.cls = c;
+                a.pz_items[sg_pz0[sgi] + i] = pi;
+            }
+        }
     }
 }
 
@@ -366,7 +390,7 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_p(EcdaArgs a) {
             dj[u] = jok[u] ? a.pos_dom[pos] : 0;
         }
         sums[0] = sums[1] = sums[2] = 0.f;
-#pragma unroll 2
+#pragma unroll 4  // four rows' G loads in flight per warp (the pass is L2-latency bound)
         for (int rr = 0; rr < 16; ++rr) {
             const int r = warp * 16 + rr;
             const bool iok = r < gi.n_rows;
