@@ -170,6 +170,9 @@ typedef struct dad_ecda_args {
     float* loss_out;                       /* out [2] = this rank's share of the (unweighted) ECDA loss */
     void* ws;
     size_t ws_bytes;
+    int32_t phases;                        /* 0 or 3 = everything; 1 = statistics + the two tensor-core GEMMs (reads the pack, the mask
+                                              and nothing of g_*), 2 = fold into g_* + loss.  Splitting lets the caller run phase 1
+                                              concurrently with dad_head_bwd (which WRITES g_*) on another stream. */
 } dad_ecda_args;
 size_t dad_ecda_workspace_bytes(int32_t B_local, int32_t world);
 int dad_ecda(const dad_ecda_args* a, void* stream);

@@ -69,7 +69,7 @@ class EcdaArgs(C.Structure):
     _fields_ = [("pack", Pack), ("rank", C.c_int32), ("class_aware", C.c_int32), ("mask", C.c_void_p), ("nmask", C.c_void_p),
                 ("w_class", C.c_void_p), ("lambda_cls", C.c_float), ("gamma_comp", C.c_float), ("delta_rep", C.c_float),
                 ("w_ecda", C.c_float), ("g_clean", C.c_void_p), ("g_strong", C.c_void_p), ("loss_out", C.c_void_p),
-                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t), ("phases", C.c_int32)]
 
 
 class SclArgs(C.Structure):

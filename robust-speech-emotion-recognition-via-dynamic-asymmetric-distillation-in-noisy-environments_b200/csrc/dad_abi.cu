@@ -316,7 +316,7 @@ static EcdaCarve ecda_carve(int B_local, int world) {
     c.p_hi = o; o = align_up(o + g_rows * ldg * sizeof(unsigned short), 1024);
     c.p_lo = o; o = align_up(o + g_rows * ldg * sizeof(unsigned short), 1024);
     c.rowp_part = o; o = align_up(o + (ldg / 256) * g_rows * sizeof(float), 256);
-    c.accz = o; o = align_up(o + g_rows * DAD_H * sizeof(float), 256);
+    c.accz = o; o = align_up(o + (size_t)ECDA_PZ_SPLITS * g_rows * DAD_H * sizeof(float), 256);
     c.item_sums = o; o = align_up(o + (size_t)ecda_max_gram_items(B_local, world) * 3 * sizeof(float), 256);
     c.pos_nsq = o; o = align_up(o + (size_t)2 * Bg * sizeof(float), 256);
     c.pos_om = o; o = align_up(o + (size_t)2 * Bg * sizeof(float), 256);
@@ -357,6 +357,7 @@ int dad_ecda(const dad_ecda_args* a, void* stream) {
     k.accz = (float*)(w + c.accz); k.item_sums = (float*)(w + c.item_sums); k.pos_nsq = (float*)(w + c.pos_nsq);
     k.pos_om = (float*)(w + c.pos_om); k.pos_dom = (int*)(w + c.pos_dom); k.pz_items = (PzItem*)(w + c.pz_items);
     k.max_pz_items = ecda_max_pz_items(a->pack.B_local); k.g_rows_alloc = 2 * a->pack.B_local + 8 * 128;
+    k.phases = (a->phases & 3) ? (a->phases & 3) : 3;
     k.max_tiles = ecda_max_tiles(a->pack.B_local);
     k.prep_grid = ecda_prep_grid(a->pack.B_local * a->pack.world);
     return launch_ecda(k, (cudaStream_t)stream);

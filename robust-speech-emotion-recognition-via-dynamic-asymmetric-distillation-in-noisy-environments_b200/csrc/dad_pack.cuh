@@ -31,7 +31,9 @@ constexpr float ECDA_ZS = 256.0f;  // power-of-two scale of the centred embeddin
 struct EcdaTile { int cls, row_begin, row_count, feasible, g_row, pad_[3]; };  // g_row: first row of this tile in the Gram buffer
 // 128 list rows from a_row (n_rows valid) x 256 list rows from b_row (columns g_col.. of the class's n_cols members) -> G[g_row.., g_col..]
 struct GramItem { int a_row, b_row, g_row, g_col, n_rows, n_cols, cls, pad_; };
-struct PzItem { int g_row, b_row, n_kb, cls; };  // (P Z') block: P rows g_row..+127, Z' rows from b_row, n_kb k-blocks of 64 members
+// (P Z') block: P rows g_row..+127, Z' rows from b_row; this item covers k-blocks [kb0, kb0 + n_kb) of 64 members (split-K slice `slice`)
+struct PzItem { int g_row, b_row, kb0, n_kb, slice, cls, pad_[2]; };
+constexpr int ECDA_PZ_SPLITS = 4;  // max split-K slices of the (P Z') GEMM (fills the SMs when a rank owns few row blocks)
 
 struct EcdaStats {  // written by k_ecda_stats, read by the Gram / P / fold / loss kernels
     int n_s[ECDA_MAXC], n_t[ECDA_MAXC], feasible[ECDA_MAXC], list_off[ECDA_MAXC];
@@ -42,7 +44,7 @@ struct EcdaStats {  // written by k_ecda_stats, read by the Gram / P / fold / lo
     float rep;                                                // repulsion loss (<= 0)
     float rho;                                                // delta * sum_{feasible} a_c
     int n_tiles, any_feasible, n_classes, active;
-    int n_gram_items, n_pz_items, pad_[2];
+    int n_gram_items, n_pz_items, pz_splits, pad_;
     float p_scale[ECDA_MAXC];                                 // power-of-two scale of P before its fp16 split
 };
 
@@ -75,7 +77,7 @@ struct EcdaArgs {
     unsigned short* p_hi;   // [g_rows_alloc][ldg] fp16 hi / lo split of the scaled gradient weights P (k_ecda_p)
     unsigned short* p_lo;
     float* rowp_part;       // [ldg/256][g_rows_alloc] row sums of (scaled) P per 256-column block
-    float* accz;            // [g_rows_alloc][256] (scaled) P Z' (k_pz_tc)
+    float* accz;            // [ECDA_PZ_SPLITS][g_rows_alloc][256] (scaled) P Z' split-K slices (k_pz_tc), summed in slice order by k_ecda_fold
     float* item_sums;       // [max_gram_items][3] weighted block sums of K per Gram item
     float* pos_nsq;         // [2*B_global] |z'|^2, omega, domain of every list position (k_ecda_pack)
     float* pos_om;
@@ -86,7 +88,7 @@ struct EcdaArgs {
     float *g_clean, *g_strong;  // [B_local,256], accumulated (+=)
     float* loss_out;        // [2] = ecda loss share, [3] = full-batch ecda loss when world == 1
     unsigned* counter;      // [2] zero-initialised, self-resetting
-    int max_tiles, prep_grid;
+    int max_tiles, prep_grid, phases;
 };
 
 // supervised contrastive loss (csrc/k_scl.cu)

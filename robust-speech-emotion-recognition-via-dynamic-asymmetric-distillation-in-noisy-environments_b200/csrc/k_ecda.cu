@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
     // all threads emit the entries in parallel (a serial loop over ~700 entries cost 30 us of this single CTA).
     __threadfence();
     __syncthreads();
-    __shared__ int sg_first[8], sg_last[8], sg_grow[8], sg_tile0[8], sg_item0[8], sg_pz0[8], sg_feas[8], sg_on[8], s_tot[3];
+    __shared__ int sg_first[8], sg_last[8], sg_grow[8], sg_tile0[8], sg_item0[8], sg_pz0[8], sg_feas[8], sg_on[8], s_tot[4];
     if (tid == 0) {
         int nt_ = 0, ng_ = 0, np_ = 0, g_rows = 0;
         for (int sgi = 0; sgi < 8; ++sgi) {
@@ -319,9 +319,11 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
                 g_rows += rb * 128;
             }
         }
-        if (ng_ > a.max_gram_items || np_ > a.max_pz_items) { ng_ = 0; np_ = 0; }  // cannot happen (tables are sized for the worst case)
-        s_tot[0] = nt_; s_tot[1] = ng_; s_tot[2] = np_;
-        st->n_tiles = nt_; st->n_gram_items = ng_; st->n_pz_items = np_;
+        if (ng_ > a.max_gram_items || np_ * ECDA_PZ_SPLITS > a.max_pz_items) { ng_ = 0; np_ = 0; }  // cannot happen (tables are sized for the worst case)
+        int spl = np_ > 0 ? 148 / np_ : 1;  // split-K slices of (P Z'): one wave of items over the SMs
+        spl = spl < 1 ? 1 : (spl > ECDA_PZ_SPLITS ? ECDA_PZ_SPLITS : spl);
+        s_tot[0] = nt_; s_tot[1] = ng_; s_tot[2] = np_; s_tot[3] = spl;
+        st->n_tiles = nt_; st->n_gram_items = ng_; st->n_pz_items = np_ * spl; st->pz_splits = spl;
     }
     __syncthreads();
     for (int sgi = 0; sgi < 8; ++sgi) {
@@ -347,10 +349,13 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
                 gi.n_rows = min(128, last - p); gi.n_cols = n_c; gi.cls = c; gi.pad_ = 0;
                 a.gram_items[sg_item0[sgi] + i] = gi;
             }
-            for (int i = tid; i < rb; i += EP_THREADS) {
+            const int spl = s_tot[3], nkb = (n_c + 63) / 64, per = (nkb + spl - 1) / spl;
+            for (int i = tid; i < rb * spl; i += EP_THREADS) {
+                const int r = i / spl, sl = i - r * spl;
                 PzItem pi;
-                pi.g_row = grow + i * 128; pi.b_row = off; pi.n_kb = (n_c + 63) / 64; pi.cls = c;
-                a.pz_items[sg_pz0[sgi] + i] = pi;
+                pi.g_row = grow + r * 128; pi.b_row = off; pi.kb0 = sl * per; pi.n_kb = max(0, min(per, nkb - sl * per));
+                pi.slice = sl; pi.cls = c; pi.pad_[0] = pi.pad_[1] = 0;
+                a.pz_items[(sg_pz0[sgi] + r) * spl + sl] = pi;
             }
         }
     }
@@ -512,10 +517,13 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_fold(EcdaArgs a) {
         const int n_cb = (st->n_s[c] + st->n_t[c] + 255) >> 8;
         for (int cb = 0; cb < n_cb; ++cb) rp += a.rowp_part[(int64_t)cb * a.g_rows_alloc + t.g_row + row];
         rp *= unscale;
-        const float* pa = a.accz + (int64_t)(t.g_row + row) * DAD_H;
-        const float4 u0 = *reinterpret_cast<const float4*>(pa + lane * 4), u1 = *reinterpret_cast<const float4*>(pa + 128 + lane * 4);
-        g8[0] = u0.x * unscale; g8[1] = u0.y * unscale; g8[2] = u0.z * unscale; g8[3] = u0.w * unscale;
-        g8[4] = u1.x * unscale; g8[5] = u1.y * unscale; g8[6] = u1.z * unscale; g8[7] = u1.w * unscale;
+        for (int sl = 0; sl < st->pz_splits; ++sl) {  // split-K slices in fixed order
+            const float* pa = a.accz + ((int64_t)sl * a.g_rows_alloc + t.g_row + row) * DAD_H;
+            const float4 u0 = *reinterpret_cast<const float4*>(pa + lane * 4), u1 = *reinterpret_cast<const float4*>(pa + 128 + lane * 4);
+            g8[0] += u0.x; g8[1] += u0.y; g8[2] += u0.z; g8[3] += u0.w; g8[4] += u1.x; g8[5] += u1.y; g8[6] += u1.z; g8[7] += u1.w;
+        }
+#pragma unroll
+        for (int f = 0; f < 8; ++f) g8[f] *= unscale;
     }
     const int gi = rid < Bg ? rid : rid - Bg;
     const float* z = rid < Bg ? pack_emb_clean(a.pack, rid) : pack_emb_strong(a.pack, rid - Bg);
@@ -533,7 +541,7 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_fold(EcdaArgs a) {
 int launch_ecda_gram(const EcdaArgs& a, cudaStream_t st);  // k_gram_tc.cu: pack + Gram GEMM
 int launch_ecda_pz(const EcdaArgs& a, cudaStream_t st);    // k_gram_tc.cu: (P Z') GEMM
 int ecda_max_gram_items(int B_local, int world) { return (ceil_div(2 * B_local, 128) + 8) * (ceil_div(2 * B_local * world, 256) + 1); }
-int ecda_max_pz_items(int B_local) { return ceil_div(2 * B_local, 128) + 8; }
+int ecda_max_pz_items(int B_local) { return (ceil_div(2 * B_local, 128) + 8) * ECDA_PZ_SPLITS; }
 int ecda_prep_grid(int B_global) {
     // rows per CTA <= 256 (k_ecda_prep classifies its chunk with one thread per row); aim at ~16 rows per CTA
     int g = ceil_div(2 * B_global, 16);
@@ -551,22 +559,26 @@ int launch_ecda(const EcdaArgs& a, cudaStream_t st) {
         cudaError_t e = cudaFuncSetAttribute(k_ecda_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "ecda: cannot opt in to shared memory: %s", cudaGetErrorString(e));
     }
-    k_ecda_prep<<<a.prep_grid, EP_THREADS, 0, st>>>(a);
-    DAD_CHECK_LAUNCH("k_ecda_prep");
-    k_ecda_reduce<<<32, EP_THREADS, 0, st>>>(a, a.prep_grid);
-    DAD_CHECK_LAUNCH("k_ecda_reduce");
-    k_ecda_stats<<<1, EP_THREADS, stats_smem, st>>>(a);
-    DAD_CHECK_LAUNCH("k_ecda_stats");
-    int rc = launch_ecda_gram(a, st);  // z' -> fp16 hi/lo, G = Z' Z'^T on tcgen05
-    if (rc) return rc;
-    const int pg = a.max_gram_items < 4 * 148 ? a.max_gram_items : 4 * 148;
-    k_ecda_p<<<pg < 1 ? 1 : pg, EP_THREADS, 0, st>>>(a);
-    DAD_CHECK_LAUNCH("k_ecda_p");
-    rc = launch_ecda_pz(a, st);        // (P Z') on tcgen05
-    if (rc) return rc;
-    k_ecda_fold<<<dim3(a.max_tiles, ECDA_TR / 8), EP_THREADS, 0, st>>>(a);
-    DAD_CHECK_LAUNCH("k_ecda_fold");
-    k_ecda_loss<<<1, EP_THREADS, 0, st>>>(a);
-    DAD_CHECK_LAUNCH("k_ecda_loss");
+    if (a.phases & 1) {
+        k_ecda_prep<<<a.prep_grid, EP_THREADS, 0, st>>>(a);
+        DAD_CHECK_LAUNCH("k_ecda_prep");
+        k_ecda_reduce<<<32, EP_THREADS, 0, st>>>(a, a.prep_grid);
+        DAD_CHECK_LAUNCH("k_ecda_reduce");
+        k_ecda_stats<<<1, EP_THREADS, stats_smem, st>>>(a);
+        DAD_CHECK_LAUNCH("k_ecda_stats");
+        int rc = launch_ecda_gram(a, st);  // z' -> fp16 hi/lo, G = Z' Z'^T on tcgen05
+        if (rc) return rc;
+        const int pg = a.max_gram_items < 4 * 148 ? a.max_gram_items : 4 * 148;
+        k_ecda_p<<<pg < 1 ? 1 : pg, EP_THREADS, 0, st>>>(a);
+        DAD_CHECK_LAUNCH("k_ecda_p");
+        rc = launch_ecda_pz(a, st);        // (P Z') on tcgen05
+        if (rc) return rc;
+    }
+    if (a.phases & 2) {
+        k_ecda_fold<<<dim3(a.max_tiles, ECDA_TR / 8), EP_THREADS, 0, st>>>(a);
+        DAD_CHECK_LAUNCH("k_ecda_fold");
+        k_ecda_loss<<<1, EP_THREADS, 0, st>>>(a);
+        DAD_CHECK_LAUNCH("k_ecda_loss");
+    }
     return DAD_OK;
 }

@@ -154,7 +154,8 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 k_pz_tc(const __grid_constant__ CUtensorMap tm_ph, const __grid_constant__ CUtensorMap tm_pl, const __grid_constant__ CUtensorMap tm_zh,
-        const __grid_constant__ CUtensorMap tm_zl, const PzItem* __restrict__ items, const int* __restrict__ n_items_ptr, float* __restrict__ accz) {
+        const __grid_constant__ CUtensorMap tm_zl, const PzItem* __restrict__ items, const int* __restrict__ n_items_ptr, float* __restrict__ accz,
+        int g_rows_alloc) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GOFF_BARS);
@@ -189,7 +190,8 @@ k_pz_tc(const __grid_constant__ CUtensorMap tm_ph, const __grid_constant__ CUten
             uint32_t it = 0;
             for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
                 const PzItem pi = items[w];
-                for (int kb = 0; kb < pi.n_kb; ++kb, ++it) {
+                for (int kk = 0; kk < pi.n_kb; ++kk, ++it) {
+                    const int kb = pi.kb0 + kk;
                     const uint32_t s = it % GSTAGES, ph = (it / GSTAGES) & 1;
                     tc::mbar_wait(&empty[s], ph ^ 1);
                     tc::mbar_arrive_expect_tx(&full[s], GSTAGE);
@@ -212,6 +214,11 @@ k_pz_tc(const __grid_constant__ CUtensorMap tm_ph, const __grid_constant__ CUten
             const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
             tc::mbar_wait(&tempty[acc], tph ^ 1);
             tc::tcgen05_fence_after();
+            if (n_kb == 0) {  // empty split-K slice (class smaller than the slice count): nothing to accumulate, the epilogue writes zeros
+                if (lane == 0) tc::umma_commit(&tfull[acc]);
+                __syncwarp();
+                continue;
+            }
             const uint32_t d_tmem = tmem_base + acc * GBN;
             for (int kb = 0; kb < n_kb; ++kb, ++it) {
                 const uint32_t s = it % GSTAGES, ph = (it / GSTAGES) & 1;
@@ -244,14 +251,19 @@ k_pz_tc(const __grid_constant__ CUtensorMap tm_ph, const __grid_constant__ CUten
             const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
             tc::mbar_wait(&tfull[acc], tph);
             tc::tcgen05_fence_after();
-            float* row = accz + (int64_t)(pi.g_row + q * 32 + lane) * DAD_H;
+            float* row = accz + ((int64_t)pi.slice * g_rows_alloc + pi.g_row + q * 32 + lane) * DAD_H;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * GBN;
-            constexpr float unscale = 1.0f / ECDA_ZS;  // the P scale (per class) is removed by k_ecda_fold
+            const float unscale = pi.n_kb > 0 ? 1.0f / ECDA_ZS : 0.f;  // the P scale (per class) is removed by k_ecda_fold
 #pragma unroll 1
             for (int c = 0; c < GBN / 32; ++c) {
                 uint32_t r[32];
-                tc::tmem_ld_32x32(taddr + c * 32, r);
-                tc::tmem_ld_wait();
+                if (pi.n_kb > 0) {
+                    tc::tmem_ld_32x32(taddr + c * 32, r);
+                    tc::tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(row + c * 32 + j) = make_float4(__uint_as_float(r[j]) * unscale, __uint_as_float(r[j + 1]) * unscale,
@@ -350,7 +362,7 @@ int launch_ecda_pz(const EcdaArgs& a, cudaStream_t st) {
     }
     int grid = a.max_pz_items < sm_count() ? a.max_pz_items : sm_count();
     if (grid < 1) grid = 1;
-    k_pz_tc<<<grid, GRAM_THREADS, GRAM_SMEM, st>>>(ph, pl, zh, zl, a.pz_items, &a.stats->n_pz_items, a.accz);
+    k_pz_tc<<<grid, GRAM_THREADS, GRAM_SMEM, st>>>(ph, pl, zh, zl, a.pz_items, &a.stats->n_pz_items, a.accz, a.g_rows_alloc);
     DAD_CHECK_LAUNCH("k_pz_tc");
     return DAD_OK;
 }

@@ -187,6 +187,7 @@ class DADStepEngine:
         self._dWp = z(2, s_max * D_HID * D_IN)
         self._dbp = z(2, s_max * D_HID)
         self._graphs = {}
+        self._side = None
         self.max_graphs = 64
         self._scalars = None
         self.launches_per_step = 0
@@ -490,18 +491,31 @@ class DADStepEngine:
         hb.g_clean, hb.g_strong = self.g_clean.data_ptr(), self.g_strong.data_ptr()
         hb.dWc, hb.dbc = self.dWc_dbc.data_ptr(), self.dWc_dbc.data_ptr() + N_CLS * D_HID * 4
         hb.part, hb.loss_out, hb.counter = self.head_part.data_ptr(), self.g_ext.data_ptr() + NPARAM * 4, self.counters.data_ptr()
-        check(L.dad_head_bwd(C.byref(hb), s))
-        self.launches_per_step += 1
         if noisy and sc.use_ecda:
+            # ECDA phase 1 (statistics + the two tensor-core GEMMs) touches neither g_* nor anything head_bwd writes, so the head
+            # backward runs beside it on a second stream (fork / join; inside a capture this becomes a parallel graph branch);
+            # phase 2 accumulates into g_* and therefore follows the join
             ea = EcdaArgs()
             ea.pack, ea.rank, ea.class_aware = pk, self.rank, int(sc.class_aware)
             ea.mask, ea.nmask, ea.w_class = self.mask.data_ptr(), self.nmask.data_ptr(), self.out_w.data_ptr()
             ea.lambda_cls, ea.gamma_comp, ea.delta_rep, ea.w_ecda = sc.lambda_cls, sc.gamma_comp, sc.delta_rep, _f32(sc.w_ecda)
             ea.g_clean, ea.g_strong, ea.loss_out = hb.g_clean, hb.g_strong, hb.loss_out
             ea.ws, ea.ws_bytes = self.ecda_ws.data_ptr(), self.ecda_ws.numel()
+            main = torch.cuda.current_stream(self.dev)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.dev)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                check(L.dad_head_bwd(C.byref(hb), _lib.stream_ptr()))
+            ea.phases = 1
             check(L.dad_ecda(C.byref(ea), s))
-            self.launches_per_step += 9
+            main.wait_stream(self._side)
+            ea.phases = 2
+            check(L.dad_ecda(C.byref(ea), s))
+            self.launches_per_step += 10
         else:
+            check(L.dad_head_bwd(C.byref(hb), s))
+            self.launches_per_step += 1
             self.g_ext[NPARAM + 2:NPARAM + 3].zero_()
         if noisy and sc.w_scl > 0:
             if self.scl_ws is None:
