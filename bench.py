@@ -317,13 +317,18 @@ def run_ours(args):
                        "labels": b["labels"].cpu().pin_memory()})
         h2d = sum(t.numel() * t.element_size() for b in hb for t in (b["net_input"]["feats"], b["net_input"]["padding_mask"], b["labels"]))
         n_e2e = max(3, min(args.steps, 10))
+        # pipelined public API: the H2D copy of step k+1's batches (copy stream, into staging buffers) overlaps step k; every
+        # step's inputs still cross PCIe inside the timed region and every step's losses are read back
         for _ in range(2):
-            eng.set_inputs(hb[0], hb[1]); eng.step(args.epoch); eng.losses()
+            eng.prefetch_inputs(hb[0], hb[1]); eng.commit_prefetched(); eng.step(args.epoch); eng.losses()
         sync()
         t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            eng.set_inputs(hb[0], hb[1])
+        eng.prefetch_inputs(hb[0], hb[1])
+        for i in range(n_e2e):
+            eng.commit_prefetched()
             eng.step(args.epoch)
+            if i + 1 < n_e2e:
+                eng.prefetch_inputs(hb[0], hb[1])
             eng.losses()  # D2H read of the step's losses (sync)
         sync()
         dt = (time.perf_counter() - t0) / n_e2e

@@ -374,6 +374,58 @@ class DADStepEngine:
             self.feat_keep.copy_((rng["feat_keep_u"] > drop_p).float(), non_blocking=True)
             put(self.t_start, rng["t_start"], Bn)
 
+    # ------------------------------------------------------------------ pipelined input staging
+    def prefetch_inputs(self, clean_batch, noisy_batch=None):
+        """Start copying the NEXT step's (pinned host or device) batches into a staging copy of the input buffers on a copy
+        stream, so that the transfer overlaps the step that is running; `commit_prefetched()` then makes them current with
+        device-to-device copies.  In-kernel-noise mode only (no supplied RNG draws).  The reference does one blocking pageable
+        H2D copy per batch on the training stream (I/train.py:398,405)."""
+        if self.noise_mode != "philox":
+            raise DadError("prefetch_inputs is for the in-kernel-noise mode")
+        dev = self.dev
+        if getattr(self, "_in_stage", None) is None:
+            n = self.Bcap * self.Tcap
+            self._in_stage = {"xc": torch.empty(n * D_IN, dtype=torch.float32, device=dev), "xn": torch.empty(n * D_IN, dtype=torch.float32, device=dev),
+                           "pc": torch.empty(n, dtype=torch.uint8, device=dev), "pn": torch.empty(n, dtype=torch.uint8, device=dev),
+                           "lab": torch.empty(self.Bcap, dtype=torch.int32, device=dev)}
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staged_ready = torch.cuda.Event()
+            self._staged_free = torch.cuda.Event()
+            self._staged_free.record(torch.cuda.current_stream(dev))
+        xc = clean_batch["net_input"]["feats"]
+        xn = noisy_batch["net_input"]["feats"] if noisy_batch is not None else None
+        Bc, Tc = int(xc.shape[0]), int(xc.shape[1])
+        Bn, Tn = (int(xn.shape[0]), int(xn.shape[1])) if xn is not None else (Bc, Tc)
+        if max(Bc, Bn) > self.Bcap or max(Tc, Tn) > self.Tcap:
+            raise DadError("prefetched batch exceeds the engine capacity")
+        st = self._in_stage
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._staged_free)  # the previous commit has finished reading the staging buffers
+            st["xc"][:Bc * Tc * D_IN].view(Bc, Tc, D_IN).copy_(xc, non_blocking=True)
+            pm = clean_batch["net_input"].get("padding_mask")
+            pc = st["pc"][:Bc * Tc].view(Bc, Tc)
+            pc.zero_() if pm is None else pc.copy_(pm, non_blocking=True)
+            st["lab"][:Bc].copy_(clean_batch["labels"], non_blocking=True)
+            if xn is not None:
+                st["xn"][:Bn * Tn * D_IN].view(Bn, Tn, D_IN).copy_(xn, non_blocking=True)
+                pm = noisy_batch["net_input"].get("padding_mask")
+                pn = st["pn"][:Bn * Tn].view(Bn, Tn)
+                pn.zero_() if pm is None else pn.copy_(pm, non_blocking=True)
+            self._staged_ready.record(self._copy_stream)
+        self._staged_shape = (Bc, Tc, Bn, Tn, xn is not None)
+
+    def commit_prefetched(self, n_clean_global=None):
+        """Make the prefetched batches the current inputs (device-to-device, on the current stream, after the transfer landed)."""
+        Bc, Tc, Bn, Tn, has_noisy = self._staged_shape
+        st = self._in_stage
+        main = torch.cuda.current_stream(self.dev)
+        main.wait_event(self._staged_ready)
+        dev_batch = lambda x, p, B, T: {"net_input": {"feats": st[x][:B * T * D_IN].view(B, T, D_IN), "padding_mask": st[p][:B * T].view(B, T)}}
+        c = dev_batch("xc", "pc", Bc, Tc)
+        c["labels"] = st["lab"][:Bc]
+        self.set_inputs(c, dev_batch("xn", "pn", Bn, Tn) if has_noisy else None, n_clean_global=n_clean_global)
+        self._staged_free.record(main)
+
     # ------------------------------------------------------------------ the step
     def _pack_struct(self):
         return Pack(self.pack.data_ptr(), self.B, self.world)

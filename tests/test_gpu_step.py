@@ -251,3 +251,33 @@ def test_optional_scl_term_vs_oracle(mode):
         well = g_orc.abs() >= 1e-6
         p_orc = torch.cat([orc.p[key].detach().reshape(-1) for key in O.PARAM_KEYS])
         assert float((eng.p.cpu() - p_orc).abs()[well].max()) <= 1e-5, (mode, k, "weights")
+
+
+def test_prefetched_inputs_equal_direct_inputs():
+    """engine.prefetch_inputs / commit_prefetched (H2D on a copy stream into staging buffers, overlapped with the running step)
+    feeds the step exactly what set_inputs would: same weights bit for bit after several pipelined steps, ragged batches included."""
+    from dad_b200 import _lib, synth
+    from dad_b200.engine import DADStepEngine
+    from helpers import cfg_for, pretrained_state
+    cfg = cfg_for("iemocap")
+    batches = [synth.make_batches(B, T, 900 + k, variable_len=True) for k, (B, T) in enumerate(((24, 48), (24, 64), (17, 40), (24, 56)))]
+    pin = lambda b: {"net_input": {k: v.pin_memory() for k, v in b["net_input"].items()}, "labels": b["labels"].pin_memory()}
+    outs = []
+    for pipelined in (False, True):
+        eng = DADStepEngine(cfg, 24, 64, gemm_mode=_lib.GEMM_TC, use_graph=True, noise_mode="philox", seed=3)
+        eng.load_state_dict(pretrained_state())
+        eng.set_lr(5e-4)
+        if pipelined:
+            eng.prefetch_inputs(pin(batches[0][0]), pin(batches[0][1]))
+        for k, (c, n) in enumerate(batches):
+            if pipelined:
+                eng.commit_prefetched()
+                eng.step(45)
+                if k + 1 < len(batches):
+                    eng.prefetch_inputs(pin(batches[k + 1][0]), pin(batches[k + 1][1]))
+            else:
+                eng.set_inputs(_to_dev(c), _to_dev(n))
+                eng.step(45)
+        outs.append((eng.p.clone(), eng.t.clone(), eng.ema_thr.clone(), eng.losses()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert outs[0][3] == outs[1][3]
