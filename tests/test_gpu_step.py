@@ -281,3 +281,41 @@ def test_prefetched_inputs_equal_direct_inputs():
         outs.append((eng.p.clone(), eng.t.clone(), eng.ema_thr.clone(), eng.losses()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
     assert outs[0][3] == outs[1][3]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_randomised_edge_batches_vs_oracle(seed):
+    """Randomised stress of the data-dependent paths (DACP quantiles, ECDA class feasibility / work tables, KD gate): odd batch
+    sizes, skewed or missing classes, anchors that mask almost everything out, both ECDA variants -- engine == oracle each step."""
+    from dad_b200 import _lib, synth
+    from dad_b200.engine import DADStepEngine
+    g = torch.Generator().manual_seed(1000 + seed)
+    B = int(torch.randint(3, 41, (1,), generator=g))
+    T = int(torch.randint(32, 72, (1,), generator=g))
+    over = {"USE_CLASS_AWARE_MMD": bool(seed % 2), "USE_ENTROPY_IN_SCORE": bool((seed // 2) % 2)}
+    orc, cfg, hp = make_oracle("iemocap", over)
+    eng = DADStepEngine(cfg, B, T, gemm_mode=_lib.GEMM_TC, use_graph=False, noise_mode="supplied")
+    for k in range(4):
+        epoch = 40 + 7 * k
+        orc.lr = O.cosine_lr(hp.LEARNING_RATE, epoch, hp.EPOCHS)
+        c, n = synth.make_batches(B, T, 5000 + 10 * seed + k, variable_len=True)
+        if k == 1:   # only two classes present in the clean batch
+            c["labels"] = c["labels"] % 2
+        if k == 2:   # one clean class with a single member, the rest in one class
+            c["labels"] = torch.zeros_like(c["labels"]); c["labels"][0] = 3
+        if k == 3:   # anchors above every score: (almost) nothing is masked in -> KD / ECDA gates close
+            orc.anchors = torch.full((4,), 0.999)
+        else:
+            orc.anchors = torch.rand(4, generator=g) * 0.3
+        rng = synth.make_rng_inputs(B, T, 6000 + 10 * seed + k)
+        push_oracle_state(eng, orc)
+        eng.set_inputs(_to_dev(c), _to_dev(n), {kk: v.cuda() for kk, v in rng.items()})
+        eng.step(epoch)
+        ref, _ = oracle_step_adopting_ties(orc, eng, c, n, epoch, rng, "tc")
+        got = eng.losses()
+        for key in LOSS_KEYS:
+            assert abs(got[key] - ref[key]) <= 1e-4 * max(abs(ref[key]), 1e-3), (seed, k, key, got[key], ref[key])
+        assert torch.equal(eng.mask.cpu().bool(), orc.last["mask"]), (seed, k)
+        g_orc = torch.cat([orc.p[key].grad.reshape(-1) for key in O.PARAM_KEYS])
+        p_orc = torch.cat([orc.p[key].detach().reshape(-1) for key in O.PARAM_KEYS])
+        assert float((eng.p.cpu() - p_orc).abs()[g_orc.abs() >= 1e-6].max()) <= 1e-5, (seed, k, "weights")
