@@ -312,3 +312,36 @@ def test_device_batch_assembly_equals_host_collator():
         assert torch.equal(db["labels"].cpu(), hb["labels"]) and torch.equal(db["id"], hb["id"])
         n += 1
     assert n == len(host) == 6
+
+
+@pytest.mark.parametrize("B,class_aware", [(700, True), (300, False)])
+def test_ecda_multi_tile_vs_fp64_gram_oracle(B, class_aware):
+    """Large classes: several Gram row / column blocks, many (P Z') k-blocks and split-K slices per class (the tiny fixtures use
+    one tile).  Checked against the oracle's fp64 Gram-form restatement (itself validated against the reference form at small B)."""
+    from dad_b200.utils import ECDALoss, use_config
+    from oracle import dad_oracle as O
+    from helpers import cfg_for
+    cfg = cfg_for("iemocap", {"USE_CLASS_AWARE_MMD": class_aware})
+    use_config(cfg)
+    try:
+        hp = O.HParams.from_cfg(cfg)
+        g = torch.Generator().manual_seed(77)
+        mu = torch.randn(4, 256, generator=g)
+        yc, yn = torch.randint(0, 4, (B,), generator=g), torch.randint(0, 4, (B,), generator=g)
+        clean = (mu[yc] + 0.5 * torch.randn(B, 256, generator=g))
+        noisy = (mu[yn] + 0.7 * torch.randn(B, 256, generator=g))
+        mask = torch.rand(B, generator=g) > 0.2
+        scores = torch.rand(B, generator=g) * 0.5 + 0.5
+        w = torch.rand(4, generator=g)
+        c64, n64 = clean.double().requires_grad_(True), noisy.double().requires_grad_(True)
+        ref = O.ecda_loss_gram(c64, n64, yc, yn, mask, scores.double(), w.double(), hp)
+        ref.backward()
+        c2, n2 = clean.cuda().requires_grad_(True), noisy.cuda().requires_grad_(True)
+        got = ECDALoss()(c2, n2, yc.cuda(), yn.cuda(), mask.cuda(), scores.cuda(), w.cuda())
+        got.backward()
+        assert abs(float(got.detach()) - float(ref.detach())) <= 1e-4 * abs(float(ref.detach())), (float(got.detach()), float(ref.detach()))
+        for a, b in ((c2.grad, c64.grad), (n2.grad, n64.grad)):
+            assert float((a.cpu().double() - b).abs().max()) <= 2e-4 * float(b.abs().max()), float((a.cpu().double() - b).abs().max()) / float(b.abs().max())
+    finally:
+        from dad_b200 import config
+        use_config(config)
