@@ -319,3 +319,33 @@ def test_randomised_edge_batches_vs_oracle(seed):
         g_orc = torch.cat([orc.p[key].grad.reshape(-1) for key in O.PARAM_KEYS])
         p_orc = torch.cat([orc.p[key].detach().reshape(-1) for key in O.PARAM_KEYS])
         assert float((eng.p.cpu() - p_orc).abs()[g_orc.abs() >= 1e-6].max()) <= 1e-5, (seed, k, "weights")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+def test_medium_batch_step_vs_oracle(mode):
+    """B = 200 (not a multiple of the tile sizes), T = 48: every kernel runs multi-CTA (split reductions, several ECDA tiles and
+    Gram blocks per class, DACP select over > 128 scores, split-K dW partials) -- the golden fixtures use B = 16."""
+    from dad_b200 import _lib
+    from dad_b200.engine import DADStepEngine
+    orc, cfg, hp = make_oracle("iemocap")
+    B, T = 200, 48
+    gm = {"fp32": _lib.GEMM_FP32, "tc": _lib.GEMM_TC}[mode]
+    eng = DADStepEngine(cfg, B, T, gemm_mode=gm, use_graph=False, noise_mode="supplied")
+    meta = {"B": B, "T": T, "seed": 12000, "snr_db": 10.0, "variable_len": True}
+    for k, epoch in enumerate((41, 55, 70)):
+        orc.lr = O.cosine_lr(hp.LEARNING_RATE, epoch, hp.EPOCHS)
+        c, n, rng = step_inputs(meta, k, cfg)
+        push_oracle_state(eng, orc)
+        eng.set_inputs(_to_dev(c), _to_dev(n), {kk: v.cuda() for kk, v in rng.items()})
+        eng.step(epoch)
+        ref, ties = oracle_step_adopting_ties(orc, eng, c, n, epoch, rng, mode)
+        got = eng.losses()
+        for key in LOSS_KEYS:
+            assert abs(got[key] - ref[key]) <= 1e-4 * max(abs(ref[key]), 1e-3), (mode, k, key, got[key], ref[key])
+        assert torch.equal(eng.mask.cpu().bool(), orc.last["mask"]), (mode, k, "mask")
+        assert float((eng.ema_thr.cpu() - orc.dacp.ema_thr).abs().max()) <= 1e-6
+        g_orc = torch.cat([orc.p[key].grad.reshape(-1) for key in O.PARAM_KEYS])
+        p_orc = torch.cat([orc.p[key].detach().reshape(-1) for key in O.PARAM_KEYS])
+        t_orc = torch.cat([orc.t[key].reshape(-1) for key in O.TEACHER_KEYS])
+        assert float((eng.p.cpu() - p_orc).abs()[g_orc.abs() >= 1e-6].max()) <= 1e-5, (mode, k, "weights")
+        assert float((eng.t.cpu() - t_orc).abs().max()) <= 1e-5
