@@ -83,7 +83,7 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], const int la
 // MODE 0 clean, 1 weak, 2 strong (I/utils.py:328-375); PHILOX: canonical in-kernel noise field, else supplied noise tensor.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int MODE, bool PHILOX>
-__device__ __forceinline__ void fwd_convert(const FwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, volatile int* progress, const int cw,
+__device__ __forceinline__ void fwd_convert(const FwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, const int cw,
                                             const int lane) {
     const int kq = lane & 15;
     const int rbase = cw * 16 + (lane >> 4) * 8;
@@ -222,7 +222,6 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
     uint64_t* tfull = bars + 4;       // [2]       1 (tcgen05.commit)
     uint64_t* tempty = bars + 6;      // [2]       4 (epilogue warps)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
-    volatile int* progress = reinterpret_cast<volatile int*>(bars + 9);  // flat (tile, k-block) iteration the converters have reached
     float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,7 +231,6 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
         tc::prefetch_tmap(&tm_wlo);
     }
     if (warp == 1 && lane == 0) {
-        *progress = 0;
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1 + N_CONV_WARPS); tc::mbar_init(&empty[s], 1 + (p.cache ? 1 : 0)); }
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], 4); }
         tc::fence_barrier_init();
@@ -304,11 +302,11 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
         const int cw = warp - CONV_WARP0;
         const int variant = p.ap.mode == 0 ? 0 : (p.ap.mode * 2 - 1 + (p.ap.noise_src == 1 ? 1 : 0));  // 0 | 1,2 weak | 3,4 strong (supplied, philox)
         switch (variant) {
-            case 0: fwd_convert<0, false>(p, smem, full, empty, progress, cw, lane); break;
-            case 1: fwd_convert<1, false>(p, smem, full, empty, progress, cw, lane); break;
-            case 2: fwd_convert<1, true>(p, smem, full, empty, progress, cw, lane); break;
-            case 3: fwd_convert<2, false>(p, smem, full, empty, progress, cw, lane); break;
-            default: fwd_convert<2, true>(p, smem, full, empty, progress, cw, lane); break;
+            case 0: fwd_convert<0, false>(p, smem, full, empty, cw, lane); break;
+            case 1: fwd_convert<1, false>(p, smem, full, empty, cw, lane); break;
+            case 2: fwd_convert<1, true>(p, smem, full, empty, cw, lane); break;
+            case 3: fwd_convert<2, false>(p, smem, full, empty, cw, lane); break;
+            default: fwd_convert<2, true>(p, smem, full, empty, cw, lane); break;
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: TMEM -> bias + ReLU + mask -> ReLU bits + pooled partial sums =====================
@@ -669,7 +667,7 @@ struct BwdRegs {
 struct BwdTab { uint4 gh, gl; int b; };  // this lane's g/len table chunk (fp16 hi, lo) of utterance b; slot = b & 1
 
 template <int MODE, bool PHILOX, bool XS>
-__device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, volatile int* progress, const int cw, const int lane,
+__device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, const int cw, const int lane,
                                             const int dslice, const int64_t n_begin, const int64_t n_end, const int nkb) {
     const AugParams& ap = p.ap;
     const uint32_t smem_a = tc::smem_u32(smem);
@@ -859,7 +857,6 @@ k_enc_bwd_tc(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__
     uint64_t* empty = bars + BWD_STAGES;    // [3] 1 (tcgen05.commit)
     uint64_t* tfull = bars + 2 * BWD_STAGES;  // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * BWD_STAGES + 1);
-    volatile int* progress = reinterpret_cast<volatile int*>(bars + 2 * BWD_STAGES + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dslice = blockIdx.x, split = blockIdx.y;
@@ -868,7 +865,6 @@ k_enc_bwd_tc(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__
     const int nkb = n_end > n_begin ? (int)ceil_div64(n_end - n_begin, BWD_BK) : 0;
 
     if (warp == 1 && lane == 0) {
-        *progress = 0;
         for (int s = 0; s < BWD_STAGES; ++s) { tc::mbar_init(&full[s], N_CONV_WARPS + (p.use_xs ? 1 : 0)); tc::mbar_init(&empty[s], 1); }
         tc::mbar_init(tfull, 1);
         tc::fence_barrier_init();
@@ -937,12 +933,12 @@ k_enc_bwd_tc(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__
         const int cw = warp - CONV_WARP0;
         const int variant = p.use_xs ? 5 : (p.ap.mode == 0 ? 0 : (p.ap.mode * 2 - 1 + (p.ap.noise_src == 1 ? 1 : 0)));
         switch (variant) {
-            case 0: bwd_convert<0, false, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 1: bwd_convert<1, false, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 2: bwd_convert<1, true, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 3: bwd_convert<2, false, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 4: bwd_convert<2, true, false>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;
-            default: bwd_convert<0, false, true>(p, smem, full, empty, progress, cw, lane, dslice, n_begin, n_end, nkb); break;  // A operand only
+            case 0: bwd_convert<0, false, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 1: bwd_convert<1, false, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 2: bwd_convert<1, true, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 3: bwd_convert<2, false, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 4: bwd_convert<2, true, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            default: bwd_convert<0, false, true>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;  // A operand only
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: TMEM -> split-K partial dW =====================

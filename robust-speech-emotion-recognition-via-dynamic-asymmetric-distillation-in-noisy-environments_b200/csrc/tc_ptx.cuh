@@ -77,10 +77,6 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 
 // ---------------------------------------------------------------- proxies / fences
 // generic-proxy st.shared -> visible to the async proxy (tcgen05.mma / TMA reads of shared memory)
-// bring [p, p+bytes) into L2 ahead of use (bytes % 16 == 0, p 16-byte aligned); no smem, no completion tracking
-__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
