@@ -317,7 +317,7 @@ static EcdaCarve ecda_carve(int B_local, int world) {
     c.p_lo = o; o = align_up(o + g_rows * ldg * sizeof(unsigned short), 1024);
     c.rowp_part = o; o = align_up(o + (ldg / 256) * g_rows * sizeof(float), 256);
     c.accz = o; o = align_up(o + (size_t)ECDA_PZ_SPLITS * g_rows * DAD_H * sizeof(float), 256);
-    c.item_sums = o; o = align_up(o + (size_t)ecda_max_gram_items(B_local, world) * 3 * sizeof(float), 256);
+    c.item_sums = o; o = align_up(o + (size_t)ecda_max_gram_items(B_local, world) * 4 * 3 * sizeof(float), 256);
     c.pos_nsq = o; o = align_up(o + (size_t)2 * Bg * sizeof(float), 256);
     c.pos_om = o; o = align_up(o + (size_t)2 * Bg * sizeof(float), 256);
     c.pos_dom = o; o = align_up(o + (size_t)2 * Bg * sizeof(int), 256);

@@ -44,7 +44,7 @@ struct EcdaStats {  // written by k_ecda_stats, read by the Gram / P / fold / lo
     float rep;                                                // repulsion loss (<= 0)
     float rho;                                                // delta * sum_{feasible} a_c
     int n_tiles, any_feasible, n_classes, active;
-    int n_gram_items, n_pz_items, pz_splits, pad_;
+    int n_gram_items, n_pz_items, pz_splits, p_split;       // p_split: CTAs per Gram item in k_ecda_p (1, 2 or 4)
     float p_scale[ECDA_MAXC];                                 // power-of-two scale of P before its fp16 split
 };
 
@@ -78,7 +78,7 @@ struct EcdaArgs {
     unsigned short* p_lo;
     float* rowp_part;       // [ldg/256][g_rows_alloc] row sums of (scaled) P per 256-column block
     float* accz;            // [ECDA_PZ_SPLITS][g_rows_alloc][256] (scaled) P Z' split-K slices (k_pz_tc), summed in slice order by k_ecda_fold
-    float* item_sums;       // [max_gram_items][3] weighted block sums of K per Gram item
+    float* item_sums;       // [max_gram_items * 4][3] weighted block sums of K per k_ecda_p work unit (<= 4 per Gram item)
     float* pos_nsq;         // [2*B_global] |z'|^2, omega, domain of every list position (k_ecda_pack)
     float* pos_om;
     int* pos_dom;

@@ -19,16 +19,6 @@ namespace {
 
 constexpr int EP_THREADS = 256;
 
-__device__ __forceinline__ double block_sum_d(double v, double* s_red) {
-    v = warp_sum_d(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-    for (int w = 0; w < EP_THREADS / 32; ++w) t += s_red[w];
-    return t;
-}
-
 // row r in [0, 2*Bg): r < Bg clean sample r, else noisy sample r-Bg.  Returns slot = dom*4+cls or -1.
 __device__ __forceinline__ int row_slot(const EcdaArgs& a, int r, int Bg, float& omega, const float*& z) {
     if (r < Bg) {
@@ -45,53 +35,87 @@ __device__ __forceinline__ int row_slot(const EcdaArgs& a, int r, int Bg, float&
     return 4 + (a.class_aware ? pack_pred(a.pack, gi) : 0);
 }
 
+// 1/n to fp64 accuracy without the fp64 divide (a ~35-instruction dependent chain on a pipe that issues one warp instruction every
+// 16 cycles -- the divides of the class statistics used to be most of k_ecda_stats): fp32 reciprocal seed + two Newton steps.
+__device__ __forceinline__ double recip_int(int n) {
+    const double dn = (double)n;
+    double r = (double)__frcp_rn((float)n);
+    r = r * (2.0 - dn * r);
+    r = r * (2.0 - dn * r);
+    return r;
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(EP_THREADS) k_ecda_prep(EcdaArgs a) {
-    __shared__ double s_red[EP_THREADS / 32];
+    __shared__ double s_red[EP_THREADS / 32], s_redw[EP_THREADS / 32];
+    __shared__ int s_redc[EP_THREADS / 32];
     __shared__ int s_slot[EP_THREADS];
     __shared__ float s_om[EP_THREADS];
+    __shared__ double s_vec[8][EP_THREADS], s_sq[8][EP_THREADS];  // per-slot accumulators of thread tid (= feature h)
+    __shared__ const float* s_ptr[EP_THREADS];                    // embedding row of each chunk row
     const int tid = threadIdx.x, G = gridDim.x;
     const int Bg = a.pack.B_local * a.pack.world;
     const int R = 2 * Bg;
     const bool active = a.nmask[0] > 1;
 
-    // ---------------- phase 1: partial sums of this CTA's row chunk (thread = feature h)
-    float vec[8];
-    double sq[8], wsum[8];
-    int cnt[8];
+    // ---------------- partial sums of this CTA's row chunk (thread = feature h)
+    // The chunk's rows are classified in parallel first (slot, weight, row pointer -> shared memory); the accumulation then walks
+    // them in ascending order in batches of eight with all eight embedding loads in flight -- UNCONDITIONAL loads (a non-member
+    // row is read and ignored): guarded loads end up in one branch region each together with their use, which serialises one
+    // L2 round trip per row.  The sums are fp64 (the class bandwidth is a difference of two nearly equal moments) and live in
+    // shared memory indexed by the row's slot: one add and one fma per row and thread.
 #pragma unroll
-    for (int s = 0; s < 8; ++s) { vec[s] = 0.f; sq[s] = 0.0; wsum[s] = 0.0; cnt[s] = 0; }
+    for (int s = 0; s < 8; ++s) { s_vec[s][tid] = 0.0; s_sq[s][tid] = 0.0; }
+    s_slot[tid] = -1;  // threads beyond the chunk: no row
+    s_om[tid] = 0.f;
     if (active) {
         const int chunk = ceil_div(R, G);  // <= EP_THREADS (host guarantees)
         const int r0 = blockIdx.x * chunk, r1 = min(R, r0 + chunk);
-        if (r0 + tid < r1) {  // classify the chunk's rows in parallel first (no dependent-load chain in the loop below)
+        if (r0 + tid < r1) {
             float om = 0.f;
             const float* z;
             s_slot[tid] = row_slot(a, r0 + tid, Bg, om, z);
             s_om[tid] = om;
-            a.slot_of[r0 + tid] = (uint8_t)(s_slot[tid] < 0 ? 255 : s_slot[tid]);  // for the ordered scatter of phase 3
+            s_ptr[tid] = z;
+            a.slot_of[r0 + tid] = (uint8_t)(s_slot[tid] < 0 ? 255 : s_slot[tid]);  // for the ordered scatter of k_ecda_stats
         }
         __syncthreads();
-        for (int r = r0; r < r1; ++r) {
-            const int slot = s_slot[r - r0];
-            if (slot < 0) continue;
-            const float omega = s_om[r - r0];
-            const float* z = r < Bg ? pack_emb_clean(a.pack, r) : pack_emb_strong(a.pack, r - Bg);
-            const float v = z[tid];
+        const int nrow = r1 - r0;
+        for (int rb = 0; rb < nrow; rb += 8) {
+            float v8[8];
 #pragma unroll
-            for (int s = 0; s < 8; ++s)
-                if (s == slot) { vec[s] += v; sq[s] += (double)v * (double)v; wsum[s] += (double)omega; cnt[s] += 1; }
+            for (int u = 0; u < 8; ++u) v8[u] = __ldcg(s_ptr[min(rb + u, nrow - 1)] + tid);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int slot = rb + u < nrow ? s_slot[rb + u] : -1;
+                if (slot < 0) continue;  // CTA-uniform
+                const double v = (double)v8[u];
+                s_vec[slot][tid] += v;
+                s_sq[slot][tid] = fma(v, v, s_sq[slot][tid]);
+            }
         }
     }
+    // per-slot scalars: sum of squares over the 256 features (thread tid holds feature tid) and, over the chunk's rows (thread tid
+    // classified row r0 + tid), the weight sum and the member count -- three reductions behind one barrier pair per slot
+    const int my_slot = s_slot[tid];
+    const double my_om = my_slot >= 0 ? (double)s_om[tid] : 0.0;
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
-        a.part_vec[((int64_t)blockIdx.x * 8 + s) * DAD_H + tid] = vec[s];
-        const double t = block_sum_d(sq[s], s_red);
+        a.part_vec[((int64_t)blockIdx.x * 8 + s) * DAD_H + tid] = (float)s_vec[s][tid];
+        const double q = warp_sum_d(s_sq[s][tid]);
+        const double w = warp_sum_d(my_slot == s ? my_om : 0.0);
+        const int c = __popc(__ballot_sync(0xffffffffu, my_slot == s));
+        __syncthreads();
+        if ((tid & 31) == 0) { s_red[tid >> 5] = q; s_redw[tid >> 5] = w; s_redc[tid >> 5] = c; }
+        __syncthreads();
         if (tid == 0) {
-            a.part_sc[((int64_t)blockIdx.x * 8 + s) * 2 + 0] = t;
-            a.part_sc[((int64_t)blockIdx.x * 8 + s) * 2 + 1] = wsum[s];
-            a.part_cnt[blockIdx.x * 8 + s] = cnt[s];
+            double tq = 0.0, tw = 0.0;
+            int tc = 0;
+            for (int ww = 0; ww < EP_THREADS / 32; ++ww) { tq += s_red[ww]; tw += s_redw[ww]; tc += s_redc[ww]; }
+            a.part_sc[((int64_t)blockIdx.x * 8 + s) * 2 + 0] = tq;
+            a.part_sc[((int64_t)blockIdx.x * 8 + s) * 2 + 1] = tw;
+            a.part_cnt[blockIdx.x * 8 + s] = tc;
         }
     }
 }
@@ -111,7 +135,9 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_reduce(EcdaArgs a, int G) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) t8[u] += (double)a.part_vec[((int64_t)(g + u) * 8 + s) * DAD_H + f];
     }
-    for (int u = 0; g < g1; ++g, ++u) t8[u] += (double)a.part_vec[((int64_t)g * 8 + s) * DAD_H + f];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)  // tail (static register indices: a runtime index would put t8 in local memory)
+        if (g + u < g1) t8[u] += (double)a.part_vec[((int64_t)(g + u) * 8 + s) * DAD_H + f];
     s_part[part][tid & 63] = ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
     __syncthreads();
     if (tid < 64) a.red_vec[s * DAD_H + f] = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
@@ -133,113 +159,171 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_reduce(EcdaArgs a, int G) {
 
 // k_ecda_stats (one CTA): class statistics, ordered member lists, row-tile table
 __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
-    __shared__ double s_red[EP_THREADS / 32];
-    __shared__ int s_cnt[8], s_off[8], s_wc[EP_THREADS / 32][8];
-    __shared__ double s_sq[8], s_ws[8];
-    __shared__ float s_dist[ECDA_MAXC][ECDA_MAXC];
-    const int tid = threadIdx.x;
+    static_assert(ECDA_MAXC == 4, "six centroid pairs below");
+    constexpr int NW = EP_THREADS / 32;
+    constexpr int NBS = 2 * ECDA_MAXC + 6;  // block sums: |m_c|^2, |mu_c|^2 per class, |mu_c - mu_d|^2 per centroid pair
+    __shared__ double s_bs[NBS][NW], s_bt[NBS];
+    __shared__ int s_cnt[8], s_off[8], s_wc[NW][8];
+    __shared__ double s_sq[8], s_ws[8], s_rcp[8];
+    __shared__ double s_invd[ECDA_MAXC][ECDA_MAXC], s_pd[6], s_gs[ECDA_MAXC];
+    __shared__ float s_att[ECDA_MAXC];
+    __shared__ int s_feas[ECDA_MAXC], s_loff[ECDA_MAXC];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Bg = a.pack.B_local * a.pack.world;
     const int R = 2 * Bg;
     const bool active = a.nmask[0] > 1;
 
     // ---------------- phase 2: class statistics
+    // fp64 issues at 1/16 rate and an fp64 divide is a ~35-instruction dependent chain, so the arithmetic is laid out for
+    // latency: reciprocals of the counts once (recip_int), all 14 block sums behind ONE barrier pair, the per-class scalars on
+    // four threads of four different warps, the centroid-pair scalars on six more; divides that the reference itself does in
+    // fp32 (1/beta_r, the block normalisers) stay fp32.  (One thread doing ~40 fp64 divides in sequence was ~25 us.)
     EcdaStats* st = a.stats;
     if (tid == 0) st->active = active ? 1 : 0;
     if (!active) {
-        if (tid == 0) { st->n_tiles = 0; st->n_gram_items = 0; st->n_pz_items = 0; st->any_feasible = 0; st->rep = 0.f; st->rho = 0.f; }
+        if (tid == 0) { st->n_tiles = 0; st->n_gram_items = 0; st->n_pz_items = 0; st->p_split = 1; st->any_feasible = 0; st->rep = 0.f; st->rho = 0.f; }
         return;
     }
+    const int NC = a.class_aware ? ECDA_MAXC : 1;
     double tv[8];
 #pragma unroll
     for (int s = 0; s < 8; ++s) tv[s] = a.red_vec[s * DAD_H + tid];
-    if (tid < 8) { s_sq[tid] = a.red_sc[tid * 2 + 0]; s_ws[tid] = a.red_sc[tid * 2 + 1]; s_cnt[tid] = a.red_cnt[tid]; }
+    if (tid < 8) {
+        s_sq[tid] = a.red_sc[tid * 2 + 0]; s_ws[tid] = a.red_sc[tid * 2 + 1]; s_cnt[tid] = a.red_cnt[tid];
+        const int c = tid & 3;
+        const int ns = c < NC ? a.red_cnt[c] : 0, nt = c < NC ? a.red_cnt[4 + c] : 0;
+        const int n = tid < 4 ? ns + nt : nt;  // s_rcp[c] = 1/(n_s+n_t), s_rcp[4+c] = 1/n_t  (0 when empty)
+        s_rcp[tid] = n > 0 ? recip_int(n) : 0.0;
+    }
     __syncthreads();
-    const int NC = a.class_aware ? ECDA_MAXC : 1;
+    int nvalid = 0;  // classes with >= 1 masked noisy member
+    for (int c = 0; c < NC; ++c) nvalid += (s_cnt[4 + c] > 0);
+    const int npairs = nvalid * (nvalid - 1) / 2;
+    double m[ECDA_MAXC], mu[ECDA_MAXC], bsv[NBS];  // this thread's component of the class mean / the noisy centroid
+#pragma unroll
+    for (int c = 0; c < ECDA_MAXC; ++c) {
+        m[c] = c < NC ? (tv[c] + tv[4 + c]) * s_rcp[c] : 0.0;
+        mu[c] = c < NC ? tv[4 + c] * s_rcp[4 + c] : 0.0;
+        bsv[c] = m[c] * m[c];
+        bsv[4 + c] = mu[c] * mu[c];
+    }
+    {
+        int p = 0;
+#pragma unroll
+        for (int c = 0; c < ECDA_MAXC; ++c)
+#pragma unroll
+            for (int d = c + 1; d < ECDA_MAXC; ++d, ++p) {
+                const bool on = a.class_aware && c < NC && d < NC && s_cnt[4 + c] > 0 && s_cnt[4 + d] > 0;
+                const double df = on ? mu[c] - mu[d] : 0.0;
+                bsv[8 + p] = df * df;
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < NBS; ++k) {
+        const double v = warp_sum_d(bsv[k]);
+        if (lane == 0) s_bs[k][warp] = v;
+    }
+    __syncthreads();
+    if (tid < NBS) {
+        double t = 0.0;
+        for (int w = 0; w < NW; ++w) t += s_bs[tid][w];
+        s_bt[tid] = t;
+    }
+    __syncthreads();
     float wmean = 0.f;
     for (int c = 0; c < ECDA_MAXC; ++c) wmean += a.w_class[c];
     wmean *= 0.25f;
-    double mu[ECDA_MAXC];  // this thread's component of the noisy centroid of each class
-    double rho = 0.0;
-    for (int c = 0; c < ECDA_MAXC; ++c) {
+    if (lane == 0 && warp < ECDA_MAXC) {  // per-class scalars: class c on warp c
+        const int c = warp;
         const int ns = (c < NC) ? s_cnt[c] : 0, nt = (c < NC) ? s_cnt[4 + c] : 0;
         const int n = ns + nt;
-        const double m = n > 0 ? (tv[c] + tv[4 + c]) / (double)n : 0.0;
-        mu[c] = nt > 0 ? tv[4 + c] / (double)nt : 0.0;
-        const double m2 = block_sum_d(m * m, s_red);
-        const double mu2 = block_sum_d(mu[c] * mu[c], s_red);
-        if (tid == 0) {
-            const bool feas = ns >= 2 && nt >= 2;
-            st->n_s[c] = ns; st->n_t[c] = nt; st->feasible[c] = feas ? 1 : 0;
-            double centred = s_sq[c] + s_sq[4 + c] - (double)n * m2;
-            if (centred < 0.0) centred = 0.0;
-            double bw = n > 1 ? 2.0 * (double)n * centred / ((double)n * n - (double)n) : 1.0;  // utils.py:540
-            bw /= 4.0;                                                                          // kernel_mul^(kernel_num//2)
-            for (int r = 0; r < 5; ++r) st->inv_beta[c][r] = (float)(1.0 / (bw * (double)(1 << r) + 1e-8));
-            const double wt = a.class_aware ? s_ws[4 + c] : (double)nt;
-            st->c_ss[c] = (float)(1.0 / ((double)ns * ns + 1e-8));
-            st->c_tt[c] = (float)(1.0 / (wt * wt + 1e-8));
-            st->c_st[c] = (float)(1.0 / ((double)ns * wt + 1e-8));
-            const float att = a.class_aware ? expf(a.lambda_cls * (wmean - a.w_class[c])) : 1.f;  // utils.py:598-599
-            st->att[c] = att;
-            // power-of-two operand scale of this class's gradient weights P = coef K' before their fp16 hi/lo split (k_ecda_p):
-            // |P| <= 4 att w_ecda max(c_ss, c_tt, c_st) sum_r 1/beta_r (scores <= 1, exp <= 1); the largest value lands below 2^13
-            {
-                float cmax = fmaxf(st->c_ss[c], fmaxf(st->c_tt[c], st->c_st[c]));
-                float sb = 0.f;
-                for (int r = 0; r < 5; ++r) sb += st->inv_beta[c][r];
-                const float pmax = 4.f * att * fabsf(a.w_ecda) * cmax * sb;
-                float sc = 1.0f;
-                if (pmax > 0.f && pmax < 3.0e38f) {
-                    int e = (int)((__float_as_uint(pmax) >> 23) & 0xFFu) - 127;  // floor(log2 pmax)
-                    int se = 12 - e;
-                    se = se > 100 ? 100 : (se < -100 ? -100 : se);
-                    sc = __uint_as_float((uint32_t)(127 + se) << 23);
-                }
-                st->p_scale[c] = sc;
-            }
-            double comp = nt > 0 ? s_sq[4 + c] / (double)nt - mu2 : 0.0;  // mean |z - mu|^2
-            st->comp[c] = (float)(comp > 0.0 ? comp : 0.0);
+        const double m2 = s_bt[c], mu2 = s_bt[4 + c];
+        const bool feas = ns >= 2 && nt >= 2;
+        st->n_s[c] = ns; st->n_t[c] = nt; st->feasible[c] = feas ? 1 : 0;
+        s_feas[c] = feas ? 1 : 0;
+        double centred = s_sq[c] + s_sq[4 + c] - (double)n * m2;
+        if (centred < 0.0) centred = 0.0;
+        double bw = n > 1 ? 2.0 * (double)n * centred / ((double)n * n - (double)n) : 1.0;  // utils.py:540
+        bw *= 0.25;                                                                          // / kernel_mul^(kernel_num//2)
+        const float bwf = (float)bw;
+        float sb = 0.f;
+        for (int r = 0; r < 5; ++r) {
+            const float ib = 1.0f / (bwf * (float)(1 << r) + 1e-8f);
+            st->inv_beta[c][r] = ib;
+            sb += ib;
         }
-        a.mu_t[c * DAD_H + tid] = (float)mu[c];
-        a.mu_all[c * DAD_H + tid] = (float)m;
+        const double wt = a.class_aware ? s_ws[4 + c] : (double)nt;
+        const float css = 1.0f / ((float)ns * (float)ns + 1e-8f);
+        const float ctt = 1.0f / (float)(wt * wt + 1e-8);
+        const float cst = 1.0f / (float)((double)ns * wt + 1e-8);
+        st->c_ss[c] = css; st->c_tt[c] = ctt; st->c_st[c] = cst;
+        const float att = a.class_aware ? expf(a.lambda_cls * (wmean - a.w_class[c])) : 1.f;  // utils.py:598-599
+        st->att[c] = att;
+        s_att[c] = att;
+        // power-of-two operand scale of this class's gradient weights P = coef K' before their fp16 hi/lo split (k_ecda_p):
+        // |P| <= 4 att w_ecda max(c_ss, c_tt, c_st) sum_r 1/beta_r (scores <= 1, exp <= 1); the largest value lands below 2^13
+        {
+            const float cmax = fmaxf(css, fmaxf(ctt, cst));
+            const float pmax = 4.f * att * fabsf(a.w_ecda) * cmax * sb;
+            float sc = 1.0f;
+            if (pmax > 0.f && pmax < 3.0e38f) {
+                int e = (int)((__float_as_uint(pmax) >> 23) & 0xFFu) - 127;  // floor(log2 pmax)
+                int se = 12 - e;
+                se = se > 100 ? 100 : (se < -100 ? -100 : se);
+                sc = __uint_as_float((uint32_t)(127 + se) << 23);
+            }
+            st->p_scale[c] = sc;
+        }
+        const double comp = nt > 0 ? s_sq[4 + c] * s_rcp[4 + c] - mu2 : 0.0;  // mean |z - mu|^2
+        st->comp[c] = (float)(comp > 0.0 ? comp : 0.0);
+        // d rep / d mu_c scale: -1 / (npairs * n_t)   (utils.py:582-595 differentiated)
+        s_gs[c] = (a.class_aware && nvalid > 1 && c < NC && nt > 0) ? -1.0 / ((double)npairs * (double)nt) : 0.0;
+    }
+    if (warp >= 4 && lane < 2) {  // centroid pairs: pair p on warp 4 + (p & 3), lane p >> 2
+        const int p = (warp - 4) + 4 * lane;
+        if (p < 6) {
+            const int c = p < 3 ? 0 : (p < 5 ? 1 : 2), d = p < 3 ? p + 1 : (p < 5 ? p - 1 : 3);
+            const bool on = a.class_aware && c < NC && d < NC && s_cnt[4 + c] > 0 && s_cnt[4 + d] > 0;
+            const double dist = sqrt(s_bt[8 + p]);
+            const float distf = (float)dist;
+            s_pd[p] = on ? dist : 0.0;
+            const double inv = (on && distf > 0.f) ? 1.0 / (double)distf : 0.0;
+            s_invd[c][d] = inv;
+            s_invd[d][c] = inv;
+        }
     }
     __syncthreads();
-    for (int c = 0; c < NC; ++c)
-        if (st->feasible[c]) rho += (double)st->att[c];
-    rho *= (double)a.delta_rep;
     // repulsion: -mean pairwise distance between noisy centroids of classes with >= 1 masked member (utils.py:582-595)
-    int nvalid = 0;
-    for (int c = 0; c < NC; ++c) nvalid += (s_cnt[4 + c] > 0);
-    double rep = 0.0;
-    for (int c = 0; c < ECDA_MAXC; ++c)
-        for (int d = c + 1; d < ECDA_MAXC; ++d) {
-            const bool on = a.class_aware && c < NC && d < NC && s_cnt[4 + c] > 0 && s_cnt[4 + d] > 0;
-            const double df = on ? mu[c] - mu[d] : 0.0;
-            const double d2 = block_sum_d(df * df, s_red);
-            if (tid == 0) { s_dist[c][d] = s_dist[d][c] = (float)sqrt(d2); }
-            if (on) rep += sqrt(d2);
-        }
-    __syncthreads();
-    const int npairs = nvalid * (nvalid - 1) / 2;
-    rep = (a.class_aware && nvalid > 1) ? -rep / (double)npairs : 0.0;
+    double rho = 0.0;
+    for (int c = 0; c < NC; ++c)
+        if (s_feas[c]) rho += (double)s_att[c];
+    rho *= (double)a.delta_rep;
+#pragma unroll
     for (int c = 0; c < ECDA_MAXC; ++c) {
         double g = 0.0;
         if (a.class_aware && nvalid > 1 && c < NC && s_cnt[4 + c] > 0) {
-            for (int d = 0; d < NC; ++d)
-                if (d != c && s_cnt[4 + d] > 0 && s_dist[c][d] > 0.f) g += (mu[c] - mu[d]) / (double)s_dist[c][d];
-            g = -g / (double)npairs / (double)s_cnt[4 + c];
+#pragma unroll
+            for (int d = 0; d < ECDA_MAXC; ++d)
+                if (d != c && d < NC && s_cnt[4 + d] > 0) g += (mu[c] - mu[d]) * s_invd[c][d];
+            g *= s_gs[c];
         }
         a.rep_grad[c * DAD_H + tid] = (float)(rho * g);
+        a.mu_t[c * DAD_H + tid] = (float)mu[c];
+        a.mu_all[c * DAD_H + tid] = (float)m[c];
     }
     if (tid == 0) {
+        double rep = 0.0;
+        for (int p = 0; p < 6; ++p) rep += s_pd[p];
+        rep = (a.class_aware && nvalid > 1) ? -rep / (double)npairs : 0.0;
         st->rep = (float)rep;
         st->rho = (float)rho;
         st->n_classes = NC;
         int any = 0, off = 0;
         for (int c = 0; c < ECDA_MAXC; ++c) {
             st->list_off[c] = off;
+            s_loff[c] = off;
             off += s_cnt[c] + s_cnt[4 + c];
-            any |= st->feasible[c];
+            any |= s_feas[c];
         }
         st->any_feasible = any;
     }
@@ -248,7 +332,7 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
     // once), so the ordered scatter below touches no global memory on its critical path.  (The first version re-derived each
     // slot from the pack inside the loop -- 32 dependent global round trips -- and then binary-searched the lists it had just
     // written with L2-latency probes from one thread: together ~0.15 ms of a single CTA at global batch 4096.)
-    extern __shared__ uint8_t s_sl[];  // [R]
+    extern __shared__ __align__(16) uint8_t s_sl[];  // [R], padded to 16 bytes
     __shared__ int s_lt_lo[8], s_lt_hi[8];
     if (tid < 8) {
         const int c = tid & 3, dom = tid >> 2;
@@ -257,10 +341,13 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
         s_off[tid] = off + (dom ? s_cnt[c] : 0);
         s_lt_lo[tid] = 0; s_lt_hi[tid] = 0;
     }
-    for (int r = tid; r < R; r += EP_THREADS) s_sl[r] = __ldcg(a.slot_of + r);
+    {   // 16 rows per load (the table is 256-byte aligned and padded to a multiple of 16 bytes)
+        const uint4* src = reinterpret_cast<const uint4*>(a.slot_of);
+        uint4* dst = reinterpret_cast<uint4*>(s_sl);
+        for (int q = tid; q < (R + 15) / 16; q += EP_THREADS) dst[q] = __ldcg(src + q);
+    }
     __syncthreads();
     const int own_lo = a.rank * a.pack.B_local, own_hi = own_lo + a.pack.B_local;
-    const int warp = tid >> 5, lane = tid & 31;
     for (int base = 0; base < R; base += EP_THREADS) {
         const int r = base + tid;
         int slot = -1;
@@ -302,8 +389,8 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
             const int c = sgi >> 1, dom = sgi & 1;
             sg_on[sgi] = 0;
             if (c >= NC) continue;
-            const int off = st->list_off[c], ns = s_cnt[c], n_c = s_cnt[c] + s_cnt[4 + c];
-            const bool feas = st->feasible[c] != 0;
+            const int off = s_loff[c], ns = s_cnt[c], n_c = s_cnt[c] + s_cnt[4 + c];
+            const bool feas = s_feas[c] != 0;
             if (dom == 0 && !feas) continue;                              // clean rows only matter through the MMD
             if (dom == 1 && !feas && !(a.class_aware && nvalid > 1)) continue;  // noisy rows: MMD/comp or repulsion
             const int b0 = off + (dom ? ns : 0);
@@ -323,13 +410,16 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
         int spl = np_ > 0 ? 148 / np_ : 1;  // split-K slices of (P Z'): one wave of items over the SMs
         spl = spl < 1 ? 1 : (spl > ECDA_PZ_SPLITS ? ECDA_PZ_SPLITS : spl);
         s_tot[0] = nt_; s_tot[1] = ng_; s_tot[2] = np_; s_tot[3] = spl;
-        st->n_tiles = nt_; st->n_gram_items = ng_; st->n_pz_items = np_ * spl; st->pz_splits = spl;
+        // k_ecda_p splits the 128 rows of a Gram item over 1, 2 or 4 CTAs: with few items (a data-parallel rank owns 1/world of the
+        // rows) a single CTA per item leaves most SMs idle while each warp walks 16 rows back to back
+        const int psp = ng_ <= 148 ? 4 : (ng_ <= 296 ? 2 : 1);
+        st->n_tiles = nt_; st->n_gram_items = ng_; st->n_pz_items = np_ * spl; st->pz_splits = spl; st->p_split = psp;
     }
     __syncthreads();
     for (int sgi = 0; sgi < 8; ++sgi) {
         if (!sg_on[sgi]) continue;
         const int c = sgi >> 1;
-        const int off = st->list_off[c], n_c = s_cnt[c] + s_cnt[4 + c];
+        const int off = s_loff[c], n_c = s_cnt[c] + s_cnt[4 + c];
         const int first = sg_first[sgi], last = sg_last[sgi], grow = sg_grow[sgi], feas = sg_feas[sgi];
         const int ntl = min((last - first + ECDA_TR - 1) / ECDA_TR, a.max_tiles - sg_tile0[sgi]);
         for (int i = tid; i < ntl; i += EP_THREADS) {
@@ -362,11 +452,12 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_stats(EcdaArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// k_ecda_p: elementwise pass over the tensor-core Gram G -- one CTA per Gram work item (128 owned rows x 256 members of the class):
+// k_ecda_p: elementwise pass over the tensor-core Gram G -- one CTA per Gram work item (128 owned rows x 256 members of the class),
+// or per half / quarter of its rows when the rank has few items (EcdaStats::p_split, chosen by k_ecda_stats):
 //   L2_ij = |z'_i|^2 + |z'_j|^2 - 2 G_ij (exactly 0 on the diagonal),  K = sum_r exp(-L2/beta_r),  K' = sum_r exp(-L2/beta_r)/beta_r
 //   -> weighted block sums of K (the three MMD terms, I/utils.py:546-563) and P_ij = coef * K' (the gradient weights), written as a
 //      per-class power-of-two scaled fp16 hi/lo split for the second tensor-core GEMM (k_pz_tc: sum_j P_ij z'_j), plus the row sums
-//      of P per column block.  Warp = 16 of the 128 rows, lane = 8 consecutive columns: 32-byte G loads, 16-byte P stores.
+//      of P per column block.  Warp = 16 (8, 4) of the rows, lane = 8 consecutive columns: 32-byte G loads, 16-byte P stores.
 // Deterministic: per-item sums and per-(column block, row) partial row sums are folded in fixed order by k_ecda_fold / k_ecda_loss.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EP_THREADS) k_ecda_p(EcdaArgs a) {
@@ -374,9 +465,11 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_p(EcdaArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const EcdaStats* st = a.stats;
     float sums[3] = {0.f, 0.f, 0.f};
-    const int n_items = st->n_gram_items;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-        const GramItem gi = a.gram_items[w];
+    const int split = st->p_split, rpw = 16 / split;  // rows per warp
+    const int n_units = st->n_gram_items * split;
+    for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
+        const GramItem gi = a.gram_items[w / split];
+        const int row0 = (w % split) * (128 / split) + warp * rpw;
         const int c = gi.cls;
         const float ib0 = st->inv_beta[c][0], ib1 = st->inv_beta[c][1], ib2 = st->inv_beta[c][2], ib3 = st->inv_beta[c][3], ib4 = st->inv_beta[c][4];
         const float css = st->c_ss[c], ctt = st->c_tt[c], cst = st->c_st[c];
@@ -396,8 +489,8 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_p(EcdaArgs a) {
         }
         sums[0] = sums[1] = sums[2] = 0.f;
 #pragma unroll 4  // four rows' G loads in flight per warp (the pass is L2-latency bound)
-        for (int rr = 0; rr < 16; ++rr) {
-            const int r = warp * 16 + rr;
+        for (int rr = 0; rr < rpw; ++rr) {
+            const int r = row0 + rr;
             const bool iok = r < gi.n_rows;
             const int pos_i = gi.a_row + r;
             const float nii = iok ? a.pos_nsq[pos_i] : 0.f, om_i = iok ? a.pos_om[pos_i] : 0.f;
@@ -456,12 +549,12 @@ __global__ void __launch_bounds__(EP_THREADS) k_ecda_loss(EcdaArgs a) {
     __shared__ float s_cs[ECDA_MAXC * 3][EP_THREADS / 32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const EcdaStats* st = a.stats;
-    const int n_items = st->n_gram_items;
+    const int split = st->p_split, n_items = st->n_gram_items * split;  // one entry per k_ecda_p work unit
     float cs[ECDA_MAXC][3];
 #pragma unroll
     for (int c = 0; c < ECDA_MAXC; ++c) cs[c][0] = cs[c][1] = cs[c][2] = 0.f;
     for (int e = tid; e < n_items; e += EP_THREADS) {
-        const int c = a.gram_items[e].cls;
+        const int c = a.gram_items[e / split].cls;
         const float v0 = a.item_sums[e * 3 + 0], v1 = a.item_sums[e * 3 + 1], v2 = a.item_sums[e * 3 + 2];
 #pragma unroll
         for (int cc = 0; cc < ECDA_MAXC; ++cc)
@@ -543,9 +636,10 @@ int launch_ecda_pz(const EcdaArgs& a, cudaStream_t st);    // k_gram_tc.cu: (P Z
 int ecda_max_gram_items(int B_local, int world) { return (ceil_div(2 * B_local, 128) + 8) * (ceil_div(2 * B_local * world, 256) + 1); }
 int ecda_max_pz_items(int B_local) { return (ceil_div(2 * B_local, 128) + 8) * ECDA_PZ_SPLITS; }
 int ecda_prep_grid(int B_global) {
-    // rows per CTA <= 256 (k_ecda_prep classifies its chunk with one thread per row); aim at ~16 rows per CTA
+    // rows per CTA <= 256 (k_ecda_prep classifies its chunk with one thread per row); aim at ~16 rows per CTA, at most one CTA
+    // per SM (every partial is one more term of the fixed-order fold in k_ecda_reduce)
     int g = ceil_div(2 * B_global, 16);
-    if (g > 296) g = 296;
+    if (g > 148) g = 148;
     const int gmin = ceil_div(2 * B_global, EP_THREADS);
     if (g < gmin) g = gmin;
     return g < 1 ? 1 : g;
@@ -553,7 +647,7 @@ int ecda_prep_grid(int B_global) {
 int ecda_max_tiles(int B_local) { return ceil_div(2 * B_local, ECDA_TR) + 2 * ECDA_MAXC; }
 
 int launch_ecda(const EcdaArgs& a, cudaStream_t st) {
-    const size_t stats_smem = (size_t)2 * a.pack.B_local * a.pack.world;  // row slots, one byte each
+    const size_t stats_smem = ((size_t)2 * a.pack.B_local * a.pack.world + 15) & ~(size_t)15;  // row slots, one byte each
     if (stats_smem > 160 * 1024) return dad_set_error(DAD_ERR_UNSUPPORTED, "ecda: global batch too large for the single-CTA list builder");
     if (stats_smem > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_ecda_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -568,7 +662,7 @@ int launch_ecda(const EcdaArgs& a, cudaStream_t st) {
         DAD_CHECK_LAUNCH("k_ecda_stats");
         int rc = launch_ecda_gram(a, st);  // z' -> fp16 hi/lo, G = Z' Z'^T on tcgen05
         if (rc) return rc;
-        const int pg = a.max_gram_items < 4 * 148 ? a.max_gram_items : 4 * 148;
+        const int pg = a.max_gram_items * 4 < 4 * 148 ? a.max_gram_items * 4 : 4 * 148;  // work units: up to 4 per Gram item
         k_ecda_p<<<pg < 1 ? 1 : pg, EP_THREADS, 0, st>>>(a);
         DAD_CHECK_LAUNCH("k_ecda_p");
         rc = launch_ecda_pz(a, st);        // (P Z') on tcgen05

@@ -415,6 +415,20 @@ __global__ void __launch_bounds__(DAD_H) k_pool_finalize(const float* __restrict
     __shared__ float s_w[DAD_H / 32];
     __shared__ float s_len;
     const int b = blockIdx.x, h = threadIdx.x;
+    // partial sums first (their loads do not depend on the length): ascending 32-frame groups, eight loads in flight.  A group
+    // that straddles two utterances keeps the earlier one in slot 0 and the later one in slot 1 (T >= 32: never more than two),
+    // so only this utterance's FIRST group can be a slot-1 read.
+    const int64_t r0 = (int64_t)b * T, r1 = r0 + T - 1;
+    const int64_t g0 = r0 >> 5, g1 = r1 >> 5;
+    float s = __ldg(part + (g0 * 2 + (g0 * 32 == r0 ? 0 : 1)) * DAD_H + h);
+    for (int64_t g = g0 + 1; g <= g1; g += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = g + u <= g1 ? __ldg(part + (g + u) * 2 * DAD_H + h) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (g + u <= g1) s += v[u];
+    }
     if (pad) {
         float c = 0.f;
         for (int t = h; t < T; t += DAD_H) c += pad[(int64_t)b * T + t] ? 0.f : 1.f;
@@ -430,12 +444,6 @@ __global__ void __launch_bounds__(DAD_H) k_pool_finalize(const float* __restrict
         s_len = (float)T;
     }
     __syncthreads();
-    const int64_t r0 = (int64_t)b * T, r1 = r0 + T - 1;
-    float s = 0.f;
-    for (int64_t g = r0 / 32; g <= r1 / 32; ++g) {
-        const int slot = ((g * 32) / T == b) ? 0 : 1;
-        s += __ldg(part + (g * 2 + slot) * DAD_H + h);
-    }
     emb[(int64_t)b * DAD_H + h] = s / s_len;
     if (h == 0 && lens_out) lens_out[b] = s_len;
 }
@@ -579,56 +587,90 @@ __global__ void __launch_bounds__(DAD_H) k_bwd_prep(const float* __restrict__ g_
 }
 
 // db[h] = sum over valid frames of relu_bit(n,h) * g[b,h]/len_b = sum_b (g[b,h]/len_b) * count_b[h].
-// One WARP per utterance counts its ReLU bits per hidden unit with SIMD-in-register adds: lane (w = lane & 7, q = lane >> 3)
-// walks frames q, q+4, ... and keeps, for its 32-bit mask word w, sixteen registers of two 16-bit counters
-// ((word >> k) & 0x00010001 counts bits k and k+16) -- 48 integer ops per frame instead of 256 warp ballots.  The four q-lanes
-// of a word are folded with two shuffles per register; contrib[b][h] = count * g/len, and k_bwd_db_fold then sums utterance
-// groups in fixed order into the split partials consumed by dad_grad_reduce.  (Frames per lane <= 65535: T < 2^18.)
+// `wpu` (1, 2, 4 or 8) WARPS per utterance, each counting the ReLU bits of a contiguous 1/wpu of the frames.  Lane (w = lane & 7,
+// q = lane >> 3) walks frames q, q+4, ... of the warp's range for its 32-bit mask word w and counts all 32 hidden units at once
+// in a VERTICAL counter: bit plane i holds bit i of the 32 counts.  Eight frames enter through a carry-save adder tree (7 CSAs =
+// 14 LOP3 update the ones / twos / fours planes and emit one carry word that ripples through the upper planes): ~3-5 integer ops
+// per frame, against 48 for sixteen registers of paired 16-bit counters ((word >> k) & 0x00010001 ...) and 256 for warp ballots.
+// The four q-lanes of a word add their vertical counters with a shuffle butterfly (bit-serial full adder per plane), each then
+// expands a quarter of the counts to integers; the warps of an utterance are summed through shared memory (integer: order-free).
+// contrib[b][h] = count * g/len, and k_bwd_db_fold sums utterance groups in fixed order into the split partials consumed by
+// dad_grad_reduce.  NPL planes per lane: frames per lane < 2^NPL.
+// At small batch the kernel is a chain of dependent L2 round trips per warp (25 us at 512 utterances per data-parallel rank with
+// one warp per utterance, 10 us with eight): the launcher picks wpu so that the grid has enough warps to cover the latency.
 constexpr int DB_WARPS = 8;
+static_assert(DB_WARPS * 32 == DAD_H, "k_bwd_db: one thread per hidden unit in the epilogue");
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
+    const uint32_t s = a ^ b ^ c, cy = (a & b) | (c & (a | b));
+    sum = s;
+    carry = cy;
+}
+template <int NPL>
 __global__ void __launch_bounds__(DB_WARPS * 32) k_bwd_db(const uint32_t* __restrict__ bits, const uint8_t* __restrict__ pad, const float* __restrict__ g_emb,
-                                                         const float* __restrict__ lens, float* __restrict__ contrib, int T, int B) {
+                                                         const float* __restrict__ lens, float* __restrict__ contrib, int T, int B, int wpu) {
     __shared__ int s_cnt[DB_WARPS][DAD_H];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * DB_WARPS + warp;
-    if (b >= B) return;
+    const int upc = DB_WARPS / wpu;                   // utterances per CTA
+    const int b = blockIdx.x * upc + warp / wpu;      // this warp's utterance (may be >= B in the last CTA)
+    const int sub = warp % wpu;
     const int w = lane & 7, q = lane >> 3;
-    uint32_t c[16];
+    const int per = ((T + wpu - 1) / wpu + 3) & ~3;   // frames per warp, a multiple of the 4 frames a warp reads at once
+    const int tb = sub * per;
+    const int te = b < B ? (tb + per < T ? tb + per : T) : 0;
+    uint32_t P[NPL + 2];                              // + 2 planes for the sum over the four q-lanes
 #pragma unroll
-    for (int k = 0; k < 16; ++k) c[k] = 0u;
+    for (int i = 0; i < NPL + 2; ++i) P[i] = 0u;
     const int64_t n0 = (int64_t)b * T;
-    // 8 independent loads in flight per lane (one utterance = T/4 frames per lane: a plain loop was one L2 latency per frame)
-    for (int t0 = q; t0 < T; t0 += 32) {
-        uint32_t wd[8];
+    for (int t0 = tb + q; t0 < te; t0 += 32) {  // 8 independent loads in flight per lane
+        uint32_t x[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int t = t0 + 4 * u;
             const int64_t n = n0 + t;
-            wd[u] = t < T ? __ldg(bits + n * DAD_HW + w) : 0u;  // a warp reads 4 frames x 32 B = 128 contiguous bytes
-            if (pad && t < T && pad[n]) wd[u] = 0u;
+            x[u] = t < te ? __ldg(bits + n * DAD_HW + w) : 0u;  // a warp reads 4 frames x 32 B = 128 contiguous bytes
+            if (pad && t < te && pad[n]) x[u] = 0u;
         }
+        uint32_t t0_, t1_, t2_, t3_, f0, f1, e0;
+        csa(P[0], x[0], x[1], P[0], t0_);
+        csa(P[0], x[2], x[3], P[0], t1_);
+        csa(P[1], t0_, t1_, P[1], f0);
+        csa(P[0], x[4], x[5], P[0], t2_);
+        csa(P[0], x[6], x[7], P[0], t3_);
+        csa(P[1], t2_, t3_, P[1], f1);
+        csa(P[2], f0, f1, P[2], e0);
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-#pragma unroll
-            for (int k = 0; k < 16; ++k) c[k] += (wd[u] >> k) & 0x00010001u;
-    }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        c[k] += __shfl_xor_sync(0xffffffffu, c[k], 8);
-        c[k] += __shfl_xor_sync(0xffffffffu, c[k], 16);
-    }
-    if (q == 0) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            s_cnt[warp][w * 32 + k] = (int)(c[k] & 0xFFFFu);
-            s_cnt[warp][w * 32 + 16 + k] = (int)(c[k] >> 16);
+        for (int i = 3; i < NPL; ++i) {  // ripple the eights carry through the upper planes
+            const uint32_t cy = P[i] & e0;
+            P[i] ^= e0;
+            e0 = cy;
         }
     }
-    __syncwarp();
-    const float inv = lens[b];
 #pragma unroll
-    for (int m = 0; m < DAD_H / 32; ++m) {
-        const int h = lane + 32 * m;
-        contrib[(int64_t)b * DAD_H + h] = (float)s_cnt[warp][h] * (g_emb[(int64_t)b * DAD_H + h] / inv);
+    for (int o = 8; o <= 16; o <<= 1) {  // add the vertical counters of the four q-lanes (all four end up with the total)
+        uint32_t cy = 0u;
+#pragma unroll
+        for (int i = 0; i < NPL + 2; ++i) {
+            const uint32_t y = __shfl_xor_sync(0xffffffffu, P[i], o);
+            csa(P[i], y, cy, P[i], cy);
+        }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {  // this lane expands bits k and k + 16 of its word for k = 4q .. 4q+3
+        const int k = 4 * q + kk;
+        uint32_t acc = 0u;
+#pragma unroll
+        for (int i = 0; i < NPL + 2; ++i) acc += ((P[i] >> k) & 0x00010001u) << i;  // counts < 2^16: the two halves never meet
+        s_cnt[warp][w * 32 + k] = (int)(acc & 0xFFFFu);
+        s_cnt[warp][w * 32 + 16 + k] = (int)(acc >> 16);
+    }
+    __syncthreads();
+    const int h = threadIdx.x;
+    for (int j = 0; j < upc; ++j) {
+        const int bj = blockIdx.x * upc + j;
+        if (bj >= B) break;
+        int cnt = 0;
+        for (int ww = 0; ww < wpu; ++ww) cnt += s_cnt[j * wpu + ww][h];
+        contrib[(int64_t)bj * DAD_H + h] = (float)cnt * (g_emb[(int64_t)bj * DAD_H + h] / lens[bj]);
     }
 }
 __global__ void __launch_bounds__(DAD_H) k_bwd_db_fold(const float* __restrict__ contrib, float* __restrict__ dbp, int B, int per) {
@@ -1044,7 +1086,16 @@ int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, c
     }
     k_enc_bwd_tc<<<dim3(DAD_D / 256, splits), BWD_THREADS, BWD_SMEM, st>>>(tm_hi, tm_lo, p);
     DAD_CHECK_LAUNCH("k_enc_bwd_tc");
-    k_bwd_db<<<(unsigned)ceil_div64(B, DB_WARPS), DB_WARPS * 32, 0, st>>>(bits, pad, g_emb, lens, contrib, (int)T, (int)B);
+    int wpu = 1;  // warps per utterance: enough warps in the grid to cover the load latency (~16 per SM)
+    while (wpu < DB_WARPS && B * wpu < (int64_t)sm_count() * 16) wpu *= 2;
+    const unsigned db_grid = (unsigned)ceil_div64(B * wpu, DB_WARPS);
+    const int64_t frames_per_lane = ceil_div64(ceil_div64(T, wpu) + 3, 4) + 1;
+    if (frames_per_lane < 256)
+        k_bwd_db<8><<<db_grid, DB_WARPS * 32, 0, st>>>(bits, pad, g_emb, lens, contrib, (int)T, (int)B, wpu);
+    else if (frames_per_lane < 16384)
+        k_bwd_db<14><<<db_grid, DB_WARPS * 32, 0, st>>>(bits, pad, g_emb, lens, contrib, (int)T, (int)B, wpu);
+    else
+        return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_bwd: T = %lld frames is beyond the bias-gradient counters (T < 65536)", (long long)T);
     DAD_CHECK_LAUNCH("k_bwd_db");
     k_bwd_db_fold<<<splits, DAD_H, 0, st>>>(contrib, dbp, (int)B, (int)ceil_div64(B, splits));
     DAD_CHECK_LAUNCH("k_bwd_db_fold");

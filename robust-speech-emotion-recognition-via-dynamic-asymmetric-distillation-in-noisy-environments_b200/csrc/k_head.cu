@@ -176,13 +176,13 @@ __global__ void __launch_bounds__(1024) k_dacp(DacpArgs a) {
     __shared__ int s_cnt[DAD_C];
     __shared__ float s_thr[DAD_C];
     __shared__ int s_nmask;
-    __shared__ double s_sum[DAD_C];
+    __shared__ unsigned long long s_sum[DAD_C];  // per-class score sums in 2^-40 fixed point (integer adds: order-free)
     __shared__ int s_hist[2 * DAD_C][256];   // radix-select histograms: target = class * 2 + {lo, hi}
     __shared__ uint32_t s_prefix[2 * DAD_C]; // key bits fixed so far
     __shared__ int s_rank[2 * DAD_C];        // remaining 0-based rank inside the prefix bucket (-1: class empty)
     const int tid = threadIdx.x, nt = blockDim.x;
     const int Bg = a.pack.B_local * a.pack.world;
-    if (tid < DAD_C) { s_cnt[tid] = 0; s_sum[tid] = 0.0; }
+    if (tid < DAD_C) { s_cnt[tid] = 0; s_sum[tid] = 0ull; }
     if (tid == 0) s_nmask = 0;
     __syncthreads();
 
@@ -293,25 +293,32 @@ __global__ void __launch_bounds__(1024) k_dacp(DacpArgs a) {
     }
     __syncthreads();
     int local = 0;
-    for (int i0 = 0; i0 < Bg; i0 += nt) {  // warp-uniform trip count
+    // per-class epoch accumulators (utils.py:503-505) in 2^-40 fixed point: scores in [2^-16, 1] convert exactly, sums of up
+    // to 2^13 of them stay below 2^53, and integer adds commute -- bit-reproducible whatever the order, without fp64 (which issues
+    // at 1/16 rate: the four fp64 warp reductions per 1024 samples were ~5 us of this single CTA)
+    long long acc[DAD_C];
+#pragma unroll
+    for (int cc = 0; cc < DAD_C; ++cc) acc[cc] = 0;
+    for (int i0 = 0; i0 < Bg; i0 += nt) {
         const int i = i0 + tid;
-        int c = -1;
-        float s = 0.f;
         if (i < Bg) {
-            c = pack_pred(a.pack, i);
-            s = pack_score(a.pack, i);
+            const int c = pack_pred(a.pack, i);
+            const float s = pack_score(a.pack, i);
             const int m = c >= 0 && s >= s_thr[c < 0 ? 0 : c];
             a.mask[i] = (uint8_t)m;
             local += m;
-        }
-        if (a.use_dacp) {
-            // per-class epoch accumulators (utils.py:503-505): warp sums first, then one shared fp64 add per warp and class
-            // (fp64 sums of <= 2^24 fp32 scores in [2^-20, 1] are exact, so the order of the adds cannot change the result)
+            const long long q = __float2ll_rn(s * 1099511627776.0f);
 #pragma unroll
-            for (int cc = 0; cc < DAD_C; ++cc) {
-                const double v = warp_sum_d(c == cc ? (double)s : 0.0);
-                if ((tid & 31) == 0 && v != 0.0) atomicAdd(&s_sum[cc], v);
-            }
+            for (int cc = 0; cc < DAD_C; ++cc) acc[cc] += c == cc ? q : 0ll;
+        }
+    }
+    if (a.use_dacp) {
+#pragma unroll
+        for (int cc = 0; cc < DAD_C; ++cc) {
+            long long v = acc[cc];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((tid & 31) == 0 && v != 0) atomicAdd(&s_sum[cc], (unsigned long long)v);
         }
     }
     local = (int)warp_sum((float)local);
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(1024) k_dacp(DacpArgs a) {
     if (tid < DAD_C) {
         a.out_thr[tid] = s_thr[tid];
         if (a.use_dacp) {
-            a.epoch_sum[tid] += s_sum[tid];
+            a.epoch_sum[tid] += (double)(long long)s_sum[tid] * 9.094947017729282e-13;  // 2^-40
             a.epoch_cnt[tid] += (int64_t)s_cnt[tid];
         }
     }

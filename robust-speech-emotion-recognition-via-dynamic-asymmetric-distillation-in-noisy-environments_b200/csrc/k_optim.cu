@@ -41,8 +41,22 @@ __global__ void __launch_bounds__(OPT_THREADS) k_grad_reduce(GradReduceArgs a) {
 }
 
 
+// x^t for an integer t >= 0 by binary powering in fp64 (<= 2 log2 t dependent multiplies, relative error < 1e-14): the generic
+// pow(double, double) is a few hundred fp64 instructions, and fp64 issues at 1/16 rate -- two of them on one thread were most of
+// this kernel's tail.
+__device__ __forceinline__ double pow_int(double x, long long t) {
+    double r = 1.0;
+    while (t > 0) {
+        if (t & 1) r *= x;
+        x *= x;
+        t >>= 1;
+    }
+    return r;
+}
+
 __global__ void __launch_bounds__(OPT_THREADS) k_grad_norm(NormArgs a) {
     __shared__ double s_red[OPT_THREADS / 32];
+    __shared__ double s_bc[2];
     __shared__ int s_last;
     double acc = 0.0;
     for (int e = blockIdx.x * OPT_THREADS + threadIdx.x; e < NP; e += gridDim.x * OPT_THREADS) {
@@ -61,16 +75,25 @@ __global__ void __launch_bounds__(OPT_THREADS) k_grad_norm(NormArgs a) {
         s_last = (prev == gridDim.x - 1u);
     }
     __syncthreads();
-    if (!s_last || threadIdx.x != 0) return;
+    if (!s_last) return;
+    // last CTA: warp 0 folds the per-CTA partials (lane-strided, fixed order), warps 1 and 2 the two Adam bias corrections
     __threadfence();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t = *a.step + 1;
     double tot = 0.0;
-    for (unsigned gI = 0; gI < gridDim.x; ++gI) tot += __ldcg(a.part + gI);
+    if (warp == 0) {
+        for (unsigned gI = lane; gI < gridDim.x; gI += 32) tot += __ldcg(a.part + gI);
+        tot = warp_sum_d(tot);
+    } else if (warp <= 2 && lane == 0) {
+        s_bc[warp - 1] = 1.0 - pow_int(warp == 1 ? 0.9 : 0.999, t);
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     const float norm = (float)sqrt(tot);
     float coef = 1.0f;
     if (a.max_norm > 0.f) coef = fminf(a.max_norm / (norm + 1e-6f), 1.0f);  // clip_grad_norm_: clamp(max/(norm+1e-6), max=1)
-    const long long t = *a.step + 1;
     *a.step = t;
-    const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
+    const double bc1 = s_bc[0], bc2 = s_bc[1];
     a.scal[0] = norm;
     a.scal[1] = coef;
     a.scal[2] = (float)(*a.lr / bc1);
