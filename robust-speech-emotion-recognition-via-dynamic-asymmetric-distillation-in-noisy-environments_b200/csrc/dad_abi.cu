@@ -129,6 +129,12 @@ int dad_encoder_fwd(const float* x, const uint8_t* pad, const float* W, const fl
     char* rest = reinterpret_cast<char*>(ws) + align_up((size_t)(2 * B) * sizeof(unsigned), 256);
     if (gemm_mode == DAD_GEMM_FP32) {
         DAD_REQUIRE(W && aligned16(W), "encoder_fwd: W null or unaligned");
+        // the arrival counters occupy the first 2*B words of the workspace, i.e. a region whose SIZE depends on B: a caller that
+        // reuses one workspace across batch sizes (ragged last batch, cached op workspace) would hand over words that a previous,
+        // smaller launch used for pooled partials.  Zero them here (a memset node under graph capture) instead of relying on the
+        // caller's zero-initialisation plus the kernel's self-reset.
+        cudaError_t e = cudaMemsetAsync(counters, 0, (size_t)(2 * B) * sizeof(unsigned), (cudaStream_t)stream);
+        if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "encoder_fwd: counter memset: %s", cudaGetErrorString(e));
         return launch_enc_fwd_simt(x, pad, W, bias, ap, emb, relu_bits, lens, reinterpret_cast<float*>(rest), counters, B, T, (cudaStream_t)stream);
     } else if (gemm_mode == DAD_GEMM_TC_F16X3) {
         DAD_REQUIRE(W_hi && W_lo, "encoder_fwd: TC mode needs the bf16 hi/lo weight splits (dad_split_f16)");

@@ -136,6 +136,22 @@ def test_encoder_forward_backward_vs_oracle(mode, B, T, aug):
     assert float((db.cpu() - b.grad).abs().max()) <= tolW * sb + 1e-7
 
 
+def test_fp32_encoder_workspace_reuse_across_batch_sizes():
+    """The op workspace is cached and reused across calls, and the fp32 kernel's arrival counters occupy its first 2*B words:
+    a larger batch must not inherit the pooled partials a smaller batch left in those words (regression: lens / emb garbage at
+    B=4096 after a B=512 call; dad_encoder_fwd now zeroes the counters itself)."""
+    from dad_b200 import _lib, ops
+    from oracle import dad_oracle as O
+    st = pretrained_state()
+    W0, b0 = st["student_encoder.pre_net.weight"], st["student_encoder.pre_net.bias"]
+    for B in (8, 100, 3, 300, 100):
+        c, _, _ = _inputs(B, 40, 99 + B)
+        x, pad = c["net_input"]["feats"], c["net_input"]["padding_mask"]
+        emb, _, lens = ops.encoder_pool_fwd(x.cuda(), pad.cuda(), W0.cuda(), b0.cuda(), gemm_mode=_lib.GEMM_FP32)
+        assert torch.equal(lens.cpu(), (~pad).sum(1).float()), B
+        assert torch.allclose(emb.cpu(), O.encoder(x, pad, W0, b0), rtol=2e-5, atol=2e-6), B
+
+
 @pytest.mark.parametrize("B,T,aug", [(4, 64, 0), (5, 200, 2), (3, 97, 1), (2, 33, 2), (37, 41, 2)])
 def test_operand_cache_backward_is_bit_identical(B, T, aug):
     """tcgen05 mode: the backward fed by TMA from the forward's fp16 hi/lo operand cache == the backward that re-reads,
@@ -314,7 +330,7 @@ def test_device_batch_assembly_equals_host_collator():
     assert n == len(host) == 6
 
 
-@pytest.mark.parametrize("B,class_aware", [(700, True), (300, False)])
+@pytest.mark.parametrize("B,class_aware", [(700, True), (300, False), (4096, True), (2048, False)])
 def test_ecda_multi_tile_vs_fp64_gram_oracle(B, class_aware):
     """Large classes: several Gram row / column blocks, many (P Z') k-blocks and split-K slices per class (the tiny fixtures use
     one tile).  Checked against the oracle's fp64 Gram-form restatement (itself validated against the reference form at small B)."""
