@@ -348,7 +348,7 @@ def run_ours(args):
                "sample": f"oracle port of the reference step, B=64, T={T}, full loss stack, median of {8 if T <= 200 else 2} steps"}
     if rank == 0:
         print(json.dumps({
-            "metric": "DAD train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "metric": "DAD train samples/sec", "value": value, "unit": "samples/s", "utterances_per_s": 2 * value, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
             "dtype": "f32 (scaled fp16 hi/lo split, 3 tcgen05 products per GEMM, fp32 accumulate)" if args.gemm == "tc" else "f32", "data": "synthetic",
             "config": {"workload": wl["label"], "global_batch": Bg, "per_gpu_batch": B, "T": T, "parallelism": f"dp{world}",
