@@ -11,7 +11,8 @@
  *  - every op enqueues on `stream` (a cudaStream_t passed as void*), never synchronises the host and is CUDA-graph
  *    capturable; state that advances (DACP thresholds, Adam moments, step counter, parameters) is updated in place;
  *  - return value 0 = ok, negative = error (dad_last_error() holds a thread-local message); nothing throws or aborts;
- *  - workspaces must be zero-initialised once when allocated (they hold self-resetting arrival counters);
+ *  - workspaces must be zero-initialised once when allocated (they hold self-resetting arrival counters at offsets that do
+ *    not depend on the batch shape, so one workspace sized for the largest batch serves every smaller one);
  *    use a separate workspace per concurrently-running op;
  *  - fp32 tensors are contiguous row-major and 16-byte aligned; D = 768, H = 256, C = 4 are compile-time widths
  *    (I/config.py:54-55,48).
@@ -45,7 +46,7 @@ int dad_device_check(void);
 /* ---- augmentation parameters (I/utils.py:317-375 DataAugmentation) ------------------------------------------- */
 typedef struct dad_aug {
     int32_t mode;       /* 0 none, 1 weak (noise only), 2 strong (noise + feature keep + temporal span) */
-    int32_t noise_src;  /* 0 = supplied `noise` tensor (parity mode, bit-exact), 1 = in-kernel Philox4x32-10 + Box-Muller */
+    int32_t noise_src;  /* 0 = supplied `noise` tensor (parity mode, bit-exact), 1 = in-kernel Philox4x32-7 + Box-Muller */
     const float* noise; /* [B,T,D] unit normal draws (noise_src 0) */
     uint64_t seed;      /* Philox key (noise_src 1) */
     uint64_t stream;    /* Philox stream id: weak and strong views use different streams */

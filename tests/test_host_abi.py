@@ -94,3 +94,70 @@ def test_runner_style_override_is_seen_live():
         assert StepScalars(config, 60, "iemocap").use_ecda
     finally:
         config.USE_ECDA = old
+
+
+def test_ctypes_mirrors_match_the_c_structs(tmp_path):
+    """include/dad_sm100a.h is plain C: compile it with gcc (no CUDA headers needed) and compare sizeof / offsetof of every
+    argument struct with the ctypes mirrors in dad_b200/_lib.py, field by field and by NAME (a field renamed, reordered or
+    re-typed on one side only would otherwise surface as silent garbage in a kernel argument)."""
+    import ctypes
+    import subprocess
+    from dad_b200 import _lib
+    pairs = [("dad_aug", _lib.Aug), ("dad_pack", _lib.Pack), ("dad_head_fwd_args", _lib.HeadFwdArgs), ("dad_dacp_args", _lib.DacpArgs),
+             ("dad_head_bwd_args", _lib.HeadBwdArgs), ("dad_ecda_args", _lib.EcdaArgs), ("dad_scl_args", _lib.SclArgs)]
+    inc = os.path.join(ROOT, "include")
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dad_sm100a.h"', "int main(void) {"]
+    for cname, cls in pairs:
+        lines.append(f'    printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'    printf("{cname}.{fname} %zu %zu\\n", offsetof({cname}, {fname}), sizeof((({cname}*)0)->{fname}));')
+    lines += ['    printf("version %d nparam %d world %d\\n", DAD_ABI_VERSION, DAD_NPARAM, DAD_MAX_WORLD);', "    return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = {}
+    for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines():
+        k, *v = ln.split()
+        got[k] = v
+    for cname, cls in pairs:
+        assert int(got[cname][0]) == ctypes.sizeof(cls), (cname, got[cname], ctypes.sizeof(cls))
+        for fname, ftype in cls._fields_:
+            off, size = (int(t) for t in got[f"{cname}.{fname}"])
+            assert off == getattr(cls, fname).offset and size == ctypes.sizeof(ftype), (cname, fname, off, size)
+    assert got["version"] == ["2", "nparam", str(_lib.NPARAM), "world", "16"]
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/dad_sm100a.h against the argtypes / restype dad_b200/_lib.py declares: same arity, and the same
+    kind (pointer / int32 / int64 / uint64 / size_t / float) in every position."""
+    L = _lib.lib()
+    src = open(os.path.join(ROOT, "include", "dad_sm100a.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b(int|size_t|int32_t|int64_t|const char\*)\s+(dad_\w+)\s*\(([^)]*)\)\s*;", src)
+    assert len(protos) >= 25
+    scalar = {"int": ctypes.c_int32, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64,
+              "size_t": ctypes.c_size_t, "float": ctypes.c_float}
+    checked = 0
+    for ret, name, params in protos:
+        fn = getattr(L, name)
+        plist = [] if params.strip() in ("", "void") else [q.strip() for q in params.split(",")]
+        if fn.argtypes is None:
+            # undeclared argtypes are only safe for functions without pointer / 64-bit / float parameters
+            assert all("*" not in q and q.split()[0] in ("int", "int32_t") for q in plist), (name, params)
+            continue
+        assert len(fn.argtypes) == len(plist), (name, len(fn.argtypes), plist)
+        for i, (q, at) in enumerate(zip(plist, fn.argtypes)):
+            if "*" in q:
+                ok = at is ctypes.c_void_p or isinstance(at, type) and issubclass(at, ctypes._Pointer)
+            else:
+                base = q.replace("const", "").split()[0]
+                ok = at is scalar[base] or (ctypes.sizeof(at) == ctypes.sizeof(scalar[base]) and at._type_ == scalar[base]._type_)
+            assert ok, (name, i, q, at)
+        if ret == "size_t":
+            assert fn.restype is ctypes.c_size_t, name
+        if ret == "int64_t":
+            assert fn.restype is ctypes.c_int64, name
+        checked += 1
+    assert checked >= 20
