@@ -184,22 +184,35 @@ def ops_case(student):
     print("ops_small: weak/strong/encoder/dacp/ecda vectors written")
 
 
-def main():
+# name -> (dataset, overrides, B, T, epochs, steps_per_epoch, seed, full_final)
+CASES = {
+    "step_iemocap": ("iemocap", {}, 16, 40, list(range(40, 50)), 10, 9000, True),
+    "step_iemocap_warmup": ("iemocap", {}, 16, 40, [3], 5, 9500, False),
+    "step_iemocap_noentropy_globalmmd": ("iemocap", {"USE_ENTROPY_IN_SCORE": False, "USE_CLASS_AWARE_MMD": False}, 16, 40, [40, 41], 5, 9600, False),
+    "step_iemocap_fixedthr": ("iemocap", {"USE_DACP": False, "FIXED_CONFIDENCE_THRESHOLD": 0.6}, 16, 40, [45, 46], 5, 9700, False),
+    "step_casia_default": ("casia", {}, 16, 40, [40, 41], 5, 9800, False),
+    "step_casia_full": ("casia", {"USE_DACP": True, "USE_ECDA": True}, 16, 40, [40, 41], 5, 9900, False),
+    "step_emodb": ("emodb", {}, 16, 40, [40, 41], 5, 10000, False),
+    # BASELINE.json configs[0] / configs[1] at their exact shapes (EMODB batch 32, IEMOCAP batch 64, T=200)
+    "step_emodb_b32_t200": ("emodb", {}, 32, 200, [40, 41], 3, 11000, False),
+    "step_iemocap_b64_t200": ("iemocap", {}, 64, 200, [60, 61], 3, 12000, False),
+}
+
+
+def main(only=None):
+    """No arguments: regenerate everything (pretrained student included).  With case names: ADD / refresh only those cases, starting
+    from the committed tests/golden/pretrained_student.pt (so that the other fixtures, written on another host, stay untouched)."""
     os.makedirs(OUT, exist_ok=True)
-    student = pretrain()
-    torch.save(student, os.path.join(OUT, "pretrained_student.pt"))
-    ops_case(student)
-    ep = list(range(40, 50))
-    run_case("step_iemocap", "iemocap", student, {}, 16, 40, ep, 10, 9000, full_final=True)
-    run_case("step_iemocap_warmup", "iemocap", student, {}, 16, 40, [3], 5, 9500)
-    run_case("step_iemocap_noentropy_globalmmd", "iemocap", student,
-             {"USE_ENTROPY_IN_SCORE": False, "USE_CLASS_AWARE_MMD": False}, 16, 40, [40, 41], 5, 9600)
-    run_case("step_iemocap_fixedthr", "iemocap", student, {"USE_DACP": False, "FIXED_CONFIDENCE_THRESHOLD": 0.6},
-             16, 40, [45, 46], 5, 9700)
-    run_case("step_casia_default", "casia", student, {}, 16, 40, [40, 41], 5, 9800)
-    run_case("step_casia_full", "casia", student, {"USE_DACP": True, "USE_ECDA": True}, 16, 40, [40, 41], 5, 9900)
-    run_case("step_emodb", "emodb", student, {}, 16, 40, [40, 41], 5, 10000)
+    if only:
+        student = torch.load(os.path.join(OUT, "pretrained_student.pt"), weights_only=False)
+    else:
+        student = pretrain()
+        torch.save(student, os.path.join(OUT, "pretrained_student.pt"))
+        ops_case(student)
+    for name, (dataset, over, B, T, epochs, spe, seed, full) in CASES.items():
+        if not only or name in only:
+            run_case(name, dataset, student, over, B, T, epochs, spe, seed, full_final=full)
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])

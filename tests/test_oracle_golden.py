@@ -26,7 +26,8 @@ from oracle import dad_oracle as O
 from oracle import ref_harness
 
 CASES = ["step_iemocap_warmup", "step_iemocap_noentropy_globalmmd", "step_iemocap_fixedthr", "step_casia_default",
-         "step_casia_full", "step_emodb", "step_iemocap"]
+         "step_casia_full", "step_emodb", "step_iemocap",
+         "step_emodb_b32_t200", "step_iemocap_b64_t200"]  # the last two: BASELINE.json configs[0] / configs[1] at their exact shapes
 
 
 def run_case(name, max_steps=None):
