@@ -181,3 +181,22 @@ def test_tensor_core_kernels_are_tcgen05_and_tma_in_sass():
     assert s["k_enc_fwd_tc"]["UTMASTG"] > 0
     assert all(d["HMMA"] == 0 for d in s.values())
     assert len(s) >= 35
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU step, oracle port) needs no GPU: ONE JSON line on stdout carrying the
+    bench contract's keys for the reference arm; a non-zero rank under torchrun prints nothing and exits 0."""
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "DAD train samples/sec" and d["unit"] == "samples/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "configs[3]" in d["config"]["workload"] and d["vs_baseline"] is None
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
