@@ -200,3 +200,20 @@ def test_bench_reference_arm_contract():
     assert "configs[3]" in d["config"]["workload"] and d["vs_baseline"] is None
     r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_bench_dominant_kernel_is_averaged_over_its_launches_per_step():
+    """bench.py's roofline entry: the dominant kernel SYMBOL (3 forward launches or 2 backward launches per step) with its AVERAGE
+    launch time over those variants -- not the fastest variant -- and the ncu DRAM traffic averaged the same way."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    kern = {"encoder_fwd": {"ms": 0.9}, "encoder_fwd_weak": {"ms": 1.1}, "encoder_fwd_strong": {"ms": 1.3},
+            "encoder_bwd": {"ms": 1.2}, "encoder_bwd_strong": {"ms": 1.0}}
+    table = {"encoder_fwd": 10.0, "encoder_fwd_weak": 20.0, "encoder_fwd_strong": 60.0, "encoder_bwd": 1.0, "encoder_bwd_strong": 3.0, "_source": "x"}
+    d = bench.dominant_kernel(kern, 2.2e9, 4.4e11, table)
+    assert d["kernel"] == "encoder_fwd" and d["launches_per_step"] == 3 and abs(d["avg_launch_ms"] - 1.1) < 1e-12
+    assert abs(d["GBps"] - 2.2e9 / 1.1 / 1e6) < 1e-6 and abs(d["TFLOPs"] - 4.4e11 / 1.1 / 1e9) < 1e-6 and d["traffic"] == 30.0
+    kern["encoder_bwd"]["ms"] = 3.0
+    d = bench.dominant_kernel(kern, 2.2e9, 4.4e11, {"encoder_bwd": 1.0})
+    assert d["kernel"] == "encoder_bwd" and d["launches_per_step"] == 2 and d["avg_launch_ms"] == 2.0 and d["traffic"] is None
