@@ -357,7 +357,7 @@ def run_ours(args):
             t = torch.tensor([dt], device=dev)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             dt = float(t)
-        e2e = {"value": Bg / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16, "ms_per_step": dt * 1e3}
+        e2e = {"value": Bg / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20, "ms_per_step": dt * 1e3}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
