@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DAD_ABI_VERSION 2
+#define DAD_ABI_VERSION 3
 #define DAD_D 768
 #define DAD_H 256
 #define DAD_C 4
@@ -49,20 +49,29 @@ typedef struct dad_aug {
     int32_t noise_src;  /* 0 = supplied `noise` tensor (parity mode, bit-exact), 1 = in-kernel Philox4x32-7 + Box-Muller */
     const float* noise; /* [B,T,D] unit normal draws (noise_src 0) */
     uint64_t seed;      /* Philox key (noise_src 1) */
-    uint64_t stream;    /* Philox stream id: weak and strong views use different streams */
+    uint64_t stream;    /* Philox stream id: weak and strong views use different streams.  Streams 2k and 2k+1 share their Philox
+                           blocks (one call yields the four normals of a float4 for BOTH): the weak / strong views of one batch
+                           use such a pair so that dad_aug_encoder_fwd draws both from one call */
     float sigma;        /* WEAK_NOISE_STD / STRONG_NOISE_STD: out = x + (n*sigma), two fp32 roundings */
     const float* feat_keep;  /* [D] 0/1 multiplier shared by the whole batch, no rescale (I/utils.py:343-344); NULL = none */
     const int32_t* t_start;  /* [B] temporal span starts (I/utils.py:371); NULL = none */
     int32_t mask_len;        /* int(T_padded * TEMPORAL_MASK_RATIO) (I/utils.py:366); rows [s, s+len) := +0 */
     const int64_t* step_ptr; /* nullable device counter mixed into the Philox key, so a replayed CUDA graph draws fresh noise
                                 every step while the forward and backward kernels of one step regenerate identical noise */
+    int64_t frame_offset;    /* index of this call's first frame in the GLOBAL noise field (noise_src 1): rank * B_local * T under
+                                data parallelism, so that the ranks draw disjoint parts of one i.i.d. field as the reference's
+                                single randn_like over the whole batch does (I/utils.py:330,338); 0 on one GPU */
 } dad_aug;
 
 /* per-step device-side draws for the throughput mode (replaces the host RNG calls of I/model.py:62 nn.Dropout x2,
  * I/utils.py:343 torch.rand(D) and I/utils.py:371 B x torch.randint): keep_* [B,H] 0/1 with P(keep)=1-p_drop,
- * feat_keep [D] 0/1 with P(keep)=1-feat_rate, t_start [B] uniform in [0, max(1, T-mask_len+1)).  Any output may be NULL. */
+ * feat_keep [D] 0/1 with P(keep)=1-feat_rate, t_start [B] uniform in [0, max(1, T-mask_len+1)).  Any output may be NULL.
+ * sample_offset = index of this call's first sample in the global batch (rank * B_local under data parallelism, else 0): the
+ * per-sample draws (keep_*, t_start) of the ranks are disjoint parts of one field; feat_keep is the same on every rank (the
+ * reference shares it over the whole batch). */
 int dad_step_rng(uint64_t seed, const int64_t* step_ptr, float* keep_clean, float* keep_strong, int64_t B, float p_drop,
-                 float* feat_keep, float feat_rate, int32_t* t_start, int64_t T, int32_t mask_len, void* stream);
+                 float* feat_keep, float feat_rate, int32_t* t_start, int64_t T, int32_t mask_len, int64_t sample_offset,
+                 void* stream);
 
 /* replaces DataAugmentation.weak_augment / strong_augment (I/utils.py:328-375): out[B,T,D] = aug(x) */
 int dad_augment(const float* x, float* out, const dad_aug* aug, int64_t B, int64_t T, void* stream);
@@ -77,19 +86,40 @@ int dad_gather_pad(const float* feats, const int64_t* offsets, const int32_t* si
 size_t dad_encoder_fwd_workspace_bytes(int64_t B, int64_t T, int32_t gemm_mode);
 /* emb[B,H] = masked-mean_t relu(W aug(x)[b,t,:] + bias).  pad: [B,T] uint8, 1 = padded frame, NULL = none.
  * relu_bits (nullable): [B*T, H/32] uint32, bit j of word w of frame n = (pre[n, 32w+j] > 0) -- all the backward needs.
- * xs_hi / xs_lo (nullable, TC mode only): OPERAND CACHE, two fp16 [B*T, D] buffers.  When given, the forward also writes the
- *   hi/lo split of the augmented, power-of-two-scaled input it feeds to the tensor cores; dad_encoder_bwd given the same
- *   buffers loads its B operand from them by TMA instead of re-reading x and regenerating the augmentation (same values,
- *   bit-identical dW; trades one extra N*D*4-byte write + read for the converter work of the backward).
+ * xs_hi / xs_lo (nullable, TC mode only): OPERAND CACHE, fp16 [B*T, D] buffers.  When given, the forward also writes the
+ *   hi (and, if xs_lo is given, lo) half of the split of the augmented, power-of-two-scaled input it feeds to the tensor cores;
+ *   dad_encoder_bwd given the same buffers loads its B operand from them by TMA instead of re-reading x and regenerating the
+ *   augmentation (same values, bit-identical dW).  The default 2-product backward (dad_tc_set_bwd_products) needs xs_hi only:
+ *   N*D*2 bytes written + read instead of the N*D*4 bytes of x read again.
  * lens (nullable): [B] valid length clamped to >= 1 (I/model.py:36).  W_hi/W_lo: fp16 [H,D] splits from dad_split_f16 (TC mode only). */
 int dad_encoder_fwd(const float* x, const uint8_t* pad, const float* W, const float* bias, const void* W_hi,
                     const void* W_lo, const dad_aug* aug, float* emb, uint32_t* relu_bits, void* xs_hi, void* xs_lo,
                     float* lens, void* ws, size_t ws_bytes, int64_t B, int64_t T, int32_t gemm_mode, void* stream);
 
+/* Fused noisy forward (SURVEY.md 8b `aug_encoder_pool_fwd`; replaces I/train.py:405-409,439 = weak_augment + teacher encoder,
+ * strong_augment + student encoder, I/utils.py:328-375 + I/model.py:18-41 twice): x [B,T,D] is read ONCE; the weak view
+ * (aug_weak, mode 1) feeds the teacher weights, the strong view (aug_strong, mode 2) the student weights, on the tcgen05 path.
+ * Outputs: emb_teacher, emb_student [B,H]; relu_bits / xs_hi / xs_lo (nullable) of the STUDENT view as in dad_encoder_fwd.
+ * In Philox mode the two descriptors must share seed / step_ptr / frame_offset and use the streams (2k, 2k+1). */
+size_t dad_aug_encoder_fwd_workspace_bytes(int64_t B, int64_t T);
+int dad_aug_encoder_fwd(const float* x, const uint8_t* pad, const void* Wt_hi, const void* Wt_lo, const float* bias_t,
+                        const dad_aug* aug_weak, float* emb_teacher, const void* Ws_hi, const void* Ws_lo, const float* bias_s,
+                        const dad_aug* aug_strong, float* emb_student, uint32_t* relu_bits, void* xs_hi, void* xs_lo, float* lens,
+                        void* ws, size_t ws_bytes, int64_t B, int64_t T, void* stream);
+
+/* Process-wide switches of the tcgen05 encoder kernels (also DAD_TC_CTA2 / DAD_TC_BWD_PRODUCTS in the environment):
+ *  cta_pair      1 (default) = forward kernels run as CTA pairs (cluster of 2, tcgen05.mma.cta_group::2), 0 = one CTA per tile
+ *  bwd_products  2 (default) = dW GEMM as dpre_hi*x_hi + dpre_lo*x_hi (x_hi only: xs_lo unused), 3 = adds dpre_hi*x_lo (fp32-grade) */
+void dad_tc_set_cta_pair(int32_t on);
+int32_t dad_tc_get_cta_pair(void);
+void dad_tc_set_bwd_products(int32_t n);
+int32_t dad_tc_get_bwd_products(void);
+
 int32_t dad_encoder_bwd_splits(int64_t B, int64_t T, int32_t gemm_mode);
 /* split-K partials: dW_part[splits, H, D], db_part[splits, H]; dad_grad_reduce sums them in fixed order.
  * g_emb[B,H] = dL/d emb; x / pad / aug identical to the forward call (the augmented view is regenerated) -- or, in TC
- * mode, xs_hi / xs_lo = the operand cache the forward call filled (then x and aug are ignored and may be NULL). */
+ * mode, xs_hi (/ xs_lo for the 3-product backward) = the operand cache the forward call filled (then x and aug are ignored
+ * and may be NULL). */
 int dad_encoder_bwd(const float* x, const uint8_t* pad, const dad_aug* aug, const uint32_t* relu_bits, const void* xs_hi,
                     const void* xs_lo, const float* g_emb, const float* lens, float* dW_part, float* db_part,
                     int32_t splits, void* ws, size_t ws_bytes, int64_t B, int64_t T, int32_t gemm_mode, void* stream);

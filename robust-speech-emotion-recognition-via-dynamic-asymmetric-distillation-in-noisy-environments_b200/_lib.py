@@ -22,6 +22,8 @@ EXPORTS = (
     "dad_ecda_workspace_bytes", "dad_ecda", "dad_grad_reduce", "dad_grad_norm", "dad_adam_ema", "dad_ema",
     "dad_split_f16", "dad_step_rng", "dad_certainty_scores", "dad_scl_workspace_bytes", "dad_scl",
     "dad_peer_push", "dad_peer_barrier", "dad_grad_sum_ranks", "dad_max_world", "dad_gather_pad",
+    "dad_aug_encoder_fwd", "dad_aug_encoder_fwd_workspace_bytes", "dad_tc_set_cta_pair", "dad_tc_get_cta_pair",
+    "dad_tc_set_bwd_products", "dad_tc_get_bwd_products",
 )
 
 
@@ -32,7 +34,7 @@ class DadError(RuntimeError):
 class Aug(C.Structure):
     _fields_ = [("mode", C.c_int32), ("noise_src", C.c_int32), ("noise", C.c_void_p), ("seed", C.c_uint64),
                 ("stream", C.c_uint64), ("sigma", C.c_float), ("feat_keep", C.c_void_p), ("t_start", C.c_void_p),
-                ("mask_len", C.c_int32), ("step_ptr", C.c_void_p)]
+                ("mask_len", C.c_int32), ("step_ptr", C.c_void_p), ("frame_offset", C.c_int64)]
 
 
 class Pack(C.Structure):
@@ -92,7 +94,8 @@ def lib():
     L = C.CDLL(LIB_PATH)
     L.dad_last_error.restype = C.c_char_p
     L.dad_abi_version.restype = C.c_int
-    for name in ("dad_encoder_fwd_workspace_bytes", "dad_encoder_bwd_workspace_bytes", "dad_ecda_workspace_bytes", "dad_scl_workspace_bytes"):
+    for name in ("dad_encoder_fwd_workspace_bytes", "dad_encoder_bwd_workspace_bytes", "dad_ecda_workspace_bytes", "dad_scl_workspace_bytes",
+                 "dad_aug_encoder_fwd_workspace_bytes"):
         getattr(L, name).restype = C.c_size_t
     L.dad_pack_rank_words.restype = C.c_int64
     L.dad_encoder_fwd_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int32]
@@ -104,6 +107,13 @@ def lib():
     vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
     L.dad_augment.argtypes = [vp, vp, C.POINTER(Aug), i64, i64, vp]
     L.dad_encoder_fwd.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(Aug), vp, vp, vp, vp, vp, vp, C.c_size_t, i64, i64, i32, vp]
+    L.dad_aug_encoder_fwd_workspace_bytes.argtypes = [i64, i64]
+    L.dad_aug_encoder_fwd.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Aug), vp, vp, vp, vp, C.POINTER(Aug), vp, vp, vp, vp, vp, vp, C.c_size_t,
+                                      i64, i64, vp]
+    L.dad_tc_set_cta_pair.argtypes = [i32]
+    L.dad_tc_set_cta_pair.restype = None
+    L.dad_tc_set_bwd_products.argtypes = [i32]
+    L.dad_tc_set_bwd_products.restype = None
     L.dad_encoder_bwd.argtypes = [vp, vp, C.POINTER(Aug), vp, vp, vp, vp, vp, vp, vp, i32, vp, C.c_size_t, i64, i64, i32, vp]
     L.dad_head_fwd.argtypes = [C.POINTER(HeadFwdArgs), vp]
     L.dad_dacp_mask.argtypes = [C.POINTER(DacpArgs), vp]
@@ -121,8 +131,8 @@ def lib():
     L.dad_ema.argtypes = [vp, vp, f32, f32, i64, vp]
     L.dad_split_f16.argtypes = [vp, vp, vp, i64, vp]
     L.dad_certainty_scores.argtypes = [vp, i32, i32, vp, vp, vp]
-    L.dad_step_rng.argtypes = [C.c_uint64, vp, vp, vp, i64, f32, vp, f32, vp, i64, i32, vp]
-    if L.dad_abi_version() != 2:
+    L.dad_step_rng.argtypes = [C.c_uint64, vp, vp, vp, i64, f32, vp, f32, vp, i64, i32, i64, vp]
+    if L.dad_abi_version() != 3:
         raise DadError("libdad_sm100a.so ABI version mismatch")
     _lib = L
     return L
@@ -164,7 +174,10 @@ def ptr(t, dtype=None, name="tensor"):
     return t.data_ptr()
 
 
-def make_aug(mode=0, noise=None, sigma=0.0, feat_keep=None, t_start=None, mask_len=0, seed=None, stream=0, step_ptr=None):
+STREAM_WEAK, STREAM_STRONG = 2, 3  # Philox streams of the two views of a noisy batch: a (2k, 2k+1) pair shares its Philox blocks
+
+
+def make_aug(mode=0, noise=None, sigma=0.0, feat_keep=None, t_start=None, mask_len=0, seed=None, stream=0, step_ptr=None, frame_offset=0):
     """Build a dad_aug.  noise tensor -> parity mode (noise_src 0); seed -> in-kernel Philox (noise_src 1)."""
     a = Aug()
     a.mode = int(mode)
@@ -177,6 +190,7 @@ def make_aug(mode=0, noise=None, sigma=0.0, feat_keep=None, t_start=None, mask_l
             raise DadError("augmentation needs either a supplied noise tensor or a Philox seed")
         a.noise_src, a.seed, a.stream = 1, int(seed) & (2 ** 64 - 1), int(stream)
         a.step_ptr = step_ptr
+        a.frame_offset = int(frame_offset)
     a.sigma = float(sigma)
     if mode == 2:
         a.feat_keep = ptr(feat_keep, torch.float32, "aug.feat_keep")

@@ -8,7 +8,7 @@
 // ---- kernels (other translation units)
 int launch_augment(const float* x, float* out, const AugParams& ap, int64_t B, int64_t T, int64_t D, cudaStream_t st);
 int launch_step_rng(unsigned long long seed, const int64_t* step_ptr, float* keep_clean, float* keep_strong, int64_t B, float p_drop,
-                    float* feat_keep, float feat_rate, int32_t* t_start, int64_t T, int mask_len, cudaStream_t st);
+                    float* feat_keep, float feat_rate, int32_t* t_start, int64_t T, int mask_len, int64_t sample_offset, cudaStream_t st);
 size_t enc_fwd_simt_ws_bytes(int64_t B, int64_t T);
 int launch_enc_fwd_simt(const float* x, const uint8_t* pad, const float* W, const float* bias, const AugParams& ap, float* emb,
                         uint32_t* bits, float* lens_out, float* part_ws, unsigned* counters, int64_t B, int64_t T, cudaStream_t st);
@@ -16,9 +16,13 @@ int enc_bwd_simt_splits(int64_t N);
 int launch_enc_bwd_simt(const float* x, const uint8_t* pad, const AugParams& ap, const uint32_t* bits, const float* g_emb, const float* lens,
                         float* dWp, float* dbp, int splits, int64_t B, int64_t T, cudaStream_t st);
 size_t enc_fwd_tc_ws_bytes(int64_t B, int64_t T);
-int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W_hi, const void* W_lo, const float* bias, const AugParams& ap,
-                      float* emb, uint32_t* bits, void* xs_hi, void* xs_lo, float* lens_out, void* ws, size_t ws_bytes, int64_t B, int64_t T,
-                      cudaStream_t st);
+int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W0_hi, const void* W0_lo, const float* bias0, const AugParams& ap0, float* emb0,
+                      uint32_t* bits0, const void* W1_hi, const void* W1_lo, const float* bias1, const AugParams* ap1, float* emb1, uint32_t* bits1,
+                      void* xs_hi, void* xs_lo, float* lens_out, void* ws, size_t ws_bytes, int64_t B, int64_t T, cudaStream_t st);
+void enc_tc_set_cta_pair(int on);
+int enc_tc_get_cta_pair();
+void enc_tc_set_bwd_products(int n);
+int enc_tc_get_bwd_products();
 int enc_bwd_tc_splits(int64_t N);
 size_t enc_bwd_tc_ws_bytes(int64_t B, int64_t T);
 int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, const uint32_t* bits, const void* xs_hi, const void* xs_lo,
@@ -97,9 +101,10 @@ int dad_augment(const float* x, float* out, const dad_aug* aug, int64_t B, int64
 }
 
 int dad_step_rng(uint64_t seed, const int64_t* step_ptr, float* keep_clean, float* keep_strong, int64_t B, float p_drop, float* feat_keep,
-                 float feat_rate, int32_t* t_start, int64_t T, int32_t mask_len, void* stream) {
-    DAD_REQUIRE(B >= 0 && T >= 0 && mask_len >= 0, "step_rng: negative size");
-    return launch_step_rng(seed, step_ptr, keep_clean, keep_strong, B, p_drop, feat_keep, feat_rate, t_start, T, mask_len, (cudaStream_t)stream);
+                 float feat_rate, int32_t* t_start, int64_t T, int32_t mask_len, int64_t sample_offset, void* stream) {
+    DAD_REQUIRE(B >= 0 && T >= 0 && mask_len >= 0 && sample_offset >= 0, "step_rng: negative size");
+    return launch_step_rng(seed, step_ptr, keep_clean, keep_strong, B, p_drop, feat_keep, feat_rate, t_start, T, mask_len, sample_offset,
+                           (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------- encoder
@@ -137,14 +142,42 @@ int dad_encoder_fwd(const float* x, const uint8_t* pad, const float* W, const fl
         if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "encoder_fwd: counter memset: %s", cudaGetErrorString(e));
         return launch_enc_fwd_simt(x, pad, W, bias, ap, emb, relu_bits, lens, reinterpret_cast<float*>(rest), counters, B, T, (cudaStream_t)stream);
     } else if (gemm_mode == DAD_GEMM_TC_F16X3) {
-        DAD_REQUIRE(W_hi && W_lo, "encoder_fwd: TC mode needs the bf16 hi/lo weight splits (dad_split_f16)");
-        DAD_REQUIRE((xs_hi == nullptr) == (xs_lo == nullptr), "encoder_fwd: xs_hi and xs_lo must be given together");
+        DAD_REQUIRE(W_hi && W_lo, "encoder_fwd: TC mode needs the fp16 hi/lo weight splits (dad_split_f16)");
+        DAD_REQUIRE(xs_hi || !xs_lo, "encoder_fwd: xs_lo without xs_hi");
         DAD_REQUIRE(!xs_hi || (aligned16(xs_hi) && aligned16(xs_lo)), "encoder_fwd: xs_hi/xs_lo not 16-byte aligned");
-        return launch_enc_fwd_tc(x, pad, W_hi, W_lo, bias, ap, emb, relu_bits, xs_hi, xs_lo, lens, rest, ws_bytes - (size_t)(rest - (char*)ws), B, T,
-                                 (cudaStream_t)stream);
+        return launch_enc_fwd_tc(x, pad, W_hi, W_lo, bias, ap, emb, relu_bits, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, xs_hi, xs_lo, lens,
+                                 rest, ws_bytes - (size_t)(rest - (char*)ws), B, T, (cudaStream_t)stream);
     }
     return dad_set_error(DAD_ERR_ARG, "encoder_fwd: unknown gemm_mode %d", gemm_mode);
 }
+
+// fused noisy forward (I/train.py:405-409,439): weak view -> teacher, strong view -> student, x_noisy read once
+size_t dad_aug_encoder_fwd_workspace_bytes(int64_t B, int64_t T) { return enc_fwd_tc_ws_bytes(B, T); }
+int dad_aug_encoder_fwd(const float* x, const uint8_t* pad, const void* Wt_hi, const void* Wt_lo, const float* bias_t, const dad_aug* aug_weak,
+                        float* emb_teacher, const void* Ws_hi, const void* Ws_lo, const float* bias_s, const dad_aug* aug_strong, float* emb_student,
+                        uint32_t* relu_bits, void* xs_hi, void* xs_lo, float* lens, void* ws, size_t ws_bytes, int64_t B, int64_t T, void* stream) {
+    DAD_REQUIRE(B >= 0 && T >= 0, "aug_encoder_fwd: negative size");
+    if (B == 0) return DAD_OK;
+    DAD_REQUIRE(T > 0 && B <= 0x7fffffff / 2 && T <= 0x7fffffff, "aug_encoder_fwd: bad size");
+    DAD_REQUIRE(x && aligned16(x), "aug_encoder_fwd: x null or not 16-byte aligned");
+    DAD_REQUIRE(Wt_hi && Wt_lo && Ws_hi && Ws_lo && bias_t && bias_s, "aug_encoder_fwd: null weight split / bias");
+    DAD_REQUIRE(emb_teacher && emb_student && aligned16(emb_teacher) && aligned16(emb_student), "aug_encoder_fwd: emb null or unaligned");
+    DAD_REQUIRE(aug_weak && aug_strong, "aug_encoder_fwd: both augmentation descriptors are required");
+    DAD_REQUIRE(xs_hi || !xs_lo, "aug_encoder_fwd: xs_lo without xs_hi");
+    int rc = check_aug(aug_weak, true);
+    if (!rc) rc = check_aug(aug_strong, true);
+    if (rc) return rc;
+    const size_t need = dad_aug_encoder_fwd_workspace_bytes(B, T);
+    if (!ws || ws_bytes < need) return dad_set_error(DAD_ERR_WS, "aug_encoder_fwd: workspace %zu < %zu bytes", ws_bytes, need);
+    return launch_enc_fwd_tc(x, pad, Wt_hi, Wt_lo, bias_t, *aug_weak, emb_teacher, nullptr, Ws_hi, Ws_lo, bias_s, aug_strong, emb_student, relu_bits, xs_hi,
+                             xs_lo, lens, ws, ws_bytes, B, T, (cudaStream_t)stream);
+}
+
+/* process-wide tuning switches of the tcgen05 encoder kernels */
+void dad_tc_set_cta_pair(int32_t on) { enc_tc_set_cta_pair(on); }
+int32_t dad_tc_get_cta_pair(void) { return enc_tc_get_cta_pair(); }
+void dad_tc_set_bwd_products(int32_t n) { enc_tc_set_bwd_products(n); }
+int32_t dad_tc_get_bwd_products(void) { return enc_tc_get_bwd_products(); }
 
 int32_t dad_encoder_bwd_splits(int64_t B, int64_t T, int32_t gemm_mode) {
     return gemm_mode == DAD_GEMM_TC_F16X3 ? enc_bwd_tc_splits(B * T) : enc_bwd_simt_splits(B * T);
@@ -157,7 +190,7 @@ int dad_encoder_bwd(const float* x, const uint8_t* pad, const dad_aug* aug, cons
                     const float* g_emb, const float* lens, float* dW_part, float* db_part, int32_t splits, void* ws, size_t ws_bytes,
                     int64_t B, int64_t T, int32_t gemm_mode, void* stream) {
     DAD_REQUIRE(B > 0 && T > 0, "encoder_bwd: empty batch");
-    DAD_REQUIRE((xs_hi == nullptr) == (xs_lo == nullptr), "encoder_bwd: xs_hi and xs_lo must be given together");
+    DAD_REQUIRE(xs_hi || !xs_lo, "encoder_bwd: xs_lo without xs_hi");
     const bool cached = xs_hi != nullptr && gemm_mode == DAD_GEMM_TC_F16X3;
     DAD_REQUIRE(cached || (x && aligned16(x)), "encoder_bwd: x null/unaligned (and no operand cache given)");
     DAD_REQUIRE(relu_bits && g_emb && aligned16(g_emb) && lens, "encoder_bwd: null/unaligned input");

@@ -82,14 +82,15 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 }
 // ---------------------------------------------------------------------------------------------
 // Canonical in-kernel noise field (throughput mode; the parity mode reads supplied noise instead).
-// One Philox4x32 call -- counter (n2, c4, stream, 0), key = seed -- yields the 8 unit normals of the float4 column
-// group c4 (columns 4*c4 .. 4*c4+3, c4 < 192) of the frame-row pair (2*n2, 2*n2+1): each 32-bit word feeds one
-// Box-Muller pair with a 16-bit radius uniform u = (k + 0.5) / 65536 and a 16-bit angle (|z| <= 4.86; the
-// truncated tail mass is 1.2e-6).  word j -> (r_j cos_j, r_j sin_j); words 0,1 belong to the even row, words 2,3 to the odd row.
-// Every kernel that needs the noise (materialising augment, CUDA-core and tcgen05 encoder forward AND backward)
-// regenerates it from this function, so the field is identical wherever it is consumed.
+// One Philox4x32 call -- counter (n, c4, stream >> 1, 0), key = seed -- yields the four 32-bit words of the float4 column
+// group c4 (columns 4*c4 .. 4*c4+3, c4 < 192) of frame n.  The LOW BIT of the stream id selects the word pair: even streams
+// take words (x, y), odd streams (z, w) -- so the weak (stream 2) and strong (stream 3) views of the same noisy batch share
+// every Philox block, and the fused weak+strong forward (k_enc_fwd_tc, two views from one read of x) pays one Philox call per
+// float4 for both.  Each word feeds one Box-Muller pair with a 16-bit radius uniform u = (k + 0.5) / 65536 and a 16-bit
+// angle (|z| <= 4.86; the truncated tail mass is 1.2e-6): first word -> columns 4*c4, 4*c4+1 (r cos, r sin), second word ->
+// columns 4*c4+2, 4*c4+3.  Every kernel that needs the noise (materialising augment, CUDA-core and tcgen05 encoder forward
+// AND backward) regenerates it from these functions, so the field is identical wherever it is consumed.
 // radius_k: -2 ln2 * sigma^2 folds the noise scale into the radius (r = sigma * sqrt(-2 ln u)); pass -2 ln2 for unit normals.
-// Cost: ~60 integer ops + 16 MUFU per 8 normals (no I2F: the uniforms are built in the mantissa of [1,2) floats).
 // ---------------------------------------------------------------------------------------------
 constexpr float NOISE_UNIT_K = -1.3862943611198906f;  // -2 ln 2
 __device__ __forceinline__ float fast_sqrt(float x) {
@@ -97,24 +98,38 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-struct NoiseBM8 { float r[4], c[4], s[4]; };
-__device__ __forceinline__ void philox_bm8(unsigned long long seed, uint32_t stream, uint32_t n2, uint32_t c4, float radius_k, NoiseBM8& o) {
-    const uint4 w4 = philox4x32_10(make_uint4(n2, c4, stream, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float u = __uint_as_float(0x3f800040u | ((w[j] & 0xffffu) << 7)) - 1.0f;  // (k + 0.5) / 65536 in (0, 1)
-        o.r[j] = fast_sqrt(__log2f(u) * radius_k);
-        const float turns = __uint_as_float(0x3f800000u | ((w[j] >> 16) << 7));        // 1 + a / 65536: sin/cos are 1-periodic in turns
-        __sincosf(6.283185307179586f * turns, &o.s[j], &o.c[j]);
-    }
+// n = GLOBAL frame index (ap.frame_offset + local frame: under data parallelism every rank draws its own part of one field)
+__device__ __forceinline__ uint4 noise_words(unsigned long long seed, uint32_t stream_block, unsigned long long n, uint32_t c4) {
+    return philox4x32_10(make_uint4((uint32_t)n, c4 | ((uint32_t)(n >> 32) << 8), stream_block, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
-// four unit normals for the aligned group of 4 consecutive elements starting at flat index 4*idx4 of a [N, 768] tensor
-__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long stream, unsigned long long idx4) {
+// one word -> (radius, cos, sin): the two normals are r*c and r*s
+__device__ __forceinline__ void bm_word(uint32_t w, float radius_k, float& r, float& c, float& s) {
+    const float u = __uint_as_float(0x3f800040u | ((w & 0xffffu) << 7)) - 1.0f;  // (k + 0.5) / 65536 in (0, 1)
+    r = fast_sqrt(__log2f(u) * radius_k);
+    const float turns = __uint_as_float(0x3f800000u | ((w >> 16) << 7));         // 1 + a / 65536: sin/cos are 1-periodic in turns
+    __sincosf(6.283185307179586f * turns, &s, &c);
+}
+struct NoiseBM4 { float r[2], c[2], s[2]; };
+__device__ __forceinline__ void bm4_from_words(uint32_t wa, uint32_t wb, float radius_k, NoiseBM4& o) {
+    bm_word(wa, radius_k, o.r[0], o.c[0], o.s[0]);
+    bm_word(wb, radius_k, o.r[1], o.c[1], o.s[1]);
+}
+// x + noise for one float4 (single rounding per element: the radius already carries sigma)
+__device__ __forceinline__ float4 bm4_add(const NoiseBM4& z, const float4& v) {
+    return make_float4(fmaf(z.r[0], z.c[0], v.x), fmaf(z.r[0], z.s[0], v.y), fmaf(z.r[1], z.c[1], v.z), fmaf(z.r[1], z.s[1], v.w));
+}
+__device__ __forceinline__ void philox_bm4(unsigned long long seed, uint32_t stream, unsigned long long n, uint32_t c4, float radius_k, NoiseBM4& o) {
+    const uint4 w = noise_words(seed, stream >> 1, n, c4);
+    if (stream & 1u) bm4_from_words(w.z, w.w, radius_k, o);
+    else bm4_from_words(w.x, w.y, radius_k, o);
+}
+// four unit normals for the aligned group of 4 consecutive elements starting at flat index 4*idx4 of a [N, 768] tensor whose
+// first frame is frame `frame_offset` of the global field
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long stream, unsigned long long idx4,
+                                                 unsigned long long frame_offset) {
     const unsigned long long n = idx4 / (DAD_D / 4);
     const uint32_t c4 = (uint32_t)(idx4 - n * (DAD_D / 4));
-    NoiseBM8 z;
-    philox_bm8(seed, (uint32_t)stream, (uint32_t)(n >> 1), c4, NOISE_UNIT_K, z);
-    return (n & 1ull) ? make_float4(z.r[2] * z.c[2], z.r[2] * z.s[2], z.r[3] * z.c[3], z.r[3] * z.s[3])
-                      : make_float4(z.r[0] * z.c[0], z.r[0] * z.s[0], z.r[1] * z.c[1], z.r[1] * z.s[1]);
+    NoiseBM4 z;
+    philox_bm4(seed, (uint32_t)stream, n + frame_offset, c4, NOISE_UNIT_K, z);
+    return make_float4(z.r[0] * z.c[0], z.r[0] * z.s[0], z.r[1] * z.c[1], z.r[1] * z.s[1]);
 }

@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(256) k_augment(const float* __restrict__ x, fl
         const int d4 = (int)(i - row * dv);
         float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
         float4 n;
-        if (kPhilox) n = philox_normal4(seed, ap.stream, (unsigned long long)i);
+        if (kPhilox) n = philox_normal4(seed, ap.stream, (unsigned long long)i, (unsigned long long)ap.frame_offset);
         else n = __ldg(reinterpret_cast<const float4*>(ap.noise) + i);
         v.x = aug_add_noise(v.x, n.x, ap.sigma);
         v.y = aug_add_noise(v.y, n.y, ap.sigma);
@@ -78,13 +78,16 @@ int launch_gather_pad(const float* feats, const int64_t* offsets, const int32_t*
 // Per-step draws of the throughput mode (dropout keep masks, feature keep mask, temporal span starts).
 __global__ void __launch_bounds__(256) k_step_rng(unsigned long long seed, const int64_t* step_ptr, float* keep_clean, float* keep_strong,
                                                   int64_t n_keep, float p_drop, float* feat_keep, float feat_rate, int32_t* t_start,
-                                                  int64_t B, int64_t T, int mask_len) {
+                                                  int64_t B, int64_t T, int mask_len, int64_t sample_offset) {
     const unsigned long long s = seed + (step_ptr ? (unsigned long long)(*step_ptr) * 0x9E3779B97F4A7C15ull : 0ull);
     const float k = 2.3283064365386963e-10f;
     const int64_t n4 = (n_keep + 3) / 4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 101u, 0u), make_uint2((uint32_t)s, (uint32_t)(s >> 32)));
-        const uint4 q = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 102u, 0u), make_uint2((uint32_t)s, (uint32_t)(s >> 32)));
+        // per-sample draws are indexed by the GLOBAL sample (sample_offset = rank * B_local under data parallelism): ranks draw
+        // disjoint parts of one field, as the reference's single nn.Dropout over the whole batch does; n_keep = B * 256 is a multiple of 4
+        const int64_t gi = i + sample_offset * (DAD_H / 4);
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), 101u, 0u), make_uint2((uint32_t)s, (uint32_t)(s >> 32)));
+        const uint4 q = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), 102u, 0u), make_uint2((uint32_t)s, (uint32_t)(s >> 32)));
         const uint32_t rv[4] = {r.x, r.y, r.z, r.w}, qv[4] = {q.x, q.y, q.z, q.w};
         for (int j = 0; j < 4; ++j) {
             const int64_t e = i * 4 + j;
@@ -102,19 +105,20 @@ __global__ void __launch_bounds__(256) k_step_rng(unsigned long long seed, const
         }
         const int64_t span = (T - mask_len + 1) > 1 ? (T - mask_len + 1) : 1;
         for (int64_t b = threadIdx.x; t_start && b < B; b += blockDim.x) {
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(b >> 32), 104u, 0u), make_uint2((uint32_t)s, (uint32_t)(s >> 32)));
+            const int64_t gb = b + sample_offset;
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)gb, (uint32_t)(gb >> 32), 104u, 0u), make_uint2((uint32_t)s, (uint32_t)(s >> 32)));
             t_start[b] = (int32_t)(((unsigned long long)r.x * (unsigned long long)span) >> 32);
         }
     }
 }
 
 int launch_step_rng(unsigned long long seed, const int64_t* step_ptr, float* keep_clean, float* keep_strong, int64_t B, float p_drop,
-                    float* feat_keep, float feat_rate, int32_t* t_start, int64_t T, int mask_len, cudaStream_t st) {
+                    float* feat_keep, float feat_rate, int32_t* t_start, int64_t T, int mask_len, int64_t sample_offset, cudaStream_t st) {
     const int64_t n_keep = B * DAD_H;
     int64_t blocks = ceil_div64((n_keep + 3) / 4, 256);
     if (blocks < 1) blocks = 1;
     if (blocks > 592) blocks = 592;
-    k_step_rng<<<(unsigned)blocks, 256, 0, st>>>(seed, step_ptr, keep_clean, keep_strong, n_keep, p_drop, feat_keep, feat_rate, t_start, B, T, mask_len);
+    k_step_rng<<<(unsigned)blocks, 256, 0, st>>>(seed, step_ptr, keep_clean, keep_strong, n_keep, p_drop, feat_keep, feat_rate, t_start, B, T, mask_len, sample_offset);
     DAD_CHECK_LAUNCH("k_step_rng");
     return DAD_OK;
 }

@@ -17,7 +17,7 @@ __device__ __forceinline__ float4 load_x_aug(const float* __restrict__ x, const 
     float4 v = __ldg(reinterpret_cast<const float4*>(x + e));
     if (ap.mode == 0) return v;
     float4 n;
-    if (ap.noise_src == 1) n = philox_normal4(seed, ap.stream, (unsigned long long)(e >> 2));
+    if (ap.noise_src == 1) n = philox_normal4(seed, ap.stream, (unsigned long long)(e >> 2), (unsigned long long)ap.frame_offset);
     else n = __ldg(reinterpret_cast<const float4*>(ap.noise + e));
     v.x = aug_add_noise(v.x, n.x, ap.sigma);
     v.y = aug_add_noise(v.y, n.y, ap.sigma);

@@ -9,13 +9,19 @@
 // contractions run here; everything else stays on CUDA cores.
 //
 // Forward  (I/model.py:18-41):  pre[N,256] = aug(x)[N,768] . W^T,  emb[b] = sum_t valid relu(pre + bias) / len_b
-//   persistent CTAs (one per SM), 128-frame x 256-unit tiles, K loop of 12 x 64.  Warp roles:
-//     warp 0      TMA producer: W_hi / W_lo k-blocks (fp16, SWIZZLE_128B) -> smem ring
-//     warp 1      MMA issuer : 12 tcgen05.mma (3 products x 4 k-steps) per k-block into one of two TMEM accumulators
-//     warp 2      TMEM allocator
-//     warps 4-11  converters : coalesced LDG of fp32 x (+ fused weak/strong augmentation, I/utils.py:328-375),
-//                              fp16 hi/lo split, swizzled st.shared of the A operand (K-major, SWIZZLE_128B)
-//     warps 12-15 epilogue   : tcgen05.ld -> bias + ReLU + padding mask -> 1-bit ReLU mask + per-32-frame pooled partial sums
+//   k_enc_fwd_tc<NV, CTA2>: persistent CTAs (one per SM), 128-frame x 256-unit tiles, K loop of 24 x 32 (64-byte rows, SWIZZLE_64B).
+//   NV = 2 is the fused noisy forward (I/train.py:405-409,439): x_noisy is read ONCE, the converters form the weak and the strong
+//   view of every element (one Philox block serves both) and two accumulators receive weak x teacher-W and strong x student-W.
+//   CTA2 pairs two SMs (cluster of 2, tcgen05.mma.cta_group::2, M = 256 over the pair): every CTA converts ITS 128 frames and
+//   TMA-loads HALF of every W k-block; the leader's one thread issues the MMAs for both, the peer's producers arrive on the
+//   leader's barriers through the cluster address space, commits are multicast to both CTAs.  Warp roles (640 threads):
+//     warp 0       TMA producer: W_hi / W_lo k-blocks (fp16) -> smem ring (2-6 stages)
+//     warp 1       MMA issuer  : 6 tcgen05.mma (3 products x 2 k-steps) per k-block and view into TMEM accumulators
+//     warp 2       TMEM allocator
+//     warp 3       operand-cache store: the student view's fp16 hi A tiles, smem -> xs_hi by TMA (B operand of the backward)
+//     warps 4-11   converters  : coalesced LDG of fp32 x (+ fused weak/strong augmentation, I/utils.py:328-375),
+//                                fp16 hi/lo split, swizzled st.shared of the A operand(s) (K-major)
+//     warps 12-19  epilogue    : tcgen05.ld -> bias + ReLU + padding mask -> 1-bit ReLU mask + per-32-frame pooled partial sums
 //   k_pool_finalize then sums the partials of each utterance in fixed order and divides by its valid length.
 #include "dad_common.cuh"
 #include "tc_ptx.cuh"
@@ -25,32 +31,45 @@
 #include <stdlib.h>
 #include <string.h>
 
+
 namespace {
 
-constexpr int BM = 128, BK = 64, KB = DAD_D / BK, STAGES = 2;
-constexpr int FWD_THREADS = 512;
-constexpr int CONV_WARP0 = 4, N_CONV_WARPS = 8, EPI_WARP0 = 12;
-constexpr uint32_t A_BYTES = BM * BK * 2;        // 16 KB  (one of hi / lo)
-constexpr uint32_t W_BYTES = DAD_H * BK * 2;     // 32 KB
-constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;  // 96 KB
-constexpr uint32_t OFF_AHI = 0, OFF_ALO = A_BYTES, OFF_WHI = 2 * A_BYTES, OFF_WLO = 2 * A_BYTES + W_BYTES;
-constexpr uint32_t OFF_SCRATCH = STAGES * STAGE_BYTES;                 // 4 warps x [32][33] f32
-constexpr uint32_t OFF_BIAS = OFF_SCRATCH + 4 * 32 * 33 * 4;
-constexpr uint32_t OFF_BARS = OFF_BIAS + DAD_H * 4;
-constexpr uint32_t FWD_SMEM = OFF_BARS + 128 + 1024;                   // + alignment slack
-constexpr uint32_t TMEM_COLS = 512;                                     // two 128 x 256 fp32 accumulators
+constexpr int BM = 128, BK = 32, KB = DAD_D / BK;  // 24 k-blocks of 32
+constexpr int FWD_THREADS = 640;
+constexpr int CONV_WARP0 = 4, N_CONV_WARPS = 8, EPI_WARP0 = 12, N_EPI_WARPS = 8;
+constexpr uint32_t A_BYTES = BM * BK * 2;  // 8 KB: one of hi / lo of one view, [128 frames][32 k] fp16, 64-byte rows, SWIZZLE_64B
+constexpr uint32_t TMEM_COLS = 512;        // two 128 x 256 fp32 accumulators
 
+// NV = views per launch (1: one accumulator per tile, double-buffered across tiles; 2: weak -> teacher W and strong -> student W from
+// ONE read of x, both accumulators belong to the same tile).  CTA2: CTA pair, cta_group::2 MMA, every CTA stages half of the W rows.
+template <int NV, bool CTA2>
+struct FwdCfg {
+    static constexpr uint32_t W_ROWS = CTA2 ? 128 : 256;
+    static constexpr uint32_t W_BYTES = W_ROWS * BK * 2;  // 8 / 16 KB (one of hi / lo of one view)
+    static constexpr uint32_t OFF_A = 0;                   // [view][hi, lo]
+    static constexpr uint32_t OFF_W = NV * 2 * A_BYTES;    // [view][hi, lo]
+    static constexpr uint32_t STAGE_BYTES = NV * 2 * (A_BYTES + W_BYTES);  // 48 / 32 / 96 / 64 KB
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;              // 4 / 6 / 2 / 3
+    static constexpr uint32_t OFF_SCRATCH = STAGES * STAGE_BYTES;          // 8 epilogue warps x [32 rows][8 words + 1 pad]
+    static constexpr uint32_t OFF_BIAS = OFF_SCRATCH + N_EPI_WARPS * 32 * 9 * 4;
+    static constexpr uint32_t OFF_BARS = OFF_BIAS + 2 * DAD_H * 4;
+    static constexpr uint32_t SMEM = OFF_BARS + 256 + 1024;  // + alignment slack
+    static constexpr int MAX_STAGES = 6;
+};
+
+struct FwdView {
+    const float* bias;  // [256] of the network this view feeds
+    AugParams ap;
+    float* part;        // [num_groups][2][256] pooled partial sums
+    uint32_t* bits;     // [N][8] ReLU bits or null
+};
 struct FwdParams {
     const float* x;
     const uint8_t* pad;
-    const float* bias;
-    AugParams ap;
-    float* part;        // [num_groups][2][256]
-    uint32_t* bits;     // [N][8] or null
-    int dbg;            // DAD_TC_DBG timing experiments (never set in production): 1 = one product instead of three, 2 = W k-blocks
-                        //   TMA-loaded for the first STAGES iterations only (stale weights afterwards): isolates MMA time / smem fill traffic
-    int cache;          // operand cache on: every A tile (the fp16 hi/lo split of the augmented, scaled input) is also TMA-stored from
-                        //   shared memory to xs_hi / xs_lo [N][768] for the backward kernel (tm_xhi / tm_xlo), at no converter cost
+    FwdView v[2];
+    int cache;  // operand cache of the LAST view (the student view): 0 off, 1 = its hi A tiles are also TMA-stored from shared memory
+                //   to xs_hi [N][768] for the backward kernel, 2 = hi and lo
+    int dbg;    // DAD_TC_DBG timing experiments (never set in production): 1 = one product instead of three
     int64_t N;
     int T;
     int num_tiles;
@@ -73,251 +92,332 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], const int la
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Converter warp body of the forward kernel.  Thread (cw, lane): 8-byte k-slot kq = lane & 15 of the 64-wide k-block and
-// the 8 CONSECUTIVE tile rows rbase = cw*16 + (lane>>4)*8 .. +7 (exactly one 8-row SWIZZLE_128B atom, 4 noise row pairs):
-//   - a warp-wide LDG.128 reads two fully used 256-byte row segments; the two shared-memory stores of a row hit all 32 banks once;
-//   - every address is  base + compile-time immediate  (no per-element index arithmetic);
-//   - two register sets ping-pong (flat (tile, k-block) iteration space unrolled by 2): the loads of iteration i+1 are in
-//     flight while iteration i is converted, and nothing is copied between the sets;
+// Converter warp body of the forward kernel.  Thread (cw, lane): float4 column c4 = lane & 7 of the 32-wide k-block and the four
+// tile rows cw*16 + g + 4 i (g = lane >> 3, i = 0..3):
+//   - one warp-wide LDG.128 reads four fully used 128-byte row segments; the warp's stores of one i cover four CONSECUTIVE
+//     64-byte tile rows (256 contiguous, swizzle-permuted bytes): two shared-memory wavefronts per 8-byte store, no conflicts;
+//   - every address is  base + compile-time immediate;
+//   - NSET register sets rotate over the flat (tile, k-block) iteration space (KB = 24 is a multiple of NSET, so a group never
+//     straddles a tile): the loads of the next NSET-1 k-blocks are in flight while one is converted;
 //   - rows that contribute zeros (beyond N, or inside the temporal mask span of the strong view) are flagged per tile.
-// MODE 0 clean, 1 weak, 2 strong (I/utils.py:328-375); PHILOX: canonical in-kernel noise field, else supplied noise tensor.
+// NV == 1: MODE 0 clean, 1 weak, 2 strong (I/utils.py:328-375).  NV == 2: view 0 = weak, view 1 = strong of the same x; in the
+// Philox mode both views' normals come from the same Philox block (dad_common.cuh).  PHILOX: in-kernel noise, else supplied tensors.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int MODE, bool PHILOX>
-__device__ __forceinline__ void fwd_convert(const FwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, const int cw,
-                                            const int lane) {
-    const int kq = lane & 15;
-    const int rbase = cw * 16 + (lane >> 4) * 8;
-    const uint32_t c16 = (uint32_t)kq >> 1;
-    const uint32_t sbase = (uint32_t)rbase * 128u + (uint32_t)(kq & 1) * 8u;
-    const AugParams& ap = p.ap;
+template <int NV, bool CTA2, int MODE, bool PHILOX, int NSET>
+__device__ __forceinline__ void fwd_convert(const FwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* afull, uint64_t* empty, const int cw,
+                                            const int lane, const uint32_t rank, const int unit0, const int ustride, const int n_units) {
+    using Cfg = FwdCfg<NV, CTA2>;
+    constexpr int STAGES = Cfg::STAGES;
+    static_assert(KB % NSET == 0, "a group of NSET k-blocks must not straddle a tile");
+    constexpr bool WEAK = NV == 2 || MODE == 1, STRONG = NV == 2 || MODE == 2;
+    const int c4 = lane & 7, g = lane >> 3;
+    const int rbase = cw * 16 + g;
+    const uint32_t a_sw = ((uint32_t)rbase >> 1) & 3u, c16 = (uint32_t)c4 >> 1;
+    const uint32_t sbase = (uint32_t)rbase * 64u + (uint32_t)(c4 & 1) * 8u;
+    const uint32_t sw_even = (c16 ^ a_sw) << 4, sw_odd = (c16 ^ a_sw ^ 2u) << 4;  // ((rbase + 4 i) >> 1) & 3 = a_sw ^ ((i & 1) << 1)
+    const AugParams& apw = p.v[0].ap;        // weak view (NV == 2) or the single view
+    const AugParams& aps = p.v[NV - 1].ap;   // strong view (NV == 2) or the single view
     const uint32_t smem_a = tc::smem_u32(smem);
-    const unsigned long long seed = (MODE != 0 && PHILOX) ? aug_seed(ap) : 0ull;
-    const float radius_k = NOISE_UNIT_K * ap.sigma * ap.sigma;
-    const int n_my_tiles = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int n_iter = n_my_tiles * KB;  // even (KB = 12)
+    const uint32_t full_remote = CTA2 ? tc::mapa(tc::smem_u32(full), 0) : 0u;  // the leader CTA's full[] (cluster address)
+    const unsigned long long seed = ((NV == 2 || MODE != 0) && PHILOX) ? aug_seed(aps) : 0ull;
+    const float rk_w = NOISE_UNIT_K * apw.sigma * apw.sigma, rk_s = NOISE_UNIT_K * aps.sigma * aps.sigma;
+    const uint32_t blk = (uint32_t)(aps.stream >> 1);
+    const bool odd_stream = (aps.stream & 1ull) != 0;  // NV == 1: which word pair of the block this view uses
+    const unsigned long long foff = (unsigned long long)aps.frame_offset;
+    const int n_my = n_units > unit0 ? (n_units - unit0 + ustride - 1) / ustride : 0;
+    const int n_iter = n_my * KB;
 
-    auto tile_of = [&](int it) { return (int)blockIdx.x + (it / KB) * (int)gridDim.x; };
-    // bit i set: row rbase+i of `tile` contributes zeros
+    auto tile_of = [&](int it) {
+        const int u = unit0 + (it / KB) * ustride;
+        return CTA2 ? u * 2 + (int)rank : u;
+    };
+    // bits 0-3: row rbase + 4 i lies beyond N (zeros in every view); bits 4-7: inside the temporal mask span (strong view only)
     auto row_flags = [&](int tile) -> uint32_t {
         const int64_t row0 = (int64_t)tile * BM + rbase;
         uint32_t z = 0;
-        if (row0 + 8 > p.N) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) z |= (row0 + i >= p.N ? 1u : 0u) << i;
-        }
-        if (MODE == 2 && ap.t_start && ap.mask_len > 0 && row0 < p.N) {
-            const uint32_t r0 = (uint32_t)row0;  // N < 2^31 on this path (launch check)
-            uint32_t b = r0 / (uint32_t)p.T, t = r0 - b * (uint32_t)p.T;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if ((int64_t)r0 + i < p.N) {
-                    const int s0 = __ldg(ap.t_start + b);
-                    z |= (((int)t >= s0 && (int)t < s0 + ap.mask_len) ? 1u : 0u) << i;
-                }
-                if (++t == (uint32_t)p.T) { t = 0; ++b; }
+        for (int i = 0; i < 4; ++i) {
+            const int64_t n = row0 + 4 * i;
+            if (n >= p.N) z |= 1u << i;
+            else if (STRONG && aps.t_start && aps.mask_len > 0) {
+                const uint32_t b = (uint32_t)n / (uint32_t)p.T, t = (uint32_t)n - b * (uint32_t)p.T;  // N < 2^31 on this path (launch check)
+                const int s0 = __ldg(aps.t_start + b);
+                if ((int)t >= s0 && (int)t < s0 + aps.mask_len) z |= 16u << i;
             }
         }
         return z;
     };
-    auto load = [&](float4 (&dst)[8], int it) {
+    auto load = [&](float4 (&dst)[4], int it) {
         const int tile = tile_of(it), kb = it % KB;
         const int64_t row0 = (int64_t)tile * BM + rbase;
-        const float* src = p.x + row0 * DAD_D + kb * BK + kq * 4;
-        if (row0 + 8 <= p.N) {
+        const float* src = p.x + row0 * DAD_D + kb * BK + c4 * 4;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = __ldg(reinterpret_cast<const float4*>(src + i * DAD_D));
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                dst[i] = (row0 + i < p.N) ? __ldg(reinterpret_cast<const float4*>(src + i * DAD_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int i = 0; i < 4; ++i)
+            dst[i] = (row0 + 4 * i < p.N) ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)(4 * i) * DAD_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    // zeroed rows (beyond N, temporal mask span) are multiplied by 0 instead of TC_XS: no branch, no select
-    auto store_row = [&](uint32_t a_hi, uint32_t a_lo, const float4& v, int i, uint32_t zmask) {
-        const float sc = ((zmask >> i) & 1u) ? 0.f : TC_XS;
+    // zeroed rows are multiplied by 0 instead of TC_XS: no branch, no select
+    auto store_row = [&](uint32_t a_hi, const float4& v, int i, bool zero) {
+        const float sc = zero ? 0.f : TC_XS;
         uint32_t h01, l01, h23, l23;
         tc::split2_f16(v.x * sc, v.y * sc, h01, l01);
         tc::split2_f16(v.z * sc, v.w * sc, h23, l23);
-        const uint32_t off = sbase + (uint32_t)i * 128u + ((c16 ^ (uint32_t)i) << 4);
+        const uint32_t off = sbase + (uint32_t)i * 256u + ((i & 1) ? sw_odd : sw_even);
         tc::sts64(a_hi + off, h01, h23);
-        tc::sts64(a_lo + off, l01, l23);
+        tc::sts64(a_hi + A_BYTES + off, l01, l23);
     };
-    auto convert = [&](float4 (&cur)[8], int it, uint32_t zmask) {
+    auto convert = [&](float4 (&cur)[4], int it, uint32_t flags) {
         const int tile = tile_of(it), kb = it % KB;
         const uint32_t s = (uint32_t)it % STAGES, ph = ((uint32_t)it / STAGES) & 1u;
         tc::mbar_wait(&empty[s], ph ^ 1u);
-        const uint32_t a_hi = smem_a + s * STAGE_BYTES + OFF_AHI;
-        const uint32_t a_lo = smem_a + s * STAGE_BYTES + OFF_ALO;
-        if (MODE != 0) {
-            const int64_t row0 = (int64_t)tile * BM + rbase;
-            float4 keep = make_float4(1.f, 1.f, 1.f, 1.f);
-            const bool has_keep = MODE == 2 && ap.feat_keep != nullptr;
-            if (has_keep) keep = __ldg(reinterpret_cast<const float4*>(ap.feat_keep + kb * BK + kq * 4));
+        const uint32_t a0 = smem_a + s * Cfg::STAGE_BYTES + Cfg::OFF_A;  // view 0 hi (lo at + A_BYTES); view 1 at + 2 A_BYTES
+        const int64_t row0 = (int64_t)tile * BM + rbase;
+        float4 keep = make_float4(1.f, 1.f, 1.f, 1.f);
+        const bool has_keep = STRONG && aps.feat_keep != nullptr;
+        if (has_keep) keep = __ldg(reinterpret_cast<const float4*>(aps.feat_keep + kb * BK + c4 * 4));
 #pragma unroll
-            for (int rp = 0; rp < 4; ++rp) {
-                float4& va = cur[2 * rp];
-                float4& vb = cur[2 * rp + 1];
+        for (int i = 0; i < 4; ++i) {
+            const int64_t n = row0 + 4 * i;
+            const bool zrow = (flags >> i) & 1u, zspan = (flags >> (4 + i)) & 1u;
+            float4 vw = cur[i], vs = cur[i];
+            if (WEAK || STRONG) {
                 if (PHILOX) {
-                    NoiseBM8 z;
-                    philox_bm8(seed, (uint32_t)ap.stream, (uint32_t)((row0 + 2 * rp) >> 1), (uint32_t)(kb * (BK / 4) + kq), radius_k, z);
-                    va.x = fmaf(z.r[0], z.c[0], va.x); va.y = fmaf(z.r[0], z.s[0], va.y); va.z = fmaf(z.r[1], z.c[1], va.z); va.w = fmaf(z.r[1], z.s[1], va.w);
-                    vb.x = fmaf(z.r[2], z.c[2], vb.x); vb.y = fmaf(z.r[2], z.s[2], vb.y); vb.z = fmaf(z.r[3], z.c[3], vb.z); vb.w = fmaf(z.r[3], z.s[3], vb.w);
+                    const uint4 w = noise_words(seed, blk, (unsigned long long)n + foff, (uint32_t)(kb * (BK / 4) + c4));
+                    NoiseBM4 z;
+                    if (NV == 2) {
+                        bm4_from_words(w.x, w.y, rk_w, z);
+                        vw = bm4_add(z, vw);
+                        bm4_from_words(w.z, w.w, rk_s, z);
+                        vs = bm4_add(z, vs);
+                    } else {
+                        bm4_from_words(odd_stream ? w.z : w.x, odd_stream ? w.w : w.y, rk_s, z);
+                        vs = bm4_add(z, vs);
+                        vw = vs;
+                    }
                 } else {
                     // parity mode: supplied unit normals, out = x + (n * sigma) with two fp32 roundings (bit-exact vs I/utils.py:330,338)
-                    const float* nz = ap.noise + (row0 + 2 * rp) * DAD_D + kb * BK + kq * 4;
-                    const bool ina = row0 + 2 * rp < p.N, inb = row0 + 2 * rp + 1 < p.N;
-                    const float4 na = ina ? __ldg(reinterpret_cast<const float4*>(nz)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 nb = inb ? __ldg(reinterpret_cast<const float4*>(nz + DAD_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    va.x = aug_add_noise(va.x, na.x, ap.sigma); va.y = aug_add_noise(va.y, na.y, ap.sigma);
-                    va.z = aug_add_noise(va.z, na.z, ap.sigma); va.w = aug_add_noise(va.w, na.w, ap.sigma);
-                    vb.x = aug_add_noise(vb.x, nb.x, ap.sigma); vb.y = aug_add_noise(vb.y, nb.y, ap.sigma);
-                    vb.z = aug_add_noise(vb.z, nb.z, ap.sigma); vb.w = aug_add_noise(vb.w, nb.w, ap.sigma);
+                    const int64_t e = n * DAD_D + kb * BK + c4 * 4;
+                    if (NV == 2) {
+                        const float4 nw = zrow ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(apw.noise + e));
+                        vw.x = aug_add_noise(vw.x, nw.x, apw.sigma); vw.y = aug_add_noise(vw.y, nw.y, apw.sigma);
+                        vw.z = aug_add_noise(vw.z, nw.z, apw.sigma); vw.w = aug_add_noise(vw.w, nw.w, apw.sigma);
+                    }
+                    const float4 ns = zrow ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(aps.noise + e));
+                    vs.x = aug_add_noise(vs.x, ns.x, aps.sigma); vs.y = aug_add_noise(vs.y, ns.y, aps.sigma);
+                    vs.z = aug_add_noise(vs.z, ns.z, aps.sigma); vs.w = aug_add_noise(vs.w, ns.w, aps.sigma);
+                    if (NV == 1) vw = vs;
                 }
                 if (has_keep) {
-                    va.x = __fmul_rn(va.x, keep.x); va.y = __fmul_rn(va.y, keep.y); va.z = __fmul_rn(va.z, keep.z); va.w = __fmul_rn(va.w, keep.w);
-                    vb.x = __fmul_rn(vb.x, keep.x); vb.y = __fmul_rn(vb.y, keep.y); vb.z = __fmul_rn(vb.z, keep.z); vb.w = __fmul_rn(vb.w, keep.w);
+                    vs.x = __fmul_rn(vs.x, keep.x); vs.y = __fmul_rn(vs.y, keep.y); vs.z = __fmul_rn(vs.z, keep.z); vs.w = __fmul_rn(vs.w, keep.w);
                 }
             }
+            if (NV == 2) {
+                store_row(a0, vw, i, zrow);
+                store_row(a0 + 2 * A_BYTES, vs, i, zrow || zspan);
+            } else {
+                store_row(a0, vs, i, zrow || zspan);
+            }
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) store_row(a_hi, a_lo, cur[i], i, zmask);
-        tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
+        tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma / TMA (async proxy)
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&full[s]);
+        if (lane == 0) {
+            if (CTA2) tc::mbar_arrive_cluster(full_remote + s * 8u);
+            else tc::mbar_arrive(&full[s]);
+            if (p.cache) tc::mbar_arrive(&afull[s]);
+        }
     };
 
     if (n_iter == 0) return;
-    // Three register sets rotate over the flat iteration space (KB = 12 is a multiple of 3, so a group of three iterations never
-    // straddles a tile): the loads of iterations i+1 and i+2 (64 KB per SM) are in flight while iteration i is converted.  One set
-    // ahead was not enough: with ~2 us of loaded DRAM latency the kernel ran at one k-block per latency (ncu: converters
-    // stalled on the first use of the loaded registers, tensor pipe 55 % active).
-    float4 bufA[8], bufB[8], bufC[8];
-    uint32_t zcur = row_flags(tile_of(0));
-    load(bufA, 0);
-    load(bufB, 1);
-    for (int it = 0; it < n_iter; it += 3) {
-        load(bufC, it + 2);
-        convert(bufA, it, zcur);
-        uint32_t znext = zcur;
-        const bool more = it + 3 < n_iter;
-        if (more) {
-            if ((it + 3) % KB == 0) znext = row_flags(tile_of(it + 3));
-            load(bufA, it + 3);
+    float4 buf[NSET][4];
+#pragma unroll
+    for (int j = 0; j < NSET - 1; ++j) load(buf[j], j);
+    uint32_t flags = 0;
+    for (int it = 0; it < n_iter; it += NSET) {
+        if (it % KB == 0) flags = row_flags(tile_of(it));
+#pragma unroll
+        for (int j = 0; j < NSET; ++j) {
+            if (it + j + NSET - 1 < n_iter) load(buf[(j + NSET - 1) % NSET], it + j + NSET - 1);
+            convert(buf[j], it + j, flags);
         }
-        convert(bufB, it + 1, zcur);
-        if (more) load(bufB, it + 4);
-        convert(bufC, it + 2, zcur);
-        zcur = znext;
     }
 }
 
+template <int NV, bool CTA2>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
-k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_xhi,
-             const __grid_constant__ CUtensorMap tm_xlo, FwdParams p) {
+k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant__ CUtensorMap tm_w0lo, const __grid_constant__ CUtensorMap tm_w1hi,
+             const __grid_constant__ CUtensorMap tm_w1lo, const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
+             FwdParams p) {
+    using Cfg = FwdCfg<NV, CTA2>;
+    constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
-    uint64_t* full = bars;            // [STAGES]  1 (TMA expect_tx) + 8 (converter warps)
-    uint64_t* empty = bars + 2;       // [STAGES]  1 (tcgen05.commit) + 1 (operand-cache store warp, when caching)
-    uint64_t* tfull = bars + 4;       // [2]       1 (tcgen05.commit)
-    uint64_t* tempty = bars + 6;      // [2]       4 (epilogue warps)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
-    float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS);
+    uint64_t* full = bars;                          // [STAGES] leader CTA: 1 (TMA expect_tx) + 8 converter warps per CTA of the pair
+    uint64_t* afull = bars + Cfg::MAX_STAGES;       // [STAGES] 8 local converter warps: the A tiles of THIS CTA are written (operand-cache store)
+    uint64_t* empty = bars + 2 * Cfg::MAX_STAGES;   // [STAGES] 1 (tcgen05.commit, multicast to both CTAs of a pair) + 1 (operand-cache store warp)
+    uint64_t* tfull = bars + 3 * Cfg::MAX_STAGES;   // [2]      1 (tcgen05.commit)
+    uint64_t* tempty = tfull + 2;                   // [2]      leader CTA: 8 epilogue warps per CTA of the pair
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* s_bias = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < DAD_H) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+    const uint32_t rank = CTA2 ? tc::cluster_ctarank() : 0u;
+    const int unit0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // tile (pair) index this CTA (pair) starts with
+    const int ustride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_units = CTA2 ? (p.num_tiles + 1) / 2 : p.num_tiles;         // a pair works on tiles 2u (leader) and 2u+1 (peer)
+    constexpr uint32_t NCTA = CTA2 ? 2u : 1u;
+
+    if (threadIdx.x < NV * DAD_H) s_bias[threadIdx.x] = p.v[threadIdx.x / DAD_H].bias[threadIdx.x % DAD_H];
     if (warp == 0 && lane == 0) {
-        tc::prefetch_tmap(&tm_whi);
-        tc::prefetch_tmap(&tm_wlo);
+        tc::prefetch_tmap(&tm_w0hi);
+        tc::prefetch_tmap(&tm_w0lo);
+        if (NV == 2) { tc::prefetch_tmap(&tm_w1hi); tc::prefetch_tmap(&tm_w1lo); }
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1 + N_CONV_WARPS); tc::mbar_init(&empty[s], 1 + (p.cache ? 1 : 0)); }
-        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], 4); }
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&full[s], 1 + N_CONV_WARPS * NCTA);
+            tc::mbar_init(&afull[s], N_CONV_WARPS);
+            tc::mbar_init(&empty[s], 1 + (p.cache ? 1 : 0));
+        }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], N_EPI_WARPS * NCTA); }
         tc::fence_barrier_init();
     }
+    if (CTA2) tc::cluster_sync();  // the peer's barriers exist before anyone arrives on them remotely
+    else __syncthreads();
     if (warp == 2) {
-        tc::tmem_alloc(tmem_ptr, TMEM_COLS);
-        tc::tmem_relinquish();
+        if (CTA2) { tc::tmem_alloc_pair(tmem_ptr, TMEM_COLS); tc::tmem_relinquish_pair(); }
+        else { tc::tmem_alloc(tmem_ptr, TMEM_COLS); tc::tmem_relinquish(); }
     }
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    // register budget follows the roles (setmaxnreg, one per role branch): 128 x 40 (control warps 0-3) + 256 x 168 (converters)
-    // + 128 x 128 (epilogue) <= 64 K registers
+    // register budget follows the roles (setmaxnreg, one per role branch; 640 threads launch with 96 each):
+    // 128 x 40 (control warps 0-3) + 256 x 136 (converters) + 256 x 96 (epilogue) <= 64 K registers
 
     if (warp == 0) {
-        // ===================== TMA producer (weights) =====================
+        // ===================== TMA producer (weights; in a pair every CTA loads ITS half of the hidden units) =====================
         tc::reg_dec<40>();
         if (lane == 0) {
+            const uint32_t full_remote = CTA2 ? tc::mapa(tc::smem_u32(full), 0) : 0u;
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+            for (int u = unit0; u < n_units; u += ustride)
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     tc::mbar_wait(&empty[s], ph ^ 1);
-                    if ((p.dbg & 2) && it >= STAGES) { tc::mbar_arrive(&full[s]); continue; }
-                    tc::mbar_arrive_expect_tx(&full[s], 2 * W_BYTES);
-                    tc::tma_load_2d(smem + s * STAGE_BYTES + OFF_WHI, &tm_whi, &full[s], kb * BK, 0);
-                    tc::tma_load_2d(smem + s * STAGE_BYTES + OFF_WLO, &tm_wlo, &full[s], kb * BK, 0);
-                }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        tc::reg_dec<40>();
-        constexpr uint32_t idesc = tc::make_idesc_f16(BM, DAD_H, 0, 0);
-        uint32_t it = 0, ti = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
-            const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
-            tc::mbar_wait(&tempty[acc], tph ^ 1);
-            tc::tcgen05_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * DAD_H;
-            for (int kb = 0; kb < KB; ++kb, ++it) {
-                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                tc::mbar_wait(&full[s], ph);
-                tc::tcgen05_fence_after();
-                if (lane == 0) {
-                    const uint32_t base = tc::smem_u32(smem + s * STAGE_BYTES);
-#pragma unroll
-                    for (int prod = 0; prod < 3; ++prod) {
-                        if ((p.dbg & 1) && prod > 0) break;
-                        const uint32_t a_off = (prod == 2) ? OFF_ALO : OFF_AHI;  // hi*hi, hi*lo, lo*hi
-                        const uint32_t b_off = (prod == 1) ? OFF_WLO : OFF_WHI;
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            const uint64_t ad = tc::make_smem_desc(base + a_off + k * 32, 16, 1024);
-                            const uint64_t bd = tc::make_smem_desc(base + b_off + k * 32, 16, 1024);
-                            tc::umma_f16(d_tmem, ad, bd, idesc, (kb | prod | k) != 0);
+                    uint8_t* w0 = smem + s * Cfg::STAGE_BYTES + Cfg::OFF_W;
+                    if (!CTA2) {
+                        tc::mbar_arrive_expect_tx(&full[s], NV * 2 * Cfg::W_BYTES);
+                        tc::tma_load_2d(w0, &tm_w0hi, &full[s], kb * BK, 0);
+                        tc::tma_load_2d(w0 + Cfg::W_BYTES, &tm_w0lo, &full[s], kb * BK, 0);
+                        if (NV == 2) {
+                            tc::tma_load_2d(w0 + 2 * Cfg::W_BYTES, &tm_w1hi, &full[s], kb * BK, 0);
+                            tc::tma_load_2d(w0 + 3 * Cfg::W_BYTES, &tm_w1lo, &full[s], kb * BK, 0);
+                        }
+                    } else {
+                        // the leader arms its barrier with the bytes of BOTH CTAs; the peer's copies complete on the leader's barrier too
+                        if (rank == 0) tc::mbar_arrive_expect_tx(&full[s], 2 * NV * 2 * Cfg::W_BYTES);
+                        const uint32_t fb = full_remote + s * 8u;
+                        const int r0 = (int)rank * (int)Cfg::W_ROWS;
+                        tc::tma_load_2d_pair(w0, &tm_w0hi, fb, kb * BK, r0);
+                        tc::tma_load_2d_pair(w0 + Cfg::W_BYTES, &tm_w0lo, fb, kb * BK, r0);
+                        if (NV == 2) {
+                            tc::tma_load_2d_pair(w0 + 2 * Cfg::W_BYTES, &tm_w1hi, fb, kb * BK, r0);
+                            tc::tma_load_2d_pair(w0 + 3 * Cfg::W_BYTES, &tm_w1lo, fb, kb * BK, r0);
                         }
                     }
-                    tc::umma_commit(&empty[s]);                  // smem slot free once these MMAs retire
-                    if (kb == KB - 1) tc::umma_commit(&tfull[acc]);  // accumulator complete
                 }
-                __syncwarp();
+            // tail: every commit (possibly multicast from the leader) to this CTA's empty[] has landed before the CTA may exit
+            for (int k = 0; k < STAGES; ++k, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                tc::mbar_wait(&empty[s], ph ^ 1);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (the leader CTA's for a pair) =====================
+        tc::reg_dec<40>();
+        if (!CTA2 || rank == 0) {
+            constexpr uint32_t idesc = tc::make_idesc_f16(CTA2 ? 256 : 128, DAD_H, 0, 0);
+            uint32_t it = 0, ti = 0;
+            for (int u = unit0; u < n_units; u += ustride, ++ti) {
+                const uint32_t acc = NV == 1 ? (ti & 1) : 0u, tph = NV == 1 ? ((ti >> 1) & 1) : (ti & 1);
+                if (CTA2) tc::mbar_wait_cluster(&tempty[acc], tph ^ 1);
+                else tc::mbar_wait(&tempty[acc], tph ^ 1);
+                tc::tcgen05_fence_after();
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    if (CTA2) tc::mbar_wait_cluster(&full[s], ph);
+                    else tc::mbar_wait(&full[s], ph);
+                    tc::tcgen05_fence_after();
+                    if (lane == 0) {
+                        const uint32_t base = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            const uint32_t d_tmem = tmem_base + (NV == 1 ? acc : (uint32_t)v) * DAD_H;
+#pragma unroll
+                            for (int prod = 0; prod < 3; ++prod) {
+                                if ((p.dbg & 1) && prod > 0) break;
+                                const uint32_t a_off = Cfg::OFF_A + v * 2 * A_BYTES + ((prod == 2) ? A_BYTES : 0u);      // hi*hi, hi*lo, lo*hi
+                                const uint32_t b_off = Cfg::OFF_W + v * 2 * Cfg::W_BYTES + ((prod == 1) ? Cfg::W_BYTES : 0u);
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k) {
+                                    const uint64_t ad = tc::make_smem_desc_sw64(base + a_off + k * 32);
+                                    const uint64_t bd = tc::make_smem_desc_sw64(base + b_off + k * 32);
+                                    if (CTA2) tc::umma_f16_pair(d_tmem, ad, bd, idesc, (kb | prod | k) != 0);
+                                    else tc::umma_f16(d_tmem, ad, bd, idesc, (kb | prod | k) != 0);
+                                }
+                            }
+                        }
+                        if (CTA2) {
+                            tc::umma_commit_pair(&empty[s], 3);                     // smem slot free in BOTH CTAs once these MMAs retire
+                            if (kb == KB - 1) tc::umma_commit_pair(&tfull[acc], 3);  // accumulators complete (each CTA holds its 128 rows)
+                        } else {
+                            tc::umma_commit(&empty[s]);
+                            if (kb == KB - 1) tc::umma_commit(&tfull[acc]);
+                        }
+                    }
+                    __syncwarp();
+                }
             }
         }
     } else if (warp >= CONV_WARP0 && warp < CONV_WARP0 + N_CONV_WARPS) {
-        // ===================== converters: fp32 x (+ augmentation) -> fp16 hi/lo A operand =====================
-        tc::reg_inc<168>();
+        // ===================== converters: fp32 x (+ augmentation) -> fp16 hi/lo A operand(s) =====================
+        tc::reg_inc<136>();
         const int cw = warp - CONV_WARP0;
-        const int variant = p.ap.mode == 0 ? 0 : (p.ap.mode * 2 - 1 + (p.ap.noise_src == 1 ? 1 : 0));  // 0 | 1,2 weak | 3,4 strong (supplied, philox)
-        switch (variant) {
-            case 0: fwd_convert<0, false>(p, smem, full, empty, cw, lane); break;
-            case 1: fwd_convert<1, false>(p, smem, full, empty, cw, lane); break;
-            case 2: fwd_convert<1, true>(p, smem, full, empty, cw, lane); break;
-            case 3: fwd_convert<2, false>(p, smem, full, empty, cw, lane); break;
-            default: fwd_convert<2, true>(p, smem, full, empty, cw, lane); break;
+        const bool philox = p.v[NV - 1].ap.noise_src == 1;
+        if (NV == 2) {
+            if (philox) fwd_convert<2, CTA2, 2, true, 3>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units);
+            else fwd_convert<2, CTA2, 2, false, 3>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units);
+        } else {
+            const int variant = p.v[0].ap.mode == 0 ? 0 : (p.v[0].ap.mode * 2 - 1 + (philox ? 1 : 0));  // 0 | 1,2 weak | 3,4 strong (supplied, philox)
+            switch (variant) {
+                case 0: fwd_convert<1, CTA2, 0, false, 6>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
+                case 1: fwd_convert<1, CTA2, 1, false, 4>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
+                case 2: fwd_convert<1, CTA2, 1, true, 4>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
+                case 3: fwd_convert<1, CTA2, 2, false, 4>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
+                default: fwd_convert<1, CTA2, 2, true, 4>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
+            }
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: TMEM -> bias + ReLU + mask -> ReLU bits + pooled partial sums =====================
         // Lane = frame row (tcgen05.ld 32x32b), 32 hidden units per chunk.  The per-utterance column sums over the 32 rows are a
         // register transpose-reduce: 31 shuffles + 31 adds per 32 x 32 block leave lane j with the sum of column j -- no shared
-        // memory, no serial chain (the first version staged through smem with a 32-deep dependent add chain per chunk and made
-        // the whole kernel epilogue-bound at ~40 k cycles per tile; measured with the MMA / loads / conversion stubbed out).
-        const int q = warp - EPI_WARP0;  // == warp % 4: this warp may touch TMEM lanes [32q, 32q+32)
+        // memory, no serial chain.  Eight warps: warp % 4 = TMEM lane quadrant; NV == 2: warps 12-15 drain the weak / teacher
+        // accumulator, 16-19 the strong / student one (both belong to the same tile and are NOT double-buffered: the drain is the
+        // exposed part of a tile, so it is spread over twice the warps); NV == 1: the two warps of a quadrant take four chunks each.
+        const int ew = warp - EPI_WARP0;
+        const int q = ew & 3, sel = ew >> 2;
+        const int view = NV == 2 ? sel : 0;
+        const int c_begin = NV == 2 ? 0 : sel * 4, c_end = NV == 2 ? 8 : sel * 4 + 4;
+        const FwdView& V = p.v[view];
+        const uint32_t wstage = tc::smem_u32(smem + Cfg::OFF_SCRATCH) + (uint32_t)(ew * 32 * 9 + lane * 9) * 4u;  // [32 rows][8 words + 1 pad]
+        const uint32_t bias_a = tc::smem_u32(s_bias + view * DAD_H);
+        const uint32_t tempty_remote = CTA2 ? tc::mapa(tc::smem_u32(tempty), 0) : 0u;
         uint32_t ti = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
-            const uint32_t acc = ti & 1, tph = (ti >> 1) & 1;
+        for (int u = unit0; u < n_units; u += ustride, ++ti) {
+            const int tile = CTA2 ? u * 2 + (int)rank : u;
+            const bool live = tile < p.num_tiles;  // the peer's tile of the last pair may not exist
+            const uint32_t acc = NV == 1 ? (ti & 1) : 0u, tph = NV == 1 ? ((ti >> 1) & 1) : (ti & 1);
             const int64_t n0 = (int64_t)tile * BM + q * 32;
             const int64_t n = n0 + lane;
             const bool in = n < p.N;
@@ -328,14 +428,12 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
             const bool first = lane < split;
             tc::mbar_wait(&tfull[acc], tph);
             tc::tcgen05_fence_after();
-            const int64_t g = (int64_t)tile * 4 + q;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * DAD_H;
-            const uint32_t wstage = tc::smem_u32(smem + OFF_SCRATCH) + (uint32_t)(q * 32 * 9 + lane * 9) * 4u;  // [32 rows][8 words + 1 pad]
-            const uint32_t bias_a = tc::smem_u32(s_bias);
-            uint32_t r[32];
-            tc::tmem_ld_32x32(taddr, r);
-#pragma unroll 1  // keep the body small: the unrolled version (19 k SASS instructions in the kernel) was instruction-fetch bound
-            for (int c = 0; c < 8; ++c) {
+            const int64_t gidx = (int64_t)tile * 4 + q;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (NV == 1 ? acc : (uint32_t)view) * DAD_H;
+#pragma unroll 1  // keep the body small: the unrolled version was instruction-fetch bound
+            for (int c = c_begin; c < c_end; ++c) {
+                uint32_t r[32];
+                tc::tmem_ld_32x32(taddr + c * 32, r);
                 tc::tmem_ld_wait();
                 float v[32];
                 uint32_t w = 0;
@@ -344,77 +442,103 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__
                     const uint4 bs = tc::lds128(bias_a + (uint32_t)(c * 32 + j4) * 4u);
                     const float bj[4] = {__uint_as_float(bs.x), __uint_as_float(bs.y), __uint_as_float(bs.z), __uint_as_float(bs.w)};
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float pre = fmaf(__uint_as_float(r[j4 + u]), TC_INV_XW, bj[u]);  // exact power-of-two unscale, then + bias
+                    for (int uu = 0; uu < 4; ++uu) {
+                        const float pre = fmaf(__uint_as_float(r[j4 + uu]), TC_INV_XW, bj[uu]);  // exact power-of-two unscale, then + bias
                         const bool pos = pre > 0.f;
-                        w |= (pos ? 1u : 0u) << (j4 + u);
-                        v[j4 + u] = (pos && valid) ? pre : 0.f;
+                        w |= (pos ? 1u : 0u) << (j4 + uu);
+                        v[j4 + uu] = (pos && valid && first) ? pre : 0.f;
                     }
                 }
-                tc::sts32(wstage + (uint32_t)c * 4u, w);
-                if (c + 1 < 8) tc::tmem_ld_32x32(taddr + (c + 1) * 32, r);  // next chunk flies while this one is reduced
-                float s0, s1 = 0.f;
+                tc::sts32(wstage + (uint32_t)(c - c_begin) * 4u, w);
+                const float s0 = transpose_reduce32(v, lane);
+                float s1 = 0.f;
                 if (split < 32) {  // the 32 rows straddle two utterances: a second masked reduction (warp-uniform branch)
-                    float v1[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { v1[j] = first ? 0.f : v[j]; v[j] = first ? v[j] : 0.f; }
-                    s1 = transpose_reduce32(v1, lane);
+                    for (int j4 = 0; j4 < 32; j4 += 4) {
+                        const uint4 bs = tc::lds128(bias_a + (uint32_t)(c * 32 + j4) * 4u);
+                        const float bj[4] = {__uint_as_float(bs.x), __uint_as_float(bs.y), __uint_as_float(bs.z), __uint_as_float(bs.w)};
+#pragma unroll
+                        for (int uu = 0; uu < 4; ++uu) {
+                            const float pre = fmaf(__uint_as_float(r[j4 + uu]), TC_INV_XW, bj[uu]);
+                            v[j4 + uu] = (pre > 0.f && valid && !first) ? pre : 0.f;
+                        }
+                    }
+                    s1 = transpose_reduce32(v, lane);
                 }
-                s0 = transpose_reduce32(v, lane);
-                p.part[(g * 2 + 0) * DAD_H + c * 32 + lane] = s0;
-                p.part[(g * 2 + 1) * DAD_H + c * 32 + lane] = s1;
+                if (live) {
+                    V.part[(gidx * 2 + 0) * DAD_H + c * 32 + lane] = s0;
+                    V.part[(gidx * 2 + 1) * DAD_H + c * 32 + lane] = s1;
+                }
             }
             tc::tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&tempty[acc]);
-            if (p.bits && in) {
-                uint4* dst = reinterpret_cast<uint4*>(p.bits + n * DAD_HW);
-                dst[0] = make_uint4(tc::lds32(wstage), tc::lds32(wstage + 4), tc::lds32(wstage + 8), tc::lds32(wstage + 12));
-                dst[1] = make_uint4(tc::lds32(wstage + 16), tc::lds32(wstage + 20), tc::lds32(wstage + 24), tc::lds32(wstage + 28));
+            if (lane == 0) {
+                if (CTA2) tc::mbar_arrive_cluster(tempty_remote + acc * 8u);
+                else tc::mbar_arrive(&tempty[acc]);
+            }
+            if (V.bits && in) {
+                uint4* dst = reinterpret_cast<uint4*>(V.bits + n * DAD_HW);
+                if (NV == 2) {
+                    dst[0] = make_uint4(tc::lds32(wstage), tc::lds32(wstage + 4), tc::lds32(wstage + 8), tc::lds32(wstage + 12));
+                    dst[1] = make_uint4(tc::lds32(wstage + 16), tc::lds32(wstage + 20), tc::lds32(wstage + 24), tc::lds32(wstage + 28));
+                } else {
+                    dst[sel] = make_uint4(tc::lds32(wstage), tc::lds32(wstage + 4), tc::lds32(wstage + 8), tc::lds32(wstage + 12));
+                }
             }
             __syncwarp();
         }
     } else if (warp == 3) {
-        // ===================== operand-cache store: A tiles shared -> global by TMA =====================
-        // The A tile of a stage ([128 frames][64 k] fp16, SWIZZLE_128B) is exactly one TMA box of xs_hi / xs_lo; the slot is handed
-        // back (second arrival on empty[s]) once the bulk store has finished READING shared memory.  Frames beyond N are clipped.
+        // ===================== operand-cache store: the student view's A tiles, shared -> global by TMA =====================
+        // The hi A tile of a stage ([128 frames][32 k] fp16, SWIZZLE_64B) is exactly one TMA box of xs_hi [N][768] (and the lo tile
+        // of xs_lo when the 3-product backward is selected); the slot is handed back (second arrival on empty[s]) once the bulk
+        // store has finished READING shared memory.  Frames beyond N are clipped by the tensor map.
         tc::reg_dec<40>();
         if (p.cache && lane == 0) {
             tc::prefetch_tmap(&tm_xhi);
-            tc::prefetch_tmap(&tm_xlo);
+            if (p.cache > 1) tc::prefetch_tmap(&tm_xlo);
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+            for (int u = unit0; u < n_units; u += ustride) {
+                const int tile = CTA2 ? u * 2 + (int)rank : u;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                    tc::mbar_wait(&full[s], ph);
-                    tc::tma_store_2d(&tm_xhi, smem + s * STAGE_BYTES + OFF_AHI, kb * BK, tile * BM);
-                    tc::tma_store_2d(&tm_xlo, smem + s * STAGE_BYTES + OFF_ALO, kb * BK, tile * BM);
-                    tc::bulk_commit();
-                    tc::bulk_wait_read0();
+                    tc::mbar_wait(&afull[s], ph);
+                    const uint8_t* a = smem + s * Cfg::STAGE_BYTES + Cfg::OFF_A + (NV - 1) * 2 * A_BYTES;
+                    if (tile < p.num_tiles) {
+                        tc::tma_store_2d(&tm_xhi, a, kb * BK, tile * BM);
+                        if (p.cache > 1) tc::tma_store_2d(&tm_xlo, a + A_BYTES, kb * BK, tile * BM);
+                        tc::bulk_commit();
+                        tc::bulk_wait_read0();
+                    }
                     tc::mbar_arrive(&empty[s]);
                 }
+            }
             tc::bulk_wait0();
         }
     } else {
-        // warp 2 (TMEM allocator).  Negative result kept for the record: bulk L2 prefetch (cp.async.bulk.prefetch.L2) of this
-        // CTA's next x tile from here made the kernel 25 % SLOWER (0.875 -> 1.105 ms at B=4096): the prefetches compete with the
-        // demand loads for the same HBM bandwidth instead of hiding their latency.
-        tc::reg_dec<40>();
+        tc::reg_dec<40>();  // warp 2 (TMEM allocator)
     }
     tc::tcgen05_fence_before();
     __syncthreads();
+    if (CTA2) tc::cluster_sync();  // nobody frees TMEM / leaves while the pair's MMAs, remote arrivals or multicast commits are in flight
     if (warp == 2) {
         tc::tcgen05_fence_after();
-        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+        if (CTA2) tc::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else tc::tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
-// emb[b,:] = (sum of the 32-frame partials of utterance b, in frame order) / max(len_b, 1);  grid = B, 256 threads
-__global__ void __launch_bounds__(DAD_H) k_pool_finalize(const float* __restrict__ part, const uint8_t* __restrict__ pad, float* __restrict__ emb,
-                                                         float* __restrict__ lens_out, int T) {
+// emb[b,:] = (sum of the 32-frame partials of utterance b, in frame order) / max(len_b, 1);  grid = (B, views), 256 threads
+struct PoolArgs {
+    const float* part[2];
+    float* emb[2];
+    float* lens_out;  // written by view 0
+};
+__global__ void __launch_bounds__(DAD_H) k_pool_finalize(PoolArgs a, const uint8_t* __restrict__ pad, int T) {
     __shared__ float s_w[DAD_H / 32];
     __shared__ float s_len;
     const int b = blockIdx.x, h = threadIdx.x;
+    const float* __restrict__ part = a.part[blockIdx.y];
+    float* __restrict__ emb = a.emb[blockIdx.y];
     // partial sums first (their loads do not depend on the length): ascending 32-frame groups, eight loads in flight.  A group
     // that straddles two utterances keeps the earlier one in slot 0 and the later one in slot 1 (T >= 32: never more than two),
     // so only this utterance's FIRST group can be a slot-1 read.
@@ -445,58 +569,143 @@ __global__ void __launch_bounds__(DAD_H) k_pool_finalize(const float* __restrict
     }
     __syncthreads();
     emb[(int64_t)b * DAD_H + h] = s / s_len;
-    if (h == 0 && lens_out) lens_out[b] = s_len;
+    if (h == 0 && blockIdx.y == 0 && a.lens_out) a.lens_out[b] = s_len;
+}
+
+// CTA pairs on / off (cta_group::2): process-wide switch, DAD_TC_CTA2=0|1 in the environment or dad_tc_set_cta_pair()
+int g_cta2 = -1;
+int cta2_enabled() {
+    if (g_cta2 < 0) {
+        const char* e = getenv("DAD_TC_CTA2");
+        g_cta2 = e ? (atoi(e) != 0) : 1;
+    }
+    return g_cta2;
+}
+
+// fp16 [rows][768] row-major, box = [box_rows][32 cols] (64 bytes inner), SWIZZLE_64B
+int make_tmap_f16_sw64(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return dad_set_error(DAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {DAD_D, rows};
+    cuuint64_t strides[1] = {DAD_D * 2};
+    cuuint32_t box[2] = {BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return dad_set_error(DAD_ERR_CUDA, "cuTensorMapEncodeTiled (SWIZZLE_64B) failed (%d)", (int)r);
+    return DAD_OK;
+}
+
+template <int NV, bool CTA2>
+int launch_fwd_variant(const CUtensorMap (&tw)[4], const CUtensorMap& txh, const CUtensorMap& txl, const FwdParams& p, cudaStream_t st) {
+    using Cfg = FwdCfg<NV, CTA2>;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_enc_fwd_tc<NV, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "encoder_fwd(tc): cannot opt in to %u B shared memory: %s", Cfg::SMEM, cudaGetErrorString(e));
+        attr = true;
+    }
+    const int sms = sm_count();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute at[1];
+    if (CTA2) {
+        const int pairs = (p.num_tiles + 1) / 2, max_pairs = sms / 2;
+        cfg.gridDim = dim3(2 * (pairs < max_pairs ? pairs : max_pairs));
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+    } else {
+        cfg.gridDim = dim3(p.num_tiles < sms ? p.num_tiles : sms);
+    }
+    cfg.blockDim = dim3(FWD_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_enc_fwd_tc<NV, CTA2>, tw[0], tw[1], tw[2], tw[3], txh, txl, p);
+    if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "k_enc_fwd_tc<%d,%d> launch: %s", NV, (int)CTA2, cudaGetErrorString(e));
+    return DAD_OK;
 }
 
 }  // namespace
 
-size_t enc_fwd_tc_ws_bytes(int64_t B, int64_t T) {
-    const int64_t tiles = ceil_div64(B * T, BM);
-    return (size_t)(tiles * 4 * 2 * DAD_H * sizeof(float));
+void enc_tc_set_cta_pair(int on) { g_cta2 = on ? 1 : 0; }
+int enc_tc_get_cta_pair() { return cta2_enabled(); }
+// products of the dW GEMM (2: x_hi only, 3: fp32-grade): process-wide, DAD_TC_BWD_PRODUCTS=2|3 or dad_tc_set_bwd_products()
+static int g_bwd_products = -1;
+void enc_tc_set_bwd_products(int n) { g_bwd_products = n == 3 ? 3 : 2; }
+int enc_tc_get_bwd_products() {
+    if (g_bwd_products < 0) {
+        const char* e = getenv("DAD_TC_BWD_PRODUCTS");
+        g_bwd_products = (e && atoi(e) == 3) ? 3 : 2;
+    }
+    return g_bwd_products;
 }
 
-int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W_hi, const void* W_lo, const float* bias, const AugParams& ap, float* emb,
-                      uint32_t* bits, void* xs_hi, void* xs_lo, float* lens_out, void* ws, size_t ws_bytes, int64_t B, int64_t T, cudaStream_t st) {
+// pooled partials of ONE view: [tiles * 4 groups][2 slots][256] (tiles rounded up to a whole pair)
+static size_t fwd_part_bytes(int64_t B, int64_t T) {
+    const int64_t tiles = (ceil_div64(B * T, BM) + 1) / 2 * 2;
+    return (size_t)(tiles * 4 * 2 * DAD_H * sizeof(float));
+}
+size_t enc_fwd_tc_ws_bytes(int64_t B, int64_t T) { return 2 * fwd_part_bytes(B, T); }
+
+// One launch for one view (W1 == null) or for the weak -> teacher (W0, ap0) and strong -> student (W1, ap1) views of the same x.
+// xs_hi / xs_lo: operand cache of the LAST view (hi only: xs_lo == null).
+int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W0_hi, const void* W0_lo, const float* bias0, const AugParams& ap0, float* emb0,
+                      uint32_t* bits0, const void* W1_hi, const void* W1_lo, const float* bias1, const AugParams* ap1, float* emb1, uint32_t* bits1,
+                      void* xs_hi, void* xs_lo, float* lens_out, void* ws, size_t ws_bytes, int64_t B, int64_t T, cudaStream_t st) {
+    const int nv = W1_hi ? 2 : 1;
     if (T < 32) return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_fwd: the tcgen05 path needs T >= 32 (got %lld); use DAD_GEMM_FP32", (long long)T);
     if (B * T >= (1ll << 31)) return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_fwd: the tcgen05 path indexes frames with 32 bits (B*T = %lld)", (long long)(B * T));
-    if ((reinterpret_cast<uintptr_t>(W_hi) | reinterpret_cast<uintptr_t>(W_lo)) & 15u)
-        return dad_set_error(DAD_ERR_ARG, "encoder_fwd: W_hi/W_lo must be 16-byte aligned (TMA)");
+    uintptr_t al = reinterpret_cast<uintptr_t>(W0_hi) | reinterpret_cast<uintptr_t>(W0_lo) | reinterpret_cast<uintptr_t>(W1_hi) | reinterpret_cast<uintptr_t>(W1_lo) |
+                   reinterpret_cast<uintptr_t>(xs_hi) | reinterpret_cast<uintptr_t>(xs_lo);
+    if (al & 15u) return dad_set_error(DAD_ERR_ARG, "encoder_fwd: W_hi/W_lo/xs_hi/xs_lo must be 16-byte aligned (TMA)");
     if (ws_bytes < enc_fwd_tc_ws_bytes(B, T)) return dad_set_error(DAD_ERR_WS, "encoder_fwd(tc): workspace too small");
-    CUtensorMap tm_hi, tm_lo;
-    int rc = make_tmap_f16(&tm_hi, W_hi, DAD_H, DAD_D, DAD_H);
-    if (rc) return rc;
-    rc = make_tmap_f16(&tm_lo, W_lo, DAD_H, DAD_D, DAD_H);
-    if (rc) return rc;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_enc_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
-        if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "encoder_fwd(tc): cannot opt in to %u B shared memory: %s", FWD_SMEM, cudaGetErrorString(e));
-        attr = true;
+    if (nv == 2) {
+        if (!ap1 || ap0.mode != 1 || ap1->mode != 2) return dad_set_error(DAD_ERR_ARG, "aug_encoder_fwd: view 0 must be the weak and view 1 the strong augmentation");
+        if (ap0.noise_src != ap1->noise_src) return dad_set_error(DAD_ERR_ARG, "aug_encoder_fwd: both views must use the same noise source");
+        if (ap0.noise_src == 1 && (ap0.seed != ap1->seed || ap0.step_ptr != ap1->step_ptr || ap0.frame_offset != ap1->frame_offset ||
+                                   ap0.stream + 1 != ap1->stream || (ap0.stream & 1ull)))
+            return dad_set_error(DAD_ERR_ARG, "aug_encoder_fwd: Philox views must share seed / step / frame offset and use streams (2k, 2k+1)");
     }
+    const bool cta2 = cta2_enabled() != 0;
+    const uint32_t wrows = cta2 ? 128 : 256;
+    CUtensorMap tw[4], txh, txl;
+    memset(tw, 0, sizeof(tw));
+    memset(&txh, 0, sizeof(txh));
+    memset(&txl, 0, sizeof(txl));
+    int rc = make_tmap_f16_sw64(&tw[0], W0_hi, DAD_H, wrows);
+    if (!rc) rc = make_tmap_f16_sw64(&tw[1], W0_lo, DAD_H, wrows);
+    if (!rc && nv == 2) rc = make_tmap_f16_sw64(&tw[2], W1_hi, DAD_H, wrows);
+    if (!rc && nv == 2) rc = make_tmap_f16_sw64(&tw[3], W1_lo, DAD_H, wrows);
+    if (rc) return rc;
     FwdParams p;
-    p.x = x; p.pad = pad; p.bias = bias; p.ap = ap; p.part = reinterpret_cast<float*>(ws); p.bits = bits;
+    memset(&p, 0, sizeof(p));
+    p.x = x; p.pad = pad;
+    const size_t pb = fwd_part_bytes(B, T);
+    p.v[0].bias = bias0; p.v[0].ap = ap0; p.v[0].part = reinterpret_cast<float*>(ws); p.v[0].bits = bits0;
+    if (nv == 2) {
+        p.v[1].bias = bias1; p.v[1].ap = *ap1; p.v[1].part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + pb); p.v[1].bits = bits1;
+    }
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("DAD_TC_DBG"); dbg = e ? atoi(e) : 0; }
         p.dbg = dbg;
     }
-    p.cache = (xs_hi && xs_lo) ? 1 : 0;
-    CUtensorMap tm_xhi, tm_xlo;
-    memset(&tm_xhi, 0, sizeof(tm_xhi));
-    memset(&tm_xlo, 0, sizeof(tm_xlo));
+    p.cache = xs_hi ? (xs_lo ? 2 : 1) : 0;
     if (p.cache) {
-        if ((reinterpret_cast<uintptr_t>(xs_hi) | reinterpret_cast<uintptr_t>(xs_lo)) & 15u)
-            return dad_set_error(DAD_ERR_ARG, "encoder_fwd: xs_hi/xs_lo must be 16-byte aligned (TMA)");
-        rc = make_tmap_f16(&tm_xhi, xs_hi, (uint64_t)(B * T), DAD_D, BM);
-        if (rc) return rc;
-        rc = make_tmap_f16(&tm_xlo, xs_lo, (uint64_t)(B * T), DAD_D, BM);
+        rc = make_tmap_f16_sw64(&txh, xs_hi, (uint64_t)(B * T), BM);
+        if (!rc && p.cache > 1) rc = make_tmap_f16_sw64(&txl, xs_lo, (uint64_t)(B * T), BM);
         if (rc) return rc;
     }
     p.N = B * T; p.T = (int)T; p.num_tiles = (int)ceil_div64(B * T, BM);
-    const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    k_enc_fwd_tc<<<grid, FWD_THREADS, FWD_SMEM, st>>>(tm_hi, tm_lo, tm_xhi, tm_xlo, p);
-    DAD_CHECK_LAUNCH("k_enc_fwd_tc");
-    k_pool_finalize<<<(unsigned)B, DAD_H, 0, st>>>(p.part, pad, emb, lens_out, (int)T);
+    if (nv == 2) rc = cta2 ? launch_fwd_variant<2, true>(tw, txh, txl, p, st) : launch_fwd_variant<2, false>(tw, txh, txl, p, st);
+    else rc = cta2 ? launch_fwd_variant<1, true>(tw, txh, txl, p, st) : launch_fwd_variant<1, false>(tw, txh, txl, p, st);
+    if (rc) return rc;
+    PoolArgs pa;
+    pa.part[0] = p.v[0].part; pa.part[1] = p.v[1].part;
+    pa.emb[0] = emb0; pa.emb[1] = emb1;
+    pa.lens_out = lens_out;
+    k_pool_finalize<<<dim3((unsigned)B, nv), DAD_H, 0, st>>>(pa, pad, (int)T);
     DAD_CHECK_LAUNCH("k_pool_finalize");
     return DAD_OK;
 }
@@ -512,12 +721,22 @@ int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W_hi, cons
 // =====================================================================================================================
 namespace {
 
-constexpr int BWD_BK = 32, BWD_STAGES = 3, BWD_THREADS = 512;
+constexpr int BWD_BK = 32, BWD_THREADS = 512;
 constexpr uint32_t BOP_BYTES = DAD_H * BWD_BK * 2;                  // 16 KB: one operand (hi or lo), 256 x 32 fp16
-constexpr uint32_t BSTAGE_BYTES = 4 * BOP_BYTES;                    // A_hi, A_lo, B_hi, B_lo = 64 KB
 constexpr uint32_t BOFF_AHI = 0, BOFF_ALO = BOP_BYTES, BOFF_BHI = 2 * BOP_BYTES, BOFF_BLO = 3 * BOP_BYTES;
-constexpr uint32_t BOFF_BARS = BWD_STAGES * BSTAGE_BYTES;
-constexpr uint32_t BWD_SMEM = BOFF_BARS + 128 + 1024;
+// PRODS = 3: dpre_hi*x_hi + dpre_hi*x_lo + dpre_lo*x_hi (fp32-grade, as the forward).  PRODS = 2 (default): the B operand is x_hi
+// only -- dpre_hi*x_hi + dpre_lo*x_hi.  Dropping x_lo perturbs every term of the 819 200-frame sum by an independent relative
+// 2^-12 (the fp16 rounding of x); Adam divides the gradient by its own running magnitude, so the weight update moves by
+// lr * O(1e-4) relative -- measured against the oracle in tests/test_gpu_ops.py / test_gpu_step.py, numbers in DESIGN.md section 3.
+// One third less tensor work on two of the five GEMMs, no B_lo tile in shared memory (a fourth pipeline stage instead) and an
+// operand cache of half the size (xs_hi only).
+template <int PRODS>
+struct BwdCfg {
+    static constexpr uint32_t STAGE_BYTES = (PRODS == 3 ? 4 : 3) * BOP_BYTES;  // A_hi, A_lo, B_hi (, B_lo) = 48 / 64 KB
+    static constexpr int STAGES = PRODS == 3 ? 3 : 4;
+    static constexpr uint32_t OFF_BARS = STAGES * STAGE_BYTES;
+    static constexpr uint32_t SMEM = OFF_BARS + 128 + 1024;
+};
 constexpr uint32_t MN_LBO = (BWD_BK / 8) * 1024;                    // pitch between 64-element M/N chunks (4 k-groups of 1 KB)
 constexpr uint32_t MN_SBO = 1024;                                   // pitch between 8-frame groups
 
@@ -708,9 +927,12 @@ struct BwdRegs {
 };
 struct BwdTab { uint4 gh, gl; int b; };  // this lane's g/len table chunk (fp16 hi, lo) of utterance b; slot = b & 1
 
-template <int MODE, bool PHILOX, bool XS>
+template <int PRODS, int MODE, bool PHILOX, bool XS>
 __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, const int cw, const int lane,
                                             const int dslice, const int64_t n_begin, const int64_t n_end, const int nkb) {
+    using Cfg = BwdCfg<PRODS>;
+    constexpr int BWD_STAGES = Cfg::STAGES;
+    constexpr uint32_t BSTAGE_BYTES = Cfg::STAGE_BYTES;
     const AugParams& ap = p.ap;
     const uint32_t smem_a = tc::smem_u32(smem);
     const unsigned long long seed = (MODE != 0 && PHILOX) ? aug_seed(ap) : 0ull;
@@ -822,31 +1044,24 @@ __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, u
         // ---- B operand: aug(x) rows -> fp16 hi/lo (scaled by TC_XS); with the operand cache (XS) the TMA warp loads it instead
         if (!XS && MODE != 0) {
 #pragma unroll
-            for (int rp = 0; rp < 2; ++rp) {
+            for (int j = 0; j < 4; ++j) {
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    float4& va = R.x[(2 * rp) * 2 + half];
-                    float4& vb = R.x[(2 * rp + 1) * 2 + half];
+                    float4& va = R.x[2 * j + half];
                     const int f = lane + 32 * half;
                     if (PHILOX) {
-                        NoiseBM8 z;
-                        philox_bm8(seed, (uint32_t)ap.stream, (uint32_t)((n0 + 2 * rp) >> 1), (uint32_t)(dslice * 64 + f), radius_k, z);
-                        va.x = fmaf(z.r[0], z.c[0], va.x); va.y = fmaf(z.r[0], z.s[0], va.y); va.z = fmaf(z.r[1], z.c[1], va.z); va.w = fmaf(z.r[1], z.s[1], va.w);
-                        vb.x = fmaf(z.r[2], z.c[2], vb.x); vb.y = fmaf(z.r[2], z.s[2], vb.y); vb.z = fmaf(z.r[3], z.c[3], vb.z); vb.w = fmaf(z.r[3], z.s[3], vb.w);
+                        NoiseBM4 z;
+                        philox_bm4(seed, (uint32_t)ap.stream, (unsigned long long)(n0 + j) + (unsigned long long)ap.frame_offset, (uint32_t)(dslice * 64 + f), radius_k, z);
+                        va = bm4_add(z, va);
                     } else {
-                        const float* nz = ap.noise + (n0 + 2 * rp) * DAD_D + dslice * 256 + f * 4;
-                        const bool ina = n0 + 2 * rp < n_end, inb = n0 + 2 * rp + 1 < n_end;
-                        const float4 na = ina ? __ldg(reinterpret_cast<const float4*>(nz)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float4 nb = inb ? __ldg(reinterpret_cast<const float4*>(nz + DAD_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float* nz = ap.noise + (n0 + j) * DAD_D + dslice * 256 + f * 4;
+                        const float4 na = (n0 + j < n_end) ? __ldg(reinterpret_cast<const float4*>(nz)) : make_float4(0.f, 0.f, 0.f, 0.f);
                         va.x = aug_add_noise(va.x, na.x, ap.sigma); va.y = aug_add_noise(va.y, na.y, ap.sigma);
                         va.z = aug_add_noise(va.z, na.z, ap.sigma); va.w = aug_add_noise(va.w, na.w, ap.sigma);
-                        vb.x = aug_add_noise(vb.x, nb.x, ap.sigma); vb.y = aug_add_noise(vb.y, nb.y, ap.sigma);
-                        vb.z = aug_add_noise(vb.z, nb.z, ap.sigma); vb.w = aug_add_noise(vb.w, nb.w, ap.sigma);
                     }
                     if (has_keep) {
                         const float4 kp = half ? keep1 : keep0;
                         va.x = __fmul_rn(va.x, kp.x); va.y = __fmul_rn(va.y, kp.y); va.z = __fmul_rn(va.z, kp.z); va.w = __fmul_rn(va.w, kp.w);
-                        vb.x = __fmul_rn(vb.x, kp.x); vb.y = __fmul_rn(vb.y, kp.y); vb.z = __fmul_rn(vb.z, kp.z); vb.w = __fmul_rn(vb.w, kp.w);
                     }
                 }
             }
@@ -864,7 +1079,7 @@ __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, u
                 tc::split2_f16(v.z * sc, v.w * sc, h23, l23);
                 const uint32_t off = roff + (uint32_t)half * 2u * MN_LBO;
                 tc::sts64(st + BOFF_BHI + off, h01, h23);
-                tc::sts64(st + BOFF_BLO + off, l01, l23);
+                if (PRODS == 3) tc::sts64(st + BOFF_BLO + off, l01, l23);
             }
         }
         tc::fence_proxy_async_smem();
@@ -890,13 +1105,17 @@ __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, u
     }
 }
 
+template <int PRODS>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 k_enc_bwd_tc(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo, BwdParams p) {
+    using Cfg = BwdCfg<PRODS>;
+    constexpr int BWD_STAGES = Cfg::STAGES;
+    constexpr uint32_t BSTAGE_BYTES = Cfg::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BOFF_BARS);
-    uint64_t* full = bars;                  // [3] 8 converter warps
-    uint64_t* empty = bars + BWD_STAGES;    // [3] 1 (tcgen05.commit)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS);
+    uint64_t* full = bars;                  // [STAGES] 8 converter warps (+ 1 TMA expect_tx with the operand cache)
+    uint64_t* empty = bars + BWD_STAGES;    // [STAGES] 1 (tcgen05.commit)
     uint64_t* tfull = bars + 2 * BWD_STAGES;  // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * BWD_STAGES + 1);
 
@@ -927,17 +1146,17 @@ k_enc_bwd_tc(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__
         tc::reg_dec<40>();
         if (p.use_xs && lane == 0) {
             tc::prefetch_tmap(&tm_xhi);
-            tc::prefetch_tmap(&tm_xlo);
+            if (PRODS == 3) tc::prefetch_tmap(&tm_xlo);
             for (int kb = 0; kb < nkb; ++kb) {
                 const uint32_t s = kb % BWD_STAGES, ph = (kb / BWD_STAGES) & 1;
                 tc::mbar_wait(&empty[s], ph ^ 1);
-                tc::mbar_arrive_expect_tx(&full[s], 2 * BOP_BYTES);
+                tc::mbar_arrive_expect_tx(&full[s], (PRODS == 3 ? 2 : 1) * BOP_BYTES);
                 const int row = (int)(n_begin + (int64_t)kb * BWD_BK);
                 uint8_t* st = smem + s * BSTAGE_BYTES;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     tc::tma_load_2d(st + BOFF_BHI + c * MN_LBO, &tm_xhi, &full[s], dslice * 256 + c * 64, row);
-                    tc::tma_load_2d(st + BOFF_BLO + c * MN_LBO, &tm_xlo, &full[s], dslice * 256 + c * 64, row);
+                    if (PRODS == 3) tc::tma_load_2d(st + BOFF_BLO + c * MN_LBO, &tm_xlo, &full[s], dslice * 256 + c * 64, row);
                 }
             }
         }
@@ -954,9 +1173,10 @@ k_enc_bwd_tc(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__
 #pragma unroll
                 for (int mh = 0; mh < 2; ++mh)
 #pragma unroll
-                    for (int prod = 0; prod < 3; ++prod) {
-                        const uint32_t a_off = ((prod == 2) ? BOFF_ALO : BOFF_AHI) + mh * 2 * MN_LBO;  // hi*hi, hi*lo, lo*hi
-                        const uint32_t b_off = (prod == 1) ? BOFF_BLO : BOFF_BHI;
+                    for (int prod = 0; prod < PRODS; ++prod) {
+                        // 3 products: hi*hi, hi*lo, lo*hi;  2 products: hi*hi, lo*hi (B = x_hi only)
+                        const uint32_t a_off = ((prod == PRODS - 1) ? BOFF_ALO : BOFF_AHI) + mh * 2 * MN_LBO;
+                        const uint32_t b_off = (PRODS == 3 && prod == 1) ? BOFF_BLO : BOFF_BHI;
 #pragma unroll
                         for (int ks = 0; ks < BWD_BK / 16; ++ks) {
                             const uint64_t ad = tc::make_smem_desc(base + a_off + ks * 2 * MN_SBO, MN_LBO, MN_SBO);
@@ -975,12 +1195,12 @@ k_enc_bwd_tc(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__
         const int cw = warp - CONV_WARP0;
         const int variant = p.use_xs ? 5 : (p.ap.mode == 0 ? 0 : (p.ap.mode * 2 - 1 + (p.ap.noise_src == 1 ? 1 : 0)));
         switch (variant) {
-            case 0: bwd_convert<0, false, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 1: bwd_convert<1, false, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 2: bwd_convert<1, true, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 3: bwd_convert<2, false, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 4: bwd_convert<2, true, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
-            default: bwd_convert<0, false, true>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;  // A operand only
+            case 0: bwd_convert<PRODS, 0, false, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 1: bwd_convert<PRODS, 1, false, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 2: bwd_convert<PRODS, 1, true, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 3: bwd_convert<PRODS, 2, false, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            case 4: bwd_convert<PRODS, 2, true, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
+            default: bwd_convert<PRODS, 0, false, true>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;  // A operand only
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: TMEM -> split-K partial dW =====================
@@ -1053,10 +1273,12 @@ int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, c
     if (ws_bytes < cv.total) return dad_set_error(DAD_ERR_WS, "encoder_bwd(tc): workspace too small");
     if (T < 32) return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_bwd: the tcgen05 path needs T >= 32 (got %lld); use DAD_GEMM_FP32", (long long)T);
     if (B * T >= (1ll << 31)) return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_bwd: the tcgen05 path indexes frames with 32 bits (B*T = %lld)", (long long)(B * T));
+    const int prods = enc_tc_get_bwd_products();
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_enc_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
-        if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "encoder_bwd(tc): cannot opt in to %u B shared memory: %s", BWD_SMEM, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(k_enc_bwd_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdCfg<2>::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_bwd_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdCfg<3>::SMEM);
+        if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "encoder_bwd(tc): cannot opt in to %u B shared memory: %s", BwdCfg<2>::SMEM, cudaGetErrorString(e));
         attr = true;
     }
     uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
@@ -1075,16 +1297,18 @@ int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, c
     CUtensorMap tm_hi, tm_lo;
     memset(&tm_hi, 0, sizeof(tm_hi));
     memset(&tm_lo, 0, sizeof(tm_lo));
-    p.use_xs = (xs_hi && xs_lo) ? 1 : 0;
+    p.use_xs = xs_hi ? 1 : 0;
     if (p.use_xs) {
+        if (prods == 3 && !xs_lo) return dad_set_error(DAD_ERR_ARG, "encoder_bwd: the 3-product backward needs xs_lo next to xs_hi");
         if ((reinterpret_cast<uintptr_t>(xs_hi) | reinterpret_cast<uintptr_t>(xs_lo)) & 15u)
             return dad_set_error(DAD_ERR_ARG, "encoder_bwd: xs_hi/xs_lo must be 16-byte aligned (TMA)");
         int rc = make_tmap_f16(&tm_hi, xs_hi, (uint64_t)p.N, DAD_D, BWD_BK);
         if (rc) return rc;
-        rc = make_tmap_f16(&tm_lo, xs_lo, (uint64_t)p.N, DAD_D, BWD_BK);
+        if (prods == 3) rc = make_tmap_f16(&tm_lo, xs_lo, (uint64_t)p.N, DAD_D, BWD_BK);
         if (rc) return rc;
     }
-    k_enc_bwd_tc<<<dim3(DAD_D / 256, splits), BWD_THREADS, BWD_SMEM, st>>>(tm_hi, tm_lo, p);
+    if (prods == 3) k_enc_bwd_tc<3><<<dim3(DAD_D / 256, splits), BWD_THREADS, BwdCfg<3>::SMEM, st>>>(tm_hi, tm_lo, p);
+    else k_enc_bwd_tc<2><<<dim3(DAD_D / 256, splits), BWD_THREADS, BwdCfg<2>::SMEM, st>>>(tm_hi, tm_lo, p);
     DAD_CHECK_LAUNCH("k_enc_bwd_tc");
     int wpu = 1;  // warps per utterance: enough warps in the grid to cover the load latency (~16 per SM)
     while (wpu < DB_WARPS && B * wpu < (int64_t)sm_count() * 16) wpu *= 2;

@@ -42,16 +42,66 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar_addr, uint32_t parity
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t a = smem_u32(bar);
-    while (!mbar_try_wait(a, parity)) {
-    }
+// A protocol error must surface as a CUDA error, not as a hung GPU: every 64 K failed polls the waiter reads the global timer and
+// traps once a single wait has lasted longer than MBAR_TIMEOUT_NS (seconds: no legitimate wait comes near).
+constexpr unsigned long long MBAR_TIMEOUT_NS = 4000000000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
+template <bool CLUSTER> __device__ __forceinline__ void mbar_wait_guarded(uint32_t a, uint32_t parity);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_guarded<false>(smem_u32(bar), parity); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// acquire at cluster scope: the arrivals that complete the phase come from the peer CTA of a pair (remote mbarrier.arrive.release.cluster)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar_addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+template <bool CLUSTER> __device__ __forceinline__ void mbar_wait_guarded(uint32_t a, uint32_t parity) {
+    uint32_t spins = 0;
+    unsigned long long t0 = 0;
+    while (!(CLUSTER ? mbar_try_wait_cluster(a, parity) : mbar_try_wait(a, parity))) {
+        if ((++spins & 0xFFFFu) == 0) {
+            const unsigned long long t = globaltimer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > MBAR_TIMEOUT_NS) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait_guarded<true>(smem_u32(bar), parity); }
+
+// ---------------------------------------------------------------- CTA pairs (thread-block clusters of two)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+// arrive on a barrier that may live in the peer CTA (address from mapa); release at cluster scope orders this thread's earlier
+// shared-memory writes (made visible to the async proxy by fence.proxy.async) before the arrival
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 // explicit shared-space stores on 32-bit addresses (a pointer derived from the aligned dynamic-smem base is generic to the
@@ -92,6 +142,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
                  : "memory");
 }
 
+// the same for a CTA pair: the data lands in THIS CTA's shared memory, the bytes are counted on the barrier at `bar_cluster_addr`
+// (the leader CTA's, from mapa) -- both CTAs of the pair feed one barrier that the single MMA-issuing thread waits on
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
 // 2D tile store shared -> global (bulk async-group completion); rows / columns outside the tensor are clipped
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
@@ -111,6 +170,15 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+// CTA-pair forms: executed by the same warp of BOTH CTAs of the pair (same destination offset); both get the same columns
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -119,6 +187,22 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// CTA-pair MMA (M = 256 over the pair): issued by ONE thread of the leader CTA; each CTA contributes its 128 rows of A and its
+// half of the B rows from the SAME shared-memory offsets, and receives its 128 accumulator rows in its own TMEM
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this shared-memory offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
 }
 // make `bar` complete when all previously issued tcgen05.mma of this thread have retired (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -146,15 +230,22 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   [46,48) version = 1         [49,52) base offset = 0 (tiles are 1024-B aligned)   [61,64) layout: 2 = SWIZZLE_128B
 // K-major  (rows = M/N index, 128-B rows of 64 fp16 along K): SBO = 1024 B (8-row group pitch), LBO unused (=1).
 // MN-major (rows = K index, 128-B rows of 64 fp16 along M/N): SBO = pitch between 8-k groups, LBO = pitch between 64-element M/N chunks.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW64 = 4;  // [61,64) swizzling mode: 0 none, 1 128B (32B atoms), 2 128B, 4 64B, 6 32B
+__device__ __forceinline__ uint64_t make_smem_desc_l(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout << 61;
     return d;
 }
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return make_smem_desc_l(smem_addr, lbo_bytes, sbo_bytes, LAYOUT_SW128);
+}
+// K-major SWIZZLE_64B tile: 64-byte rows (32 fp16 along K), 8-row / 512-byte atoms, 16-byte chunk index ^= (row >> 1) & 3
+// (Swizzle<2,4,3>: address bits [4,6) ^= bits [7,9)).  SBO = 512 B, LBO unused (= 1).
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) { return make_smem_desc_l(smem_addr, 16, 512, LAYOUT_SW64); }
 // Instruction descriptor, kind::f16: fp16 x fp16 -> fp32.  [4,6) D fmt 1=F32  [7,10) A fmt 0=F16 (1=BF16)  [10,13) B fmt 0=F16
 // [15] A major (0=K,1=MN)  [16] B major  [17,23) N>>3  [24,29) M>>4
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {

@@ -90,7 +90,7 @@ class StepScalars:
 
 class DADStepEngine:
     def __init__(self, cfg, B_local, T, device=None, dataset="iemocap", world=1, rank=0, process_group=None, gemm_mode=None,
-                 use_graph=True, seed=42, noise_mode="philox", operand_cache="strong", exchange="auto"):
+                 use_graph=True, seed=42, noise_mode="philox", operand_cache="strong", exchange="auto", fused_noisy=True):
         _lib.require_device()
         self.cfg, self.dataset = cfg, dataset
         self.Bcap, self.Tcap = int(B_local), int(T)
@@ -110,6 +110,8 @@ class DADStepEngine:
         if self.gemm_mode != GEMM_TC:
             operand_cache = "none"
         self.operand_cache = operand_cache
+        # the weak-teacher and strong-student forwards as ONE kernel that reads x_noisy once (dad_aug_encoder_fwd; tcgen05 path only)
+        self.fused_noisy = bool(fused_noisy) and self.gemm_mode == GEMM_TC
         B, T, dev = self.Bcap, self.Tcap, self.dev
         Bg = B * self.world
         f32 = dict(dtype=torch.float32, device=dev)
@@ -162,8 +164,10 @@ class DADStepEngine:
         self._emb_t = z(B * D_HID)
         self._bits_c = torch.zeros(B * T * (D_HID // 32), dtype=torch.int32, device=dev)
         self._bits_s = torch.zeros(B * T * (D_HID // 32), dtype=torch.int32, device=dev)
-        # operand cache: fp16 hi/lo split of the augmented input, written by the student forwards and TMA-loaded by the backward
-        f16 = lambda: torch.zeros(2, B * T * D_IN, dtype=torch.float16, device=dev)
+        # operand cache: fp16 hi (3-product backward: hi and lo) half of the split of the augmented input, written by the student
+        # forwards and TMA-loaded by the backward
+        self.bwd_products = int(lib().dad_tc_get_bwd_products())
+        f16 = lambda: torch.zeros(2 if self.bwd_products == 3 else 1, B * T * D_IN, dtype=torch.float16, device=dev)
         self._xs_s = f16() if operand_cache in ("strong", "both") else None
         self._xs_c = f16() if operand_cache == "both" else None
         self.lens_clean, self.lens_noisy, self.lens_scratch = z(B), z(B), z(B)
@@ -180,7 +184,7 @@ class DADStepEngine:
         self.ecda_ws = torch.zeros(lib().dad_ecda_workspace_bytes(B, self.world), dtype=torch.uint8, device=dev)
         self.scl_ws = None  # allocated on first use (the SCL term is off by default)
         modes = (GEMM_FP32, self.gemm_mode)  # frames-per-batch < 32 fall back to the exact-fp32 CUDA-core kernels
-        nb = max(max(lib().dad_encoder_fwd_workspace_bytes(B, T, m) for m in modes), 256)
+        nb = max(max(lib().dad_encoder_fwd_workspace_bytes(B, T, m) for m in modes), lib().dad_aug_encoder_fwd_workspace_bytes(B, T), 256)
         self.enc_ws = torch.zeros(nb, dtype=torch.uint8, device=dev)
         self.bwd_ws = torch.zeros(max(max(lib().dad_encoder_bwd_workspace_bytes(B, T, m) for m in modes), 256), dtype=torch.uint8, device=dev)
         s_max = max(lib().dad_encoder_bwd_splits(B, T, m) for m in modes)
@@ -435,13 +439,16 @@ class DADStepEngine:
             return None
         L = int(self.Tn * sc.mask_ratio)
         supplied = self.noise_mode == "supplied"
+        # under data parallelism rank r draws frames [r*B*T, (r+1)*B*T) of ONE global noise field (the reference draws a single
+        # randn_like over the whole batch, I/utils.py:330,338): identical local sample indices on two ranks get different noise
+        foff = self.rank * self.B * self.Tn
         if mode == 1:
-            return make_aug(1, noise=self.n_weak if supplied else None, sigma=sc.weak_std, seed=self.seed, stream=1,
-                            step_ptr=self.step_count.data_ptr())
+            return make_aug(1, noise=self.n_weak if supplied else None, sigma=sc.weak_std, seed=self.seed, stream=_lib.STREAM_WEAK,
+                            step_ptr=self.step_count.data_ptr(), frame_offset=foff)
         return make_aug(2, noise=self.n_strong if supplied else None, sigma=sc.strong_std,
                         feat_keep=self.feat_keep if sc.feat_rate > 0 else None,
-                        t_start=self.t_start if (sc.mask_ratio > 0 and L > 0) else None, mask_len=L, seed=self.seed, stream=2,
-                        step_ptr=self.step_count.data_ptr())
+                        t_start=self.t_start if (sc.mask_ratio > 0 and L > 0) else None, mask_len=L, seed=self.seed,
+                        stream=_lib.STREAM_STRONG, step_ptr=self.step_count.data_ptr(), frame_offset=foff)
 
     def _enc_fwd(self, x, pad, teacher, aug, emb_ptr, bits, lens, s, xs=None):
         flat = self.t if teacher else self.p
@@ -453,9 +460,23 @@ class DADStepEngine:
         check(lib().dad_encoder_fwd(x.data_ptr(), pad.data_ptr(), flat.data_ptr() + OFF_W * 4, flat.data_ptr() + OFF_B * 4,
                                     hi.data_ptr(), lo.data_ptr(), C.byref(aug) if aug is not None else None, emb_ptr,
                                     bits.data_ptr() if bits is not None else None,
-                                    xs[0].data_ptr() if xs is not None else None, xs[1].data_ptr() if xs is not None else None,
+                                    xs[0].data_ptr() if xs is not None else None,
+                                    xs[1].data_ptr() if (xs is not None and xs.shape[0] > 1) else None,
                                     lens.data_ptr(), self.enc_ws.data_ptr(), self.enc_ws.numel(), B, T, mode, s))
         self.launches_per_step += 2 if mode == GEMM_TC else 1
+
+    def _enc_fwd_noisy_fused(self, aug_w, aug_s, emb_strong_ptr, s):
+        """I/train.py:405-409,439 as one kernel: x_noisy is read once; weak view -> teacher weights, strong view -> student weights."""
+        x, pad, xs = self.x_noisy, self.pad_noisy, self.xs_strong
+        B, T = int(x.shape[0]), int(x.shape[1])
+        check(lib().dad_aug_encoder_fwd(x.data_ptr(), pad.data_ptr(), self.hi_lo[2].data_ptr(), self.hi_lo[3].data_ptr(),
+                                        self.t.data_ptr() + OFF_B * 4, C.byref(aug_w), self.emb_teacher.data_ptr(),
+                                        self.hi_lo[0].data_ptr(), self.hi_lo[1].data_ptr(), self.p.data_ptr() + OFF_B * 4, C.byref(aug_s),
+                                        emb_strong_ptr, self.bits_strong.data_ptr(),
+                                        xs[0].data_ptr() if xs is not None else None,
+                                        xs[1].data_ptr() if (xs is not None and xs.shape[0] > 1) else None,
+                                        self.lens_noisy.data_ptr(), self.enc_ws.data_ptr(), self.enc_ws.numel(), B, T, s))
+        self.launches_per_step += 2
 
     def _enc_bwd(self, x, pad, aug, bits, g, lens, slot, s, xs=None):
         """-> number of split-K partials written to self._dWp[slot] / self._dbp[slot]"""
@@ -465,7 +486,8 @@ class DADStepEngine:
             xs = None
         S = lib().dad_encoder_bwd_splits(B, T, mode)
         check(lib().dad_encoder_bwd(x.data_ptr(), pad.data_ptr(), C.byref(aug) if aug is not None else None, bits.data_ptr(),
-                                    xs[0].data_ptr() if xs is not None else None, xs[1].data_ptr() if xs is not None else None,
+                                    xs[0].data_ptr() if xs is not None else None,
+                                    xs[1].data_ptr() if (xs is not None and xs.shape[0] > 1) else None,
                                     g.data_ptr(), lens.data_ptr(), self._dWp[slot].data_ptr(), self._dbp[slot].data_ptr(), S,
                                     self.bwd_ws.data_ptr(), self.bwd_ws.numel(), B, T, mode, s))
         self.launches_per_step += 5 if mode == GEMM_TC else 1
@@ -489,15 +511,18 @@ class DADStepEngine:
             check(L.dad_step_rng(self.seed, self.step_count.data_ptr(), self.keep_clean.data_ptr() if drop else None,
                                  self.keep_strong.data_ptr() if (drop and noisy) else None, B, sc.drop_p,
                                  self.feat_keep.data_ptr() if noisy else None, sc.feat_rate,
-                                 self.t_start.data_ptr() if noisy else None, T, Lm, s))
+                                 self.t_start.data_ptr() if noisy else None, T, Lm, self.rank * B, s))
             self.launches_per_step += 1
         # ---- forwards (I/train.py:399, 409, 439)
         self._enc_fwd(self.x_clean, self.pad_clean, False, None, emb_clean_ptr, self.bits_clean, self.lens_clean, s, xs=self.xs_clean)
         aug_w = aug_s = None
         if noisy:
             aug_w, aug_s = self._aug(1, sc), self._aug(2, sc)
-            self._enc_fwd(self.x_noisy, self.pad_noisy, True, aug_w, self.emb_teacher.data_ptr(), None, self.lens_scratch, s)
-            self._enc_fwd(self.x_noisy, self.pad_noisy, False, aug_s, emb_strong_ptr, self.bits_strong, self.lens_noisy, s, xs=self.xs_strong)
+            if self.fused_noisy and self._mode(self.Tn) == GEMM_TC:
+                self._enc_fwd_noisy_fused(aug_w, aug_s, emb_strong_ptr, s)
+            else:
+                self._enc_fwd(self.x_noisy, self.pad_noisy, True, aug_w, self.emb_teacher.data_ptr(), None, self.lens_scratch, s)
+                self._enc_fwd(self.x_noisy, self.pad_noisy, False, aug_s, emb_strong_ptr, self.bits_strong, self.lens_noisy, s, xs=self.xs_strong)
         # ---- heads
         hf = HeadFwdArgs()
         hf.pack, hf.rank, hf.B_local, hf.noisy, hf.use_entropy = pk, self.rank, B, int(noisy), int(sc.use_entropy)

@@ -31,7 +31,8 @@ def default_gemm_mode(T):
         return GEMM_FP32
     if mode in ("tc", "f16x3"):
         return GEMM_TC
-    return GEMM_FP32
+    # tcgen05 path by default (fp32-grade 3-product fp16 split); utterances shorter than one 32-frame group use the CUDA-core kernel
+    return GEMM_TC if T >= 32 else GEMM_FP32
 
 
 def _as_u8_pad(pad, B, T, device):
@@ -65,7 +66,8 @@ def augment(x, sigma, noise=None, seed=None, stream=0, feat_keep=None, t_start=N
 
 def encoder_pool_fwd(x, pad, W, b, aug=None, gemm_mode=None, want_bits=True, W_hi=None, W_lo=None, emb_out=None, xs=None):
     """emb[B,256] = masked-mean_t relu(W aug(x) + b)  (I/model.py:18-41).  Returns (emb, relu_bits|None, lens).
-    xs = (xs_hi, xs_lo): optional fp16 [B*T,768] operand-cache buffers filled for encoder_pool_bwd (tcgen05 mode only)."""
+    xs = (xs_hi,) or (xs_hi, xs_lo): optional fp16 [B*T,768] operand-cache buffers filled for encoder_pool_bwd (tcgen05 mode only;
+    the default 2-product backward needs xs_hi alone)."""
     _lib.require_device()
     if x.dim() != 3 or x.shape[-1] != D_IN:
         raise DadError(f"encoder: expected x [B,T,{D_IN}], got {tuple(x.shape)}")
@@ -86,10 +88,41 @@ def encoder_pool_fwd(x, pad, W, b, aug=None, gemm_mode=None, want_bits=True, W_h
     check(lib().dad_encoder_fwd(ptr(x, torch.float32, "x"), ptr(pad8), ptr(W.contiguous(), torch.float32, "W"),
                                 ptr(b.contiguous(), torch.float32, "b"), ptr(W_hi), ptr(W_lo),
                                 C.byref(aug) if aug is not None else None, ptr(emb), ptr(bits),
-                                ptr(xs[0], torch.float16, "xs_hi") if xs is not None else None,
-                                ptr(xs[1], torch.float16, "xs_lo") if xs is not None else None, ptr(lens), ptr(ws), ws.numel(),
-                                B, T, mode, stream_ptr()))
+                                _xs(xs, 0), _xs(xs, 1), ptr(lens), ptr(ws), ws.numel(), B, T, mode, stream_ptr()))
     return emb, bits, lens
+
+
+def _xs(xs, i):
+    """i-th buffer of an operand cache given as (xs_hi,) or (xs_hi, xs_lo); None -> NULL."""
+    if xs is None or len(xs) <= i or xs[i] is None:
+        return None
+    return ptr(xs[i], torch.float16, "xs_hi" if i == 0 else "xs_lo")
+
+
+def aug_encoder_fwd(x, pad, Wt, bt, Ws, bs, aug_weak, aug_strong, want_bits=True, xs=None, Wt_split=None, Ws_split=None):
+    """Fused noisy forward (I/train.py:405-409,439): ONE read of x -> teacher(weak(x)) and student(strong(x)) on the tcgen05 path.
+    Returns (emb_teacher, emb_student, relu_bits_student|None, lens)."""
+    _lib.require_device()
+    if x.dim() != 3 or x.shape[-1] != D_IN:
+        raise DadError(f"encoder: expected x [B,T,{D_IN}], got {tuple(x.shape)}")
+    x = x.contiguous()
+    B, T, _ = x.shape
+    dev = x.device
+    pad8 = _as_u8_pad(pad, B, T, dev)
+    emb_t = torch.empty(B, D_HID, dtype=torch.float32, device=dev)
+    emb_s = torch.empty(B, D_HID, dtype=torch.float32, device=dev)
+    bits = torch.empty(B * T, D_HID // 32, dtype=torch.int32, device=dev) if want_bits else None
+    lens = torch.empty(B, dtype=torch.float32, device=dev)
+    if B == 0:
+        return emb_t, emb_s, bits, lens
+    t_hi, t_lo = Wt_split if Wt_split is not None else split_f16(Wt)
+    s_hi, s_lo = Ws_split if Ws_split is not None else split_f16(Ws)
+    ws = _zeros_ws(lib().dad_aug_encoder_fwd_workspace_bytes(B, T), dev, "aug_enc_fwd")
+    check(lib().dad_aug_encoder_fwd(ptr(x, torch.float32, "x"), ptr(pad8), ptr(t_hi), ptr(t_lo), ptr(bt.contiguous(), torch.float32, "bt"),
+                                    C.byref(aug_weak), ptr(emb_t), ptr(s_hi), ptr(s_lo), ptr(bs.contiguous(), torch.float32, "bs"),
+                                    C.byref(aug_strong), ptr(emb_s), ptr(bits), _xs(xs, 0), _xs(xs, 1), ptr(lens), ptr(ws), ws.numel(),
+                                    B, T, stream_ptr()))
+    return emb_t, emb_s, bits, lens
 
 
 def encoder_pool_bwd(x, pad, bits, g_emb, lens, aug=None, gemm_mode=None, xs=None):
@@ -107,8 +140,7 @@ def encoder_pool_bwd(x, pad, bits, g_emb, lens, aug=None, gemm_mode=None, xs=Non
     nb = lib().dad_encoder_bwd_workspace_bytes(B, T, mode)
     ws = _zeros_ws(nb, dev, "enc_bwd")
     check(lib().dad_encoder_bwd(ptr(x, torch.float32, "x"), ptr(pad8), C.byref(aug) if aug is not None else None,
-                                ptr(bits), ptr(xs[0], torch.float16, "xs_hi") if xs is not None else None,
-                                ptr(xs[1], torch.float16, "xs_lo") if xs is not None else None,
+                                ptr(bits), _xs(xs, 0), _xs(xs, 1),
                                 ptr(g_emb.contiguous(), torch.float32, "g_emb"), ptr(lens, torch.float32, "lens"),
                                 ptr(dWp), ptr(dbp), S, ptr(ws), ws.numel(), B, T, mode, stream_ptr()))
     g = torch.empty(NPARAM, dtype=torch.float32, device=dev)

@@ -56,17 +56,18 @@ class DataAugmentation:
 
     def __init__(self, weak_noise_std=None, strong_noise_std=None, dropout_rate=None, temporal_mask_ratio=None):
         cfg = _cfg()
-        self.weak_noise_std = weak_noise_std or cfg.WEAK_NOISE_STD
-        self.strong_noise_std = strong_noise_std or cfg.STRONG_NOISE_STD
-        self.dropout_rate = dropout_rate or cfg.DROPOUT_RATE
-        self.temporal_mask_ratio = temporal_mask_ratio or cfg.TEMPORAL_MASK_RATIO
+        # `is not None`, as the reference (I/utils.py:322-326): an explicit 0 / 0.0 disables that augmentation (ablations)
+        self.weak_noise_std = weak_noise_std if weak_noise_std is not None else cfg.WEAK_NOISE_STD
+        self.strong_noise_std = strong_noise_std if strong_noise_std is not None else cfg.STRONG_NOISE_STD
+        self.dropout_rate = dropout_rate if dropout_rate is not None else cfg.DROPOUT_RATE
+        self.temporal_mask_ratio = temporal_mask_ratio if temporal_mask_ratio is not None else cfg.TEMPORAL_MASK_RATIO
 
     @staticmethod
     def _seed():
         return int(torch.randint(0, 2 ** 62, (1,)).item())
 
     def weak_augment(self, data):
-        return ops.augment(data.float(), _f32(self.weak_noise_std), seed=self._seed(), stream=1)
+        return ops.augment(data.float(), _f32(self.weak_noise_std), seed=self._seed(), stream=_lib.STREAM_WEAK)
 
     def strong_augment(self, data):
         x = data.float()
@@ -79,7 +80,7 @@ class DataAugmentation:
         t_start = None
         if self.temporal_mask_ratio > 0 and L > 0:
             t_start = torch.randint(0, max(1, T - L + 1), (B,)).to(torch.int32).to(x.device)      # CPU generator, I/utils.py:371
-        return ops.augment(x, _f32(self.strong_noise_std), seed=self._seed(), stream=2, feat_keep=keep, t_start=t_start,
+        return ops.augment(x, _f32(self.strong_noise_std), seed=self._seed(), stream=_lib.STREAM_STRONG, feat_keep=keep, t_start=t_start,
                            mask_len=L, strong=True)
 
 
@@ -159,14 +160,21 @@ class DACPManager:
 class _EcdaFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, clean, noisy, y_clean, y_noisy, mask_u8, scores, w_class, class_aware, lambda_cls, gamma_comp, delta_rep):
-        B, dev = clean.shape[0], clean.device
+        # the reference accepts clean / noisy batches of different size (I/utils.py:565-652 indexes them separately): the shorter
+        # one is padded with null samples (label / pseudo-label -1, mask 0) that belong to no class and receive no gradient
+        Bc, Bn, dev = clean.shape[0], noisy.shape[0], clean.device
+        B = max(Bc, Bn, 1)
         pack = torch.zeros(_lib.pack_rank_words(B), dtype=torch.float32, device=dev)
         gv = _lib.pack_global_views(pack, B, 1)
-        gv["emb_clean"][0].copy_(clean)
-        gv["emb_strong"][0].copy_(noisy)
-        gv["score"][0].copy_(scores)
-        gv["pred"][0].copy_(y_noisy.int())
-        gv["label"][0].copy_(y_clean.int())
+        gv["pred"][0].fill_(-1)
+        gv["label"][0].fill_(-1)
+        gv["emb_clean"][0][:Bc].copy_(clean)
+        gv["emb_strong"][0][:Bn].copy_(noisy)
+        gv["score"][0][:Bn].copy_(scores)
+        gv["pred"][0][:Bn].copy_(y_noisy.int())
+        gv["label"][0][:Bc].copy_(y_clean.int())
+        if Bn < B:
+            mask_u8 = torch.cat([mask_u8, torch.zeros(B - Bn, dtype=torch.uint8, device=dev)])
         nmask = mask_u8.sum().to(torch.int32).reshape(1)
         g_clean, g_strong = torch.zeros(B, D_HID, device=dev), torch.zeros(B, D_HID, device=dev)
         loss3 = torch.zeros(4, device=dev)
@@ -178,7 +186,7 @@ class _EcdaFn(torch.autograd.Function):
         a.g_clean, a.g_strong, a.loss_out = g_clean.data_ptr(), g_strong.data_ptr(), loss3.data_ptr()
         a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
         check(lib().dad_ecda(C.byref(a), stream_ptr()))
-        ctx.save_for_backward(g_clean, g_strong)
+        ctx.save_for_backward(g_clean[:Bc], g_strong[:Bn])
         return loss3[2].clone()
 
     @staticmethod
@@ -190,7 +198,9 @@ class _EcdaFn(torch.autograd.Function):
 class ECDALoss(nn.Module):
     """I/utils.py:510-652: class-aware, attention-weighted 5-kernel Gaussian MMD + compactness + centroid repulsion
     (cfg.USE_CLASS_AWARE_MMD=False: one global MMD, I/utils.py:633-650), forward and analytic backward in two kernels
-    (csrc/k_ecda.cu).  Like the reference's call site (I/train.py:444,450) the loss is 0 when fewer than 2 samples are masked in."""
+    (csrc/k_ecda.cu).  The kernels skip everything when fewer than 2 noisy samples are masked in; the reference's forward
+    returns 0 in that case as well (every class needs >= 2 masked noisy members, I/utils.py:609, and so does the global branch,
+    :641), so the gate changes no value.  Clean and noisy batches may differ in size, as upstream."""
 
     def __init__(self, kernel_type="rbf", kernel_mul=2.0, kernel_num=5):
         super().__init__()
@@ -201,9 +211,8 @@ class ECDALoss(nn.Module):
     def forward(self, clean_feats, noisy_feats, clean_labels, noisy_labels, noisy_mask, noisy_scores, class_weights_wce):
         _lib.require_device()
         cfg = _cfg()
-        if clean_feats.shape != noisy_feats.shape or clean_feats.dim() != 2 or clean_feats.shape[1] != D_HID:
-            raise DadError(f"ECDALoss: clean/noisy feats must both be [B,{D_HID}] (got {tuple(clean_feats.shape)}, {tuple(noisy_feats.shape)}); "
-                           "for ragged batch pairs use engine.DADStepEngine")
+        if clean_feats.dim() != 2 or noisy_feats.dim() != 2 or clean_feats.shape[1] != D_HID or noisy_feats.shape[1] != D_HID:
+            raise DadError(f"ECDALoss: clean/noisy feats must be [B,{D_HID}] (got {tuple(clean_feats.shape)}, {tuple(noisy_feats.shape)})")
         mask = noisy_mask
         if mask.dtype != torch.bool:  # float mask of the USE_DACP=False path, re-thresholded as in I/utils.py:572-576
             mask = mask > getattr(cfg, "FIXED_CONFIDENCE_THRESHOLD", 0.9)

@@ -24,7 +24,24 @@ def _inputs(B, T, seed, variable=True):
 def test_library_loaded_and_device_ok():
     from dad_b200 import _lib
     _lib.require_device()
-    assert _lib.lib().dad_abi_version() == 2
+    assert _lib.lib().dad_abi_version() == 3
+
+
+@pytest.fixture
+def tc_switch():
+    """Set the process-wide tcgen05 switches (CTA pair on/off, products of the dW GEMM) for one test and restore them."""
+    from dad_b200 import _lib
+    L = _lib.lib()
+    old = (L.dad_tc_get_cta_pair(), L.dad_tc_get_bwd_products())
+
+    def set_(cta_pair=None, products=None):
+        if cta_pair is not None:
+            L.dad_tc_set_cta_pair(int(cta_pair))
+        if products is not None:
+            L.dad_tc_set_bwd_products(int(products))
+    yield set_
+    L.dad_tc_set_cta_pair(old[0])
+    L.dad_tc_set_bwd_products(old[1])
 
 
 @pytest.mark.parametrize("B,T", [(6, 20), (3, 7), (2, 200), (1, 1)])
@@ -65,10 +82,12 @@ def test_augment_bit_exact_vs_reference_golden():
 def test_augment_philox_statistics_and_determinism():
     from dad_b200 import ops
     x = torch.zeros(8, 64, 768, device="cuda")
-    a = ops.augment(x, 1.0, seed=5, stream=1)
-    b = ops.augment(x, 1.0, seed=5, stream=1)
-    c = ops.augment(x, 1.0, seed=5, stream=2)
-    assert torch.equal(a, b) and not torch.equal(a, c)
+    a = ops.augment(x, 1.0, seed=5, stream=2)
+    b = ops.augment(x, 1.0, seed=5, stream=2)
+    c = ops.augment(x, 1.0, seed=5, stream=3)   # the other half of the same Philox blocks (dad_common.cuh): independent normals
+    d = ops.augment(x, 1.0, seed=5, stream=4)
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, d)
+    assert abs(float((a * c).mean())) < 5e-3 and abs(float((a * d).mean())) < 5e-3
     assert abs(float(a.mean())) < 5e-3 and abs(float(a.std()) - 1.0) < 5e-3
     assert abs(float((a ** 4).mean()) - 3.0) < 0.05  # normal kurtosis
 
@@ -91,14 +110,20 @@ def test_encoder_forward_vs_reference_golden(mode):
     assert torch.equal(lens2.cpu(), torch.full((g["B"],), float(g["T"])))
 
 
-@pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("B,T,aug", [(4, 64, 0), (5, 200, 2), (3, 97, 1), (2, 33, 2), (16, 40, 2), (1, 1, 0), (2, 5, 2)])
-def test_encoder_forward_backward_vs_oracle(mode, B, T, aug):
+# tcgen05 variants: one CTA per tile / CTA pairs (cta_group::2) x 2- / 3-product dW GEMM
+TC_VARIANTS = ["fp32", "tc", "tc-single-cta", "tc-3prod"]
+
+
+@pytest.mark.parametrize("mode", TC_VARIANTS)
+@pytest.mark.parametrize("B,T,aug", [(4, 64, 0), (5, 200, 2), (3, 97, 1), (2, 33, 2), (16, 40, 2), (1, 1, 0), (2, 5, 2), (41, 100, 2)])
+def test_encoder_forward_backward_vs_oracle(mode, B, T, aug, tc_switch):
     """emb, ReLU bits, dW, db against the oracle's autograd on the same (augmented) inputs."""
     from dad_b200 import _lib, ops
     from oracle import dad_oracle as O
-    if mode == "tc" and T < 32:
+    if mode != "fp32" and T < 32:
         pytest.skip("tcgen05 path needs T >= 32")
+    tc_switch(cta_pair=mode != "tc-single-cta", products=3 if mode == "tc-3prod" else 2)
+    mode = "fp32" if mode == "fp32" else "tc"
     c, n, rng = _inputs(B, T, 4242 + B * 1000 + T)
     st = pretrained_state()
     W0, b0 = st["student_encoder.pre_net.weight"], st["student_encoder.pre_net.bias"]
@@ -152,11 +177,14 @@ def test_fp32_encoder_workspace_reuse_across_batch_sizes():
         assert torch.allclose(emb.cpu(), O.encoder(x, pad, W0, b0), rtol=2e-5, atol=2e-6), B
 
 
+@pytest.mark.parametrize("products", [2, 3])
 @pytest.mark.parametrize("B,T,aug", [(4, 64, 0), (5, 200, 2), (3, 97, 1), (2, 33, 2), (37, 41, 2)])
-def test_operand_cache_backward_is_bit_identical(B, T, aug):
-    """tcgen05 mode: the backward fed by TMA from the forward's fp16 hi/lo operand cache == the backward that re-reads,
-    re-augments and re-splits x (same operand values -> same dW partials, bit for bit); emb / bits are unaffected."""
+def test_operand_cache_backward_is_bit_identical(B, T, aug, products, tc_switch):
+    """tcgen05 mode: the backward fed by TMA from the forward's fp16 operand cache (hi only for the 2-product dW GEMM, hi and lo
+    for the 3-product one) == the backward that re-reads, re-augments and re-splits x (same operand values -> same dW partials,
+    bit for bit); emb / bits are unaffected."""
     from dad_b200 import _lib, ops
+    tc_switch(products=products)
     c, n, rng = _inputs(B, T, 777 + B * 1000 + T)
     st = pretrained_state()
     W, b = st["student_encoder.pre_net.weight"].cuda(), st["student_encoder.pre_net.bias"].cuda()
@@ -172,16 +200,105 @@ def test_operand_cache_backward_is_bit_identical(B, T, aug):
     g_emb = torch.randn(B, 256, generator=torch.Generator().manual_seed(11)).cuda()
     emb0, bits0, lens0 = ops.encoder_pool_fwd(x, pad, W, b, aug=a, gemm_mode=_lib.GEMM_TC)
     dW0, db0 = ops.encoder_pool_bwd(x, pad, bits0, g_emb, lens0, aug=a, gemm_mode=_lib.GEMM_TC)
-    xs = torch.full((2, B * T, 768), float("nan"), dtype=torch.float16, device="cuda")
-    emb1, bits1, lens1 = ops.encoder_pool_fwd(x, pad, W, b, aug=a, gemm_mode=_lib.GEMM_TC, xs=(xs[0], xs[1]))
+    xs = torch.full((products - 1, B * T, 768), float("nan"), dtype=torch.float16, device="cuda")
+    planes = tuple(xs[i] for i in range(products - 1))
+    emb1, bits1, lens1 = ops.encoder_pool_fwd(x, pad, W, b, aug=a, gemm_mode=_lib.GEMM_TC, xs=planes)
     assert torch.equal(emb0, emb1) and torch.equal(bits0, bits1)
     assert not torch.isnan(xs.float()).any()  # every frame row of the cache was written
-    dW1, db1 = ops.encoder_pool_bwd(x, pad, bits1, g_emb, lens1, aug=None, gemm_mode=_lib.GEMM_TC, xs=(xs[0], xs[1]))
+    dW1, db1 = ops.encoder_pool_bwd(x, pad, bits1, g_emb, lens1, aug=None, gemm_mode=_lib.GEMM_TC, xs=planes)
     assert torch.equal(dW0, dW1) and torch.equal(db0, db1)
-    # the cache holds the augmented view itself: hi + lo == 8 * aug(x) to ~2^-21
+    # the cache holds the augmented view itself: hi (+ lo) == 8 * aug(x) to 2^-12 (2^-21)
     if aug == 0:
-        rec = (xs[0].float() + xs[1].float()) / 8.0
-        assert float((rec.view(B, T, 768) - x).abs().max()) <= 2e-6 * float(x.abs().max())
+        rec = sum(pl.float() for pl in planes) / 8.0
+        tol = 2e-6 if products == 3 else 2.5e-4
+        assert float((rec.view(B, T, 768) - x).abs().max()) <= tol * float(x.abs().max())
+
+
+def _noisy_views(B, T, seed, philox):
+    from dad_b200 import _lib
+    c, n, rng = _inputs(B, T, seed)
+    x, pad = n["net_input"]["feats"].cuda(), n["net_input"]["padding_mask"].cuda()
+    L = int(T * 0.1)
+    keep_d, ts_d = (rng["feat_keep_u"] > 0.1).float().cuda(), rng["t_start"].to(torch.int32).cuda()
+    hold = [keep_d, ts_d]
+    if philox:
+        aw = _lib.make_aug(1, sigma=0.01, seed=77, stream=_lib.STREAM_WEAK)
+        as_ = _lib.make_aug(2, sigma=0.05, feat_keep=keep_d, t_start=ts_d if L > 0 else None, mask_len=L, seed=77, stream=_lib.STREAM_STRONG)
+    else:
+        nw, ns = rng["n_weak"].cuda(), rng["n_strong"].cuda()
+        hold += [nw, ns]
+        aw = _lib.make_aug(1, noise=nw, sigma=0.01)
+        as_ = _lib.make_aug(2, noise=ns, sigma=0.05, feat_keep=keep_d, t_start=ts_d if L > 0 else None, mask_len=L)
+    return x, pad, aw, as_, hold, (n, rng)
+
+
+@pytest.mark.parametrize("cta_pair", [True, False], ids=["pair", "single"])
+@pytest.mark.parametrize("philox", [False, True], ids=["supplied", "philox"])
+@pytest.mark.parametrize("B,T", [(4, 64), (5, 200), (3, 97), (2, 33), (37, 41), (64, 200)])
+def test_fused_noisy_forward_equals_the_two_single_view_forwards(B, T, philox, cta_pair, tc_switch):
+    """dad_aug_encoder_fwd (I/train.py:405-409,439 as one kernel, x_noisy read once) == dad_encoder_fwd of the weak view on the
+    teacher weights + dad_encoder_fwd of the strong view on the student weights: embeddings, ReLU bits and the operand cache
+    bit for bit (same operands, same accumulation order) -- with supplied noise and with the in-kernel Philox field (whose weak /
+    strong streams share their Philox blocks)."""
+    from dad_b200 import _lib, ops
+    tc_switch(cta_pair=cta_pair)
+    st = pretrained_state()
+    Ws, bs = st["student_encoder.pre_net.weight"].cuda(), st["student_encoder.pre_net.bias"].cuda()
+    g = torch.Generator().manual_seed(5)
+    Wt = (Ws.cpu() + 0.01 * torch.randn(256, 768, generator=g)).cuda()   # a teacher that differs from the student
+    bt = (bs.cpu() + 0.01 * torch.randn(256, generator=g)).cuda()
+    x, pad, aw, as_, hold, _ = _noisy_views(B, T, 31 + B * 1000 + T, philox)
+    emb_t0, _, lens0 = ops.encoder_pool_fwd(x, pad, Wt, bt, aug=aw, gemm_mode=_lib.GEMM_TC, want_bits=False)
+    xs0 = torch.full((B * T, 768), float("nan"), dtype=torch.float16, device="cuda")
+    emb_s0, bits0, _ = ops.encoder_pool_fwd(x, pad, Ws, bs, aug=as_, gemm_mode=_lib.GEMM_TC, xs=(xs0,))
+    xs1 = torch.full((B * T, 768), float("nan"), dtype=torch.float16, device="cuda")
+    emb_t1, emb_s1, bits1, lens1 = ops.aug_encoder_fwd(x, pad, Wt, bt, Ws, bs, aw, as_, xs=(xs1,))
+    assert torch.equal(emb_t0, emb_t1) and torch.equal(emb_s0, emb_s1), (float((emb_t0 - emb_t1).abs().max()), float((emb_s0 - emb_s1).abs().max()))
+    assert torch.equal(bits0, bits1) and torch.equal(lens0, lens1)
+    assert torch.equal(xs0.view(torch.int16), xs1.view(torch.int16))
+
+
+@pytest.mark.parametrize("cta_pair", [True, False], ids=["pair", "single"])
+@pytest.mark.parametrize("B,T", [(5, 200), (3, 97), (37, 41)])
+def test_fused_noisy_forward_vs_oracle(B, T, cta_pair, tc_switch):
+    """The fused kernel against the oracle's encoder on the oracle's own weak / strong views (supplied noise)."""
+    from dad_b200 import ops
+    from oracle import dad_oracle as O
+    tc_switch(cta_pair=cta_pair)
+    st = pretrained_state()
+    Ws, bs = st["student_encoder.pre_net.weight"], st["student_encoder.pre_net.bias"]
+    g = torch.Generator().manual_seed(5)
+    Wt, bt = Ws + 0.01 * torch.randn(256, 768, generator=g), bs + 0.01 * torch.randn(256, generator=g)
+    x, pad, aw, as_, hold, (n, rng) = _noisy_views(B, T, 31 + B * 1000 + T, False)
+    xh, ph = n["net_input"]["feats"], n["net_input"]["padding_mask"]
+    ref_t = O.encoder(O.weak_augment(xh, rng["n_weak"], 0.01), ph, Wt, bt)
+    ref_s = O.encoder(O.strong_augment(xh, rng["n_strong"], 0.05, rng["feat_keep_u"], 0.1, rng["t_start"], 0.1), ph, Ws, bs)
+    emb_t, emb_s, bits, lens = ops.aug_encoder_fwd(x, pad, Wt.cuda(), bt.cuda(), Ws.cuda(), bs.cuda(), aw, as_)
+    assert torch.allclose(emb_t.cpu(), ref_t, rtol=1e-4, atol=2e-5), float((emb_t.cpu() - ref_t).abs().max())
+    assert torch.allclose(emb_s.cpu(), ref_s, rtol=1e-4, atol=2e-5), float((emb_s.cpu() - ref_s).abs().max())
+    assert torch.equal(lens.cpu(), (~ph).sum(1).float())
+
+
+def test_philox_noise_field_is_global_under_data_parallel_offsets():
+    """the noise of rank r must be the frames [r*B*T, (r+1)*B*T) of ONE global field (not the same field on every
+    rank): a batch augmented in two halves with frame offsets equals the batch augmented at once."""
+    from dad_b200 import _lib
+    import ctypes as C
+    B, T = 4, 40
+    x = torch.randn(B, T, 768, device="cuda")
+    out = torch.empty_like(x)
+
+    def run(xv, ov, off):
+        a = _lib.make_aug(1, sigma=1.0, seed=9, stream=_lib.STREAM_WEAK, frame_offset=off)
+        _lib.check(_lib.lib().dad_augment(xv.data_ptr(), ov.data_ptr(), C.byref(a), xv.shape[0], T, _lib.stream_ptr()))
+    run(x, out, 0)
+    halves = torch.empty_like(x)
+    run(x[:2].contiguous(), halves[:2], 0)
+    run(x[2:].contiguous(), halves[2:], 2 * T)
+    assert torch.equal(out, halves)
+    same = torch.empty_like(x[:2])
+    run(x[2:].contiguous(), same, 0)                      # the defect: rank 1 reusing rank 0's part of the field
+    assert not torch.equal(same, halves[2:])
 
 
 def test_encoder_rejects_bad_arguments():

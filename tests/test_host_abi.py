@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     src = open(os.path.join(ROOT, "include", "dad_sm100a.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(?:int|size_t|int32_t|int64_t|const char\*)\s+(dad_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(?:void|int|size_t|int32_t|int64_t|const char\*)\s+(dad_\w+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
     assert set(_lib.EXPORTS) <= set(names), sorted(set(_lib.EXPORTS) - set(names))
-    assert _lib.lib().dad_abi_version() == 2 and _lib.lib().dad_max_world() == 16
+    assert _lib.lib().dad_abi_version() == 3 and _lib.lib().dad_max_world() == 16
     assert _lib.lib().dad_pack_rank_words(7) == 7 * (2 * 256 + 3)
 
 
@@ -126,7 +126,7 @@ def test_ctypes_mirrors_match_the_c_structs(tmp_path):
         for fname, ftype in cls._fields_:
             off, size = (int(t) for t in got[f"{cname}.{fname}"])
             assert off == getattr(cls, fname).offset and size == ctypes.sizeof(ftype), (cname, fname, off, size)
-    assert got["version"] == ["2", "nparam", str(_lib.NPARAM), "world", "16"]
+    assert got["version"] == ["3", "nparam", str(_lib.NPARAM), "world", "16"]
 
 
 def test_ctypes_signatures_match_the_header_prototypes():
@@ -175,10 +175,14 @@ def test_tensor_core_kernels_are_tcgen05_and_tma_in_sass():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     s = mod.summary()
-    for k in ("k_enc_fwd_tc", "k_enc_bwd_tc", "k_gram_tc", "k_pz_tc"):
-        assert s[k]["UTCHMMA"] > 0 and s[k]["UTCBAR"] > 0 and s[k]["LDTM"] > 0 and s[k]["UTMALDG"] > 0, (k, dict(s[k]))
-        assert s[k]["stack"] <= 8 and s[k]["regs"] <= 128, (k, dict(s[k]))
-    assert s["k_enc_fwd_tc"]["UTMASTG"] > 0
+    for base in ("k_enc_fwd_tc", "k_enc_bwd_tc", "k_gram_tc", "k_pz_tc"):
+        inst = [k for k in s if k.split("<")[0] == base]  # every template instance (views x CTA pair, products)
+        assert inst, base
+        for k in inst:
+            assert s[k]["UTCHMMA"] > 0 and s[k]["UTCBAR"] > 0 and s[k]["LDTM"] > 0 and s[k]["UTMALDG"] > 0, (k, dict(s[k]))
+            assert s[k]["stack"] <= 8 and s[k]["regs"] <= 128, (k, dict(s[k]))
+    fwd = [k for k in s if k.split("<")[0] == "k_enc_fwd_tc"]
+    assert len(fwd) == 4 and all(s[k]["UTMASTG"] > 0 for k in fwd), fwd  # one / two views x single CTA / CTA pair
     assert all(d["HMMA"] == 0 for d in s.values())
     assert len(s) >= 35
 
