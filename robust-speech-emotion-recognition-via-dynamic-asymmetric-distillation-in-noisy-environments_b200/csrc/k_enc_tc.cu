@@ -75,20 +75,22 @@ struct FwdParams {
     int num_tiles;
 };
 
-// Sum over the 32 lanes of each of the 32 per-lane values: on return lane j holds sum_lanes v[j] (fixed butterfly order).
-// Stage with partner lane^off: the lane whose `off` bit is set keeps the upper half of its live values, sends the lower half.
-__device__ __forceinline__ float transpose_reduce32(float (&v)[32], const int lane) {
+// Sum over the 32 lanes of each of the 16 per-lane values: on return lane L holds sum_lanes v[(L >> 1) & 15] (both lanes of a pair
+// hold the same column; fixed butterfly order).  Stage with partner lane^off (off = 16, 8, 4, 2): the lane whose `off` bit is set
+// keeps the upper half of its live values and sends the lower half; the last stage (off = 1) adds the two halves of the lane sum.
+__device__ __forceinline__ float transpose_reduce16(float (&v)[16], const int lane) {
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
+    for (int off = 16; off >= 2; off >>= 1) {
+        const int n = off >> 1;  // live values after this stage
         const bool upper = (lane & off) != 0;
 #pragma unroll
-        for (int i = 0; i < off; ++i) {
-            const float send = upper ? v[i] : v[i + off];
-            const float keep = upper ? v[i + off] : v[i];
+        for (int i = 0; i < n; ++i) {
+            const float send = upper ? v[i] : v[i + n];
+            const float keep = upper ? v[i + n] : v[i];
             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
         }
     }
-    return v[0];
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -292,8 +294,9 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
     tc::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    // register budget follows the roles (setmaxnreg, one per role branch; 640 threads launch with 96 each):
-    // 128 x 40 (control warps 0-3) + 256 x 136 (converters) + 256 x 96 (epilogue) <= 64 K registers
+    // register budget follows the roles (setmaxnreg, one per role branch).  640 threads launch with 96 registers each and
+    // setmaxnreg.inc can only draw on what the CTA's own warps released (NOT on the SM's unallocated registers), so the roles must
+    // fit in 640 x 96 = 61 440:  128 x 40 (control warps 0-3) + 256 x 152 (converters) + 256 x 64 (epilogue) = 60 416
 
     if (warp == 0) {
         // ===================== TMA producer (weights; in a pair every CTA loads ITS half of the hidden units) =====================
@@ -382,7 +385,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
         }
     } else if (warp >= CONV_WARP0 && warp < CONV_WARP0 + N_CONV_WARPS) {
         // ===================== converters: fp32 x (+ augmentation) -> fp16 hi/lo A operand(s) =====================
-        tc::reg_inc<136>();
+        tc::reg_inc<152>();
         const int cw = warp - CONV_WARP0;
         const bool philox = p.v[NV - 1].ap.noise_src == 1;
         if (NV == 2) {
@@ -405,6 +408,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
         // memory, no serial chain.  Eight warps: warp % 4 = TMEM lane quadrant; NV == 2: warps 12-15 drain the weak / teacher
         // accumulator, 16-19 the strong / student one (both belong to the same tile and are NOT double-buffered: the drain is the
         // exposed part of a tile, so it is spread over twice the warps); NV == 1: the two warps of a quadrant take four chunks each.
+        tc::reg_dec<64>();
         const int ew = warp - EPI_WARP0;
         const int q = ew & 3, sel = ew >> 2;
         const int view = NV == 2 ? sel : 0;
@@ -432,43 +436,47 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (NV == 1 ? acc : (uint32_t)view) * DAD_H;
 #pragma unroll 1  // keep the body small: the unrolled version was instruction-fetch bound
             for (int c = c_begin; c < c_end; ++c) {
-                uint32_t r[32];
-                tc::tmem_ld_32x32(taddr + c * 32, r);
-                tc::tmem_ld_wait();
-                float v[32];
                 uint32_t w = 0;
 #pragma unroll
-                for (int j4 = 0; j4 < 32; j4 += 4) {
-                    const uint4 bs = tc::lds128(bias_a + (uint32_t)(c * 32 + j4) * 4u);
-                    const float bj[4] = {__uint_as_float(bs.x), __uint_as_float(bs.y), __uint_as_float(bs.z), __uint_as_float(bs.w)};
+                for (int hf = 0; hf < 2; ++hf) {  // 16 hidden units at a time: r[16] + v[16] keep the epilogue warps at 64 registers
+                    const int col = c * 32 + hf * 16;
+                    uint32_t r[16];
+                    tc::tmem_ld_32x16(taddr + col, r);
+                    tc::tmem_ld_wait();
+                    float v[16];
 #pragma unroll
-                    for (int uu = 0; uu < 4; ++uu) {
-                        const float pre = fmaf(__uint_as_float(r[j4 + uu]), TC_INV_XW, bj[uu]);  // exact power-of-two unscale, then + bias
-                        const bool pos = pre > 0.f;
-                        w |= (pos ? 1u : 0u) << (j4 + uu);
-                        v[j4 + uu] = (pos && valid && first) ? pre : 0.f;
-                    }
-                }
-                tc::sts32(wstage + (uint32_t)(c - c_begin) * 4u, w);
-                const float s0 = transpose_reduce32(v, lane);
-                float s1 = 0.f;
-                if (split < 32) {  // the 32 rows straddle two utterances: a second masked reduction (warp-uniform branch)
-#pragma unroll
-                    for (int j4 = 0; j4 < 32; j4 += 4) {
-                        const uint4 bs = tc::lds128(bias_a + (uint32_t)(c * 32 + j4) * 4u);
+                    for (int j4 = 0; j4 < 16; j4 += 4) {
+                        const uint4 bs = tc::lds128(bias_a + (uint32_t)(col + j4) * 4u);
                         const float bj[4] = {__uint_as_float(bs.x), __uint_as_float(bs.y), __uint_as_float(bs.z), __uint_as_float(bs.w)};
 #pragma unroll
                         for (int uu = 0; uu < 4; ++uu) {
-                            const float pre = fmaf(__uint_as_float(r[j4 + uu]), TC_INV_XW, bj[uu]);
-                            v[j4 + uu] = (pre > 0.f && valid && !first) ? pre : 0.f;
+                            const float pre = fmaf(__uint_as_float(r[j4 + uu]), TC_INV_XW, bj[uu]);  // exact power-of-two unscale, then + bias
+                            const bool pos = pre > 0.f;
+                            w |= (pos ? 1u : 0u) << (hf * 16 + j4 + uu);
+                            v[j4 + uu] = (pos && valid && first) ? pre : 0.f;
                         }
                     }
-                    s1 = transpose_reduce32(v, lane);
+                    const float s0 = transpose_reduce16(v, lane);
+                    float s1 = 0.f;
+                    if (split < 32) {  // the 32 rows straddle two utterances: a second masked reduction (warp-uniform branch)
+#pragma unroll
+                        for (int j4 = 0; j4 < 16; j4 += 4) {
+                            const uint4 bs = tc::lds128(bias_a + (uint32_t)(col + j4) * 4u);
+                            const float bj[4] = {__uint_as_float(bs.x), __uint_as_float(bs.y), __uint_as_float(bs.z), __uint_as_float(bs.w)};
+#pragma unroll
+                            for (int uu = 0; uu < 4; ++uu) {
+                                const float pre = fmaf(__uint_as_float(r[j4 + uu]), TC_INV_XW, bj[uu]);
+                                v[j4 + uu] = (pre > 0.f && valid && !first) ? pre : 0.f;
+                            }
+                        }
+                        s1 = transpose_reduce16(v, lane);
+                    }
+                    if (live && (lane & 1) == 0) {  // lane L holds column (L >> 1) of this half
+                        V.part[(gidx * 2 + 0) * DAD_H + col + (lane >> 1)] = s0;
+                        V.part[(gidx * 2 + 1) * DAD_H + col + (lane >> 1)] = s1;
+                    }
                 }
-                if (live) {
-                    V.part[(gidx * 2 + 0) * DAD_H + c * 32 + lane] = s0;
-                    V.part[(gidx * 2 + 1) * DAD_H + c * 32 + lane] = s1;
-                }
+                tc::sts32(wstage + (uint32_t)(c - c_begin) * 4u, w);
             }
             tc::tcgen05_fence_before();
             __syncwarp();
