@@ -93,10 +93,21 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 // radius_k: -2 ln2 * sigma^2 folds the noise scale into the radius (r = sigma * sqrt(-2 ln u)); pass -2 ln2 for unit normals.
 // ---------------------------------------------------------------------------------------------
 constexpr float NOISE_UNIT_K = -1.3862943611198906f;  // -2 ln 2
+// flush-to-zero MUFU forms: one instruction each (the non-ftz forms add a denormal-rescue FSETP / FMUL pair per call, and the
+// arguments here are normal by construction)
 __device__ __forceinline__ float fast_sqrt(float x) {
     float y;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(x));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(x));
 }
 // n = GLOBAL frame index (ap.frame_offset + local frame: under data parallelism every rank draws its own part of one field)
 __device__ __forceinline__ uint4 noise_words(unsigned long long seed, uint32_t stream_block, unsigned long long n, uint32_t c4) {
@@ -105,9 +116,9 @@ __device__ __forceinline__ uint4 noise_words(unsigned long long seed, uint32_t s
 // one word -> (radius, cos, sin): the two normals are r*c and r*s
 __device__ __forceinline__ void bm_word(uint32_t w, float radius_k, float& r, float& c, float& s) {
     const float u = __uint_as_float(0x3f800040u | ((w & 0xffffu) << 7)) - 1.0f;  // (k + 0.5) / 65536 in (0, 1)
-    r = fast_sqrt(__log2f(u) * radius_k);
-    const float turns = __uint_as_float(0x3f800000u | ((w >> 16) << 7));         // 1 + a / 65536: sin/cos are 1-periodic in turns
-    __sincosf(6.283185307179586f * turns, &s, &c);
+    r = fast_sqrt(fast_lg2(u) * radius_k);
+    const float turns = __uint_as_float(0x3f800000u | ((w >> 16) << 7));         // 1 + a / 65536
+    fast_sincos(fmaf(turns, 6.283185307179586f, -9.42477796076938f), s, c);      // angle = 2 pi a / 65536 - pi in [-pi, pi)
 }
 struct NoiseBM4 { float r[2], c[2], s[2]; };
 __device__ __forceinline__ void bm4_from_words(uint32_t wa, uint32_t wb, float radius_k, NoiseBM4& o) {

@@ -389,7 +389,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
         const int cw = warp - CONV_WARP0;
         const bool philox = p.v[NV - 1].ap.noise_src == 1;
         if (NV == 2) {
-            if (philox) fwd_convert<2, CTA2, 2, true, 3>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units);
+            if (philox) fwd_convert<2, CTA2, 2, true, 4>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units);
             else fwd_convert<2, CTA2, 2, false, 3>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units);
         } else {
             const int variant = p.v[0].ap.mode == 0 ? 0 : (p.v[0].ap.mode * 2 - 1 + (philox ? 1 : 0));  // 0 | 1,2 weak | 3,4 strong (supplied, philox)

@@ -58,12 +58,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// acquire at cluster scope: the arrivals that complete the phase come from the peer CTA of a pair (remote mbarrier.arrive.release.cluster)
+// Wait on a barrier whose arrivals come from the peer CTA of a pair.  Same form as the local wait (default acquire.cta), which is
+// what CUTLASS's 2-SM pipelines use for exactly this pattern (PipelineUmmaConsumerAsync: transform warps of both CTAs -> leader's
+// MMA warp): the data those arrivals publish was written by the generic proxy and fenced to the async proxy (fence.proxy.async) by
+// its writers, and is read by tcgen05.mma, not by this thread.  The explicit .acquire.cluster form cost a measured 2x on the whole
+// kernel (it invalidates L1 at every wait: ptxas emits CCTL.IVALL for cluster-scope acquires).
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar_addr, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
         "selp.b32 %0, 1, 0, P1;\n\t}\n"
         : "=r"(ok)
         : "r"(bar_addr), "r"(parity)
@@ -98,10 +102,10 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
 }
-// arrive on a barrier that may live in the peer CTA (address from mapa); release at cluster scope orders this thread's earlier
-// shared-memory writes (made visible to the async proxy by fence.proxy.async) before the arrival
+// arrive on a barrier that may live in the peer CTA (address from mapa); the caller has made its shared-memory writes visible to
+// the async proxy (fence.proxy.async) before -- the CUTLASS 2-SM producer-commit form (cutlass/arch/barrier.h umma_arrive_2x1SM_sm0)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 // explicit shared-space stores on 32-bit addresses (a pointer derived from the aligned dynamic-smem base is generic to the

@@ -210,7 +210,7 @@ def test_operand_cache_backward_is_bit_identical(B, T, aug, products, tc_switch)
     # the cache holds the augmented view itself: hi (+ lo) == 8 * aug(x) to 2^-12 (2^-21)
     if aug == 0:
         rec = sum(pl.float() for pl in planes) / 8.0
-        tol = 2e-6 if products == 3 else 2.5e-4
+        tol = 2e-6 if products == 3 else 5e-4  # fp16 half-ulp of the top binade
         assert float((rec.view(B, T, 768) - x).abs().max()) <= tol * float(x.abs().max())
 
 
