@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-dp-check", action="store_true", help="N > 1: skip the out-of-timed-region data-parallel correctness check")
+    ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the few-step timings of the other BASELINE configs (b64, t1000)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="data-parallel exchange: NVLink peer-memory pushes or NCCL")
     ap.add_argument("--operand-cache", default="strong", choices=["none", "strong", "both"],
                     help="which student forwards write the fp16 hi/lo operand cache that feeds the dW kernels by TMA")
@@ -169,6 +171,112 @@ def device_batches(B, T, seed, dev, snr_db=10.0):
     return out[0], out[1]
 
 
+def pin_to_gpu_numa_node(dev):
+    """Bind this process (and so the pages its pinned staging buffers touch first) to the CPUs of the NUMA node the GPU hangs off:
+    with 8 ranks on one box every rank otherwise stages through node 0 (r01: 23 GB/s per rank instead of 54).  Best effort."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(dev)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
+def dp_check(cfg, world, rank, dev, pg, B, gm, exchange, T=64, epoch=45):
+    """Outside the timed region (N > 1): is the data-parallel step the single-process step?  Every rank builds the SAME global batch
+    and RNG draws (same seeds), runs its shard through a world-N engine (supplied-noise mode) and the whole batch through a
+    world-1 engine: 3 CE-only steps, teacher := student, 2 full-stack steps.  Reports the bit-identity of the replicated state
+    across ranks (all-gathered 64-bit checksum of p, t, ema_thr), the largest relative loss difference and weight difference
+    against the world-1 engine, and whether the DACP masks agree (SURVEY.md 8e "Determinism")."""
+    import torch
+    import torch.distributed as dist
+    from dad_b200 import synth
+    from dad_b200.engine import DADStepEngine
+    Bg = B * world
+    clean, noisy = device_batches(Bg, T, 777, dev)
+    g = torch.Generator(device=dev).manual_seed(778)
+    rng = {"drop_clean": (torch.rand(Bg, 256, generator=g, device=dev) >= 0.1).float(),
+           "n_weak": torch.randn(Bg, T, D_IN, generator=g, device=dev), "n_strong": torch.randn(Bg, T, D_IN, generator=g, device=dev),
+           "feat_keep_u": torch.rand(D_IN, generator=g, device=dev),
+           "t_start": torch.randint(0, T - int(T * 0.1) + 1, (Bg,), generator=g, device=dev),
+           "drop_strong": (torch.rand(Bg, 256, generator=g, device=dev) >= 0.1).float()}
+    sl = slice(rank * B, (rank + 1) * B)
+    sh = lambda b: {"net_input": {k: v[sl].contiguous() for k, v in b["net_input"].items()}, "labels": b["labels"][sl].contiguous()}
+    rng_l = {k: (v if k == "feat_keep_u" else v[sl].contiguous()) for k, v in rng.items()}
+    dp = DADStepEngine(cfg, B, T, device=dev, world=world, rank=rank, process_group=pg, gemm_mode=gm, use_graph=True,
+                       noise_mode="supplied", exchange=exchange)
+    one = DADStepEngine(cfg, Bg, T, device=dev, gemm_mode=gm, use_graph=False, noise_mode="supplied")
+    st = synth.init_state(42)
+    loss_rel = 0.0
+    for e in (dp, one):
+        e.load_state_dict(st)
+        e.set_lr(cfg.LEARNING_RATE)
+    for k in range(5):
+        ep = 0 if k < 3 else epoch
+        if k == 3:
+            dp.init_teacher(); one.init_teacher()
+        one.set_inputs(clean, noisy, rng)
+        dp.set_inputs(sh(clean), sh(noisy), rng_l)
+        one.step(ep); dp.step(ep)
+        a, b = dp.losses(), one.losses()
+        for key in a:
+            loss_rel = max(loss_rel, abs(a[key] - b[key]) / max(abs(b[key]), 1e-3))
+    mask_equal = bool(torch.equal(dp.mask, one.mask))
+    w_diff = float(torch.maximum((dp.p - one.p).abs().max(), (dp.t - one.t).abs().max()))
+    flat = torch.cat([dp.p, dp.t, dp.ema_thr]).view(torch.int32).to(torch.int64)
+    h = (flat * (torch.arange(flat.numel(), device=dev) % 65521 + 1)).sum().reshape(1)
+    hs = [torch.zeros_like(h) for _ in range(world)]
+    dist.all_gather(hs, h, group=pg)
+    out = {"state_identical": bool(all(int(x) == int(hs[0]) for x in hs)), "loss_rel": loss_rel, "weights_max_abs_diff_vs_world1": w_diff,
+           "mask_equal": mask_equal, "masked_in": int(dp.nmask.item()), "B_local": B, "B_global": Bg, "T": T, "steps": "3 CE-only + 2 full",
+           "exchange": dp.exchange}
+    dp.close(); one.close()
+    return out
+
+
+def time_small_workload(cfg, dev, gm, B, T, epoch, steps):
+    """A few device-timed steps (graph replay, CUDA events) of another BASELINE config on this GPU: ms per step."""
+    import torch
+    from dad_b200 import synth
+    from dad_b200.engine import DADStepEngine
+    eng = DADStepEngine(cfg, B, T, device=dev, gemm_mode=gm, use_graph=True, noise_mode="philox", seed=42)
+    eng.load_state_dict(synth.init_state(42))
+    clean, noisy = device_batches(B, T, 4321, dev)
+    eng.set_inputs(clean, noisy)
+    eng.set_lr(cfg.LEARNING_RATE)
+    for _ in range(10):
+        eng.step(0)
+    eng.init_teacher()
+    for _ in range(4):
+        eng.step(epoch)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    tot = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        e0.record(); eng.step(epoch); e1.record()
+        torch.cuda.synchronize(dev)
+        tot += e0.elapsed_time(e1)
+    out = {"ms_per_step": tot / steps, "samples_per_s": B / (tot / steps * 1e-3), "B": B, "T": T, "steps": steps,
+           "launches_per_step": eng.launches_per_step, "l2": "flushed between individually timed steps"}
+    eng.close()
+    del eng, clean, noisy
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_reference_steps(B, T, steps, warmup, epoch, threads=None):
     """The reference's CPU step, restated op for op in oracle/dad_oracle.py (the Python reference cannot travel to the
     GPU box; the oracle is bit-identical to it on CPU, tests/test_oracle_golden.py).  Returns seconds per step (median)."""
@@ -204,16 +312,19 @@ def run_reference(args):
     if rank != 0:
         return
     wl = workload(args.workload, args.gpus)
+    # each step = ONE bounded sample of the workload: a B=64 sub-batch (the reference's own batch size, I/config.py:36; its ECDA
+    # materialises [n,n,256] differences, I/utils.py:537 -- 4096 at once would need hundreds of GB).  --steps / --warmup are honoured
+    # as given: a B=64, T=200 step takes ~0.13 s on 16 cores, so the driver's 20 + 5 finish in seconds.
     Bs, T = 64, wl["T"]
-    steps = min(args.steps, 12 if T <= 200 else 3)
-    sec, threads = cpu_reference_steps(Bs, T, steps, min(args.warmup, 3), args.epoch)
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    sec, threads = cpu_reference_steps(Bs, T, steps, warmup, args.epoch)
     val = Bs / sec
     sample = f"each step = one B={Bs}, T={T} sub-batch of the workload (full loss stack, epoch {args.epoch}); {steps} timed steps, median"
     print(json.dumps({
         "impl": "reference", "metric": "DAD train samples/sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": wl["scaling"],
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": wl["scaling"],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["label"], "global_batch": wl["Bg"], "T": T, "device": "host CPU"},
+        "config": {"workload": wl["label"], "global_batch": wl["Bg"], "T": T, "device": "host CPU", "sub_batch": Bs},
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -229,6 +340,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = pin_to_gpu_numa_node(dev)
     pg = None
     if world > 1:
         import torch.distributed as dist
@@ -285,6 +397,9 @@ def run_ours(args):
     launches = eng.launches_per_step * args.steps
     losses = eng.losses()
     value = Bg / (ms * 1e-3)
+    cfg_snapshot = {"operand_cache": eng.operand_cache, "exchange": eng.exchange, "fused_noisy": eng.fused_noisy,
+                    "cta_pair": bool(_lib.lib().dad_tc_get_cta_pair()), "bwd_products": eng.bwd_products}
+    dtype_s = "f32" if args.gemm != "tc" else (f"f32 (scaled fp16 hi/lo split: 3 tcgen05 products per forward GEMM, {eng.bwd_products} per dW GEMM, fp32 accumulate)")
 
     # ---- the encoder launches of one step, each timed ALONE (roofline).  Every variant is captured into its own CUDA graph and the
     # graph is replayed under CUDA events, so the figure is device time of the launcher's kernels (GEMM kernel + its helpers:
@@ -362,6 +477,7 @@ def run_ours(args):
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D of the step's inputs + D2H of its losses inside
     e2e = None
+    e2e_resident = None
     if not args.no_e2e:
         hb = []
         for b in (clean, noisy):
@@ -384,12 +500,58 @@ def run_ours(args):
                 eng.prefetch_inputs(hb[0], hb[1])
             eng.losses()  # D2H read of the step's losses (sync)
         sync()
-        dt = (time.perf_counter() - t0) / n_e2e
+        dt_local = (time.perf_counter() - t0) / n_e2e
+        dt = dt_local
+        h2d_rates = [h2d / dt_local / 1e9]
         if world > 1:
             t = torch.tensor([dt], device=dev)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             dt = float(t)
-        e2e = {"value": Bg / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20, "ms_per_step": dt * 1e3}
+            rates = [torch.zeros(1, device=dev) for _ in range(world)]
+            torch.distributed.all_gather(rates, torch.tensor([h2d / dt_local / 1e9], device=dev))
+            h2d_rates = [float(r) for r in rates]
+        e2e = {"value": Bg / dt, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20, "ms_per_step": dt * 1e3,
+               "h2d_GBps_per_rank": h2d_rates, "numa_node_of_rank0": numa_node}
+        del hb
+        # the trainers' default path (cfg.DAD_DEVICE_DATA): the split's utterances stay in HBM and every batch is assembled ON the
+        # device straight into the engine's input buffers (dataload.DeviceUtteranceLoader -> dad_gather_pad) -- per step one gather
+        # of each domain's batch, the step, and the D2H read of its losses; no host->device feature traffic at all
+        from dad_b200 import dataload
+        ld_c = dataload.DeviceUtteranceLoader.from_device_batch(clean, batch_size=B, sink=lambda b_, t_: eng.input_views("clean", b_, t_))
+        ld_n = dataload.DeviceUtteranceLoader.from_device_batch(noisy, batch_size=B, sink=lambda b_, t_: eng.input_views("noisy", b_, t_), use_labels=False)
+        ids = torch.arange(B)
+        for _ in range(2):
+            eng.set_inputs(ld_c.collate(ids), ld_n.collate(ids)); eng.step(args.epoch); eng.losses()
+        sync()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            eng.set_inputs(ld_c.collate(ids), ld_n.collate(ids))
+            eng.step(args.epoch)
+            eng.losses()
+        sync()
+        dtr = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([dtr], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            dtr = float(t)
+        e2e_resident = {"value": Bg / dtr, "unit": "samples/s", "ms_per_step": dtr * 1e3, "h2d_bytes_per_step": 2 * B * 8,
+                        "d2h_bytes_per_step": 20, "path": "DeviceUtteranceLoader.collate (dad_gather_pad into the engine's buffers) -> set_inputs -> step -> losses()"}
+        del ld_c, ld_n
+
+    # ---- N > 1: correctness signal of the data-parallel step, outside the timed region
+    dpc = None
+    if world > 1 and not args.no_dp_check:
+        eng.close()
+        dpc = dp_check(cfg, world, rank, dev, pg, B, gm, args.exchange)
+    # ---- the other single-GPU BASELINE configs, a few steps each (driver-run numbers for configs[1] and configs[4])
+    extra = None
+    if world == 1 and rank == 0 and not args.no_extra and args.workload == "g4096":
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+        extra = {"b64": time_small_workload(cfg, dev, gm, 64, 200, args.epoch, 20),
+                 "t1000": time_small_workload(cfg, dev, gm, 512, 1000, args.epoch, 5)}
+        eng = None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -397,18 +559,22 @@ def run_ours(args):
         cpu = {"value": 64 / sec, "unit": "samples/s", "cores": threads, "kind": "port",
                "sample": f"oracle port of the reference step, B=64, T={T}, full loss stack, median of {8 if T <= 200 else 2} steps"}
     if rank == 0:
+        exch = dpc["exchange"] if dpc else ("none" if world == 1 else args.exchange)
         print(json.dumps({
             "metric": "DAD train samples/sec", "value": value, "unit": "samples/s", "utterances_per_s": 2 * value, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
-            "dtype": "f32 (scaled fp16 hi/lo split, 3 tcgen05 products per GEMM, fp32 accumulate)" if args.gemm == "tc" else "f32", "data": "synthetic",
+            "dtype": dtype_s, "data": "synthetic",
             "config": {"workload": wl["label"], "global_batch": Bg, "per_gpu_batch": B, "T": T, "parallelism": f"dp{world}",
-                       "noise": "in-kernel Philox", "cuda_graph": not args.no_graph, "operand_cache": eng.operand_cache, "exchange": eng.exchange,
+                       "noise": "in-kernel Philox", "cuda_graph": not args.no_graph, "operand_cache": cfg_snapshot["operand_cache"],
+                       "exchange": cfg_snapshot["exchange"], "fused_noisy_forward": cfg_snapshot["fused_noisy"],
+                       "cta_pair": cfg_snapshot["cta_pair"], "bwd_products": cfg_snapshot["bwd_products"],
                        "l2": "inputs >> L2 (126 MB)" if not small else "L2 flushed (256 MB write) between individually timed steps"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "losses_last_step": losses,
+            "clocks": clocks, "e2e": e2e, "e2e_resident": e2e_resident, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "losses_last_step": losses, "dp_check": dpc, "extra_workloads": extra,
         }))
     if world > 1:
-        eng.close()
+        if eng is not None:
+            eng.close()
         DADStepEngine.shutdown_process_group()
 
 

@@ -35,8 +35,9 @@
 namespace {
 
 constexpr int BM = 128, BK = 32, KB = DAD_D / BK;  // 24 k-blocks of 32
-constexpr int FWD_THREADS = 640;
-constexpr int CONV_WARP0 = 4, N_CONV_WARPS = 8, EPI_WARP0 = 12, N_EPI_WARPS = 8;
+constexpr int FWD_THREADS = 896;                                          // 4 control + 16 converter + 8 epilogue warps
+constexpr int FWD_CONV_WARPS = 16, FWD_EPI_WARP0 = 20, N_EPI_WARPS = 8;
+constexpr int CONV_WARP0 = 4, N_CONV_WARPS = 8, EPI_WARP0 = 12;           // backward kernel (512 threads)
 constexpr uint32_t A_BYTES = BM * BK * 2;  // 8 KB: one of hi / lo of one view, [128 frames][32 k] fp16, 64-byte rows, SWIZZLE_64B
 constexpr uint32_t TMEM_COLS = 512;        // two 128 x 256 fp32 accumulators
 
@@ -94,152 +95,175 @@ __device__ __forceinline__ float transpose_reduce16(float (&v)[16], const int la
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Converter warp body of the forward kernel.  Thread (cw, lane): float4 column c4 = lane & 7 of the 32-wide k-block and the four
-// tile rows cw*16 + g + 4 i (g = lane >> 3, i = 0..3):
+// Converter warp body of the forward kernel.  16 converter warps in two TEAMS of eight that alternate k-blocks (team = cw >> 3
+// takes the k-blocks of its parity; KB = 24 is even, so the parity of a k-block is the parity of its pipeline slot as well).
+// Inside a team, thread (w8 = cw & 7, lane): float4 column c4 = lane & 7 of the 32-wide k-block and the four tile rows
+// w8*16 + g + 4 i (g = lane >> 3, i = 0..3):
 //   - one warp-wide LDG.128 reads four fully used 128-byte row segments; the warp's stores of one i cover four CONSECUTIVE
 //     64-byte tile rows (256 contiguous, swizzle-permuted bytes): two shared-memory wavefronts per 8-byte store, no conflicts;
-//   - every address is  base + compile-time immediate;
-//   - NSET register sets rotate over the flat (tile, k-block) iteration space (KB = 24 is a multiple of NSET, so a group never
-//     straddles a tile): the loads of the next NSET-1 k-blocks are in flight while one is converted;
-//   - rows that contribute zeros (beyond N, or inside the temporal mask span of the strong view) are flagged per tile.
+//   - addresses advance incrementally (one 64-bit pointer per tile, compile-time offsets inside a group of NSET k-blocks); the
+//     first version re-derived tile / row / bounds from the flat iteration index and spent ~45 of its ~200 instructions per
+//     k-block on that (ncu source view), with two converter warps per scheduler at 55 % issue utilisation -- hence two teams:
+//     twice the warps in flight, the same 16 elements per thread and k-block to amortise the wait / fence / arrive over;
+//   - NSET register sets rotate over the team's k-blocks (12 per tile, a multiple of NSET): the loads of its next NSET-1
+//     k-blocks, which may belong to the CTA's next tile, are in flight while one is converted;
+//   - rows beyond N are loaded as zeros and otherwise treated like any row (their accumulator rows are never read, the operand-
+//     cache store clips them); rows inside the temporal mask span of the strong view are multiplied by 0 instead of TC_XS.
 // NV == 1: MODE 0 clean, 1 weak, 2 strong (I/utils.py:328-375).  NV == 2: view 0 = weak, view 1 = strong of the same x; in the
 // Philox mode both views' normals come from the same Philox block (dad_common.cuh).  PHILOX: in-kernel noise, else supplied tensors.
 // ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pin_reg(uint32_t v) {  // opaque to the optimiser: computed once, kept in a register (no rematerialisation)
+    asm volatile("" : "+r"(v));
+    return v;
+}
 template <int NV, bool CTA2, int MODE, bool PHILOX, int NSET>
 __device__ __forceinline__ void fwd_convert(const FwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* afull, uint64_t* empty, const int cw,
                                             const int lane, const uint32_t rank, const int unit0, const int ustride, const int n_units) {
     using Cfg = FwdCfg<NV, CTA2>;
     constexpr int STAGES = Cfg::STAGES;
-    static_assert(KB % NSET == 0, "a group of NSET k-blocks must not straddle a tile");
+    constexpr int KT = KB / 2;          // k-blocks of one team per tile
+    constexpr int GROUPS = KT / NSET;
+    static_assert(KB % 2 == 0 && KT % NSET == 0, "a group of NSET team k-blocks must not straddle a tile");
     constexpr bool WEAK = NV == 2 || MODE == 1, STRONG = NV == 2 || MODE == 2;
+    const int team = cw >> 3, w8 = cw & 7;
     const int c4 = lane & 7, g = lane >> 3;
-    const int rbase = cw * 16 + g;
+    const int rbase = w8 * 16 + g;  // tile rows rbase + 4 i
     const uint32_t a_sw = ((uint32_t)rbase >> 1) & 3u, c16 = (uint32_t)c4 >> 1;
-    const uint32_t sbase = (uint32_t)rbase * 64u + (uint32_t)(c4 & 1) * 8u;
-    const uint32_t sw_even = (c16 ^ a_sw) << 4, sw_odd = (c16 ^ a_sw ^ 2u) << 4;  // ((rbase + 4 i) >> 1) & 3 = a_sw ^ ((i & 1) << 1)
+    const uint32_t sbase = tc::smem_u32(smem) + Cfg::OFF_A + (uint32_t)rbase * 64u + (uint32_t)(c4 & 1) * 8u;
+    // ((rbase + 4 i) >> 1) & 3 = a_sw ^ ((i & 1) << 1): two distinct swizzled offsets, + i * 256
+    const uint32_t so_even = pin_reg(sbase + ((c16 ^ a_sw) << 4)), so_odd = pin_reg(sbase + 256u + ((c16 ^ a_sw ^ 2u) << 4));
     const AugParams& apw = p.v[0].ap;        // weak view (NV == 2) or the single view
     const AugParams& aps = p.v[NV - 1].ap;   // strong view (NV == 2) or the single view
-    const uint32_t smem_a = tc::smem_u32(smem);
-    const uint32_t full_remote = CTA2 ? tc::mapa(tc::smem_u32(full), 0) : 0u;  // the leader CTA's full[] (cluster address)
+    const uint32_t full_addr = pin_reg(CTA2 ? tc::mapa(tc::smem_u32(full), 0) : tc::smem_u32(full));  // the (leader CTA's) full[]
+    const uint32_t empty_addr = pin_reg(tc::smem_u32(empty)), afull_addr = pin_reg(tc::smem_u32(afull));
     const unsigned long long seed = ((NV == 2 || MODE != 0) && PHILOX) ? aug_seed(aps) : 0ull;
     const float rk_w = NOISE_UNIT_K * apw.sigma * apw.sigma, rk_s = NOISE_UNIT_K * aps.sigma * aps.sigma;
     const uint32_t blk = (uint32_t)(aps.stream >> 1);
     const bool odd_stream = (aps.stream & 1ull) != 0;  // NV == 1: which word pair of the block this view uses
-    const unsigned long long foff = (unsigned long long)aps.frame_offset;
-    const int n_my = n_units > unit0 ? (n_units - unit0 + ustride - 1) / ustride : 0;
-    const int n_iter = n_my * KB;
+    const bool has_keep = STRONG && aps.feat_keep != nullptr;
+    const bool has_span = STRONG && aps.t_start != nullptr && aps.mask_len > 0;
+    const bool cache = p.cache != 0;
+    if (unit0 >= n_units) return;
 
-    auto tile_of = [&](int it) {
-        const int u = unit0 + (it / KB) * ustride;
-        return CTA2 ? u * 2 + (int)rank : u;
+    // a tile's state: pointer to (row rbase, column team*32 + c4*4) of the tile and the in-range bits of the four rows
+    auto tile_of = [&](int u) { return CTA2 ? u * 2 + (int)rank : u; };
+    auto tile_ptr = [&](int tile) { return p.x + ((int64_t)tile * BM + rbase) * DAD_D + team * BK + c4 * 4; };
+    auto tile_valid = [&](int tile) -> uint32_t {
+        const int64_t r0 = (int64_t)tile * BM + rbase;
+        return (r0 < p.N ? 1u : 0u) | (r0 + 4 < p.N ? 2u : 0u) | (r0 + 8 < p.N ? 4u : 0u) | (r0 + 12 < p.N ? 8u : 0u);
     };
-    // bits 0-3: row rbase + 4 i lies beyond N (zeros in every view); bits 4-7: inside the temporal mask span (strong view only)
-    auto row_flags = [&](int tile) -> uint32_t {
-        const int64_t row0 = (int64_t)tile * BM + rbase;
-        uint32_t z = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int64_t n = row0 + 4 * i;
-            if (n >= p.N) z |= 1u << i;
-            else if (STRONG && aps.t_start && aps.mask_len > 0) {
-                const uint32_t b = (uint32_t)n / (uint32_t)p.T, t = (uint32_t)n - b * (uint32_t)p.T;  // N < 2^31 on this path (launch check)
-                const int s0 = __ldg(aps.t_start + b);
-                if ((int)t >= s0 && (int)t < s0 + aps.mask_len) z |= 16u << i;
-            }
-        }
-        return z;
-    };
-    auto load = [&](float4 (&dst)[4], int it) {
-        const int tile = tile_of(it), kb = it % KB;
-        const int64_t row0 = (int64_t)tile * BM + rbase;
-        const float* src = p.x + row0 * DAD_D + kb * BK + c4 * 4;
+    auto load = [&](float4 (&dst)[4], const float* src, uint32_t valid) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            dst[i] = (row0 + 4 * i < p.N) ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)(4 * i) * DAD_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            dst[i] = ((valid >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(src + (4 * i) * DAD_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    // zeroed rows are multiplied by 0 instead of TC_XS: no branch, no select
-    auto store_row = [&](uint32_t a_hi, const float4& v, int i, bool zero) {
-        const float sc = zero ? 0.f : TC_XS;
+    auto store_row = [&](uint32_t a_hi, const float4& v, float sc) {
         uint32_t h01, l01, h23, l23;
         tc::split2_f16(v.x * sc, v.y * sc, h01, l01);
         tc::split2_f16(v.z * sc, v.w * sc, h23, l23);
-        const uint32_t off = sbase + (uint32_t)i * 256u + ((i & 1) ? sw_odd : sw_even);
-        tc::sts64(a_hi + off, h01, h23);
-        tc::sts64(a_hi + A_BYTES + off, l01, l23);
-    };
-    auto convert = [&](float4 (&cur)[4], int it, uint32_t flags) {
-        const int tile = tile_of(it), kb = it % KB;
-        const uint32_t s = (uint32_t)it % STAGES, ph = ((uint32_t)it / STAGES) & 1u;
-        tc::mbar_wait(&empty[s], ph ^ 1u);
-        const uint32_t a0 = smem_a + s * Cfg::STAGE_BYTES + Cfg::OFF_A;  // view 0 hi (lo at + A_BYTES); view 1 at + 2 A_BYTES
-        const int64_t row0 = (int64_t)tile * BM + rbase;
-        float4 keep = make_float4(1.f, 1.f, 1.f, 1.f);
-        const bool has_keep = STRONG && aps.feat_keep != nullptr;
-        if (has_keep) keep = __ldg(reinterpret_cast<const float4*>(aps.feat_keep + kb * BK + c4 * 4));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int64_t n = row0 + 4 * i;
-            const bool zrow = (flags >> i) & 1u, zspan = (flags >> (4 + i)) & 1u;
-            float4 vw = cur[i], vs = cur[i];
-            if (WEAK || STRONG) {
-                if (PHILOX) {
-                    const uint4 w = noise_words(seed, blk, (unsigned long long)n + foff, (uint32_t)(kb * (BK / 4) + c4));
-                    NoiseBM4 z;
-                    if (NV == 2) {
-                        bm4_from_words(w.x, w.y, rk_w, z);
-                        vw = bm4_add(z, vw);
-                        bm4_from_words(w.z, w.w, rk_s, z);
-                        vs = bm4_add(z, vs);
-                    } else {
-                        bm4_from_words(odd_stream ? w.z : w.x, odd_stream ? w.w : w.y, rk_s, z);
-                        vs = bm4_add(z, vs);
-                        vw = vs;
-                    }
-                } else {
-                    // parity mode: supplied unit normals, out = x + (n * sigma) with two fp32 roundings (bit-exact vs I/utils.py:330,338)
-                    const int64_t e = n * DAD_D + kb * BK + c4 * 4;
-                    if (NV == 2) {
-                        const float4 nw = zrow ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(apw.noise + e));
-                        vw.x = aug_add_noise(vw.x, nw.x, apw.sigma); vw.y = aug_add_noise(vw.y, nw.y, apw.sigma);
-                        vw.z = aug_add_noise(vw.z, nw.z, apw.sigma); vw.w = aug_add_noise(vw.w, nw.w, apw.sigma);
-                    }
-                    const float4 ns = zrow ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(aps.noise + e));
-                    vs.x = aug_add_noise(vs.x, ns.x, aps.sigma); vs.y = aug_add_noise(vs.y, ns.y, aps.sigma);
-                    vs.z = aug_add_noise(vs.z, ns.z, aps.sigma); vs.w = aug_add_noise(vs.w, ns.w, aps.sigma);
-                    if (NV == 1) vw = vs;
-                }
-                if (has_keep) {
-                    vs.x = __fmul_rn(vs.x, keep.x); vs.y = __fmul_rn(vs.y, keep.y); vs.z = __fmul_rn(vs.z, keep.z); vs.w = __fmul_rn(vs.w, keep.w);
-                }
-            }
-            if (NV == 2) {
-                store_row(a0, vw, i, zrow);
-                store_row(a0 + 2 * A_BYTES, vs, i, zrow || zspan);
-            } else {
-                store_row(a0, vs, i, zrow || zspan);
-            }
-        }
-        tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma / TMA (async proxy)
-        __syncwarp();
-        if (lane == 0) {
-            if (CTA2) tc::mbar_arrive_cluster(full_remote + s * 8u);
-            else tc::mbar_arrive(&full[s]);
-            if (p.cache) tc::mbar_arrive(&afull[s]);
-        }
+        tc::sts64(a_hi, h01, h23);
+        tc::sts64(a_hi + A_BYTES, l01, l23);
     };
 
-    if (n_iter == 0) return;
+    uint32_t s = (uint32_t)team % STAGES, ph = 0;  // pipeline stage / phase of the team's k-block being converted (advance by 2)
+    int u = unit0;
+    int tile = tile_of(u);
+    const float* ptr_cur = tile_ptr(tile);
+    uint32_t v_cur = tile_valid(tile);
     float4 buf[NSET][4];
 #pragma unroll
-    for (int j = 0; j < NSET - 1; ++j) load(buf[j], j);
-    uint32_t flags = 0;
-    for (int it = 0; it < n_iter; it += NSET) {
-        if (it % KB == 0) flags = row_flags(tile_of(it));
+    for (int j = 0; j < NSET - 1; ++j) load(buf[j], ptr_cur + j * 2 * BK, v_cur);
+    for (; u < n_units; u += ustride) {
+        tile = tile_of(u);
+        const bool more = u + ustride < n_units;
+        const int tile_n = tile_of(u + ustride);
+        const float* ptr_next = more ? tile_ptr(tile_n) : ptr_cur;
+        const uint32_t v_next = more ? tile_valid(tile_n) : 0u;
+        const int64_t n0 = (int64_t)tile * BM + rbase;  // local frame index of row 0 (row i: + 4 i)
+        uint32_t zspan = 0;  // bit i: row i lies inside the temporal mask span (strong view)
+        if (has_span) {
 #pragma unroll
-        for (int j = 0; j < NSET; ++j) {
-            if (it + j + NSET - 1 < n_iter) load(buf[(j + NSET - 1) % NSET], it + j + NSET - 1);
-            convert(buf[j], it + j, flags);
+            for (int i = 0; i < 4; ++i) {
+                const int64_t n = n0 + 4 * i;
+                if (n < p.N) {
+                    const uint32_t bb = (uint32_t)n / (uint32_t)p.T, t = (uint32_t)n - bb * (uint32_t)p.T;  // N < 2^31 on this path (launch check)
+                    const int st0 = __ldg(aps.t_start + bb);
+                    if ((int)t >= st0 && (int)t < st0 + aps.mask_len) zspan |= 1u << i;
+                }
+            }
         }
+        const unsigned long long gn0 = (unsigned long long)n0 + (unsigned long long)aps.frame_offset;
+        const float* nzw = (!PHILOX && NV == 2) ? apw.noise + n0 * DAD_D + team * BK + c4 * 4 : nullptr;
+        const float* nzs = (!PHILOX && (WEAK || STRONG)) ? aps.noise + n0 * DAD_D + team * BK + c4 * 4 : nullptr;
+#pragma unroll 1
+        for (int grp = 0; grp < GROUPS; ++grp) {
+            const bool last = grp == GROUPS - 1;
+#pragma unroll
+            for (int j = 0; j < NSET; ++j) {
+                const int k = grp * NSET + j;   // the team's k-th k-block of this tile: kb = 2 k + team
+                // ---- prefetch the team's k-block k + NSET - 1 (of the next tile in the last group)
+                if (j == 0 || !last) load(buf[(j + NSET - 1) % NSET], ptr_cur + (k + NSET - 1) * 2 * BK, v_cur);
+                else load(buf[(j + NSET - 1) % NSET], ptr_next + (j - 1) * 2 * BK, v_next);
+                // ---- convert k-block kb
+                tc::mbar_wait_addr(empty_addr + s * 8u, ph ^ 1u);
+                const uint32_t stage_off = s * Cfg::STAGE_BYTES;
+                float4 keep = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (has_keep) keep = __ldg(reinterpret_cast<const float4*>(aps.feat_keep + (2 * k + team) * BK + c4 * 4));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 vw = buf[j][i], vs = buf[j][i];
+                    if (WEAK || STRONG) {
+                        if (PHILOX) {
+                            const uint4 w = noise_words(seed, blk, gn0 + 4 * i, (uint32_t)((2 * k + team) * (BK / 4) + c4));
+                            NoiseBM4 z;
+                            if (NV == 2) {
+                                bm4_from_words(w.x, w.y, rk_w, z);
+                                vw = bm4_add(z, vw);
+                                bm4_from_words(w.z, w.w, rk_s, z);
+                                vs = bm4_add(z, vs);
+                            } else {
+                                bm4_from_words(odd_stream ? w.z : w.x, odd_stream ? w.w : w.y, rk_s, z);
+                                vs = bm4_add(z, vs);
+                            }
+                        } else {
+                            // parity mode: supplied unit normals, out = x + (n * sigma) with two fp32 roundings (bit-exact vs I/utils.py:330,338)
+                            const bool inr = (v_cur >> i) & 1u;
+                            const int64_t e = (int64_t)(4 * i) * DAD_D + k * 2 * BK;
+                            if (NV == 2) {
+                                const float4 nw = inr ? __ldg(reinterpret_cast<const float4*>(nzw + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                vw.x = aug_add_noise(vw.x, nw.x, apw.sigma); vw.y = aug_add_noise(vw.y, nw.y, apw.sigma);
+                                vw.z = aug_add_noise(vw.z, nw.z, apw.sigma); vw.w = aug_add_noise(vw.w, nw.w, apw.sigma);
+                            }
+                            const float4 ns = inr ? __ldg(reinterpret_cast<const float4*>(nzs + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            vs.x = aug_add_noise(vs.x, ns.x, aps.sigma); vs.y = aug_add_noise(vs.y, ns.y, aps.sigma);
+                            vs.z = aug_add_noise(vs.z, ns.z, aps.sigma); vs.w = aug_add_noise(vs.w, ns.w, aps.sigma);
+                        }
+                        if (has_keep) {
+                            vs.x = __fmul_rn(vs.x, keep.x); vs.y = __fmul_rn(vs.y, keep.y); vs.z = __fmul_rn(vs.z, keep.z); vs.w = __fmul_rn(vs.w, keep.w);
+                        }
+                    }
+                    const uint32_t a_row = stage_off + ((i & 1) ? so_odd : so_even) + (uint32_t)(i >> 1) * 512u;  // rows + 4 i: + i * 256 bytes
+                    const float sc_s = (STRONG && ((zspan >> i) & 1u)) ? 0.f : TC_XS;
+                    if (NV == 2) {
+                        store_row(a_row, vw, TC_XS);
+                        store_row(a_row + 2 * A_BYTES, vs, sc_s);
+                    } else {
+                        store_row(a_row, vs, sc_s);
+                    }
+                }
+                tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma / TMA (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    if (CTA2) tc::mbar_arrive_cluster(full_addr + s * 8u);
+                    else tc::mbar_arrive_addr(full_addr + s * 8u);
+                    if (cache) tc::mbar_arrive_addr(afull_addr + s * 8u);
+                }
+                s += 2;
+                if (s >= (uint32_t)STAGES) { s -= STAGES; ph ^= 1u; }
+            }
+        }
+        ptr_cur = ptr_next;
+        v_cur = v_next;
     }
 }
 
@@ -276,8 +300,8 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            tc::mbar_init(&full[s], 1 + N_CONV_WARPS * NCTA);
-            tc::mbar_init(&afull[s], N_CONV_WARPS);
+            tc::mbar_init(&full[s], 1 + (FWD_CONV_WARPS / 2) * NCTA);  // one TEAM of eight converter warps (per CTA) fills a stage
+            tc::mbar_init(&afull[s], FWD_CONV_WARPS / 2);
             tc::mbar_init(&empty[s], 1 + (p.cache ? 1 : 0));
         }
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], N_EPI_WARPS * NCTA); }
@@ -294,13 +318,13 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
     tc::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    // register budget follows the roles (setmaxnreg, one per role branch).  640 threads launch with 96 registers each and
+    // register budget follows the roles (setmaxnreg, one per role branch).  896 threads launch with 72 registers each and
     // setmaxnreg.inc can only draw on what the CTA's own warps released (NOT on the SM's unallocated registers), so the roles must
-    // fit in 640 x 96 = 61 440:  128 x 40 (control warps 0-3) + 256 x 152 (converters) + 256 x 64 (epilogue) = 60 416
+    // fit in 896 x 72 = 64 512:  128 x 32 (control warps 0-3) + 512 x 88 (converters) + 256 x 56 (epilogue) = 63 488
 
     if (warp == 0) {
         // ===================== TMA producer (weights; in a pair every CTA loads ITS half of the hidden units) =====================
-        tc::reg_dec<40>();
+        tc::reg_dec<32>();
         if (lane == 0) {
             const uint32_t full_remote = CTA2 ? tc::mapa(tc::smem_u32(full), 0) : 0u;
             uint32_t it = 0;
@@ -338,7 +362,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (the leader CTA's for a pair) =====================
-        tc::reg_dec<40>();
+        tc::reg_dec<32>();
         if (!CTA2 || rank == 0) {
             constexpr uint32_t idesc = tc::make_idesc_f16(CTA2 ? 256 : 128, DAD_H, 0, 0);
             uint32_t it = 0, ti = 0;
@@ -383,33 +407,33 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
                 }
             }
         }
-    } else if (warp >= CONV_WARP0 && warp < CONV_WARP0 + N_CONV_WARPS) {
+    } else if (warp >= CONV_WARP0 && warp < CONV_WARP0 + FWD_CONV_WARPS) {
         // ===================== converters: fp32 x (+ augmentation) -> fp16 hi/lo A operand(s) =====================
-        tc::reg_inc<152>();
+        tc::reg_inc<88>();
         const int cw = warp - CONV_WARP0;
         const bool philox = p.v[NV - 1].ap.noise_src == 1;
         if (NV == 2) {
-            if (philox) fwd_convert<2, CTA2, 2, true, 4>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units);
-            else fwd_convert<2, CTA2, 2, false, 3>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units);
+            if (philox) fwd_convert<2, CTA2, 2, true, 2>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units);
+            else fwd_convert<2, CTA2, 2, false, 2>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units);
         } else {
             const int variant = p.v[0].ap.mode == 0 ? 0 : (p.v[0].ap.mode * 2 - 1 + (philox ? 1 : 0));  // 0 | 1,2 weak | 3,4 strong (supplied, philox)
             switch (variant) {
-                case 0: fwd_convert<1, CTA2, 0, false, 6>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
-                case 1: fwd_convert<1, CTA2, 1, false, 4>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
-                case 2: fwd_convert<1, CTA2, 1, true, 4>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
-                case 3: fwd_convert<1, CTA2, 2, false, 4>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
-                default: fwd_convert<1, CTA2, 2, true, 4>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
+                case 0: fwd_convert<1, CTA2, 0, false, 3>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
+                case 1: fwd_convert<1, CTA2, 1, false, 2>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
+                case 2: fwd_convert<1, CTA2, 1, true, 3>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
+                case 3: fwd_convert<1, CTA2, 2, false, 2>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
+                default: fwd_convert<1, CTA2, 2, true, 3>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
             }
         }
-    } else if (warp >= EPI_WARP0) {
+    } else if (warp >= FWD_EPI_WARP0) {
         // ===================== epilogue: TMEM -> bias + ReLU + mask -> ReLU bits + pooled partial sums =====================
         // Lane = frame row (tcgen05.ld 32x32b), 32 hidden units per chunk.  The per-utterance column sums over the 32 rows are a
         // register transpose-reduce: 31 shuffles + 31 adds per 32 x 32 block leave lane j with the sum of column j -- no shared
-        // memory, no serial chain.  Eight warps: warp % 4 = TMEM lane quadrant; NV == 2: warps 12-15 drain the weak / teacher
-        // accumulator, 16-19 the strong / student one (both belong to the same tile and are NOT double-buffered: the drain is the
+        // memory, no serial chain.  Eight warps: warp % 4 = TMEM lane quadrant; NV == 2: warps 20-23 drain the weak / teacher
+        // accumulator, 24-27 the strong / student one (both belong to the same tile and are NOT double-buffered: the drain is the
         // exposed part of a tile, so it is spread over twice the warps); NV == 1: the two warps of a quadrant take four chunks each.
-        tc::reg_dec<64>();
-        const int ew = warp - EPI_WARP0;
+        tc::reg_dec<56>();
+        const int ew = warp - FWD_EPI_WARP0;
         const int q = ew & 3, sel = ew >> 2;
         const int view = NV == 2 ? sel : 0;
         const int c_begin = NV == 2 ? 0 : sel * 4, c_end = NV == 2 ? 8 : sel * 4 + 4;
@@ -500,7 +524,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
         // The hi A tile of a stage ([128 frames][32 k] fp16, SWIZZLE_64B) is exactly one TMA box of xs_hi [N][768] (and the lo tile
         // of xs_lo when the 3-product backward is selected); the slot is handed back (second arrival on empty[s]) once the bulk
         // store has finished READING shared memory.  Frames beyond N are clipped by the tensor map.
-        tc::reg_dec<40>();
+        tc::reg_dec<32>();
         if (p.cache && lane == 0) {
             tc::prefetch_tmap(&tm_xhi);
             if (p.cache > 1) tc::prefetch_tmap(&tm_xlo);
@@ -523,7 +547,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
             tc::bulk_wait0();
         }
     } else {
-        tc::reg_dec<40>();  // warp 2 (TMEM allocator)
+        tc::reg_dec<32>();  // warp 2 (TMEM allocator)
     }
     tc::tcgen05_fence_before();
     __syncthreads();

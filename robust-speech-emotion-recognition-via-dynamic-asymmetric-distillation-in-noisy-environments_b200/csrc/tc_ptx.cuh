@@ -52,6 +52,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 template <bool CLUSTER> __device__ __forceinline__ void mbar_wait_guarded(uint32_t a, uint32_t parity);
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_guarded<false>(smem_u32(bar), parity); }
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) { mbar_wait_guarded<false>(bar_addr, parity); }
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -146,19 +146,47 @@ class DeviceUtteranceLoader(UtteranceLoader):
     (csrc/k_aug.cu k_gather_pad): no per-sample Python loop, no pageable host->device copy per step
     (I/dataload_clean.py:170-193, I/train.py:398,405).  An IEMOCAP training fold is ~2.2 GB of the 180 GB."""
 
-    def __init__(self, fs, indices, batch_size, shuffle, use_labels=True, with_id=True, generator=None, device=None):
+    def __init__(self, fs, indices, batch_size, shuffle, use_labels=True, with_id=True, generator=None, device=None, sink=None):
         super().__init__(fs, indices, batch_size, shuffle, use_labels, with_id, generator)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.feats_dev = self.feats.to(self.device, non_blocking=True)
         self.offsets_dev = self.offsets.to(self.device)
         self.sizes_dev = self.sizes.to(torch.int32).to(self.device)
         self.labels_dev = self.labels.to(self.device)
+        # sink(B, T) -> (x [B,T,768] f32, pad [B,T] u8): where the gathered batch is WRITTEN.  The trainers point it at the step
+        # engine's own input buffers (DADStepEngine.input_views), so a batch is assembled in place and set_inputs copies nothing.
+        self.sink = sink
+
+    @classmethod
+    def from_device_batch(cls, batch, batch_size, sink=None, use_labels=True):
+        """A resident split made of the utterances of one padded device batch [B,T,768] (benchmarks / tests): every utterance keeps
+        its valid length; the feature rows are a view of the batch (no copy)."""
+        self = cls.__new__(cls)
+        x = batch["net_input"]["feats"]
+        B, T = int(x.shape[0]), int(x.shape[1])
+        pm = batch["net_input"].get("padding_mask")
+        sizes = torch.full((B,), T, dtype=torch.int64) if pm is None else (~pm.bool()).sum(1).cpu().to(torch.int64)
+        self.device = x.device
+        self.feats = self.feats_dev = x.reshape(B * T, D_IN)
+        self.sizes = sizes
+        self.offsets = torch.arange(B, dtype=torch.int64) * T
+        lab = batch.get("labels")
+        self.labels = lab.cpu() if lab is not None else torch.zeros(B, dtype=torch.int64)
+        self.offsets_dev, self.sizes_dev = self.offsets.to(x.device), sizes.to(torch.int32).to(x.device)
+        self.labels_dev = self.labels.to(x.device)
+        self.batch_size, self.shuffle, self.use_labels, self.with_id, self.generator = int(batch_size), False, use_labels and lab is not None, True, None
+        self.dataset = self._Dataset(B)
+        self.sink = sink
+        return self
 
     def collate(self, ids):
         from . import ops
         T = int(self.sizes[ids].max())  # host copy of the lengths: no device sync
         ids_dev = ids.to(self.device, non_blocking=True)
-        feats, pad = ops.gather_pad(self.feats_dev, self.offsets_dev[ids_dev], self.sizes_dev[ids_dev], T=T)
+        x_out = pad_out = None
+        if self.sink is not None:
+            x_out, pad_out = self.sink(len(ids), T)
+        feats, pad = ops.gather_pad(self.feats_dev, self.offsets_dev[ids_dev], self.sizes_dev[ids_dev], T=T, x_out=x_out, pad_out=pad_out)
         batch = {"net_input": {"feats": feats, "padding_mask": pad}}
         if self.with_id:
             batch["id"] = ids.clone()

@@ -344,6 +344,15 @@ class DADStepEngine:
         self.lr.fill_(float(lr))
 
     # ------------------------------------------------------------------ inputs
+    def input_views(self, domain, B, T):
+        """(x [B,T,768] f32, pad [B,T] u8) views of the engine's OWN static input buffers for a batch of that shape: a producer that
+        writes its batch there (dataload.DeviceUtteranceLoader with sink=...) hands set_inputs tensors it recognises by address and
+        does not copy.  Stream order keeps this safe: the producer's kernels run after the step that last read the buffers."""
+        if not (1 <= B <= self.Bcap and 1 <= T <= self.Tcap):
+            raise DadError(f"input_views: batch shape B={B}, T={T} exceeds the engine capacity ({self.Bcap}, {self.Tcap})")
+        xf, pf = (self._xc, self._pc) if domain == "clean" else (self._xn, self._pn)
+        return xf[:B * T * D_IN].view(B, T, D_IN), pf[:B * T].view(B, T)
+
     def set_inputs(self, clean_batch, noisy_batch=None, rng=None, n_clean_global=None):
         """Copy one (clean, noisy) batch pair -- reference collator layout (I/dataload_clean.py:177-193; the CASIA / EMODB noisy
         collator has no 'labels' key, C/dataload_casia_noisy.py:72-107) -- and, in the supplied-noise mode, the step's RNG draws
@@ -359,7 +368,8 @@ class DADStepEngine:
         self.set_shape(B, Tc, Tn, n_clean=Bc, n_noisy=Bn, n_clean_global=n_clean_global)
 
         def put(dst, src, n):
-            dst[:n].copy_(src, non_blocking=True)
+            if not (src.is_cuda and src.data_ptr() == dst.data_ptr()):  # already in place (input_views): nothing to copy
+                dst[:n].copy_(src, non_blocking=True)
             if n < dst.shape[0]:
                 dst[n:].zero_()
 
