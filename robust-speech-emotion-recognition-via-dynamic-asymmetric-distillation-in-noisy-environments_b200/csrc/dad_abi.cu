@@ -23,7 +23,7 @@ void enc_tc_set_cta_pair(int on);
 int enc_tc_get_cta_pair();
 void enc_tc_set_bwd_products(int n);
 int enc_tc_get_bwd_products();
-int enc_bwd_tc_splits(int64_t N);
+int enc_bwd_tc_splits(int64_t B);
 size_t enc_bwd_tc_ws_bytes(int64_t B, int64_t T);
 int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, const uint32_t* bits, const void* xs_hi, const void* xs_lo,
                       const float* g_emb, const float* lens, float* dWp, float* dbp, int splits, void* ws, size_t ws_bytes, int64_t B, int64_t T,
@@ -180,7 +180,7 @@ void dad_tc_set_bwd_products(int32_t n) { enc_tc_set_bwd_products(n); }
 int32_t dad_tc_get_bwd_products(void) { return enc_tc_get_bwd_products(); }
 
 int32_t dad_encoder_bwd_splits(int64_t B, int64_t T, int32_t gemm_mode) {
-    return gemm_mode == DAD_GEMM_TC_F16X3 ? enc_bwd_tc_splits(B * T) : enc_bwd_simt_splits(B * T);
+    return gemm_mode == DAD_GEMM_TC_F16X3 ? enc_bwd_tc_splits(B) : enc_bwd_simt_splits(B * T);
 }
 size_t dad_encoder_bwd_workspace_bytes(int64_t B, int64_t T, int32_t gemm_mode) {
     return gemm_mode == DAD_GEMM_TC_F16X3 ? enc_bwd_tc_ws_bytes(B, T) : 256;

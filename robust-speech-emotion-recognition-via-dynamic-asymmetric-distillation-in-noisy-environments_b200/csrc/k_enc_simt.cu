@@ -124,9 +124,9 @@ __global__ void __launch_bounds__(F_THREADS) k_enc_fwd_simt(const float* __restr
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float pre = acc[i][j] + bcol[j];
-            if (pre > 0.f) {
+            if (pre > 0.f && valid) {  // padded frames carry no ReLU bits: they can never contribute to the backward
                 byte |= 1u << j;
-                if (valid) psum[j] += pre;
+                psum[j] += pre;
             }
         }
         if (bits) {  // 4 neighbouring lanes (tx%4) hold the 4 bytes of one 32-column word

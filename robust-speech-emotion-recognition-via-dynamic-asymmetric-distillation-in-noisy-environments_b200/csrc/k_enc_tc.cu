@@ -420,9 +420,9 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
             switch (variant) {
                 case 0: fwd_convert<1, CTA2, 0, false, 3>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
                 case 1: fwd_convert<1, CTA2, 1, false, 2>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
-                case 2: fwd_convert<1, CTA2, 1, true, 3>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
+                case 2: fwd_convert<1, CTA2, 1, true, 2>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
                 case 3: fwd_convert<1, CTA2, 2, false, 2>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
-                default: fwd_convert<1, CTA2, 2, true, 3>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
+                default: fwd_convert<1, CTA2, 2, true, 2>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units); break;
             }
         }
     } else if (warp >= FWD_EPI_WARP0) {
@@ -475,9 +475,9 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
 #pragma unroll
                         for (int uu = 0; uu < 4; ++uu) {
                             const float pre = fmaf(__uint_as_float(r[j4 + uu]), TC_INV_XW, bj[uu]);  // exact power-of-two unscale, then + bias
-                            const bool pos = pre > 0.f;
+                            const bool pos = pre > 0.f && valid;  // padded frames carry no ReLU bits (nothing of them reaches the backward)
                             w |= (pos ? 1u : 0u) << (hf * 16 + j4 + uu);
-                            v[j4 + uu] = (pos && valid && first) ? pre : 0.f;
+                            v[j4 + uu] = (pos && first) ? pre : 0.f;
                         }
                     }
                     const float s0 = transpose_reduce16(v, lane);
@@ -766,7 +766,8 @@ template <int PRODS>
 struct BwdCfg {
     static constexpr uint32_t STAGE_BYTES = (PRODS == 3 ? 4 : 3) * BOP_BYTES;  // A_hi, A_lo, B_hi (, B_lo) = 48 / 64 KB
     static constexpr int STAGES = PRODS == 3 ? 3 : 4;
-    static constexpr uint32_t OFF_BARS = STAGES * STAGE_BYTES;
+    static constexpr uint32_t OFF_LUT = STAGES * STAGE_BYTES;   // 256 x uint4: ReLU byte -> 8 fp16 lane masks
+    static constexpr uint32_t OFF_BARS = OFF_LUT + 256 * 16;
     static constexpr uint32_t SMEM = OFF_BARS + 128 + 1024;
 };
 constexpr uint32_t MN_LBO = (BWD_BK / 8) * 1024;                    // pitch between 64-element M/N chunks (4 k-groups of 1 KB)
@@ -783,7 +784,8 @@ struct BwdParams {
     float* dWp;                      // [S][256][768]
     int64_t N;
     int T;
-    int64_t rows_per_split;          // multiple of 32
+    int B;
+    int utt_per_split;               // utterances per frame-range split (grid.y); k-blocks are aligned to utterance starts
     int use_xs;                      // B operand comes from the forward's operand cache by TMA (tm_xhi / tm_xlo); x / ap are not touched
 };
 
@@ -940,36 +942,38 @@ __global__ void __launch_bounds__(DAD_H) k_bwd_db_fold(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Converter warp body of the backward kernel.  Warp cw owns the 4 consecutive frames cw*4 .. cw*4+3 of every 32-frame k-block
-// (two noise row pairs), for BOTH operands:
-//   B operand (aug(x), 256 d columns of this CTA's slice): lane -> float4 columns lane and lane+32 (two coalesced 512-byte loads per row);
-//   A operand (dpre^T, 256 hidden units): lane -> the 16-byte chunk of 8 hidden units hq = lane; one pre-split fp16 g/len table chunk
-//     per UTTERANCE serves all frames of that utterance, so it is fetched once per k-block together with the next k-block's
-//     data (no dependent load on the critical path); the ReLU byte of each frame masks it.
-// (utterance, frame-in-utterance) of the warp's first frame advance incrementally (T >= 32: at most one wrap per k-block).
-// Three register sets rotate over the k-blocks so the loads of k-blocks i+1 and i+2 fly while k-block i is converted (see fwd_convert);
-// the table chunks live in two tagged slots (utterance b -> slot b & 1) refreshed at load time, with an inline reload
-// when a slot was recycled before use (only possible for T < 64).
+// Converter warp body of the backward kernel.  The k-blocks (32 frames) are aligned to UTTERANCE starts: utterance b is covered by
+// KPU = ceil(T / 32) k-blocks, the last one padded with zero rows of the A operand (its B rows are whatever follows in memory:
+// they meet zeros).  Inside a k-block every frame therefore belongs to one utterance, so the pre-split fp16 g/len chunk of that
+// utterance (this lane's 8 hidden units hq = lane: two 16-byte registers sets, fetched once per utterance) serves all of it.
+// Warp cw owns the 4 consecutive frames cw*4 .. cw*4+3 of every k-block, for BOTH operands:
+//   A operand (dpre^T, 256 hidden units): the frame's ReLU byte for this lane's 8 units -> a shared-memory LUT of 256 uint4
+//     (8 fp16 lane masks) -> AND with the g/len chunk -> two 16-byte stores.  Padded frames carry zero ReLU bits (the forward
+//     kernels write them so) and frames beyond the utterance are zeroed here: no padding-mask reads, no per-frame utterance lookup.
+//     The first version spent ~490 instructions per k-block and thread on this (ncu: cached backward 0.75 ms, tensor pipe 45 %
+//     active); this one ~80.
+//   B operand (aug(x), 256 d columns of this CTA's slice), unless the operand cache feeds it by TMA (XS): lane -> float4 columns
+//     lane and lane+32 (two coalesced 512-byte loads per row), augmentation regenerated exactly as in the forward, fp16 hi (/ lo).
+// The ReLU words (and the x rows) of the next k-blocks are in flight while one is converted (NSET register sets).
 // ---------------------------------------------------------------------------------------------------------------------
 struct BwdRegs {
-    float4 x[8];     // [r4*2 + half]
-    uint32_t w[4];   // ReLU mask word holding this lane's byte, per frame
-    uint32_t flags;  // bits 0-3: x row contributes zeros; bits 4-7: A row active (in range and not padded)
-    int b0, t0;      // utterance / frame-in-utterance of the warp's first frame
+    float4 x[8];     // [r4*2 + half]  (unused with the operand cache)
+    uint32_t w[4];   // ReLU mask word holding this lane's byte, per frame (0 beyond the utterance)
 };
-struct BwdTab { uint4 gh, gl; int b; };  // this lane's g/len table chunk (fp16 hi, lo) of utterance b; slot = b & 1
 
 template <int PRODS, int MODE, bool PHILOX, bool XS>
 __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, const int cw, const int lane,
-                                            const int dslice, const int64_t n_begin, const int64_t n_end, const int nkb) {
+                                            const int dslice, const int b_begin, const int b_end) {
     using Cfg = BwdCfg<PRODS>;
     constexpr int BWD_STAGES = Cfg::STAGES;
     constexpr uint32_t BSTAGE_BYTES = Cfg::STAGE_BYTES;
     const AugParams& ap = p.ap;
     const uint32_t smem_a = tc::smem_u32(smem);
+    const uint32_t lut = smem_a + Cfg::OFF_LUT;
     const unsigned long long seed = (MODE != 0 && PHILOX) ? aug_seed(ap) : 0ull;
     const float radius_k = NOISE_UNIT_K * ap.sigma * ap.sigma;
     const int T = p.T;
+    const int KPU = (T + BWD_BK - 1) / BWD_BK;
     // shared-memory offsets (MN-major, SWIZZLE_128B): frame r = cw*4 + j -> 8-frame group cw>>1, row-in-atom r7 = (cw&1)*4 + j
     const uint32_t r7b = (uint32_t)(cw & 1) * 4u;
     const uint32_t xoff0 = (uint32_t)(lane >> 4) * MN_LBO + (uint32_t)(cw >> 1) * MN_SBO + (uint32_t)(lane & 1) * 8u;  // + 2*MN_LBO for the second half
@@ -978,161 +982,130 @@ __device__ __forceinline__ void bwd_convert(const BwdParams& p, uint8_t* smem, u
     const uint32_t ac = (uint32_t)lane & 7u;
     const uint32_t bshift = (uint32_t)(lane & 3) * 8u;
     float4 keep0 = make_float4(1.f, 1.f, 1.f, 1.f), keep1 = keep0;
-    const bool has_keep = MODE == 2 && ap.feat_keep != nullptr;
+    const bool has_keep = !XS && MODE == 2 && ap.feat_keep != nullptr;
     if (has_keep) {
         keep0 = __ldg(reinterpret_cast<const float4*>(ap.feat_keep + dslice * 256 + lane * 4));
         keep1 = __ldg(reinterpret_cast<const float4*>(ap.feat_keep + dslice * 256 + (lane + 32) * 4));
     }
-    // (utterance, frame) of frame n_begin + cw*4, advanced by 32 frames per k-block
-    int b_run, t_run;
-    {
-        const uint32_t n0 = (uint32_t)(n_begin + cw * 4);
-        b_run = (int)(n0 / (uint32_t)T);
-        t_run = (int)(n0 - (uint32_t)b_run * (uint32_t)T);
-    }
+    const int nkb = (b_end - b_begin) * KPU;
+    if (nkb <= 0) return;
 
-    const int n_utt = (int)(p.N / T);
-    BwdTab tab0, tab1;
-    tab0.b = tab1.b = -1;
-    tab0.gh = tab0.gl = tab1.gh = tab1.gl = make_uint4(0, 0, 0, 0);
-    auto tab_ldg = [&](const uint16_t* base, int b) { return __ldg(reinterpret_cast<const uint4*>(base + (int64_t)b * DAD_H + lane * 8)); };
-
-    auto load = [&](BwdRegs& R, int kb) {
-        const int64_t n0 = n_begin + (int64_t)kb * BWD_BK + cw * 4;
-        R.b0 = b_run; R.t0 = t_run;
-        t_run += BWD_BK;
-        if (t_run >= T) { t_run -= T; ++b_run; }
-        uint32_t flags = 0;
-        const float* src = p.x + n0 * DAD_D + dslice * 256 + lane * 4;
+    // flat k-block index it -> (utterance, first frame-in-utterance of this warp): advanced incrementally by the LOAD stream
+    int lb = b_begin, lk = 0;  // utterance / k-block-in-utterance of the next load
+    auto load = [&](BwdRegs& R) {
+        const int t0 = lk * BWD_BK + cw * 4;
+        const int64_t n0 = (int64_t)lb * T + t0;
+        const uint32_t* bw = p.bits + n0 * DAD_HW + (lane >> 2);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool in = n0 + j < n_end;
-            int t = R.t0 + j, b = R.b0;
-            if (t >= T) { t -= T; ++b; }
-            bool zx = !in;
-            if (!XS && MODE == 2 && in && ap.t_start && ap.mask_len > 0) {
-                const int s0 = __ldg(ap.t_start + b);
-                zx = (t >= s0 && t < s0 + ap.mask_len);
-            }
-            if (in) {
-                if (!XS) {
-                    R.x[2 * j] = __ldg(reinterpret_cast<const float4*>(src + j * DAD_D));
-                    R.x[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(src + j * DAD_D + 128));
-                }
-                R.w[j] = __ldg(p.bits + (n0 + j) * DAD_HW + (lane >> 2));
-            } else {
-                if (!XS) R.x[2 * j] = R.x[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                R.w[j] = 0u;
-            }
-            const bool on = in && !(p.pad && p.pad[n0 + j]);
-            flags |= (zx ? 1u : 0u) << j;
-            flags |= (on ? 1u : 0u) << (4 + j);
-        }
-        R.flags = flags;
-        if (n0 < n_end) {
-#pragma unroll
-            for (int d = 0; d < 2; ++d) {
-                const int bb = R.b0 + d;
-                if (bb < n_utt) {
-                    if (bb & 1) { if (tab1.b != bb) { tab1.gh = tab_ldg(p.g_hi, bb); tab1.gl = tab_ldg(p.g_lo, bb); tab1.b = bb; } }
-                    else        { if (tab0.b != bb) { tab0.gh = tab_ldg(p.g_hi, bb); tab0.gl = tab_ldg(p.g_lo, bb); tab0.b = bb; } }
-                }
-            }
-        }
-    };
-
-    auto convert = [&](BwdRegs& R, int kb) {
-        const uint32_t s = (uint32_t)kb % BWD_STAGES, ph = ((uint32_t)kb / BWD_STAGES) & 1u;
-        tc::mbar_wait(&empty[s], ph ^ 1u);
-        const uint32_t st = smem_a + s * BSTAGE_BYTES;
-        const int64_t n0 = n_begin + (int64_t)kb * BWD_BK + cw * 4;
-        // ---- A operand: dpre^T chunks = table chunk of the frame's utterance, masked by the frame's ReLU byte
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t byte = ((R.flags >> (4 + j)) & 1u) ? ((R.w[j] >> bshift) & 0xFFu) : 0u;
-            uint4 gh = make_uint4(0, 0, 0, 0), gl = make_uint4(0, 0, 0, 0);
-            if (byte) {
-                const int bj = R.b0 + (R.t0 + j >= T ? 1 : 0);
-                const bool odd = bj & 1;
-                if ((odd ? tab1.b : tab0.b) == bj) {
-                    gh = odd ? tab1.gh : tab0.gh;
-                    gl = odd ? tab1.gl : tab0.gl;
-                } else {  // slot recycled before use (short utterances): reload in place
-                    gh = tab_ldg(p.g_hi, bj);
-                    gl = tab_ldg(p.g_lo, bj);
-                }
-                const uint32_t m0 = ((byte & 1u) ? 0x0000FFFFu : 0u) | ((byte & 2u) ? 0xFFFF0000u : 0u);
-                const uint32_t m1 = ((byte & 4u) ? 0x0000FFFFu : 0u) | ((byte & 8u) ? 0xFFFF0000u : 0u);
-                const uint32_t m2 = ((byte & 16u) ? 0x0000FFFFu : 0u) | ((byte & 32u) ? 0xFFFF0000u : 0u);
-                const uint32_t m3 = ((byte & 64u) ? 0x0000FFFFu : 0u) | ((byte & 128u) ? 0xFFFF0000u : 0u);
-                gh.x &= m0; gh.y &= m1; gh.z &= m2; gh.w &= m3;
-                gl.x &= m0; gl.y &= m1; gl.z &= m2; gl.w &= m3;
-            }
-            const uint32_t r7 = r7b + (uint32_t)j;
-            const uint32_t off = aoff0 + r7 * 128u + ((ac ^ r7) << 4);
-            tc::sts128(st + BOFF_AHI + off, gh);
-            tc::sts128(st + BOFF_ALO + off, gl);
-        }
-        // ---- B operand: aug(x) rows -> fp16 hi/lo (scaled by TC_XS); with the operand cache (XS) the TMA warp loads it instead
-        if (!XS && MODE != 0) {
+        for (int j = 0; j < 4; ++j) R.w[j] = (t0 + j < T) ? __ldg(bw + j * DAD_HW) : 0u;
+        if (!XS) {
+            const float* src = p.x + n0 * DAD_D + dslice * 256 + lane * 4;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+                const bool in = n0 + j < p.N;  // rows of the NEXT utterance are read (they meet zero A rows); rows beyond N are not
+                R.x[2 * j] = in ? __ldg(reinterpret_cast<const float4*>(src + j * DAD_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                R.x[2 * j + 1] = in ? __ldg(reinterpret_cast<const float4*>(src + j * DAD_D + 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (++lk == KPU) { lk = 0; ++lb; }
+    };
+    auto tab_ldg = [&](const uint16_t* base, int b) { return __ldg(reinterpret_cast<const uint4*>(base + (int64_t)b * DAD_H + lane * 8)); };
+
+    uint32_t s = 0, ph = 0;
+    int cb = b_begin, ck = 0;  // utterance / k-block-in-utterance being converted
+    uint4 gh = tab_ldg(p.g_hi, cb), gl = tab_ldg(p.g_lo, cb);
+    uint4 gh_n = gh, gl_n = gl;
+    auto convert = [&](BwdRegs& R) {
+        if (ck == 0 && cb + 1 < b_end) { gh_n = tab_ldg(p.g_hi, cb + 1); gl_n = tab_ldg(p.g_lo, cb + 1); }  // next utterance's chunk: a whole utterance ahead
+        tc::mbar_wait(&empty[s], ph ^ 1u);
+        const uint32_t st = smem_a + s * BSTAGE_BYTES;
+        // ---- A operand: dpre^T chunks = g/len chunk of the utterance, masked by the frame's ReLU byte (LUT: byte -> 8 fp16 masks)
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float4& va = R.x[2 * j + half];
-                    const int f = lane + 32 * half;
-                    if (PHILOX) {
-                        NoiseBM4 z;
-                        philox_bm4(seed, (uint32_t)ap.stream, (unsigned long long)(n0 + j) + (unsigned long long)ap.frame_offset, (uint32_t)(dslice * 64 + f), radius_k, z);
-                        va = bm4_add(z, va);
-                    } else {
-                        const float* nz = ap.noise + (n0 + j) * DAD_D + dslice * 256 + f * 4;
-                        const float4 na = (n0 + j < n_end) ? __ldg(reinterpret_cast<const float4*>(nz)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        va.x = aug_add_noise(va.x, na.x, ap.sigma); va.y = aug_add_noise(va.y, na.y, ap.sigma);
-                        va.z = aug_add_noise(va.z, na.z, ap.sigma); va.w = aug_add_noise(va.w, na.w, ap.sigma);
-                    }
-                    if (has_keep) {
-                        const float4 kp = half ? keep1 : keep0;
-                        va.x = __fmul_rn(va.x, kp.x); va.y = __fmul_rn(va.y, kp.y); va.z = __fmul_rn(va.z, kp.z); va.w = __fmul_rn(va.w, kp.w);
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t byte = (R.w[j] >> bshift) & 0xFFu;
+            const uint4 m = tc::lds128(lut + byte * 16u);
+            const uint32_t r7 = r7b + (uint32_t)j;
+            const uint32_t off = aoff0 + r7 * 128u + ((ac ^ r7) << 4);
+            tc::sts128(st + BOFF_AHI + off, make_uint4(gh.x & m.x, gh.y & m.y, gh.z & m.z, gh.w & m.w));
+            tc::sts128(st + BOFF_ALO + off, make_uint4(gl.x & m.x, gl.y & m.y, gl.z & m.z, gl.w & m.w));
+        }
+        // ---- B operand: aug(x) rows -> fp16 hi (/ lo) (scaled by TC_XS); with the operand cache (XS) the TMA warp loads it instead
+        if (!XS) {
+            const int t0 = ck * BWD_BK + cw * 4;
+            const int64_t n0 = (int64_t)cb * T + t0;
+            uint32_t zx = 0;  // rows that contribute zeros: inside the temporal mask span of the strong view
+            if (MODE == 2 && ap.t_start && ap.mask_len > 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int t = t0 + j, bb = cb;
+                    if (t >= T) { t -= T; ++bb; }
+                    if (bb < p.B) {
+                        const int s0 = __ldg(ap.t_start + bb);
+                        if (t >= s0 && t < s0 + ap.mask_len) zx |= 1u << j;
                     }
                 }
             }
-        }
+            if (MODE != 0) {
 #pragma unroll
-        for (int j = 0; j < (XS ? 0 : 4); ++j) {
-            const uint32_t r7 = r7b + (uint32_t)j;
-            const uint32_t roff = xoff0 + r7 * 128u + ((xc ^ r7) << 4);
+                for (int j = 0; j < 4; ++j) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const float4 v = R.x[2 * j + half];
-                const float sc = ((R.flags >> j) & 1u) ? 0.f : TC_XS;
-                uint32_t h01, l01, h23, l23;
-                tc::split2_f16(v.x * sc, v.y * sc, h01, l01);
-                tc::split2_f16(v.z * sc, v.w * sc, h23, l23);
-                const uint32_t off = roff + (uint32_t)half * 2u * MN_LBO;
-                tc::sts64(st + BOFF_BHI + off, h01, h23);
-                if (PRODS == 3) tc::sts64(st + BOFF_BLO + off, l01, l23);
+                    for (int half = 0; half < 2; ++half) {
+                        float4& va = R.x[2 * j + half];
+                        const int f = lane + 32 * half;
+                        if (PHILOX) {
+                            NoiseBM4 z;
+                            philox_bm4(seed, (uint32_t)ap.stream, (unsigned long long)(n0 + j) + (unsigned long long)ap.frame_offset, (uint32_t)(dslice * 64 + f), radius_k, z);
+                            va = bm4_add(z, va);
+                        } else {
+                            const float* nz = ap.noise + (n0 + j) * DAD_D + dslice * 256 + f * 4;
+                            const float4 na = (n0 + j < p.N) ? __ldg(reinterpret_cast<const float4*>(nz)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            va.x = aug_add_noise(va.x, na.x, ap.sigma); va.y = aug_add_noise(va.y, na.y, ap.sigma);
+                            va.z = aug_add_noise(va.z, na.z, ap.sigma); va.w = aug_add_noise(va.w, na.w, ap.sigma);
+                        }
+                        if (has_keep) {
+                            const float4 kp = half ? keep1 : keep0;
+                            va.x = __fmul_rn(va.x, kp.x); va.y = __fmul_rn(va.y, kp.y); va.z = __fmul_rn(va.z, kp.z); va.w = __fmul_rn(va.w, kp.w);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t r7 = r7b + (uint32_t)j;
+                const uint32_t roff = xoff0 + r7 * 128u + ((xc ^ r7) << 4);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const float4 v = R.x[2 * j + half];
+                    const float sc = ((zx >> j) & 1u) ? 0.f : TC_XS;
+                    uint32_t h01, l01, h23, l23;
+                    tc::split2_f16(v.x * sc, v.y * sc, h01, l01);
+                    tc::split2_f16(v.z * sc, v.w * sc, h23, l23);
+                    const uint32_t off = roff + (uint32_t)half * 2u * MN_LBO;
+                    tc::sts64(st + BOFF_BHI + off, h01, h23);
+                    if (PRODS == 3) tc::sts64(st + BOFF_BLO + off, l01, l23);
+                }
             }
         }
         tc::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&full[s]);
+        if (++s == (uint32_t)BWD_STAGES) { s = 0; ph ^= 1u; }
+        if (++ck == KPU) { ck = 0; ++cb; gh = gh_n; gl = gl_n; }
     };
 
-    if (nkb == 0) return;
     BwdRegs RA, RB, RC;
-    load(RA, 0);
-    if (nkb > 1) load(RB, 1);
+    load(RA);
+    if (nkb > 1) load(RB);
     for (int kb = 0; kb < nkb; kb += 3) {
-        if (kb + 2 < nkb) load(RC, kb + 2);
-        convert(RA, kb);
+        if (kb + 2 < nkb) load(RC);
+        convert(RA);
         if (kb + 1 < nkb) {
-            if (kb + 3 < nkb) load(RA, kb + 3);
-            convert(RB, kb + 1);
+            if (kb + 3 < nkb) load(RA);
+            convert(RB);
         }
         if (kb + 2 < nkb) {
-            if (kb + 4 < nkb) load(RB, kb + 4);
-            convert(RC, kb + 2);
+            if (kb + 4 < nkb) load(RB);
+            convert(RC);
         }
     }
 }
@@ -1153,10 +1126,18 @@ k_enc_bwd_tc(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dslice = blockIdx.x, split = blockIdx.y;
-    const int64_t n_begin = (int64_t)split * p.rows_per_split;
-    const int64_t n_end = n_begin + p.rows_per_split < p.N ? n_begin + p.rows_per_split : p.N;
-    const int nkb = n_end > n_begin ? (int)ceil_div64(n_end - n_begin, BWD_BK) : 0;
+    const int b_begin = split * p.utt_per_split;
+    const int b_end = b_begin + p.utt_per_split < p.B ? b_begin + p.utt_per_split : p.B;
+    const int KPU = (p.T + BWD_BK - 1) / BWD_BK;
+    const int nkb = b_end > b_begin ? (b_end - b_begin) * KPU : 0;
 
+    if (threadIdx.x < 256) {  // ReLU byte -> eight 16-bit lane masks (bit k set -> 0xFFFF in half-word k)
+        const uint32_t v = threadIdx.x;
+        uint32_t m[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m[k] = ((v >> (2 * k)) & 1u ? 0x0000FFFFu : 0u) | ((v >> (2 * k + 1)) & 1u ? 0xFFFF0000u : 0u);
+        *reinterpret_cast<uint4*>(smem + Cfg::OFF_LUT + v * 16) = make_uint4(m[0], m[1], m[2], m[3]);
+    }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < BWD_STAGES; ++s) { tc::mbar_init(&full[s], N_CONV_WARPS + (p.use_xs ? 1 : 0)); tc::mbar_init(&empty[s], 1); }
         tc::mbar_init(tfull, 1);
@@ -1179,18 +1160,20 @@ k_enc_bwd_tc(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__
         if (p.use_xs && lane == 0) {
             tc::prefetch_tmap(&tm_xhi);
             if (PRODS == 3) tc::prefetch_tmap(&tm_xlo);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const uint32_t s = kb % BWD_STAGES, ph = (kb / BWD_STAGES) & 1;
-                tc::mbar_wait(&empty[s], ph ^ 1);
-                tc::mbar_arrive_expect_tx(&full[s], (PRODS == 3 ? 2 : 1) * BOP_BYTES);
-                const int row = (int)(n_begin + (int64_t)kb * BWD_BK);
-                uint8_t* st = smem + s * BSTAGE_BYTES;
+            int kb = 0;
+            for (int b = b_begin; b < b_end; ++b)
+                for (int kl = 0; kl < KPU; ++kl, ++kb) {
+                    const uint32_t s = kb % BWD_STAGES, ph = (kb / BWD_STAGES) & 1;
+                    tc::mbar_wait(&empty[s], ph ^ 1);
+                    tc::mbar_arrive_expect_tx(&full[s], (PRODS == 3 ? 2 : 1) * BOP_BYTES);
+                    const int row = b * p.T + kl * BWD_BK;
+                    uint8_t* st = smem + s * BSTAGE_BYTES;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    tc::tma_load_2d(st + BOFF_BHI + c * MN_LBO, &tm_xhi, &full[s], dslice * 256 + c * 64, row);
-                    if (PRODS == 3) tc::tma_load_2d(st + BOFF_BLO + c * MN_LBO, &tm_xlo, &full[s], dslice * 256 + c * 64, row);
+                    for (int c = 0; c < 4; ++c) {
+                        tc::tma_load_2d(st + BOFF_BHI + c * MN_LBO, &tm_xhi, &full[s], dslice * 256 + c * 64, row);
+                        if (PRODS == 3) tc::tma_load_2d(st + BOFF_BLO + c * MN_LBO, &tm_xlo, &full[s], dslice * 256 + c * 64, row);
+                    }
                 }
-            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -1223,16 +1206,16 @@ k_enc_bwd_tc(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__
         }
     } else if (warp >= CONV_WARP0 && warp < CONV_WARP0 + N_CONV_WARPS) {
         // ===================== converters =====================
-        tc::reg_inc<200>();  // 128 x 40 (control) + 256 x 200 (converters: three 39-register landing sets) + 128 x 64 (epilogue) <= 64 K
+        tc::reg_inc<200>();  // 128 x 40 (control) + 256 x 200 (converters: three landing sets) + 128 x 64 (epilogue) <= 64 K
         const int cw = warp - CONV_WARP0;
         const int variant = p.use_xs ? 5 : (p.ap.mode == 0 ? 0 : (p.ap.mode * 2 - 1 + (p.ap.noise_src == 1 ? 1 : 0)));
         switch (variant) {
-            case 0: bwd_convert<PRODS, 0, false, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 1: bwd_convert<PRODS, 1, false, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 2: bwd_convert<PRODS, 1, true, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 3: bwd_convert<PRODS, 2, false, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
-            case 4: bwd_convert<PRODS, 2, true, false>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;
-            default: bwd_convert<PRODS, 0, false, true>(p, smem, full, empty, cw, lane, dslice, n_begin, n_end, nkb); break;  // A operand only
+            case 0: bwd_convert<PRODS, 0, false, false>(p, smem, full, empty, cw, lane, dslice, b_begin, b_end); break;
+            case 1: bwd_convert<PRODS, 1, false, false>(p, smem, full, empty, cw, lane, dslice, b_begin, b_end); break;
+            case 2: bwd_convert<PRODS, 1, true, false>(p, smem, full, empty, cw, lane, dslice, b_begin, b_end); break;
+            case 3: bwd_convert<PRODS, 2, false, false>(p, smem, full, empty, cw, lane, dslice, b_begin, b_end); break;
+            case 4: bwd_convert<PRODS, 2, true, false>(p, smem, full, empty, cw, lane, dslice, b_begin, b_end); break;
+            default: bwd_convert<PRODS, 0, false, true>(p, smem, full, empty, cw, lane, dslice, b_begin, b_end); break;  // A operand only
         }
     } else if (warp >= EPI_WARP0) {
         // ===================== epilogue: TMEM -> split-K partial dW =====================
@@ -1277,12 +1260,11 @@ k_enc_bwd_tc(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__
 
 }  // namespace
 
-int enc_bwd_tc_splits(int64_t N) {
-    // grid = 3 d-slices x S: one wave of 147 CTAs at S = 49; keep >= 128 frames per split for small batches
-    int64_t s = N / 128;
-    if (s > 49) s = 49;
-    if (s < 1) s = 1;
-    return (int)s;
+static int bwd_utt_per_split(int64_t B) { return (int)ceil_div64(B, 49); }
+int enc_bwd_tc_splits(int64_t B) {
+    // grid = 3 d-slices x S frame-range splits of WHOLE utterances: one wave of 147 CTAs at S = 49 (B >= 49)
+    if (B < 1) return 1;
+    return (int)ceil_div64(B, bwd_utt_per_split(B));
 }
 static inline size_t bwd_align(size_t v) { return (v + 255) & ~(size_t)255; }
 struct BwdCarve { size_t g_hi, g_lo, scal, contrib, total; };
@@ -1324,8 +1306,9 @@ int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, c
     DAD_CHECK_LAUNCH("k_bwd_prep");
     BwdParams p;
     p.x = x; p.pad = pad; p.ap = ap; p.bits = bits; p.g_hi = g_hi; p.g_lo = g_lo; p.unscale = scal + ABSMAX_GRID; p.dWp = dWp;
-    p.N = B * T; p.T = (int)T;
-    p.rows_per_split = ceil_div64(ceil_div64(p.N, splits), BWD_BK) * BWD_BK;
+    p.N = B * T; p.T = (int)T; p.B = (int)B;
+    p.utt_per_split = bwd_utt_per_split(B);
+    if (splits != enc_bwd_tc_splits(B)) return dad_set_error(DAD_ERR_ARG, "encoder_bwd(tc): splits must equal dad_encoder_bwd_splits()");
     CUtensorMap tm_hi, tm_lo;
     memset(&tm_hi, 0, sizeof(tm_hi));
     memset(&tm_lo, 0, sizeof(tm_lo));

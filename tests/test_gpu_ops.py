@@ -152,8 +152,10 @@ def test_encoder_forward_backward_vs_oracle(mode, B, T, aug, tc_switch):
     pre = (xa.double() @ W0.double().t() + b0.double()).reshape(B * T, 256)
     word = bits.cpu().view(B * T, 8).to(torch.int64) & 0xFFFFFFFF
     got = ((word.unsqueeze(-1) >> torch.arange(32)) & 1).reshape(B * T, 256).bool()
-    sure = pre.abs() > 1e-4
+    valid_f = (~pad).reshape(B * T, 1)
+    sure = (pre.abs() > 1e-4) & valid_f
     assert torch.equal(got[sure], (pre > 0)[sure])
+    assert not bool(got[~valid_f.expand(-1, 256)].any())  # padded frames carry no ReLU bits (they never reach the backward)
     dW, db = ops.encoder_pool_bwd(x.cuda(), pad.cuda(), bits, g_emb.cuda(), lens, aug=a, gemm_mode=_mode(mode))
     sW, sb = float(W.grad.abs().max()), float(b.grad.abs().max())
     tolW = 2e-5 if mode == "fp32" else 1e-4

