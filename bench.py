@@ -277,6 +277,33 @@ def time_small_workload(cfg, dev, gm, B, T, epoch, steps):
     return out
 
 
+def time_predict(dev, B, T, reps=5):
+    """Validation pass (I/train.py:522-564) over one [B,T,768] batch: student + teacher predictions from ONE fused read of x
+    (dad_predict) against two single-network passes; CUDA events."""
+    import torch
+    from dad_b200 import ops, synth
+    st = synth.init_state(42)
+    cu = lambda k: st[k].to(dev)
+    Ws, bs, Wc, bc = cu("student_encoder.pre_net.weight"), cu("student_encoder.pre_net.bias"), cu("student_classifier.fc_layer.weight"), cu("student_classifier.fc_layer.bias")
+    x = torch.randn(B, T, D_IN, device=dev)
+    split = ops.split_f16(Ws)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+    both = timed(lambda: ops.predict(x, None, Ws, bs, Wc, bc, Ws, bs, Wc, bc, Ws_split=split, Wt_split=split))
+    one = timed(lambda: ops.predict(x, None, Ws, bs, Wc, bc, Ws_split=split))
+    return {"B": B, "T": T, "student_and_teacher_one_pass_ms": both, "one_network_ms": one, "two_separate_passes_ms": 2 * one}
+
+
 def cpu_reference_steps(B, T, steps, warmup, epoch, threads=None):
     """The reference's CPU step, restated op for op in oracle/dad_oracle.py (the Python reference cannot travel to the
     GPU box; the oracle is bit-identical to it on CPU, tests/test_oracle_golden.py).  Returns seconds per step (median)."""
@@ -406,26 +433,25 @@ def run_ours(args):
     # k_pool_finalize, or absmax / prep / db / fold) without host enqueue gaps.
     peaks, peak_src = measured_peaks()
     sc = eng.scalars(args.epoch)
-    s = _lib.stream_ptr()
     reps = 10 if not small else 40
     aug_w, aug_s = eng._aug(1, sc), eng._aug(2, sc)
     emb_c, emb_s = eng.pack.data_ptr(), eng.pack.data_ptr() + B * 256 * 4
     view_bytes, gemm_flops = B * T * D_IN * 4, 2 * B * T * D_IN * 256
     P = eng.bwd_products if args.gemm == "tc" else 1
     variants = [("encoder_fwd_clean", "k_enc_fwd_tc", view_bytes, gemm_flops, 3,
-                 lambda: eng._enc_fwd(eng.x_clean, eng.pad_clean, False, None, emb_c, eng.bits_clean, eng.lens_clean, s, xs=eng.xs_clean))]
+                 lambda: eng._enc_fwd(eng.x_clean, eng.pad_clean, False, None, emb_c, eng.bits_clean, eng.lens_clean, _lib.stream_ptr(), xs=eng.xs_clean))]
     if eng.fused_noisy:
         variants.append(("encoder_fwd_noisy_fused", "k_enc_fwd_tc", view_bytes, 2 * gemm_flops, 3,
-                         lambda: eng._enc_fwd_noisy_fused(aug_w, aug_s, emb_s, s)))
+                         lambda: eng._enc_fwd_noisy_fused(aug_w, aug_s, emb_s, _lib.stream_ptr())))
     else:
         variants += [("encoder_fwd_weak", "k_enc_fwd_tc", view_bytes, gemm_flops, 3,
-                      lambda: eng._enc_fwd(eng.x_noisy, eng.pad_noisy, True, aug_w, eng.emb_teacher.data_ptr(), None, eng.lens_scratch, s)),
+                      lambda: eng._enc_fwd(eng.x_noisy, eng.pad_noisy, True, aug_w, eng.emb_teacher.data_ptr(), None, eng.lens_scratch, _lib.stream_ptr())),
                      ("encoder_fwd_strong", "k_enc_fwd_tc", view_bytes, gemm_flops, 3,
-                      lambda: eng._enc_fwd(eng.x_noisy, eng.pad_noisy, False, aug_s, emb_s, eng.bits_strong, eng.lens_noisy, s, xs=eng.xs_strong))]
+                      lambda: eng._enc_fwd(eng.x_noisy, eng.pad_noisy, False, aug_s, emb_s, eng.bits_strong, eng.lens_noisy, _lib.stream_ptr(), xs=eng.xs_strong))]
     variants += [("encoder_bwd_clean", "k_enc_bwd_tc", view_bytes, gemm_flops, P,
-                  lambda: eng._enc_bwd(eng.x_clean, eng.pad_clean, None, eng.bits_clean, eng.g_clean, eng.lens_clean, 0, s, xs=eng.xs_clean)),
+                  lambda: eng._enc_bwd(eng.x_clean, eng.pad_clean, None, eng.bits_clean, eng.g_clean, eng.lens_clean, 0, _lib.stream_ptr(), xs=eng.xs_clean)),
                  ("encoder_bwd_strong", "k_enc_bwd_tc", view_bytes, gemm_flops, P,
-                  lambda: eng._enc_bwd(eng.x_noisy, eng.pad_noisy, aug_s, eng.bits_strong, eng.g_strong, eng.lens_noisy, 1, s, xs=eng.xs_strong))]
+                  lambda: eng._enc_bwd(eng.x_noisy, eng.pad_noisy, aug_s, eng.bits_strong, eng.g_strong, eng.lens_noisy, 1, _lib.stream_ptr(), xs=eng.xs_strong))]
     kern = {}
     for name, symbol, nbytes, nflops, products, fn in variants:
         for _ in range(2):
@@ -550,7 +576,8 @@ def run_ours(args):
         del eng
         torch.cuda.empty_cache()
         extra = {"b64": time_small_workload(cfg, dev, gm, 64, 200, args.epoch, 20),
-                 "t1000": time_small_workload(cfg, dev, gm, 512, 1000, args.epoch, 5)}
+                 "t1000": time_small_workload(cfg, dev, gm, 512, 1000, args.epoch, 5),
+                 "validate": time_predict(dev, 4096, 200)}
         eng = None
 
     cpu = None

@@ -107,9 +107,23 @@ int dad_aug_encoder_fwd(const float* x, const uint8_t* pad, const void* Wt_hi, c
                         const dad_aug* aug_strong, float* emb_student, uint32_t* relu_bits, void* xs_hi, void* xs_lo, float* lens,
                         void* ws, size_t ws_bytes, int64_t B, int64_t T, void* stream);
 
+/* Fused inference (replaces SSRLModel.predict's encoder + classifier, I/model.py:225-245, as used by validate
+ * and its student / teacher disagreement rate, I/train.py:522-564, and by the anchor calibration, I/train.py:317-357): x [B,T,D] is
+ * read ONCE on the tcgen05 path (T >= 32); the student and -- when Wt_hi != NULL -- the teacher encoder + classifier (eval mode:
+ * no dropout) produce emb_* [B,H], logits_* [B,C] and pred_* [B] (first arg-max; nullable). */
+size_t dad_predict_workspace_bytes(int64_t B, int64_t T);
+int dad_predict(const float* x, const uint8_t* pad, const void* Ws_hi, const void* Ws_lo, const float* bias_s, const float* Wc_s,
+                const float* bc_s, const void* Wt_hi, const void* Wt_lo, const float* bias_t, const float* Wc_t, const float* bc_t,
+                float* emb_s, float* emb_t, float* logits_s, float* logits_t, int32_t* pred_s, int32_t* pred_t, void* ws,
+                size_t ws_bytes, int64_t B, int64_t T, void* stream);
+
 /* Process-wide switches of the tcgen05 encoder kernels (also DAD_TC_CTA2 / DAD_TC_BWD_PRODUCTS in the environment):
- *  cta_pair      1 (default) = forward kernels run as CTA pairs (cluster of 2, tcgen05.mma.cta_group::2), 0 = one CTA per tile
- *  bwd_products  2 (default) = dW GEMM as dpre_hi*x_hi + dpre_lo*x_hi (x_hi only: xs_lo unused), 3 = adds dpre_hi*x_lo (fp32-grade) */
+ *  cta_pair      forward kernels as CTA pairs (cluster of 2, tcgen05.mma.cta_group::2): 0 = never, 1 = always, 2 (default) = for
+ *                the clean / inference launches (bound by the MMAs' shared-memory operand traffic), not for the noisy ones
+ *                (bound by their converters)
+ *  bwd_products  3 (default) = dW GEMM as dpre_hi*x_hi + dpre_hi*x_lo + dpre_lo*x_hi (fp32-grade); 2 = x_hi only (xs_lo unused):
+ *                a third less tensor work and half the operand cache, but gradient errors of ~1e-4 relative on cancelling
+ *                elements -- outside the parity tolerances, opt-in */
 void dad_tc_set_cta_pair(int32_t on);
 int32_t dad_tc_get_cta_pair(void);
 void dad_tc_set_bwd_products(int32_t n);

@@ -23,7 +23,7 @@ EXPORTS = (
     "dad_split_f16", "dad_step_rng", "dad_certainty_scores", "dad_scl_workspace_bytes", "dad_scl",
     "dad_peer_push", "dad_peer_barrier", "dad_grad_sum_ranks", "dad_max_world", "dad_gather_pad",
     "dad_aug_encoder_fwd", "dad_aug_encoder_fwd_workspace_bytes", "dad_tc_set_cta_pair", "dad_tc_get_cta_pair",
-    "dad_tc_set_bwd_products", "dad_tc_get_bwd_products",
+    "dad_tc_set_bwd_products", "dad_tc_get_bwd_products", "dad_predict", "dad_predict_workspace_bytes",
 )
 
 
@@ -95,7 +95,7 @@ def lib():
     L.dad_last_error.restype = C.c_char_p
     L.dad_abi_version.restype = C.c_int
     for name in ("dad_encoder_fwd_workspace_bytes", "dad_encoder_bwd_workspace_bytes", "dad_ecda_workspace_bytes", "dad_scl_workspace_bytes",
-                 "dad_aug_encoder_fwd_workspace_bytes"):
+                 "dad_aug_encoder_fwd_workspace_bytes", "dad_predict_workspace_bytes"):
         getattr(L, name).restype = C.c_size_t
     L.dad_pack_rank_words.restype = C.c_int64
     L.dad_encoder_fwd_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int32]
@@ -110,6 +110,8 @@ def lib():
     L.dad_aug_encoder_fwd_workspace_bytes.argtypes = [i64, i64]
     L.dad_aug_encoder_fwd.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Aug), vp, vp, vp, vp, C.POINTER(Aug), vp, vp, vp, vp, vp, vp, C.c_size_t,
                                       i64, i64, vp]
+    L.dad_predict_workspace_bytes.argtypes = [i64, i64]
+    L.dad_predict.argtypes = [vp] * 19 + [C.c_size_t, i64, i64, vp]
     L.dad_tc_set_cta_pair.argtypes = [i32]
     L.dad_tc_set_cta_pair.restype = None
     L.dad_tc_set_bwd_products.argtypes = [i32]

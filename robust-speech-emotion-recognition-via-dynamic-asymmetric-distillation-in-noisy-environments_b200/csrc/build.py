@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 INC = os.path.join(ROOT, "include")
 OUT = os.path.join(os.path.dirname(HERE), "libdad_sm100a.so")
-SRCS = ["dad_abi.cu", "k_aug.cu", "k_enc_simt.cu", "k_enc_tc.cu", "k_head.cu", "k_ecda.cu", "k_gram_tc.cu", "k_scl.cu", "k_peer.cu", "k_optim.cu"]
+SRCS = ["dad_abi.cu", "k_aug.cu", "k_enc_simt.cu", "k_enc_tc.cu", "k_head.cu", "k_ecda.cu", "k_gram_tc.cu", "k_scl.cu", "k_peer.cu", "k_optim.cu", "k_predict.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-I", INC, "-I", HERE]
 

@@ -19,6 +19,8 @@ size_t enc_fwd_tc_ws_bytes(int64_t B, int64_t T);
 int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W0_hi, const void* W0_lo, const float* bias0, const AugParams& ap0, float* emb0,
                       uint32_t* bits0, const void* W1_hi, const void* W1_lo, const float* bias1, const AugParams* ap1, float* emb1, uint32_t* bits1,
                       void* xs_hi, void* xs_lo, float* lens_out, void* ws, size_t ws_bytes, int64_t B, int64_t T, cudaStream_t st);
+int launch_predict_heads(const float* emb_s, const float* Wc_s, const float* bc_s, float* logits_s, int32_t* pred_s, const float* emb_t,
+                         const float* Wc_t, const float* bc_t, float* logits_t, int32_t* pred_t, int64_t B, cudaStream_t st);
 void enc_tc_set_cta_pair(int on);
 int enc_tc_get_cta_pair();
 void enc_tc_set_bwd_products(int n);
@@ -171,6 +173,28 @@ int dad_aug_encoder_fwd(const float* x, const uint8_t* pad, const void* Wt_hi, c
     if (!ws || ws_bytes < need) return dad_set_error(DAD_ERR_WS, "aug_encoder_fwd: workspace %zu < %zu bytes", ws_bytes, need);
     return launch_enc_fwd_tc(x, pad, Wt_hi, Wt_lo, bias_t, *aug_weak, emb_teacher, nullptr, Ws_hi, Ws_lo, bias_s, aug_strong, emb_student, relu_bits, xs_hi,
                              xs_lo, lens, ws, ws_bytes, B, T, (cudaStream_t)stream);
+}
+
+// fused inference: encoder + classifier + arg-max of the student and (optionally) the teacher from ONE read of x
+size_t dad_predict_workspace_bytes(int64_t B, int64_t T) { return enc_fwd_tc_ws_bytes(B, T); }
+int dad_predict(const float* x, const uint8_t* pad, const void* Ws_hi, const void* Ws_lo, const float* bias_s, const float* Wc_s, const float* bc_s,
+                const void* Wt_hi, const void* Wt_lo, const float* bias_t, const float* Wc_t, const float* bc_t, float* emb_s, float* emb_t,
+                float* logits_s, float* logits_t, int32_t* pred_s, int32_t* pred_t, void* ws, size_t ws_bytes, int64_t B, int64_t T, void* stream) {
+    DAD_REQUIRE(B >= 0 && T >= 0, "predict: negative size");
+    if (B == 0) return DAD_OK;
+    DAD_REQUIRE(T > 0 && B <= 0x7fffffff / 2 && T <= 0x7fffffff, "predict: bad size");
+    DAD_REQUIRE(x && aligned16(x), "predict: x null or not 16-byte aligned");
+    DAD_REQUIRE(Ws_hi && Ws_lo && bias_s && Wc_s && bc_s && emb_s && logits_s && aligned16(emb_s) && aligned16(logits_s), "predict: null / unaligned student tensor");
+    const bool two = Wt_hi != nullptr;
+    DAD_REQUIRE(!two || (Wt_lo && bias_t && Wc_t && bc_t && emb_t && logits_t && aligned16(emb_t) && aligned16(logits_t)), "predict: null / unaligned teacher tensor");
+    const size_t need = dad_predict_workspace_bytes(B, T);
+    if (!ws || ws_bytes < need) return dad_set_error(DAD_ERR_WS, "predict: workspace %zu < %zu bytes", ws_bytes, need);
+    AugParams ap;
+    memset(&ap, 0, sizeof(ap));
+    int rc = launch_enc_fwd_tc(x, pad, Ws_hi, Ws_lo, bias_s, ap, emb_s, nullptr, two ? Wt_hi : nullptr, two ? Wt_lo : nullptr, bias_t, two ? &ap : nullptr,
+                               emb_t, nullptr, nullptr, nullptr, nullptr, ws, ws_bytes, B, T, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_predict_heads(emb_s, Wc_s, bc_s, logits_s, pred_s, two ? emb_t : nullptr, Wc_t, bc_t, logits_t, pred_t, B, (cudaStream_t)stream);
 }
 
 /* process-wide tuning switches of the tcgen05 encoder kernels */

@@ -103,11 +103,29 @@ class SSRLModel(nn.Module):
             else:
                 raise ops.DadError("update_teacher_ema: model is on the CPU; dad_b200 has no CPU path (move it to cuda)")
 
+    def _fused_ok(self, x):
+        return x.is_cuda and x.dim() == 3 and x.shape[1] >= 32 and x.shape[0] > 0
+
     def predict(self, x: torch.Tensor, padding_mask=None, use_teacher=False):
+        """logits [B,4] in eval mode (I/model.py:225-245): encoder + classifier in one fused pass on the tcgen05 path (dad_predict)."""
         self.eval()  # the reference flips the WHOLE model to eval here (I/model.py:237); train_epoch flips it back
         with torch.no_grad():
             enc, cls = (self.teacher_encoder, self.teacher_classifier) if use_teacher else (self.student_encoder, self.student_classifier)
-            return cls(enc(x, padding_mask))
+            if self._fused_ok(x):
+                return ops.predict(x, padding_mask, enc.pre_net.weight, enc.pre_net.bias, cls.fc_layer.weight, cls.fc_layer.bias)["logits_s"]
+            return cls(enc(x, padding_mask))  # 2-D input / utterances shorter than one 32-frame group: CUDA-core encoder kernel
+
+    def predict_both(self, x: torch.Tensor, padding_mask=None):
+        """(student logits, teacher logits) from ONE read of x (validate's disagreement rate, I/train.py:522-564, runs both
+        networks over the same batches): the two weight sets share the converted A operand of one tcgen05 pass."""
+        self.eval()
+        with torch.no_grad():
+            if self._fused_ok(x):
+                se, sc, te, tc = self.student_encoder, self.student_classifier, self.teacher_encoder, self.teacher_classifier
+                o = ops.predict(x, padding_mask, se.pre_net.weight, se.pre_net.bias, sc.fc_layer.weight, sc.fc_layer.bias,
+                                te.pre_net.weight, te.pre_net.bias, tc.fc_layer.weight, tc.fc_layer.bias)
+                return o["logits_s"], o["logits_t"]
+            return (self.student_classifier(self.student_encoder(x, padding_mask)), self.teacher_classifier(self.teacher_encoder(x, padding_mask)))
 
     def get_embeddings(self, x: torch.Tensor, padding_mask=None, use_teacher=False):
         self.eval()

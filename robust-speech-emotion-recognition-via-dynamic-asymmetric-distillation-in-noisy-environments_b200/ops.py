@@ -149,6 +149,34 @@ def encoder_pool_bwd(x, pad, bits, g_emb, lens, aug=None, gemm_mode=None, xs=Non
     return g[:_lib.OFF_B].view(D_HID, D_IN), g[_lib.OFF_B:_lib.OFF_WC]
 
 
+def predict(x, pad, Ws, bs, Wcs, bcs, Wt=None, bt=None, Wct=None, bct=None, Ws_split=None, Wt_split=None):
+    """Fused inference (dad_predict): ONE read of x [B,T,768] on the tcgen05 path -> student (and, with Wt given, teacher) encoder +
+    classifier in eval mode.  Returns dict(logits_s, pred_s, emb_s[, logits_t, pred_t, emb_t]).  T >= 32."""
+    _lib.require_device()
+    if x.dim() != 3 or x.shape[-1] != D_IN:
+        raise DadError(f"predict: expected x [B,T,{D_IN}], got {tuple(x.shape)}")
+    x = x.contiguous().float()
+    B, T, _ = x.shape
+    dev = x.device
+    two = Wt is not None
+    pad8 = _as_u8_pad(pad, B, T, dev)
+    f32 = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=dev)
+    i32 = lambda *sh: torch.empty(*sh, dtype=torch.int32, device=dev)
+    out = {"logits_s": f32(B, _lib.N_CLS), "pred_s": i32(B), "emb_s": f32(B, D_HID)}
+    if two:
+        out.update({"logits_t": f32(B, _lib.N_CLS), "pred_t": i32(B), "emb_t": f32(B, D_HID)})
+    if B == 0:
+        return out
+    s_hi, s_lo = Ws_split if Ws_split is not None else split_f16(Ws)
+    t_hi, t_lo = (Wt_split if Wt_split is not None else split_f16(Wt)) if two else (None, None)
+    ws = _zeros_ws(lib().dad_predict_workspace_bytes(B, T), dev, "predict")
+    c = lambda t: ptr(t.contiguous().float(), torch.float32) if t is not None else None
+    check(lib().dad_predict(ptr(x, torch.float32, "x"), ptr(pad8), ptr(s_hi), ptr(s_lo), c(bs), c(Wcs), c(bcs), ptr(t_hi), ptr(t_lo), c(bt),
+                            c(Wct), c(bct), ptr(out["emb_s"]), ptr(out.get("emb_t")), ptr(out["logits_s"]), ptr(out.get("logits_t")),
+                            ptr(out["pred_s"]), ptr(out.get("pred_t")), ptr(ws), ws.numel(), B, T, stream_ptr()))
+    return out
+
+
 def gather_pad(feats, offsets, sizes, T=None, x_out=None, pad_out=None):
     """Device-side collate (I/dataload_clean.py:177-193): utterances (offsets, sizes) of a resident [sum T, 768] feature array ->
     zero-padded x [B,T,768] and padding mask [B,T] (bool, True = pad).  offsets int64, sizes int32, all on the device."""

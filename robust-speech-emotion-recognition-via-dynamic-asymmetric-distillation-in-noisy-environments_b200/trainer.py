@@ -349,17 +349,29 @@ class CrossDomainTrainer:
                 labels.append(batch["labels"])
         return torch.cat(preds).cpu().numpy(), torch.cat(labels).cpu().numpy()
 
+    def _predict_all_both(self, data_loader):
+        """student AND teacher predictions of a whole split from one pass over its batches (SSRLModel.predict_both)."""
+        ps, pt, labels = [], [], []
+        with torch.no_grad():
+            for batch in data_loader:
+                feats, mask = self._batch_to_device(batch)
+                ls, lt = self.model.predict_both(feats, mask)
+                ps.append(ls.argmax(dim=1)); pt.append(lt.argmax(dim=1))
+                labels.append(batch["labels"])
+        return torch.cat(ps).cpu().numpy(), torch.cat(pt).cpu().numpy(), torch.cat(labels).cpu().numpy()
+
     def validate(self, data_loader, domain_name="unknown"):
         """Accuracy, balanced ('weighted') accuracy, F1s, per-class stats, confusion matrix (I/train.py:522-564)."""
         from sklearn.metrics import accuracy_score, balanced_accuracy_score, confusion_matrix, f1_score, precision_recall_fscore_support
         if getattr(self, "_eval_from_engine", True):
             self._sync_model_from_engine()
         self.model.eval()
-        p_student, y = self._predict_all(data_loader, use_teacher=False)
         if "noisy" in domain_name.lower() and not self.is_warmup_phase(getattr(self, "current_epoch", 0)):
-            p_teacher, _ = self._predict_all(data_loader, use_teacher=True)
-            if len(p_teacher) == len(p_student):
-                self.training_history[f"disagreement_rate_{domain_name.lower()}"].append(float(np.mean(p_student != p_teacher)))
+            # I/train.py:530-540 runs the loader twice (student, then teacher); here both networks see each batch in one pass
+            p_student, p_teacher, y = self._predict_all_both(data_loader)
+            self.training_history[f"disagreement_rate_{domain_name.lower()}"].append(float(np.mean(p_student != p_teacher)))
+        else:
+            p_student, y = self._predict_all(data_loader, use_teacher=False)
         lab = list(range(self.num_classes))
         cm = confusion_matrix(y, p_student, labels=lab)
         prec, rec, f1, sup = precision_recall_fscore_support(y, p_student, average=None, zero_division=0, labels=lab)

@@ -34,7 +34,7 @@ def tc_switch():
     L = _lib.lib()
     old = (L.dad_tc_get_cta_pair(), L.dad_tc_get_bwd_products())
 
-    def set_(cta_pair=None, products=None):
+    def set_(cta_pair=None, products=None):  # cta_pair: 0 never, 1 always, 2 auto (bool accepted)
         if cta_pair is not None:
             L.dad_tc_set_cta_pair(int(cta_pair))
         if products is not None:
@@ -110,8 +110,8 @@ def test_encoder_forward_vs_reference_golden(mode):
     assert torch.equal(lens2.cpu(), torch.full((g["B"],), float(g["T"])))
 
 
-# tcgen05 variants: one CTA per tile / CTA pairs (cta_group::2) x 2- / 3-product dW GEMM
-TC_VARIANTS = ["fp32", "tc", "tc-single-cta", "tc-3prod"]
+# tcgen05 variants: default (CTA pairs where they pay, 3-product dW GEMM), pairs forced on / off, the opt-in 2-product dW GEMM
+TC_VARIANTS = ["fp32", "tc", "tc-single-cta", "tc-pair", "tc-2prod"]
 
 
 @pytest.mark.parametrize("mode", TC_VARIANTS)
@@ -122,7 +122,7 @@ def test_encoder_forward_backward_vs_oracle(mode, B, T, aug, tc_switch):
     from oracle import dad_oracle as O
     if mode != "fp32" and T < 32:
         pytest.skip("tcgen05 path needs T >= 32")
-    tc_switch(cta_pair=mode != "tc-single-cta", products=3 if mode == "tc-3prod" else 2)
+    tc_switch(cta_pair={"tc-single-cta": 0, "tc-pair": 1}.get(mode, 2), products=2 if mode == "tc-2prod" else 3)
     mode = "fp32" if mode == "fp32" else "tc"
     c, n, rng = _inputs(B, T, 4242 + B * 1000 + T)
     st = pretrained_state()
@@ -279,6 +279,67 @@ def test_fused_noisy_forward_vs_oracle(B, T, cta_pair, tc_switch):
     assert torch.allclose(emb_t.cpu(), ref_t, rtol=1e-4, atol=2e-5), float((emb_t.cpu() - ref_t).abs().max())
     assert torch.allclose(emb_s.cpu(), ref_s, rtol=1e-4, atol=2e-5), float((emb_s.cpu() - ref_s).abs().max())
     assert torch.equal(lens.cpu(), (~ph).sum(1).float())
+
+
+@pytest.mark.parametrize("B,T,padded", [(6, 64, True), (37, 41, True), (64, 200, False), (5, 97, True)])
+def test_fused_predict_vs_oracle(B, T, padded):
+    """dad_predict: student + teacher logits / arg-max from one read of x == the oracle's encoder + classifier in
+    eval mode (I/model.py:225-245): logits 1e-5 (+1e-4 relative), arg-max exact away from ties, so the student / teacher
+    disagreement rate of validate (I/train.py:522-564) is exact; the one-network form agrees bit for bit with the two-network one."""
+    from dad_b200 import ops
+    from oracle import dad_oracle as O
+    st = pretrained_state()
+    c, n, _ = _inputs(B, T, 900 + B + T, variable=padded)
+    x, pad = n["net_input"]["feats"], n["net_input"]["padding_mask"]
+    g = torch.Generator().manual_seed(3)
+    Ws, bs = st["student_encoder.pre_net.weight"], st["student_encoder.pre_net.bias"]
+    Wcs, bcs = st["student_classifier.fc_layer.weight"], st["student_classifier.fc_layer.bias"]
+    Wt, bt = Ws + 0.02 * torch.randn(256, 768, generator=g), bs + 0.02 * torch.randn(256, generator=g)
+    Wct, bct = Wcs + 0.05 * torch.randn(4, 256, generator=g), bcs + 0.05 * torch.randn(4, generator=g)
+    ref_s = O.classifier(O.encoder(x, pad, Ws, bs), None, 0.0, Wcs, bcs)
+    ref_t = O.classifier(O.encoder(x, pad, Wt, bt), None, 0.0, Wct, bct)
+    cu = lambda t: t.cuda()
+    o = ops.predict(cu(x), cu(pad) if padded else None, cu(Ws), cu(bs), cu(Wcs), cu(bcs), cu(Wt), cu(bt), cu(Wct), cu(bct))
+    for got, ref in ((o["logits_s"], ref_s), (o["logits_t"], ref_t)):
+        assert torch.allclose(got.cpu(), ref, rtol=1e-4, atol=1e-5), float((got.cpu() - ref).abs().max())
+    unclear = torch.zeros(B, dtype=torch.bool)
+    for pred, ref in ((o["pred_s"], ref_s), (o["pred_t"], ref_t)):
+        top2 = ref.topk(2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-4
+        unclear |= ~clear
+        assert torch.equal(pred.cpu().long()[clear], ref.argmax(1)[clear])
+    # validate's student / teacher disagreement rate: exact unless a sample sits on a logit tie
+    dis_ref = float((ref_s.argmax(1) != ref_t.argmax(1)).float().mean())
+    dis_got = float((o["pred_s"] != o["pred_t"]).float().mean())
+    assert abs(dis_got - dis_ref) <= float(unclear.sum()) / B + 1e-12
+    one = ops.predict(cu(x), cu(pad) if padded else None, cu(Ws), cu(bs), cu(Wcs), cu(bcs))
+    assert torch.equal(one["logits_s"], o["logits_s"]) and torch.equal(one["pred_s"], o["pred_s"])
+
+
+def test_model_predict_uses_the_fused_path_and_matches_the_module_path():
+    """SSRLModel.predict / predict_both (drop-in surface, I/model.py:225-245) on the fused tcgen05 pass == the module path
+    (torch.ops.dad.encoder_pool + nn.Linear) within the kernels' tolerance; eval mode is set as upstream."""
+    from dad_b200 import config as cfg
+    from dad_b200.model import SSRLModel
+    model = SSRLModel(cfg).cuda()
+    model.load_state_dict(pretrained_state())
+    with torch.no_grad():
+        for p_ in model.teacher_encoder.parameters():
+            p_.add_(0.01 * torch.randn_like(p_))
+    c, n, _ = _inputs(9, 70, 77)
+    x, pad = n["net_input"]["feats"].cuda(), n["net_input"]["padding_mask"].cuda()
+    model.train()
+    ls = model.predict(x, pad)
+    assert not model.training  # I/model.py:237
+    lt = model.predict(x, pad, use_teacher=True)
+    bs_, bt_ = model.predict_both(x, pad)
+    assert torch.allclose(ls, bs_, rtol=1e-5, atol=1e-6) and torch.allclose(lt, bt_, rtol=1e-5, atol=1e-6)
+    with torch.no_grad():
+        ref_s = model.student_classifier(model.student_encoder(x, pad))
+        ref_t = model.teacher_classifier(model.teacher_encoder(x, pad))
+    assert torch.allclose(ls, ref_s, rtol=1e-4, atol=1e-5) and torch.allclose(lt, ref_t, rtol=1e-4, atol=1e-5)
+    short = model.predict(x[:, :20].contiguous(), pad[:, :20].contiguous())   # T < 32: CUDA-core encoder kernel
+    assert short.shape == (9, 4)
 
 
 def test_philox_noise_field_is_global_under_data_parallel_offsets():
