@@ -38,6 +38,7 @@ _COMMON = dict(
     # B200 additions (not in the reference): kernel arithmetic + noise source of the fused step
     DAD_GEMM_MODE=os.environ.get("DAD_GEMM", "tc"), DAD_USE_CUDA_GRAPH=True,
     DAD_DEVICE_DATA=True,  # keep each split's features resident in HBM and assemble batches on the device (dataload.DeviceUtteranceLoader)
+    DAD_SYNTHETIC_DATA=False,  # trainers built without explicit loaders use synthetic stand-in features (offline runs, runner tests)
 )
 
 

@@ -125,6 +125,11 @@ class CrossDomainTrainer:
         self._bias_pending = []
         self.dacp_manager = None
         self.calibrated_anchors = None
+        if loaders is None and getattr(cfg, "DAD_SYNTHETIC_DATA", False):
+            # offline stand-in data, selectable the way the runners select everything else: setattr on the config module
+            # (I/run_granular_ablations.py:25-30) -- no dataset files, no stage-1 checkpoint
+            loaders = self.synthetic_loaders(fold, device=self._data_device_for(cfg))
+            require_pretrained = False
         self._loaders = loaders
         self._require_pretrained = require_pretrained
         logger.info(f"{self.DISPLAY} cross-domain trainer (DACP+ECDA), fold {fold + 1}/{self.N_FOLDS_TOTAL}, noise {self.noise_info['display_name']}, "
@@ -179,6 +184,10 @@ class CrossDomainTrainer:
     def _make_loaders(self, batch_size):
         """-> ((clean_train, clean_val, clean_test, class_names, num_classes), (student, teacher, noisy_val, noisy_test))"""
         raise NotImplementedError
+
+    @staticmethod
+    def _data_device_for(cfg):
+        return "cuda" if getattr(cfg, "DAD_DEVICE_DATA", True) else None
 
     def _data_device(self):
         """Device the loaders keep the splits on (None = pinned host memory + one H2D copy per batch)."""
@@ -256,6 +265,10 @@ class CrossDomainTrainer:
                                     use_graph=bool(getattr(cfg, "DAD_USE_CUDA_GRAPH", True)), noise_mode="philox",
                                     seed=int(getattr(cfg, "RANDOM_SEED", 42)))
         self.engine.load_state_dict(self.model.state_dict())
+        # HBM-resident training splits assemble every batch straight into the engine's input buffers (no copy in set_inputs)
+        for ld, dom in ((self.clean_train_loader, "clean"), (self.noisy_student_loader, "noisy")):
+            if hasattr(ld, "sink"):
+                ld.sink = (lambda b_, t_, d_=dom: self.engine.input_views(d_, b_, t_))
         if self.calibrated_anchors is not None:
             self.engine.anchors.copy_(self.calibrated_anchors)
         else:
