@@ -196,7 +196,7 @@ def pin_to_gpu_numa_node(dev):
 def dp_check(cfg, world, rank, dev, pg, B, gm, exchange, T=64, epoch=45):
     """Outside the timed region (N > 1): is the data-parallel step the single-process step?  Every rank builds the SAME global batch
     and RNG draws (same seeds), runs its shard through a world-N engine (supplied-noise mode) and the whole batch through a
-    world-1 engine: 3 CE-only steps, teacher := student, 2 full-stack steps.  Reports the bit-identity of the replicated state
+    world-1 engine: 30 CE-only steps, teacher := student, 2 full-stack steps.  Reports the bit-identity of the replicated state
     across ranks (all-gathered 64-bit checksum of p, t, ema_thr), the largest relative loss difference and weight difference
     against the world-1 engine, and whether the DACP masks agree (SURVEY.md 8e "Determinism")."""
     import torch
@@ -222,9 +222,10 @@ def dp_check(cfg, world, rank, dev, pg, B, gm, exchange, T=64, epoch=45):
     for e in (dp, one):
         e.load_state_dict(st)
         e.set_lr(cfg.LEARNING_RATE)
-    for k in range(5):
-        ep = 0 if k < 3 else epoch
-        if k == 3:
+    n_ce = 30  # CE-only steps first: the teacher must be confident for DACP to mask samples in and KD / ECDA to run
+    for k in range(n_ce + 2):
+        ep = 0 if k < n_ce else epoch
+        if k == n_ce:
             dp.init_teacher(); one.init_teacher()
         one.set_inputs(clean, noisy, rng)
         dp.set_inputs(sh(clean), sh(noisy), rng_l)
@@ -234,12 +235,15 @@ def dp_check(cfg, world, rank, dev, pg, B, gm, exchange, T=64, epoch=45):
             loss_rel = max(loss_rel, abs(a[key] - b[key]) / max(abs(b[key]), 1e-3))
     mask_equal = bool(torch.equal(dp.mask, one.mask))
     w_diff = float(torch.maximum((dp.p - one.p).abs().max(), (dp.t - one.t).abs().max()))
+    well = one.g_ext[:dp.p.numel()].abs() >= 1e-6  # elements whose Adam update is well conditioned (as in the parity tests)
+    w_diff_well = float((dp.p - one.p).abs()[well].max()) if bool(well.any()) else 0.0
     flat = torch.cat([dp.p, dp.t, dp.ema_thr]).view(torch.int32).to(torch.int64)
     h = (flat * (torch.arange(flat.numel(), device=dev) % 65521 + 1)).sum().reshape(1)
     hs = [torch.zeros_like(h) for _ in range(world)]
     dist.all_gather(hs, h, group=pg)
     out = {"state_identical": bool(all(int(x) == int(hs[0]) for x in hs)), "loss_rel": loss_rel, "weights_max_abs_diff_vs_world1": w_diff,
-           "mask_equal": mask_equal, "masked_in": int(dp.nmask.item()), "B_local": B, "B_global": Bg, "T": T, "steps": "3 CE-only + 2 full",
+           "weights_max_abs_diff_well_conditioned": w_diff_well, "last_losses": a,
+           "mask_equal": mask_equal, "masked_in": int(dp.nmask.item()), "B_local": B, "B_global": Bg, "T": T, "steps": f"{n_ce} CE-only + 2 full",
            "exchange": dp.exchange}
     dp.close(); one.close()
     return out

@@ -191,3 +191,96 @@ def test_full_size_step_downstream_of_encoders_vs_oracle():
         d = float((g_eng.cpu().double() - leaf.grad.double()).abs().max()) / float(leaf.grad.abs().max())
         print(f"[full-size step] dL/d emb_{name}: rel-to-max err {d:.2e}")
         assert d <= 2e-4, (name, d)
+
+
+def test_full_size_step_hard_noisy_domain_partial_mask_through_adam():
+    """at the headline size the easy noisy domain masks every sample in, which makes "mask exact" and the KD
+    denominator trivial.  Here the noisy domain is at -12 dB and the DACP state sits inside the score distribution: thresholds near
+    the per-class 45 % score quantile for classes 0-2 and an anchor above every score for class 3, so that roughly half of the
+    batch is masked in and one class is INFEASIBLE for ECDA (no masked noisy member).  Checked: the partial mask and the
+    pseudo-labels exactly, thresholds 1e-6, losses 1e-4, dL/d emb, the classifier gradients against the oracle's autograd, and --
+    feeding the oracle's clip / Adam / EMA (I/train.py:487-492) the ENGINE'S flat gradient -- the updated student and teacher
+    weights at 1e-5 / 1e-6 on all 197 892 elements (same gradient in, so no conditioning caveat)."""
+    from dad_b200 import _lib
+    from dad_b200.engine import DADStepEngine
+    B, T, epoch = 4096, 200, 60
+    orc, cfg, hp = make_oracle("iemocap")
+    orc.lr = O.cosine_lr(hp.LEARNING_RATE, epoch, hp.EPOCHS)
+    orc.anchors = torch.tensor([0.05, 0.05, 0.05, 5.0])
+    orc.dacp.ema_thr = torch.tensor([0.898, 0.939, 0.860, 5.0])
+    orc.nstep = 7  # mid-run Adam state: bias corrections away from their first-step special case
+    g0 = torch.Generator().manual_seed(77)
+    for k in O.PARAM_KEYS:
+        orc.m[k] = 1e-4 * torch.randn(orc.p[k].shape, generator=g0)
+        orc.v[k] = 1e-7 * torch.rand(orc.p[k].shape, generator=g0) + 1e-9
+    eng = DADStepEngine(cfg, B, T, gemm_mode=_lib.GEMM_TC, use_graph=False, noise_mode="philox", seed=43)
+    push_oracle_state(eng, orc)
+    xc, pc, yc, _ = _device_inputs(B, T, 41, variable_len=True)
+    xn, pn, yn, _ = _device_inputs(B, T, 42, variable_len=True, snr_db=-12.0)
+    eng.set_inputs({"net_input": {"feats": xc, "padding_mask": pc}, "labels": yc},
+                   {"net_input": {"feats": xn, "padding_mask": pn}, "labels": yn})
+    p_before, t_before = eng.p.cpu().clone(), eng.t.cpu().clone()
+    eng.step(epoch)
+    torch.cuda.synchronize()
+    got = eng.losses()
+    v = _lib.pack_global_views(eng.pack, B, 1)
+    emb_c = v["emb_clean"][0].detach().cpu().clone().requires_grad_(True)
+    emb_s = v["emb_strong"][0].detach().cpu().clone().requires_grad_(True)
+    emb_t = eng.emb_teacher.detach().cpu().clone()
+    queue = [emb_c, emb_t, emb_s]
+    dummy, nopad = torch.zeros(B, 1, 768), torch.zeros(B, 1, dtype=torch.bool)
+    c = {"net_input": {"feats": dummy, "padding_mask": nopad}, "labels": yc.cpu()}
+    n = {"net_input": {"feats": dummy, "padding_mask": nopad}, "labels": None}
+    rng = {"drop_clean": eng.keep_clean.cpu().clone(), "drop_strong": eng.keep_strong.cpu().clone(), "n_weak": dummy, "n_strong": dummy,
+           "feat_keep_u": torch.ones(768), "t_start": torch.zeros(B, dtype=torch.int64)}
+    real_enc, real_ecda = O.encoder, O.ecda_loss
+    O.encoder = lambda x, pad, W, b: queue.pop(0)
+    O.ecda_loss = lambda cl, nz, y1, y2, m, s, w, h: O.ecda_loss_gram(cl.double(), nz.double(), y1, y2, m, s.double(), w.double(), h)
+    try:
+        for p_ in orc.p.values():
+            p_.grad = None
+        ref = orc.forward_losses(c, n, epoch, rng)
+        ref["total_loss"].backward()
+    finally:
+        O.encoder, O.ecda_loss = real_enc, real_ecda
+    refv = {k: float(x.detach()) for k, x in ref.items()}
+    mask_o, pred_o = orc.last["mask"], orc.last["pred"]
+    nmask = int(mask_o.sum())
+    per_class = [int((mask_o & (pred_o == k)).sum()) for k in range(4)]
+    flips = int((eng.mask.cpu().bool() != mask_o).sum())
+    print(f"[full-size hard step] masked-in {nmask}/{B} per pseudo-class {per_class}, mask flips {flips}, losses engine {got} oracle {refv}")
+    assert 0.25 * B <= nmask <= 0.85 * B, nmask                 # a PARTIAL mask
+    assert per_class[3] == 0 and min(per_class[:3]) >= 2        # class 3 infeasible for ECDA, the others feasible
+    assert flips == 0 and torch.equal(v["pred"][0].cpu().long(), pred_o)
+    assert float((eng.ema_thr.cpu() - orc.dacp.ema_thr).abs().max()) <= 1e-6
+    for key in ("supervised_ce_loss", "consistency_loss", "ecda_loss", "total_loss"):
+        r = refv[key]
+        assert abs(got[key] - r) <= 1e-4 * max(abs(r), 1e-3), (key, got[key], r)
+    for name, g_eng, leaf in (("clean", eng.g_clean, emb_c), ("strong", eng.g_strong, emb_s)):
+        d = float((g_eng.cpu().double() - leaf.grad.double()).abs().max()) / float(leaf.grad.abs().max())
+        print(f"[full-size hard step] dL/d emb_{name}: rel-to-max err {d:.2e}")
+        assert d <= 2e-4, (name, d)
+    # classifier gradients (autograd of the oracle through its own heads) vs the engine's flat gradient
+    g_eng = eng.g_ext[:_lib.NPARAM].cpu()
+    for key, a0, a1 in (("student_classifier.fc_layer.weight", _lib.OFF_WC, _lib.OFF_BC), ("student_classifier.fc_layer.bias", _lib.OFF_BC, _lib.NPARAM)):
+        go = orc.p[key].grad.reshape(-1)
+        d = float((g_eng[a0:a1] - go).abs().max()) / float(go.abs().max())
+        print(f"[full-size hard step] d{key}: rel-to-max err {d:.2e}")
+        assert d <= 2e-4, (key, d)
+    # optimiser tail at full size: oracle clip + Adam + EMA on the engine's gradient == the engine's updated weights
+    grads = [g_eng[a:b].clone().view(shape) for (a, b, shape) in ((_lib.OFF_W, _lib.OFF_B, (256, 768)), (_lib.OFF_B, _lib.OFF_WC, (256,)),
+                                                                  (_lib.OFF_WC, _lib.OFF_BC, (4, 256)), (_lib.OFF_BC, _lib.NPARAM, (4,)))]
+    O.clip_grad_norm(grads, hp.MAX_GRAD_NORM)
+    orc.nstep += 1
+    with torch.no_grad():
+        for k, g_ in zip(O.PARAM_KEYS, grads):
+            O.adam_step(orc.p[k], g_, orc.m[k], orc.v[k], orc.nstep, orc.lr, hp.WEIGHT_DECAY)
+        for ks, kt in zip(O.PARAM_KEYS, O.TEACHER_KEYS):
+            orc.t[kt] = O.ema_update(orc.t[kt], orc.p[ks].detach(), hp.EMA_MOMENTUM)
+    p_orc = torch.cat([orc.p[k].detach().reshape(-1) for k in O.PARAM_KEYS])
+    t_orc = torch.cat([orc.t[k].reshape(-1) for k in O.TEACHER_KEYS])
+    dp_, dt_ = float((eng.p.cpu() - p_orc).abs().max()), float((eng.t.cpu() - t_orc).abs().max())
+    moved = float((eng.p.cpu() - p_before).abs().max())
+    print(f"[full-size hard step] after clip+Adam+EMA: student max abs diff {dp_:.2e} (update size {moved:.2e}), teacher {dt_:.2e}")
+    assert moved > 1e-5 and float((eng.t.cpu() - t_before).abs().max()) > 0
+    assert dp_ <= 1e-5 and dt_ <= 1e-6, (dp_, dt_)
