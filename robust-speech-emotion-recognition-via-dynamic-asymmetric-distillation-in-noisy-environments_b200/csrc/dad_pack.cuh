@@ -33,7 +33,7 @@ struct EcdaTile { int cls, row_begin, row_count, feasible, g_row, pad_[3]; };  /
 struct GramItem { int a_row, b_row, g_row, g_col, n_rows, n_cols, cls, pad_; };
 // (P Z') block: P rows g_row..+127, Z' rows from b_row; this item covers k-blocks [kb0, kb0 + n_kb) of 64 members (split-K slice `slice`)
 struct PzItem { int g_row, b_row, kb0, n_kb, slice, cls, pad_[2]; };
-constexpr int ECDA_PZ_SPLITS = 4;  // max split-K slices of the (P Z') GEMM (fills the SMs when a rank owns few row blocks)
+constexpr int ECDA_PZ_SPLITS = 16;  // max split-K slices of the (P Z') GEMM: k_ecda_stats picks 148 / (row blocks this rank owns), so a data-parallel rank that owns 4-12 blocks still fills the SMs (r01: 16 CTAs, 46 us at 512 samples per rank)
 
 struct EcdaStats {  // written by k_ecda_stats, read by the Gram / P / fold / loss kernels
     int n_s[ECDA_MAXC], n_t[ECDA_MAXC], feasible[ECDA_MAXC], list_off[ECDA_MAXC];
