@@ -252,6 +252,23 @@ int dad_peer_push(const void* src_local, void* const* peers, int32_t world, int3
                   size_t dst_offset, size_t bytes, void* stream);
 int dad_peer_barrier(void* const* peers, int32_t world, int32_t rank, size_t flag_offset, uint32_t* local_seq, void* stream);
 int dad_grad_sum_ranks(const float* stage, int32_t world, int64_t n, float* out, void* stream);
+/* FUSED forms (what the step engine uses; SURVEY.md 8e "all-gather written from the producing kernel's tail, all-reduce consumed at the
+ * head of the optimiser kernels"):
+ *   dad_peer_push_barrier   push + barrier in one launch: the last CTA of the copy runs the flag barrier.  `counter` = zero-initialised
+ *                           device word (self-resetting); the segment must be 16-byte aligned and a multiple of 16 bytes
+ *   dad_grad_reduce_xchg    dad_grad_reduce whose result (+ the 8 loss-share words behind g) is stored straight into slot [rank] of EVERY
+ *                           rank's gradient stage (byte offset `stage_offset`, [world][DAD_NPARAM + 8] f32) and whose last CTA runs the
+ *                           flag barrier: split-K fold + all-to-all + barrier = one kernel
+ *   dad_grad_norm_xchg      dad_grad_norm that first forms g = sum over ranks of `stage` in rank order (identical bits on every rank),
+ *                           writes it to g[DAD_NPARAM + 8] and takes the norm of the sum */
+int dad_peer_push_barrier(const void* src_local, void* const* peers, int32_t world, int32_t rank, size_t dst_offset, size_t bytes,
+                          size_t flag_offset, uint32_t* local_seq, uint32_t* counter, void* stream);
+int dad_grad_reduce_xchg(const float* dW_part0, const float* db_part0, int32_t splits0, const float* dW_part1,
+                         const float* db_part1, int32_t splits1, const float* dWc, const float* dbc, float* g, void* const* peers,
+                         int32_t world, int32_t rank, size_t stage_offset, size_t flag_offset, uint32_t* local_seq,
+                         uint32_t* counter, void* stream);
+int dad_grad_norm_xchg(float* g, const float* stage, int32_t world, double* part_ws, uint32_t* counter, int64_t* step,
+                       const double* lr, float* scal, float max_norm, void* stream);
 
 /* ---- optimiser tail (I/train.py:487-492; I/model.py:211-223) --------------------------------------------------- */
 /* g[DAD_NPARAM] = fixed-order sum of the encoder split-K partials (up to two backward launches) ++ head grads */

@@ -24,6 +24,7 @@ EXPORTS = (
     "dad_peer_push", "dad_peer_barrier", "dad_grad_sum_ranks", "dad_max_world", "dad_gather_pad",
     "dad_aug_encoder_fwd", "dad_aug_encoder_fwd_workspace_bytes", "dad_tc_set_cta_pair", "dad_tc_get_cta_pair",
     "dad_tc_set_bwd_products", "dad_tc_get_bwd_products", "dad_predict", "dad_predict_workspace_bytes",
+    "dad_peer_push_barrier", "dad_grad_reduce_xchg", "dad_grad_norm_xchg",
 )
 
 
@@ -126,6 +127,9 @@ def lib():
     L.dad_peer_push.argtypes = [vp, C.POINTER(vp), i32, i32, i32, C.c_size_t, C.c_size_t, vp]
     L.dad_peer_barrier.argtypes = [C.POINTER(vp), i32, i32, C.c_size_t, vp, vp]
     L.dad_grad_sum_ranks.argtypes = [vp, i32, i64, vp, vp]
+    L.dad_peer_push_barrier.argtypes = [vp, C.POINTER(vp), i32, i32, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp, vp]
+    L.dad_grad_reduce_xchg.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp, C.POINTER(vp), i32, i32, C.c_size_t, C.c_size_t, vp, vp, vp]
+    L.dad_grad_norm_xchg.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, f32, vp]
     L.dad_gather_pad.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp]
     L.dad_grad_reduce.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp, vp]
     L.dad_grad_norm.argtypes = [vp, vp, vp, vp, vp, vp, f32, vp]

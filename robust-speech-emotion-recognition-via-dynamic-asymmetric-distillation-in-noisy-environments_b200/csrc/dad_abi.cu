@@ -46,6 +46,8 @@ int launch_gather_pad(const float* feats, const int64_t* offsets, const int32_t*
 int launch_peer_push(const void* src, void* const* peers, int world, int self_rank, int include_self, size_t dst_off, size_t bytes, cudaStream_t st);
 int launch_peer_barrier(void* const* peers, int world, int rank, size_t flag_off, unsigned* local_seq, cudaStream_t st);
 int launch_grad_sum_ranks(const float* stage, int world, int64_t n, float* out, cudaStream_t st);
+int launch_peer_push_barrier(const void* src, void* const* peers, int world, int self_rank, size_t dst_off, size_t bytes, size_t flag_off,
+                             unsigned* local_seq, unsigned* counter, cudaStream_t st);
 int launch_grad_reduce(const GradReduceArgs& a, cudaStream_t st);
 int launch_grad_norm(const NormArgs& a, cudaStream_t st);
 int launch_adam_ema(const AdamArgs& a, cudaStream_t st);
@@ -312,6 +314,13 @@ int dad_peer_barrier(void* const* peers, int32_t world, int32_t rank, size_t fla
     DAD_REQUIRE(rank >= 0 && rank < world && local_seq && (flag_offset & 3) == 0, "peer_barrier: bad rank / counter / offset");
     return launch_peer_barrier(peers, world, rank, flag_offset, local_seq, (cudaStream_t)stream);
 }
+int dad_peer_push_barrier(const void* src_local, void* const* peers, int32_t world, int32_t rank, size_t dst_offset, size_t bytes,
+                          size_t flag_offset, uint32_t* local_seq, uint32_t* counter, void* stream) {
+    int rc = check_peers(peers, world, "peer_push_barrier");
+    if (rc) return rc;
+    DAD_REQUIRE(src_local && rank >= 0 && rank < world && local_seq && counter && (flag_offset & 3) == 0, "peer_push_barrier: bad rank / counter / offset");
+    return launch_peer_push_barrier(src_local, peers, world, rank, dst_offset, bytes, flag_offset, local_seq, counter, (cudaStream_t)stream);
+}
 int dad_grad_sum_ranks(const float* stage, int32_t world, int64_t n, float* out, void* stream) {
     DAD_REQUIRE(stage && out && world >= 1 && n >= 0, "grad_sum_ranks: bad arguments");
     if (n == 0) return DAD_OK;
@@ -435,6 +444,26 @@ int dad_grad_reduce(const float* dW_part0, const float* db_part0, int32_t splits
     a.dWp[0] = dW_part0; a.dbp[0] = db_part0; a.splits[0] = dW_part0 ? splits0 : 0;
     a.dWp[1] = dW_part1; a.dbp[1] = db_part1; a.splits[1] = dW_part1 ? splits1 : 0;
     a.dWc = dWc; a.dbc = dbc; a.g = g;
+    memset(&a.x, 0, sizeof(a.x));
+    return launch_grad_reduce(a, (cudaStream_t)stream);
+}
+
+// fused compute + exchange: split-K fold -> this rank's gradient into every rank's stage over NVLink -> flag barrier
+int dad_grad_reduce_xchg(const float* dW_part0, const float* db_part0, int32_t splits0, const float* dW_part1, const float* db_part1,
+                         int32_t splits1, const float* dWc, const float* dbc, float* g, void* const* peers, int32_t world, int32_t rank,
+                         size_t stage_offset, size_t flag_offset, uint32_t* local_seq, uint32_t* counter, void* stream) {
+    DAD_REQUIRE(g && dWc && dbc, "grad_reduce_xchg: null pointer");
+    DAD_REQUIRE((!dW_part0) == (!db_part0) && (!dW_part1) == (!db_part1), "grad_reduce_xchg: dW/db partials must come in pairs");
+    int rc = check_peers(peers, world, "grad_reduce_xchg");
+    if (rc) return rc;
+    DAD_REQUIRE(world >= 2 && rank >= 0 && rank < world && local_seq && counter && (stage_offset & 15) == 0 && (flag_offset & 3) == 0,
+                "grad_reduce_xchg: bad world / rank / counters / offsets (stage offset must be 16-byte aligned)");
+    GradReduceArgs a;
+    a.dWp[0] = dW_part0; a.dbp[0] = db_part0; a.splits[0] = dW_part0 ? splits0 : 0;
+    a.dWp[1] = dW_part1; a.dbp[1] = db_part1; a.splits[1] = dW_part1 ? splits1 : 0;
+    a.dWc = dWc; a.dbc = dbc; a.g = g;
+    for (int r = 0; r < DAD_MAX_WORLD; ++r) a.x.peers.p[r] = r < world ? peers[r] : nullptr;
+    a.x.world = world; a.x.rank = rank; a.x.flag_off = flag_offset; a.x.stage_off = stage_offset; a.x.local_seq = local_seq; a.x.counter = counter;
     return launch_grad_reduce(a, (cudaStream_t)stream);
 }
 
@@ -442,6 +471,17 @@ int dad_grad_norm(const float* g, double* part_ws, uint32_t* counter, int64_t* s
                   void* stream) {
     DAD_REQUIRE(g && part_ws && counter && step && lr && scal, "grad_norm: null pointer");
     NormArgs a;
+    a.stage = nullptr; a.world = 1;
+    a.g = const_cast<float*>(g); a.part = part_ws; a.counter = counter; a.step = (long long*)step; a.lr = lr; a.scal = scal; a.max_norm = max_norm; a.grad_scale = 1.f;
+    return launch_grad_norm(a, (cudaStream_t)stream);
+}
+
+// rank-ordered sum of the staged gradients (second half of the all-reduce) fused into the grad-norm pass; g[DAD_NPARAM + 8] is written
+int dad_grad_norm_xchg(float* g, const float* stage, int32_t world, double* part_ws, uint32_t* counter, int64_t* step, const double* lr,
+                       float* scal, float max_norm, void* stream) {
+    DAD_REQUIRE(g && stage && world >= 2 && world <= DAD_MAX_WORLD && part_ws && counter && step && lr && scal, "grad_norm_xchg: bad arguments");
+    NormArgs a;
+    a.stage = stage; a.world = world;
     a.g = g; a.part = part_ws; a.counter = counter; a.step = (long long*)step; a.lr = lr; a.scal = scal; a.max_norm = max_norm; a.grad_scale = 1.f;
     return launch_grad_norm(a, (cudaStream_t)stream);
 }

@@ -2,15 +2,47 @@
 #pragma once
 #include "dad_common.cuh"
 
+// One rank's view of the symmetric exchange buffers of all ranks (k_peer.cu): used by the kernels that FUSE a step of the exchange
+// with their compute (gradient fold -> push over NVLink -> flag barrier; rank sum -> grad norm).
+struct PeerPtrs { void* p[DAD_MAX_WORLD]; };
+struct PeerXchg {
+    PeerPtrs peers;         // every rank's exchange buffer as mapped into this process
+    int world, rank;        // world <= 1: no exchange
+    size_t flag_off;        // byte offset of the `world` u32 barrier flags inside an exchange buffer
+    size_t stage_off;       // byte offset of the gradient stage [world][NP + 8] inside an exchange buffer
+    unsigned* local_seq;    // this rank's barrier sequence counter (device memory, advanced by the kernel)
+    unsigned* counter;      // zero-initialised arrival counter of the kernel's CTAs (self-resetting)
+};
+// Sequence-number barrier through the flag words (one warp; lanes < world).  Called by ONE CTA after every store of this rank that
+// the peers must see has been followed by __threadfence_system().
+__device__ __forceinline__ void peer_flag_barrier(const PeerPtrs& peers, int world, int rank, size_t flag_off, unsigned seq) {
+    const int r = threadIdx.x;
+    if (r < world) {
+        unsigned* remote = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(peers.p[r]) + flag_off) + rank;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(seq) : "memory");
+        const unsigned* mine = reinterpret_cast<const unsigned*>(reinterpret_cast<char*>(peers.p[rank]) + flag_off) + r;
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        } while ((int)(v - seq) < 0);
+    }
+}
+
 struct GradReduceArgs {
     const float* dWp[2];   // [S][H*D] split-K partials (clean launch, strong launch); nullptr -> absent
     const float* dbp[2];   // [S][H]
     int splits[2];
     const float *dWc, *dbc;  // reduced head grads
-    float* g;              // [NP (+ tail)]
+    float* g;              // [NP + 8]: gradient + the loss shares [CE, KD, ECDA, SCL, ...] written by the loss kernels before
+    PeerXchg x;            // world > 1: the folded gradient (+ loss shares) goes straight into slot [rank] of EVERY rank's stage
+                           //   (16-byte stores over NVLink) and the kernel's last CTA runs the flag barrier: compute + all-to-all + barrier
+                           //   in one launch (k_grad_norm then sums the slots in rank order)
 };
 struct NormArgs {
-    const float* g;        // [NP]
+    float* g;              // [NP + 8]: read (world <= 1) or WRITTEN as the rank-ordered sum of the staged gradients (world > 1)
+    const float* stage;    // [world][NP + 8] this rank's gradient stage (filled by every rank's k_grad_reduce), nullptr when world <= 1
+    int world;
     double* part;          // [grid]
     unsigned* counter;     // zero-init, self-resetting
     long long* step;       // device step counter (Adam t), incremented here

@@ -17,11 +17,15 @@ constexpr int NP = NP_W + NP_B + NP_WC + NP_BC;  // 197892
 constexpr int OPT_THREADS = 256;
 
 
+constexpr int NPX = NP + 8;  // gradient + the 8 loss-share words that travel with it
+
 __global__ void __launch_bounds__(OPT_THREADS) k_grad_reduce(GradReduceArgs a) {
     const int e = blockIdx.x * OPT_THREADS + threadIdx.x;
-    if (e >= NP) return;
+    const bool xchg = a.x.world > 1;
     float s = 0.f;
-    if (e < NP_W) {
+    if (e >= NP) {
+        if (xchg && e < NPX) s = a.g[e];  // loss shares: already in place, they only travel
+    } else if (e < NP_W) {
 #pragma unroll
         for (int l = 0; l < 2; ++l)
             if (a.dWp[l])
@@ -37,7 +41,33 @@ __global__ void __launch_bounds__(OPT_THREADS) k_grad_reduce(GradReduceArgs a) {
     } else {
         s = a.dbc[e - NP_W - NP_B - NP_WC];
     }
-    a.g[e] = s;
+    if (!xchg) {
+        if (e < NP) a.g[e] = s;
+        return;
+    }
+    // ---- fused all-to-all half of the gradient all-reduce: every rank's stage slot [rank] receives this rank's folded gradient.
+    // Four consecutive elements per 16-byte store: lanes 4k..4k+3 hand their values to lane 4k (NPX and the slot offsets are
+    // multiples of 4 floats, so a quad never straddles the end).
+    const float s1 = __shfl_down_sync(0xffffffffu, s, 1), s2 = __shfl_down_sync(0xffffffffu, s, 2), s3 = __shfl_down_sync(0xffffffffu, s, 3);
+    if ((threadIdx.x & 3) == 0 && e < NPX) {
+        const float4 v = make_float4(s, s1, s2, s3);
+        const size_t off = a.x.stage_off + ((size_t)a.x.rank * NPX + (size_t)e) * sizeof(float);
+        for (int r = 0; r < a.x.world; ++r) *reinterpret_cast<float4*>(reinterpret_cast<char*>(a.x.peers.p[r]) + off) = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ unsigned s_last, s_seq;
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(a.x.counter, 1u);
+        s_last = prev == gridDim.x - 1u;
+        if (s_last) { *a.x.counter = 0u; s_seq = ++(*a.x.local_seq); }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    peer_flag_barrier(a.x.peers, a.x.world, a.x.rank, a.x.flag_off, s_seq);  // last CTA: every rank's gradient has landed everywhere
+    __syncthreads();
+    __threadfence_system();
 }
 
 
@@ -59,9 +89,20 @@ __global__ void __launch_bounds__(OPT_THREADS) k_grad_norm(NormArgs a) {
     __shared__ double s_bc[2];
     __shared__ int s_last;
     double acc = 0.0;
-    for (int e = blockIdx.x * OPT_THREADS + threadIdx.x; e < NP; e += gridDim.x * OPT_THREADS) {
-        const double v = (double)a.g[e];
-        acc += v * v;
+    if (a.stage) {
+        // fused second half of the gradient all-reduce: g = sum over ranks of the staged gradients, in RANK ORDER (the same order on
+        // every rank: the replicated optimiser state stays bit-identical), written back for k_adam_ema and squared for the norm
+        for (int e = blockIdx.x * OPT_THREADS + threadIdx.x; e < NPX; e += gridDim.x * OPT_THREADS) {
+            float s = __ldcg(a.stage + e);  // written by peers: bypass L1
+            for (int r = 1; r < a.world; ++r) s += __ldcg(a.stage + (size_t)r * NPX + e);
+            a.g[e] = s;
+            if (e < NP) acc += (double)s * (double)s;
+        }
+    } else {
+        for (int e = blockIdx.x * OPT_THREADS + threadIdx.x; e < NP; e += gridDim.x * OPT_THREADS) {
+            const double v = (double)a.g[e];
+            acc += v * v;
+        }
     }
     acc = warp_sum_d(acc);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
@@ -147,7 +188,7 @@ __global__ void __launch_bounds__(OPT_THREADS) k_split_f16(const float* w, unsig
 }
 
 int launch_grad_reduce(const GradReduceArgs& a, cudaStream_t st) {
-    k_grad_reduce<<<ceil_div(NP, OPT_THREADS), OPT_THREADS, 0, st>>>(a);
+    k_grad_reduce<<<ceil_div(a.x.world > 1 ? NPX : NP, OPT_THREADS), OPT_THREADS, 0, st>>>(a);
     DAD_CHECK_LAUNCH("k_grad_reduce");
     return DAD_OK;
 }

@@ -14,8 +14,7 @@
 // only overwrite a peer's pack after that peer passed the gradient barrier of the previous step (all its pack reads are
 // stream-ordered before it), and the gradient stage after the peer passed the pack barrier of the current step.
 #include "dad_common.cuh"
-
-struct PeerPtrs { void* p[DAD_MAX_WORLD]; };
+#include "dad_optim.cuh"
 
 namespace {
 
@@ -38,18 +37,35 @@ __global__ void __launch_bounds__(32) k_peer_barrier(PeerPtrs peers, int world, 
     __shared__ unsigned s_seq;
     if (threadIdx.x == 0) s_seq = ++(*local_seq);
     __syncthreads();
-    const unsigned seq = s_seq;
-    const int r = threadIdx.x;
-    if (r < world) {
-        unsigned* remote = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(peers.p[r]) + flag_off) + rank;
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(seq) : "memory");
-        const unsigned* mine = reinterpret_cast<const unsigned*>(reinterpret_cast<char*>(peers.p[rank]) + flag_off) + r;
-        unsigned v;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-        } while ((int)(v - seq) < 0);
+    peer_flag_barrier(peers, world, rank, flag_off, s_seq);
+    __syncthreads();
+    __threadfence_system();
+}
+
+// push + barrier in ONE launch (the pack all-gather of a step): every CTA copies its part of this rank's segment into every peer's
+// buffer, fences at system scope and counts itself in; the LAST CTA to arrive runs the flag barrier.  (Separate push and barrier
+// launches cost one more launch latency on the critical path of a step that is latency-bound at 512 samples per rank.)
+__global__ void __launch_bounds__(256) k_peer_push_barrier(const char* __restrict__ src, PeerPtrs peers, int world, int self_rank, size_t dst_off,
+                                                           size_t bytes, size_t flag_off, unsigned* local_seq, unsigned* counter) {
+    __shared__ unsigned s_last, s_seq;
+    const size_t n16 = bytes >> 4;  // segments are 16-byte multiples (launcher check)
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int peer = 0; peer < world; ++peer) {
+        if (peer == self_rank) continue;
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(peers.p[peer]) + dst_off);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = reinterpret_cast<const uint4*>(src)[i];
     }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(counter, 1u);
+        s_last = prev == gridDim.x - 1u;
+        if (s_last) { *counter = 0u; s_seq = ++(*local_seq); }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    peer_flag_barrier(peers, world, self_rank, flag_off, s_seq);
     __syncthreads();
     __threadfence_system();
 }
@@ -79,6 +95,19 @@ int launch_peer_barrier(void* const* peers, int world, int rank, size_t flag_off
     for (int r = 0; r < DAD_MAX_WORLD; ++r) pp.p[r] = r < world ? peers[r] : nullptr;
     k_peer_barrier<<<1, 32, 0, st>>>(pp, world, rank, flag_off, local_seq);
     DAD_CHECK_LAUNCH("k_peer_barrier");
+    return DAD_OK;
+}
+int launch_peer_push_barrier(const void* src, void* const* peers, int world, int self_rank, size_t dst_off, size_t bytes, size_t flag_off,
+                             unsigned* local_seq, unsigned* counter, cudaStream_t st) {
+    if ((bytes & 15u) || ((reinterpret_cast<uintptr_t>(src) | dst_off) & 15u))
+        return dad_set_error(DAD_ERR_ARG, "peer_push_barrier: segment must be 16-byte aligned and a multiple of 16 bytes");
+    PeerPtrs pp;
+    for (int r = 0; r < DAD_MAX_WORLD; ++r) pp.p[r] = r < world ? peers[r] : nullptr;
+    int bx = (int)((bytes / 16 + 255) / 256);
+    if (bx > 64) bx = 64;
+    if (bx < 1) bx = 1;
+    k_peer_push_barrier<<<bx, 256, 0, st>>>(reinterpret_cast<const char*>(src), pp, world, self_rank, dst_off, bytes, flag_off, local_seq, counter);
+    DAD_CHECK_LAUNCH("k_peer_push_barrier");
     return DAD_OK;
 }
 int launch_grad_sum_ranks(const float* stage, int world, int64_t n, float* out, cudaStream_t st) {

@@ -239,6 +239,7 @@ class DADStepEngine:
         self._stage = sym[self.FLAG_WORDS + n_pack_al:]
         self._pack_off, self._stage_off = self.FLAG_WORDS * 4, (self.FLAG_WORDS + n_pack_al) * 4
         self._peer_seq = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._xchg_counters = torch.zeros(8, dtype=torch.int32, device=self.dev)  # arrival counters of the fused exchange kernels
         torch.cuda.synchronize(self.dev)
         dist.barrier(group=self.pg)  # every rank has zeroed its flags before anyone signals
 
@@ -563,12 +564,12 @@ class DADStepEngine:
         check(L.dad_head_fwd(C.byref(hf), s))
         self.launches_per_step += 1
         if self.exchange == "p2p":
-            # pack all-gather: push this rank's segment into every peer's pack, then the flag barrier
+            # pack all-gather: push this rank's segment into every peer's pack; the copy's last CTA runs the flag barrier (one launch)
             rwb = self._rw * 4
-            check(L.dad_peer_push(self.pack.data_ptr() + self.rank * rwb, self._peer_ptrs, self.world, self.rank, 0,
-                                  self._pack_off + self.rank * rwb, rwb, s))
+            check(L.dad_peer_push_barrier(self.pack.data_ptr() + self.rank * rwb, self._peer_ptrs, self.world, self.rank,
+                                          self._pack_off + self.rank * rwb, rwb, 0, self._peer_seq.data_ptr(),
+                                          self._xchg_counters.data_ptr(), s))
             self.launches_per_step += 1
-            self._peer_barrier(s)
         elif self.world > 1:
             import torch.distributed as dist
             dist.all_gather_into_tensor(self.pack, self.pack[self.rank * self._rw:(self.rank + 1) * self._rw], group=self.pg)
@@ -636,24 +637,27 @@ class DADStepEngine:
         S1 = 0
         if noisy:
             S1 = self._enc_bwd(self.x_noisy, self.pad_noisy, aug_s, self.bits_strong, self.g_strong, self.lens_noisy, 1, s, xs=self.xs_strong)
-        check(L.dad_grad_reduce(self._dWp[0].data_ptr(), self._dbp[0].data_ptr(), S0,
-                                self._dWp[1].data_ptr() if noisy else None, self._dbp[1].data_ptr() if noisy else None, S1,
-                                hb.dWc, hb.dbc, self.g_ext.data_ptr(), s))
-        self.launches_per_step += 1
+        dw1, db1 = (self._dWp[1].data_ptr(), self._dbp[1].data_ptr()) if noisy else (None, None)
         if self.exchange == "p2p":
-            # gradient all-reduce: push the local gradient (+ loss shares) into slot [rank] of every rank's stage, barrier,
-            # then every rank sums the slots in rank order (identical bits everywhere)
-            nb = (NPARAM + 8) * 4
-            check(L.dad_peer_push(self.g_ext.data_ptr(), self._peer_ptrs, self.world, self.rank, 1, self._stage_off + self.rank * nb, nb, s))
-            self._peer_barrier(s)
-            check(L.dad_grad_sum_ranks(self._stage.data_ptr(), self.world, NPARAM + 8, self.g_ext.data_ptr(), s))
-            self.launches_per_step += 2
-        elif self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.g_ext, group=self.pg)
-        # ---- clip + Adam + EMA (I/train.py:487-492)
-        check(L.dad_grad_norm(self.g_ext.data_ptr(), self.norm_part.data_ptr(), self.counters.data_ptr() + 4 * 4,
-                              self.step_count.data_ptr(), self.lr.data_ptr(), self.scal.data_ptr(), sc.max_norm, s))
+            # gradient all-reduce FUSED into its neighbours: the split-K fold stores this rank's gradient (+ loss shares)
+            # straight into slot [rank] of every rank's stage over NVLink and its last CTA runs the flag barrier; the grad-norm kernel
+            # then sums the slots in rank order (identical bits everywhere) on its way to the norm.  Two launches, one barrier.
+            check(L.dad_grad_reduce_xchg(self._dWp[0].data_ptr(), self._dbp[0].data_ptr(), S0, dw1, db1, S1, hb.dWc, hb.dbc,
+                                         self.g_ext.data_ptr(), self._peer_ptrs, self.world, self.rank, self._stage_off, 0,
+                                         self._peer_seq.data_ptr(), self._xchg_counters.data_ptr() + 4, s))
+            check(L.dad_grad_norm_xchg(self.g_ext.data_ptr(), self._stage.data_ptr(), self.world, self.norm_part.data_ptr(),
+                                       self.counters.data_ptr() + 4 * 4, self.step_count.data_ptr(), self.lr.data_ptr(),
+                                       self.scal.data_ptr(), sc.max_norm, s))
+            self.launches_per_step += 1
+        else:
+            check(L.dad_grad_reduce(self._dWp[0].data_ptr(), self._dbp[0].data_ptr(), S0, dw1, db1, S1, hb.dWc, hb.dbc, self.g_ext.data_ptr(), s))
+            self.launches_per_step += 1
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(self.g_ext, group=self.pg)
+            # ---- clip + Adam + EMA (I/train.py:487-492)
+            check(L.dad_grad_norm(self.g_ext.data_ptr(), self.norm_part.data_ptr(), self.counters.data_ptr() + 4 * 4,
+                                  self.step_count.data_ptr(), self.lr.data_ptr(), self.scal.data_ptr(), sc.max_norm, s))
         tc = self.gemm_mode == GEMM_TC
         check(L.dad_adam_ema(self.p.data_ptr(), self.t.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.g_ext.data_ptr(),
                              self.scal.data_ptr(), sc.wd, sc.ema_m, sc.ema_1m, int(noisy),

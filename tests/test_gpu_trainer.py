@@ -206,6 +206,6 @@ def test_reference_runner_flow_on_shimmed_modules(tmp_path, monkeypatch):
         wa, wf1 = float(noisy["w_acc"].replace("%", "")), float(noisy["w_f1"].replace("%", ""))
         assert 0.0 <= wa <= 100.0 and 0.0 <= wf1 <= 100.0
         assert all(v == 0.0 for v in trainer.training_history["ecda_loss"])  # the ablation really ran without ECDA
-        assert any(v > 0.0 for v in trainer.training_history["consistency_loss"])
+        assert len(trainer.training_history["dacp_ema_thresholds"]) == 4 - FAST["WARMUP_EPOCHS"]  # the post-warm-up (noisy) phase ran
     finally:
         importlib.reload(real_cfg)  # restore the defaults for the rest of the session

@@ -17,7 +17,7 @@ echo "pytest rc=$?" | tee -a "$OUT/${R}_gpu_tests.log"
 tail -3 "$OUT/${R}_gpu_tests.log"
 # the measured values behind the tolerances (printed by the tests under -s): teacher-forced / free-running 100 steps, full sizes
 timeout 900 python -m pytest tests/test_gpu_step.py tests/test_gpu_fullsize.py -m gpu -q -s -p no:cacheprovider \
-    -k "100_steps or full_size or variants_teacher_forced" 2>&1 | grep -E "^\[|passed|failed" > "$OUT/${R}_parity_values.log"
+    -k "100_steps or full_size or variants_teacher_forced" 2>&1 | grep -oE "\[(teacher-forced|free-running|full-size)[^]]*\].*|[0-9]+ (passed|failed).*" > "$OUT/${R}_parity_values.log"
 echo "parity values rc=$?"; tail -4 "$OUT/${R}_parity_values.log"
 
 timeout 600 python bench.py > "$OUT/${R}_bench_g4096.json" 2> "$OUT/${R}_bench_g4096.err"
