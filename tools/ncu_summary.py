@@ -20,31 +20,39 @@ for r in rows[2:]:
     for k in hdr:
         if any((k + " ").startswith(x) or k == x.strip() for x in KEYS):
             print(f"   {k:85s} {d[k]:>16s} {units[hdr.index(k)]}")
-kernels = sorted({dict(zip(hdr, r))["Kernel Name"] for r in rows[2:]})
-for kn in kernels:
-    if pat and pat not in kn:
+# source page: one CSV with a section per captured launch ("Kernel Name",<name> row, then the header row starting with "Address")
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+secs, cur = [], None
+for r in csv.reader(io.StringIO(src)):
+    if r and r[0] == "Kernel Name":
+        cur = {"name": r[1], "rows": []}
+        secs.append(cur)
+    elif cur is not None:
+        cur["rows"].append(r)
+seen = set()
+for sec in secs:
+    kn = sec["name"]
+    if (pat and pat not in kn) or not sec["rows"] or sec["rows"][0][0] != "Address":
         continue
-    short = kn.split("(")[0].split("::")[-1]
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + short], capture_output=True, text=True).stdout
-    rws = list(csv.reader(io.StringIO(src)))
-    try:
-        h = next(i for i, r in enumerate(rws) if r and r[0] == "Address")
-    except StopIteration:
+    hd = sec["rows"][0]; ix = {k: i for i, k in enumerate(hd)}
+    data = [r for r in sec["rows"][1:] if len(r) == len(hd) and r[0].startswith("0x")]
+    key = (kn, sum(int(r[ix["# Samples"]]) for r in data))
+    if key in seen:  # ncu repeats a section per source view
         continue
-    hd = rws[h]; ix = {k: i for i, k in enumerate(hd)}
-    data = [r for r in rws[h + 1:] if len(r) == len(hd) and r[0].startswith("0x")]  # several launches: headers repeat
+    seen.add(key)
+    short = kn.split("(CUtensorMap")[0].split("::")[-1][:60]
     stalls = [k for k in hd if k.startswith("stall_") and "Not Issued" not in k]
     tot = sum(int(r[ix["# Samples"]]) for r in data)
     ex = sum(int(r[ix["Instructions Executed"]]) for r in data)
     agg = {k: sum(int(r[ix[k]]) for r in data) for k in stalls}
-    print(f"---- {short}: {tot} samples, {ex} warp-instructions executed; stalls:", ", ".join(f"{k[6:]}={v}" for k, v in sorted(agg.items(), key=lambda x: -x[1])[:7]))
+    print(f"---- {short}: {tot} samples, {ex} warp-instructions executed (source-counter pass); stalls:", ", ".join(f"{k[6:]}={v}" for k, v in sorted(agg.items(), key=lambda x: -x[1])[:7]))
     op = collections.Counter()
     for r in data:
         t = r[ix["Source"]].split()
         if not t: continue
         o = t[1] if t[0].startswith("@") and len(t) > 1 else t[0]
         op[o.split(".")[0]] += int(r[ix["Instructions Executed"]])
-    print("     opcode mix:", ", ".join(f"{k}={100*v/ex:.1f}%" for k, v in op.most_common(14)))
+    print("     opcode mix:", ", ".join(f"{k}={100*v/max(ex,1):.1f}%" for k, v in op.most_common(14)))
     top = sorted(range(len(data)), key=lambda i: -int(data[i][ix["# Samples"]]))[:12]
     for i in sorted(top):
         r = data[i]
