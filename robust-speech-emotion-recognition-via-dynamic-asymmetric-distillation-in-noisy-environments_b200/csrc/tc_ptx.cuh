@@ -31,14 +31,15 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // try_wait with a suspend-time hint: a waiting warp is parked by the hardware (up to the hint) instead of spinning through the
 // issue slots that the converter warps of the same SM sub-partition need
+constexpr uint32_t MBAR_SUSPEND_NS = 20000u;  // upper bound of one suspension; the warp resumes as soon as the phase completes
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar_addr, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P1;\n\t}\n"
         : "=r"(ok)
-        : "r"(bar_addr), "r"(parity)
+        : "r"(bar_addr), "r"(parity), "r"(MBAR_SUSPEND_NS)
         : "memory");
     return ok != 0;
 }
@@ -71,10 +72,10 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar_addr, uint32_
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P1;\n\t}\n"
         : "=r"(ok)
-        : "r"(bar_addr), "r"(parity)
+        : "r"(bar_addr), "r"(parity), "r"(MBAR_SUSPEND_NS)
         : "memory");
     return ok != 0;
 }

@@ -1,6 +1,6 @@
 """Profiling driver (GPU): ONE launch of each tcgen05 encoder forward / backward variant at a bench-like size, for ncu.
 Usage: python tools/prof_enc.py [B] [T] [which]     which = comma list of: clean, fused, weak, strong, bwd_clean, bwd_cached
-                                                     suffix ':single' runs the forward variants without CTA pairs (default: pairs)
+                                                     suffix ':single' runs the forward variants without CTA pairs, ':tp' with the default policy (fused -> k_enc_fwd_tp)
 e.g.   ncu --set full --import-source on -k regex:k_enc_ -o gpurun_out/enc python tools/prof_enc.py 4096 200 clean,fused"""
 import os
 import sys
@@ -31,7 +31,7 @@ emb, bits, lens = ops.encoder_pool_fwd(x, None, W, b, gemm_mode=_lib.GEMM_TC, W_
 torch.cuda.synchronize()
 for item in which:
     name, _, flavour = item.partition(":")
-    L.dad_tc_set_cta_pair(0 if flavour == "single" else 1)
+    L.dad_tc_set_cta_pair({"single": 0, "tp": 2, "auto": 2}.get(flavour, 1))  # 'fused:tp' = the transposed CTA-pair kernel
     if name == "clean":
         ops.encoder_pool_fwd(x, None, W, b, gemm_mode=_lib.GEMM_TC, W_hi=s_split[0], W_lo=s_split[1])
     elif name == "weak":

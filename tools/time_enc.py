@@ -55,6 +55,10 @@ for pair in (0, 1):
     out[f"fwd_fused_cache_hi_{tag}"] = timed(lambda: ops.aug_encoder_fwd(x, None, Wt, bt, W, b, aw, as_, xs=(xs[0],), Wt_split=t_split, Ws_split=s_split))
     out[f"fwd_fused_nocache_{tag}"] = timed(lambda: ops.aug_encoder_fwd(x, None, Wt, bt, W, b, aw, as_, Wt_split=t_split, Ws_split=s_split))
     out[f"fwd_fused_cache_hilo_{tag}"] = timed(lambda: ops.aug_encoder_fwd(x, None, Wt, bt, W, b, aw, as_, xs=(xs[0], xs[1]), Wt_split=t_split, Ws_split=s_split))
+L.dad_tc_set_cta_pair(2)  # auto: the training step's fused noisy forward runs on the transposed CTA-pair kernel (k_enc_fwd_tp)
+out["fwd_fused_cache_hi_tp"] = timed(lambda: ops.aug_encoder_fwd(x, None, Wt, bt, W, b, aw, as_, xs=(xs[0],), Wt_split=t_split, Ws_split=s_split))
+out["fwd_fused_nocache_tp"] = timed(lambda: ops.aug_encoder_fwd(x, None, Wt, bt, W, b, aw, as_, Wt_split=t_split, Ws_split=s_split))
+out["fwd_fused_cache_hilo_tp"] = timed(lambda: ops.aug_encoder_fwd(x, None, Wt, bt, W, b, aw, as_, xs=(xs[0], xs[1]), Wt_split=t_split, Ws_split=s_split))
 emb, bits, lens = state["r"]
 for prods in (2, 3):
     L.dad_tc_set_bwd_products(prods)
@@ -63,6 +67,6 @@ for prods in (2, 3):
     out[f"bwd_clean_regen_p{prods}"] = timed(lambda: ops.encoder_pool_bwd(x, None, bits, g, lens, gemm_mode=_lib.GEMM_TC))
     out[f"bwd_cached_p{prods}"] = timed(lambda: ops.encoder_pool_bwd(x, None, bits, g, lens, gemm_mode=_lib.GEMM_TC, xs=planes))
     out[f"bwd_strong_regen_p{prods}"] = timed(lambda: ops.encoder_pool_bwd(x, None, bits, g, lens, aug=as_, gemm_mode=_lib.GEMM_TC))
-L.dad_tc_set_bwd_products(2)
-L.dad_tc_set_cta_pair(1)
+L.dad_tc_set_bwd_products(3)
+L.dad_tc_set_cta_pair(2)
 print(json.dumps(out))
