@@ -780,12 +780,14 @@ __device__ __forceinline__ void tp_convert(const FwdParams& p, uint8_t* smem, ui
                 for (int i = 0; i < 2; ++i) {
                     float4 vw = buf[j][i], vs = buf[j][i];
                     if (PHILOX) {
+                        if (!(p.dbg & 4)) {
                         const uint4 w = noise_words(seed, blk, gn0 + 4 * i, (uint32_t)((2 * k + team) * (BK / 4) + c4));
                         NoiseBM4 z;
                         bm4_from_words(w.x, w.y, rk_w, z);
                         vw = bm4_add(z, vw);
                         bm4_from_words(w.z, w.w, rk_s, z);
                         vs = bm4_add(z, vs);
+                        }
                     } else {
                         // parity mode: supplied unit normals, out = x + (n * sigma) with two fp32 roundings (bit-exact vs I/utils.py:330,338)
                         const bool inr = (v_cur >> i) & 1u;
@@ -802,8 +804,10 @@ __device__ __forceinline__ void tp_convert(const FwdParams& p, uint8_t* smem, ui
                     }
                     const uint32_t a_row = stage_off + (i ? so1 : so0);
                     const float sc_s = ((zspan >> i) & 1u) ? 0.f : TC_XS;
+                    if (!(p.dbg & 8) || vw.x == 12345.f) {
                     store_row(a_row, vw, TC_XS);
                     store_row(a_row + 2 * TP_XB, vs, sc_s);
+                    }
                 }
                 tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma / TMA (async proxy)
                 __syncwarp();
@@ -870,6 +874,10 @@ k_enc_fwd_tp(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
                     const uint32_t s = it % TP_STAGES, ph = (it / TP_STAGES) & 1;
                     tc::mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* w0 = smem + s * TP_STAGE + TP_OFF_W;
+                    if ((p.dbg & 2) && it >= (uint32_t)TP_STAGES) {  // timing experiment: W stays what the first fill left
+                        if (rank == 0) tc::mbar_arrive(&full[s]);
+                        continue;
+                    }
                     if (rank == 0) tc::mbar_arrive_expect_tx(&full[s], 2 * 4 * TP_WB);  // the bytes of BOTH CTAs land on the leader's barrier
                     const uint32_t fb = full_remote + s * 8u;
                     tc::tma_load_2d_pair(w0, &tm_w0hi, fb, kb * BK, r0);
@@ -903,6 +911,7 @@ k_enc_fwd_tp(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
                             const uint32_t d_tmem = tmem_base + ab * 256u + (uint32_t)v * TP_TF;
 #pragma unroll
                             for (int prod = 0; prod < 3; ++prod) {  // x_hi*W_hi, x_hi*W_lo, x_lo*W_hi
+                                if ((p.dbg & 1) && prod > 0) break;
                                 const uint32_t w_off = TP_OFF_W + v * 2 * TP_WB + ((prod == 1) ? TP_WB : 0u);
                                 const uint32_t x_off = TP_OFF_X + v * 2 * TP_XB + ((prod == 2) ? TP_XB : 0u);
 #pragma unroll
