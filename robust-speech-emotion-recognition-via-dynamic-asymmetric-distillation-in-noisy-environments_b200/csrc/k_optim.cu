@@ -54,10 +54,10 @@ __global__ void __launch_bounds__(OPT_THREADS) k_grad_reduce(GradReduceArgs a) {
         const size_t off = a.x.stage_off + ((size_t)a.x.rank * NPX + (size_t)e) * sizeof(float);
         for (int r = 0; r < a.x.world; ++r) *reinterpret_cast<float4*>(reinterpret_cast<char*>(a.x.peers.p[r]) + off) = v;
     }
-    __threadfence_system();
     __syncthreads();
     __shared__ unsigned s_last, s_seq;
     if (threadIdx.x == 0) {
+        __threadfence_system();  // one system-scope fence per CTA (cumulative over the CTA's stores ordered by the barrier above)
         const unsigned prev = atomicAdd(a.x.counter, 1u);
         s_last = prev == gridDim.x - 1u;
         if (s_last) { *a.x.counter = 0u; s_seq = ++(*a.x.local_seq); }

@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(256) k_peer_push(const char* __restrict__ src,
         reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
     for (size_t i = (n16 << 4) + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i + 4 <= bytes; i += stride * 4)
         *reinterpret_cast<uint32_t*>(dst + i) = *reinterpret_cast<const uint32_t*>(src + i);
-    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();
 }
 
 __global__ void __launch_bounds__(32) k_peer_barrier(PeerPtrs peers, int world, int rank, size_t flag_off, unsigned* local_seq) {
@@ -50,14 +51,18 @@ __global__ void __launch_bounds__(256) k_peer_push_barrier(const char* __restric
     __shared__ unsigned s_last, s_seq;
     const size_t n16 = bytes >> 4;  // segments are 16-byte multiples (launcher check)
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (int peer = 0; peer < world; ++peer) {
-        if (peer == self_rank) continue;
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(peers.p[peer]) + dst_off);
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = reinterpret_cast<const uint4*>(src)[i];
+    // every 16-byte chunk is loaded once and stored to all peers back to back (remote stores are posted: nothing waits per store)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = reinterpret_cast<const uint4*>(src)[i];
+#pragma unroll
+        for (int peer = 0; peer < DAD_MAX_WORLD; ++peer)
+            if (peer < world && peer != self_rank) reinterpret_cast<uint4*>(reinterpret_cast<char*>(peers.p[peer]) + dst_off)[i] = v;
     }
-    __threadfence_system();
+    // ONE system-scope fence per CTA, after the CTA barrier (fences are cumulative over the stores the barrier orders before it);
+    // a membar.sys in every thread serialises in the memory system and cost ~80 us per exchange at 8 ranks
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned prev = atomicAdd(counter, 1u);
         s_last = prev == gridDim.x - 1u;
         if (s_last) { *counter = 0u; s_seq = ++(*local_seq); }
@@ -104,7 +109,7 @@ int launch_peer_push_barrier(const void* src, void* const* peers, int world, int
     PeerPtrs pp;
     for (int r = 0; r < DAD_MAX_WORLD; ++r) pp.p[r] = r < world ? peers[r] : nullptr;
     int bx = (int)((bytes / 16 + 255) / 256);
-    if (bx > 64) bx = 64;
+    if (bx > 148) bx = 148;
     if (bx < 1) bx = 1;
     k_peer_push_barrier<<<bx, 256, 0, st>>>(reinterpret_cast<const char*>(src), pp, world, self_rank, dst_off, bytes, flag_off, local_seq, counter);
     DAD_CHECK_LAUNCH("k_peer_push_barrier");

@@ -20,6 +20,7 @@ batches have different T, and the last batch of an epoch is ragged.  All buffers
 shape (so captured CUDA graphs, keyed by shape, stay valid); when the two batch sizes differ the smaller one is padded with
 "null" samples that the kernels ignore (label / pseudo-label -1: no loss, no gradient, not in any quantile or class)."""
 import ctypes as C
+import os
 import math
 
 import numpy as np
@@ -172,6 +173,10 @@ class DADStepEngine:
                     warnings.warn(f"peer-memory exchange unavailable ({err}); every rank uses NCCL collectives")
             elif exchange != "nccl":
                 raise DadError("exchange must be 'auto', 'p2p' or 'nccl'")
+            if os.environ.get("DAD_DEBUG_NO_XCHG") == "1":
+                # DIAGNOSTIC ONLY (wrong results): every rank keeps its own pack segment and gradient, no exchange kernels are
+                # enqueued -- separates the cost of the exchanges from the rank-local kernel chain in multi-rank timings
+                self.exchange = "skip"
         self._emb_t = z(B * D_HID)
         self._bits_c = torch.zeros(B * T * (D_HID // 32), dtype=torch.int32, device=dev)
         self._bits_s = torch.zeros(B * T * (D_HID // 32), dtype=torch.int32, device=dev)
@@ -570,7 +575,7 @@ class DADStepEngine:
                                           self._pack_off + self.rank * rwb, rwb, 0, self._peer_seq.data_ptr(),
                                           self._xchg_counters.data_ptr(), s))
             self.launches_per_step += 1
-        elif self.world > 1:
+        elif self.world > 1 and self.exchange != "skip":
             import torch.distributed as dist
             dist.all_gather_into_tensor(self.pack, self.pack[self.rank * self._rw:(self.rank + 1) * self._rw], group=self.pg)
         if noisy:
@@ -652,7 +657,7 @@ class DADStepEngine:
         else:
             check(L.dad_grad_reduce(self._dWp[0].data_ptr(), self._dbp[0].data_ptr(), S0, dw1, db1, S1, hb.dWc, hb.dbc, self.g_ext.data_ptr(), s))
             self.launches_per_step += 1
-            if self.world > 1:
+            if self.world > 1 and self.exchange != "skip":
                 import torch.distributed as dist
                 dist.all_reduce(self.g_ext, group=self.pg)
             # ---- clip + Adam + EMA (I/train.py:487-492)

@@ -52,3 +52,15 @@ for _ in range(10):
 e1.record()
 torch.cuda.synchronize()
 print(f"rank-0-of-{world} step without collectives (eager launches): {e0.elapsed_time(e1) / 10:.3f} ms; nmask={int(eng.nmask)} losses={eng.losses()}")
+if os.environ.get("PROF_RANK_GRAPH"):
+    # the same step as a replayed CUDA graph (what the bench runs), still without collectives: kernel chain + launch gaps only
+    eng.use_graph, eng.graph_after = True, 0
+    for _ in range(4):
+        eng.step(60)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20):
+        eng.step(60)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"rank-0-of-{world} step without collectives (graph replay): {e0.elapsed_time(e1) / 20:.3f} ms; launches/step {eng.launches_per_step}")
