@@ -445,7 +445,8 @@ def run_ours(args):
     variants = [("encoder_fwd_clean", "k_enc_fwd_tc", view_bytes, gemm_flops, 3,
                  lambda: eng._enc_fwd(eng.x_clean, eng.pad_clean, False, None, emb_c, eng.bits_clean, eng.lens_clean, _lib.stream_ptr(), xs=eng.xs_clean))]
     if eng.fused_noisy:
-        variants.append(("encoder_fwd_noisy_fused", "k_enc_fwd_tc", view_bytes, 2 * gemm_flops, 3,
+        fused_symbol = "k_enc_fwd_tp" if _lib.lib().dad_tc_get_cta_pair() == 2 else "k_enc_fwd_tc"  # default policy: the transposed CTA-pair kernel
+        variants.append(("encoder_fwd_noisy_fused", fused_symbol, view_bytes, 2 * gemm_flops, 3,
                          lambda: eng._enc_fwd_noisy_fused(aug_w, aug_s, emb_s, _lib.stream_ptr())))
     else:
         variants += [("encoder_fwd_weak", "k_enc_fwd_tc", view_bytes, gemm_flops, 3,

@@ -1689,6 +1689,7 @@ static BwdCarve bwd_carve(int64_t B) {
 }
 size_t enc_bwd_tc_ws_bytes(int64_t B, int64_t) { return bwd_carve(B).total; }
 
+static int g_bwd_lane = 0;
 int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, const uint32_t* bits, const void* xs_hi, const void* xs_lo,
                       const float* g_emb, const float* lens, float* dWp, float* dbp, int splits, void* ws, size_t ws_bytes, int64_t B, int64_t T,
                       cudaStream_t st) {
@@ -1709,6 +1710,24 @@ int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, c
     uint16_t* g_lo = reinterpret_cast<uint16_t*>(w8 + cv.g_lo);
     float* scal = reinterpret_cast<float*>(w8 + cv.scal);
     float* contrib = reinterpret_cast<float*>(w8 + cv.contrib);
+    // the bias gradient (ReLU bits x g/len, no GEMM operand) runs on the library's helper stream beside absmax -> prep -> dW GEMM
+    int wpu = 1;  // warps per utterance: enough warps in the grid to cover the load latency (~16 per SM)
+    while (wpu < DB_WARPS && B * wpu < (int64_t)sm_count() * 16) wpu *= 2;
+    const unsigned db_grid = (unsigned)ceil_div64(B * wpu, DB_WARPS);
+    const int64_t frames_per_lane = ceil_div64(ceil_div64(T, wpu) + 3, 4) + 1;
+    if (frames_per_lane >= 16384)
+        return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_bwd: T = %lld frames is beyond the bias-gradient counters (T < 65536)", (long long)T);
+    if (splits != enc_bwd_tc_splits(B)) return dad_set_error(DAD_ERR_ARG, "encoder_bwd(tc): splits must equal dad_encoder_bwd_splits()");
+    SideLane* lane = side_lane(g_bwd_lane);
+    const bool forked = side_fork(lane, st);
+    cudaStream_t sdb = forked ? lane->side : st;
+    if (frames_per_lane < 256)
+        k_bwd_db<8><<<db_grid, DB_WARPS * 32, 0, sdb>>>(bits, pad, g_emb, lens, contrib, (int)T, (int)B, wpu);
+    else
+        k_bwd_db<14><<<db_grid, DB_WARPS * 32, 0, sdb>>>(bits, pad, g_emb, lens, contrib, (int)T, (int)B, wpu);
+    DAD_CHECK_LAUNCH("k_bwd_db");
+    k_bwd_db_fold<<<splits, DAD_H, 0, sdb>>>(contrib, dbp, (int)B, (int)ceil_div64(B, splits));
+    DAD_CHECK_LAUNCH("k_bwd_db_fold");
     k_bwd_absmax<<<ABSMAX_GRID, DAD_H, 0, st>>>(g_emb, lens, scal, (int)B);
     DAD_CHECK_LAUNCH("k_bwd_absmax");
     k_bwd_prep<<<(unsigned)B, DAD_H, 0, st>>>(g_emb, lens, scal, g_hi, g_lo, scal + ABSMAX_GRID);
@@ -1717,7 +1736,6 @@ int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, c
     p.x = x; p.pad = pad; p.ap = ap; p.bits = bits; p.g_hi = g_hi; p.g_lo = g_lo; p.unscale = scal + ABSMAX_GRID; p.dWp = dWp;
     p.N = B * T; p.T = (int)T; p.B = (int)B;
     p.utt_per_split = bwd_utt_per_split(B);
-    if (splits != enc_bwd_tc_splits(B)) return dad_set_error(DAD_ERR_ARG, "encoder_bwd(tc): splits must equal dad_encoder_bwd_splits()");
     CUtensorMap tm_hi, tm_lo;
     memset(&tm_hi, 0, sizeof(tm_hi));
     memset(&tm_lo, 0, sizeof(tm_lo));
@@ -1734,18 +1752,7 @@ int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, c
     if (prods == 3) k_enc_bwd_tc<3><<<dim3(DAD_D / 256, splits), BWD_THREADS, BwdCfg<3>::SMEM, st>>>(tm_hi, tm_lo, p);
     else k_enc_bwd_tc<2><<<dim3(DAD_D / 256, splits), BWD_THREADS, BwdCfg<2>::SMEM, st>>>(tm_hi, tm_lo, p);
     DAD_CHECK_LAUNCH("k_enc_bwd_tc");
-    int wpu = 1;  // warps per utterance: enough warps in the grid to cover the load latency (~16 per SM)
-    while (wpu < DB_WARPS && B * wpu < (int64_t)sm_count() * 16) wpu *= 2;
-    const unsigned db_grid = (unsigned)ceil_div64(B * wpu, DB_WARPS);
-    const int64_t frames_per_lane = ceil_div64(ceil_div64(T, wpu) + 3, 4) + 1;
-    if (frames_per_lane < 256)
-        k_bwd_db<8><<<db_grid, DB_WARPS * 32, 0, st>>>(bits, pad, g_emb, lens, contrib, (int)T, (int)B, wpu);
-    else if (frames_per_lane < 16384)
-        k_bwd_db<14><<<db_grid, DB_WARPS * 32, 0, st>>>(bits, pad, g_emb, lens, contrib, (int)T, (int)B, wpu);
-    else
-        return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_bwd: T = %lld frames is beyond the bias-gradient counters (T < 65536)", (long long)T);
-    DAD_CHECK_LAUNCH("k_bwd_db");
-    k_bwd_db_fold<<<splits, DAD_H, 0, st>>>(contrib, dbp, (int)B, (int)ceil_div64(B, splits));
-    DAD_CHECK_LAUNCH("k_bwd_db_fold");
+    if (forked && !side_join(lane, st)) return dad_set_error(DAD_ERR_CUDA, "encoder_bwd: helper-stream join failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g_bwd_lane ^= 1;  // consecutive calls (clean view, strong view) alternate between the two helper lanes
     return DAD_OK;
 }

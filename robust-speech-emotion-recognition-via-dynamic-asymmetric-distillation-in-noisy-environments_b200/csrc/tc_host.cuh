@@ -46,5 +46,34 @@ int sm_count() {
     return n;
 }
 
+// A library-internal helper stream per device for work that is INDEPENDENT of a launcher's main chain (e.g. the bias gradient beside
+// the dW GEMM): fork() makes the helper stream wait for everything enqueued on `st` so far, join() makes `st` wait for the helper
+// stream.  Plain event record / wait: legal under stream capture (becomes a parallel branch of the captured graph).
+struct SideLane {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int dev = -1;
+};
+inline SideLane* side_lane(int which) {
+    static SideLane lanes[16][2];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    SideLane& l = lanes[dev][which & 1];
+    if (!l.side) {
+        if (cudaStreamCreateWithFlags(&l.side, cudaStreamNonBlocking) != cudaSuccess) { l.side = nullptr; return nullptr; }
+        if (cudaEventCreateWithFlags(&l.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&l.ev_join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        l.dev = dev;
+    }
+    return &l;
+}
+inline bool side_fork(SideLane* l, cudaStream_t st) {
+    return l && cudaEventRecord(l->ev_fork, st) == cudaSuccess && cudaStreamWaitEvent(l->side, l->ev_fork, 0) == cudaSuccess;
+}
+inline bool side_join(SideLane* l, cudaStream_t st) {
+    return l && cudaEventRecord(l->ev_join, l->side) == cudaSuccess && cudaStreamWaitEvent(st, l->ev_join, 0) == cudaSuccess;
+}
 
 }  // namespace

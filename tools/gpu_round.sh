@@ -36,7 +36,7 @@ echo "reference arm rc=$?"
 # full captures.  Launch arithmetic of `bench.py --no-graph` (30 CE-only pretraining steps = 1 forward + 1 backward each, then 3
 # warm-up steps of 2 forwards (clean, fused noisy) + 2 backwards): the first TIMED step's four encoder launches are launches 72..75
 # of the encoder kernels; its three ECDA tensor-core / elementwise kernels come after the 9 of the warm-up steps.
-timeout 500 ncu --set full --clock-control none --import-source on -k "regex:k_enc_(fwd|bwd)_tc" --launch-skip 72 -c 4 \
+timeout 500 ncu --set full --clock-control none --import-source on -k "regex:k_enc_(fwd|bwd)_t[cp]" --launch-skip 72 -c 4 \
     -o "$OUT/${R}_full_encoders" -f python bench.py --steps 1 --warmup 3 --no-graph --no-e2e --no-cpu-baseline --no-extra > "$OUT/${R}_ncu_full_encoders.log" 2>&1
 echo "ncu full (encoders) rc=$?"
 timeout 500 ncu --set full --clock-control none --import-source on -k "regex:k_gram_tc|k_pz_tc|k_ecda_p" --launch-skip 9 -c 3 \
