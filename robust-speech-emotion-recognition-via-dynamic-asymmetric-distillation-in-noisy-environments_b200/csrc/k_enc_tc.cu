@@ -681,28 +681,47 @@ int launch_fwd_variant(const CUtensorMap (&tw)[4], const CUtensorMap& txh, const
 //   accumulation (no shuffles), the bias is one register, and the ReLU word of (frame, 32 units) is one warp ballot.
 //   Same values as k_enc_fwd_tc<2, *>: same Philox counters, same f16x3 products in the same (k-block, product, k-step) order.
 // =====================================================================================================================
-constexpr int TP_TF = 128, TP_CF = 64;                  // frames per pair tile / frames converted by one CTA
-constexpr uint32_t TP_XB = TP_CF * BK * 2;              // 4 KB: hi or lo of one view of this CTA's frames, [64][32] fp16, SWIZZLE_64B
-constexpr uint32_t TP_WB = 128 * BK * 2;                // 8 KB: hi or lo of one net, this CTA's 128 hidden units
-constexpr uint32_t TP_OFF_X = 0, TP_OFF_W = 4 * TP_XB;  // [view][hi, lo] / [net][hi, lo]
-constexpr uint32_t TP_STAGE = 4 * TP_XB + 4 * TP_WB;    // 48 KB
-constexpr int TP_STAGES = 4;
-constexpr uint32_t TP_OFF_SCRATCH = TP_STAGES * TP_STAGE;          // 8 epilogue warps x 32 ballot words
-constexpr uint32_t TP_OFF_BARS = TP_OFF_SCRATCH + N_EPI_WARPS * 128;
-constexpr uint32_t TP_SMEM = TP_OFF_BARS + 256 + 1024;
+// NF = frames converted by one CTA per tile: 64 (N = 128 frames per pair tile: two tiles of accumulators in TMEM, four 48 KB stages) or
+// 128 (N = 256: every MMA re-reads its 4 KB W slice for 128 instead of 64 cycles of math and a W k-block is TMA-loaded once per 256
+// instead of 128 frames -- a third less shared-memory traffic per frame; one tile of accumulators fills the 512 TMEM columns, so the
+// MMAs of tile i+1 wait for the (cheap) epilogue of tile i while the converters run ahead into the three 64 KB stages).
+template <int NF>
+struct TpCfg {
+    static_assert(NF == 64 || NF == 128, "frames per CTA and tile");
+    static constexpr int CF = NF, TF = 2 * NF;                // frames per CTA / per pair tile (UMMA N)
+    static constexpr int HALVES = NF / 64;                     // a converter team walks a k-block in 64-row halves
+    static constexpr uint32_t XB = NF * BK * 2;                // 4 / 8 KB: hi or lo of one view of this CTA's frames, [NF][32] fp16, SWIZZLE_64B
+    static constexpr uint32_t WB = 128 * BK * 2;               // 8 KB: hi or lo of one net, this CTA's 128 hidden units
+    static constexpr uint32_t OFF_X = 0, OFF_W = 4 * XB;       // [view][hi, lo] / [net][hi, lo]
+    static constexpr uint32_t STAGE = 4 * XB + 4 * WB;         // 48 / 64 KB
+    static constexpr int STAGES = NF == 64 ? 4 : 3;
+    static constexpr int NBUF = NF == 64 ? 2 : 1;              // accumulator sets (2 views x TF columns each) in the 512 TMEM columns
+    static constexpr int NSET = NF == 64 ? 3 : 4;              // converter landing sets (units of 64 rows x 32 k in flight)
+    static constexpr uint32_t OFF_SCRATCH = STAGES * STAGE;    // 8 epilogue warps x 32 ballot words
+    static constexpr uint32_t OFF_BARS = OFF_SCRATCH + N_EPI_WARPS * 128;
+    static constexpr uint32_t SMEM = OFF_BARS + 256 + 1024;
+    static constexpr int MAX_STAGES = 4;
+};
 
 // converter warps: two teams of eight alternate k-blocks; thread (w8, lane) owns float4 column c4 = lane & 7 of the 32-wide k-block
-// and the rows w8*8 + (lane >> 3) + 4 i (i = 0, 1) of the CTA's 64 frames.  NSET register sets rotate over the team's k-blocks.
-template <bool PHILOX, int NSET>
+// and, per 64-row half hh, the rows 64 hh + w8*8 + (lane >> 3) + 4 i (i = 0, 1) of the CTA's frames.  A "unit" is one half of one
+// k-block (64 rows x 32 k); NSET register sets rotate over the team's units, the loads of the next NSET-1 units are in flight.
+template <int NF, bool PHILOX, int TEAMS>
 __device__ __forceinline__ void tp_convert(const FwdParams& p, uint8_t* smem, uint64_t* full, uint64_t* afull, uint64_t* empty, const int cw,
                                            const int lane, const uint32_t rank, const int unit0, const int ustride, const int n_units) {
-    constexpr int KT = KB / 2, GROUPS = KT / NSET;
-    static_assert(KT % NSET == 0, "a group of NSET team k-blocks must not straddle a tile");
+    using Cfg = TpCfg<NF>;
+    constexpr int H = Cfg::HALVES, STAGES = Cfg::STAGES;
+    constexpr int NSET = TEAMS == 3 ? 2 : Cfg::NSET;  // three teams run at 64 registers per thread: two landing sets
+    constexpr int KT = KB / TEAMS;             // k-blocks of one team per tile (kb = TEAMS k + team)
+    static_assert(KB % TEAMS == 0, "teams take the k-blocks round robin");
+    constexpr int UT = KT * H;                 // units of one team per tile
+    constexpr int GROUPS = UT / NSET, KPG = NSET / H;  // k-blocks per group
+    static_assert(UT % NSET == 0 && NSET % H == 0, "a group of NSET units must not straddle a tile and must hold whole k-blocks");
     const int team = cw >> 3, w8 = cw & 7;
     const int c4 = lane & 7, g = lane >> 3;
-    const int rbase = w8 * 8 + g;  // rows rbase, rbase + 4
+    const int rbase = w8 * 8 + g;  // rows 64 hh + rbase + 4 i
     const uint32_t a_sw = ((uint32_t)rbase >> 1) & 3u, c16 = (uint32_t)c4 >> 1;
-    const uint32_t sbase = tc::smem_u32(smem) + TP_OFF_X + (uint32_t)rbase * 64u + (uint32_t)(c4 & 1) * 8u;
+    const uint32_t sbase = tc::smem_u32(smem) + Cfg::OFF_X + (uint32_t)rbase * 64u + (uint32_t)(c4 & 1) * 8u;
     const uint32_t so0 = pin_reg(sbase + ((c16 ^ a_sw) << 4)), so1 = pin_reg(sbase + 256u + ((c16 ^ a_sw ^ 2u) << 4));
     const AugParams& apw = p.v[0].ap;
     const AugParams& aps = p.v[1].ap;
@@ -716,46 +735,51 @@ __device__ __forceinline__ void tp_convert(const FwdParams& p, uint8_t* smem, ui
     const bool cache = p.cache != 0;
     if (unit0 >= n_units) return;
 
-    auto frame0 = [&](int u) { return (int64_t)u * TP_TF + (int64_t)rank * TP_CF + rbase; };  // this thread's row 0 of unit u
-    auto tile_ptr = [&](int u) { return p.x + frame0(u) * DAD_D + team * BK + c4 * 4; };
-    auto tile_valid = [&](int u) -> uint32_t {
+    auto frame0 = [&](int u) { return (int64_t)u * Cfg::TF + (int64_t)rank * Cfg::CF + rbase; };  // this thread's row 0 of tile u
+    auto tile_ptr = [&](int u) { return p.x + frame0(u) * DAD_D + team * BK + c4 * 4; };  // + k * TEAMS * BK per team k-block
+    auto tile_valid = [&](int u) -> uint32_t {  // bit hh*2 + i: row 64 hh + 4 i of this thread lies inside the batch
         const int64_t r0 = frame0(u);
-        return (r0 < p.N ? 1u : 0u) | (r0 + 4 < p.N ? 2u : 0u);
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 2 * H; ++b) v |= (r0 + 64 * (b >> 1) + 4 * (b & 1) < p.N ? 1u : 0u) << b;
+        return v;
     };
-    auto load = [&](float4 (&dst)[2], const float* src, uint32_t valid) {
+    // unit (k, hh) of a tile: + k team-k-blocks of 2*BK floats, + hh * 64 rows
+    auto load = [&](float4 (&dst)[2], const float* tile, int k, int hh, uint32_t valid) {
+        const float* src = tile + k * TEAMS * BK + (int64_t)hh * 64 * DAD_D;
 #pragma unroll
         for (int i = 0; i < 2; ++i)
-            dst[i] = ((valid >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(src + (4 * i) * DAD_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            dst[i] = ((valid >> (hh * 2 + i)) & 1u) ? __ldg(reinterpret_cast<const float4*>(src + (4 * i) * DAD_D)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     auto store_row = [&](uint32_t a_hi, const float4& v, float sc) {
         uint32_t h01, l01, h23, l23;
         tc::split2_f16(v.x * sc, v.y * sc, h01, l01);
         tc::split2_f16(v.z * sc, v.w * sc, h23, l23);
         tc::sts64(a_hi, h01, h23);
-        tc::sts64(a_hi + TP_XB, l01, l23);
+        tc::sts64(a_hi + Cfg::XB, l01, l23);
     };
 
-    uint32_t s = (uint32_t)team, ph = 0;  // stage / phase of the team's k-block being converted (advance by 2; TP_STAGES is even)
+    uint32_t it = (uint32_t)team;  // running k-block index of the team's k-block being converted (advance by TEAMS): stage it % STAGES
     int u = unit0;
     const float* ptr_cur = tile_ptr(u);
     uint32_t v_cur = tile_valid(u);
     float4 buf[NSET][2];
 #pragma unroll
-    for (int j = 0; j < NSET - 1; ++j) load(buf[j], ptr_cur + j * 2 * BK, v_cur);
+    for (int j = 0; j < NSET - 1; ++j) load(buf[j], ptr_cur, j / H, j % H, v_cur);
     for (; u < n_units; u += ustride) {
         const bool more = u + ustride < n_units;
         const float* ptr_next = more ? tile_ptr(u + ustride) : ptr_cur;
         const uint32_t v_next = more ? tile_valid(u + ustride) : 0u;
         const int64_t n0 = frame0(u);
-        uint32_t zspan = 0;  // bit i: row i lies inside the temporal mask span (strong view)
+        uint32_t zspan = 0;  // bit hh*2 + i: the row lies inside the temporal mask span (strong view)
         if (has_span) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int64_t n = n0 + 4 * i;
+            for (int b = 0; b < 2 * H; ++b) {
+                const int64_t n = n0 + 64 * (b >> 1) + 4 * (b & 1);
                 if (n < p.N) {
                     const uint32_t bb = (uint32_t)n / (uint32_t)p.T, t = (uint32_t)n - bb * (uint32_t)p.T;
                     const int st0 = __ldg(aps.t_start + bb);
-                    if ((int)t >= st0 && (int)t < st0 + aps.mask_len) zspan |= 1u << i;
+                    if ((int)t >= st0 && (int)t < st0 + aps.mask_len) zspan |= 1u << b;
                 }
             }
         }
@@ -767,31 +791,38 @@ __device__ __forceinline__ void tp_convert(const FwdParams& p, uint8_t* smem, ui
             const bool last = grp == GROUPS - 1;
 #pragma unroll
             for (int j = 0; j < NSET; ++j) {
-                const int k = grp * NSET + j;  // the team's k-th k-block of this tile: kb = 2 k + team
+                const int k = grp * KPG + j / H;  // the team's k-th k-block of this tile: kb = TEAMS k + team
+                const int hh = j % H;
+                const int kb = TEAMS * k + team;
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                // ---- prefetch unit q + NSET - 1 (of the next tile in the last group)
+                {
+                    const int jn = (j + NSET - 1) % NSET;  // slot being refilled = the one consumed in the previous iteration
+                    if (j == 0) load(buf[jn], ptr_cur, grp * KPG + (NSET - 1) / H, (NSET - 1) % H, v_cur);
+                    else if (!last) load(buf[jn], ptr_cur, (grp + 1) * KPG + (j - 1) / H, (j - 1) % H, v_cur);
+                    else load(buf[jn], ptr_next, (j - 1) / H, (j - 1) % H, v_next);
+                }
                 float4 keep = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (has_keep) keep = __ldg(reinterpret_cast<const float4*>(aps.feat_keep + (2 * k + team) * BK + c4 * 4));
-                // ---- prefetch the team's k-block k + NSET - 1 (of the next tile in the last group)
-                if (j == 0 || !last) load(buf[(j + NSET - 1) % NSET], ptr_cur + (k + NSET - 1) * 2 * BK, v_cur);
-                else load(buf[(j + NSET - 1) % NSET], ptr_next + (j - 1) * 2 * BK, v_next);
-                // ---- convert k-block kb
-                tc::mbar_wait_addr(empty_addr + s * 8u, ph ^ 1u);
-                const uint32_t stage_off = s * TP_STAGE;
+                if (has_keep) keep = __ldg(reinterpret_cast<const float4*>(aps.feat_keep + kb * BK + c4 * 4));
+                if (hh == 0) tc::mbar_wait_addr(empty_addr + s * 8u, ph ^ 1u);
+                const uint32_t stage_off = s * Cfg::STAGE + (uint32_t)hh * 4096u;  // 64 rows x 64 bytes per half
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
+                    const int rb = hh * 2 + i;
                     float4 vw = buf[j][i], vs = buf[j][i];
                     if (PHILOX) {
                         if (!(p.dbg & 4)) {
-                        const uint4 w = noise_words(seed, blk, gn0 + 4 * i, (uint32_t)((2 * k + team) * (BK / 4) + c4));
-                        NoiseBM4 z;
-                        bm4_from_words(w.x, w.y, rk_w, z);
-                        vw = bm4_add(z, vw);
-                        bm4_from_words(w.z, w.w, rk_s, z);
-                        vs = bm4_add(z, vs);
+                            const uint4 w = noise_words(seed, blk, gn0 + 64 * hh + 4 * i, (uint32_t)(kb * (BK / 4) + c4));
+                            NoiseBM4 z;
+                            bm4_from_words(w.x, w.y, rk_w, z);
+                            vw = bm4_add(z, vw);
+                            bm4_from_words(w.z, w.w, rk_s, z);
+                            vs = bm4_add(z, vs);
                         }
                     } else {
                         // parity mode: supplied unit normals, out = x + (n * sigma) with two fp32 roundings (bit-exact vs I/utils.py:330,338)
-                        const bool inr = (v_cur >> i) & 1u;
-                        const int64_t e = (int64_t)(4 * i) * DAD_D + k * 2 * BK;
+                        const bool inr = (v_cur >> rb) & 1u;
+                        const int64_t e = (int64_t)(64 * hh + 4 * i) * DAD_D + k * TEAMS * BK;
                         const float4 nw = inr ? __ldg(reinterpret_cast<const float4*>(nzw + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
                         vw.x = aug_add_noise(vw.x, nw.x, apw.sigma); vw.y = aug_add_noise(vw.y, nw.y, apw.sigma);
                         vw.z = aug_add_noise(vw.z, nw.z, apw.sigma); vw.w = aug_add_noise(vw.w, nw.w, apw.sigma);
@@ -803,20 +834,21 @@ __device__ __forceinline__ void tp_convert(const FwdParams& p, uint8_t* smem, ui
                         vs.x = __fmul_rn(vs.x, keep.x); vs.y = __fmul_rn(vs.y, keep.y); vs.z = __fmul_rn(vs.z, keep.z); vs.w = __fmul_rn(vs.w, keep.w);
                     }
                     const uint32_t a_row = stage_off + (i ? so1 : so0);
-                    const float sc_s = ((zspan >> i) & 1u) ? 0.f : TC_XS;
+                    const float sc_s = ((zspan >> rb) & 1u) ? 0.f : TC_XS;
                     if (!(p.dbg & 8) || vw.x == 12345.f) {
-                    store_row(a_row, vw, TC_XS);
-                    store_row(a_row + 2 * TP_XB, vs, sc_s);
+                        store_row(a_row, vw, TC_XS);
+                        store_row(a_row + 2 * Cfg::XB, vs, sc_s);
                     }
                 }
-                tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma / TMA (async proxy)
-                __syncwarp();
-                if (lane == 0) {
-                    tc::mbar_arrive_cluster(full_addr + s * 8u);
-                    if (cache) tc::mbar_arrive_addr(afull_addr + s * 8u);
+                if (hh == H - 1) {
+                    tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma / TMA (async proxy)
+                    __syncwarp();
+                    if (lane == 0) {
+                        tc::mbar_arrive_cluster(full_addr + s * 8u);
+                        if (cache) tc::mbar_arrive_addr(afull_addr + s * 8u);
+                    }
+                    it += TEAMS;
                 }
-                s += 2;
-                if (s >= (uint32_t)TP_STAGES) { s -= TP_STAGES; ph ^= 1u; }
             }
         }
         ptr_cur = ptr_next;
@@ -824,35 +856,45 @@ __device__ __forceinline__ void tp_convert(const FwdParams& p, uint8_t* smem, ui
     }
 }
 
-__global__ void __launch_bounds__(FWD_THREADS, 1)
+// TEAMS = 2: 896 threads (4 control + 16 converter + 8 epilogue warps, setmaxnreg 32 / 88 / 56).  TEAMS = 3: 1024 threads at 64
+// registers (4 control + 24 converter + 4 epilogue warps, each epilogue warp drains both views of its lane quadrant): the converters
+// are bound by their own latencies (Philox rounds, MUFU chains) with four warps per scheduler -- six warps give the schedulers more
+// to choose from -- and the epilogue, hidden under the next tile, has time to spare.
+template <int NF, int TEAMS>
+__global__ void __launch_bounds__(128 + TEAMS * 256 + (TEAMS == 3 ? 128 : 256), 1)
 k_enc_fwd_tp(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant__ CUtensorMap tm_w0lo, const __grid_constant__ CUtensorMap tm_w1hi,
              const __grid_constant__ CUtensorMap tm_w1lo, const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
              FwdParams p) {
+    using Cfg = TpCfg<NF>;
+    constexpr int STAGES = Cfg::STAGES, NBUF = Cfg::NBUF;
+    constexpr uint32_t TF = Cfg::TF;
+    constexpr int CONV_WARPS = TEAMS * 8, EPI_W0 = CONV_WARP0 + CONV_WARPS, EPI_WARPS = TEAMS == 3 ? 4 : 8, VIEWS_PER_EPI = 8 / EPI_WARPS;
+    constexpr bool SETREG = TEAMS == 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TP_OFF_BARS);
-    uint64_t* full = bars;                     // [4] leader CTA: 1 (TMA expect_tx) + 8 converter warps of each CTA
-    uint64_t* afull = bars + TP_STAGES;        // [4] 8 local converter warps (operand-cache store)
-    uint64_t* empty = bars + 2 * TP_STAGES;    // [4] 1 (tcgen05.commit, multicast to both CTAs) + 1 (operand-cache store warp)
-    uint64_t* tfull = bars + 3 * TP_STAGES;    // [2] 1 (tcgen05.commit, multicast)
-    uint64_t* tempty = tfull + 2;              // [2] leader CTA: 8 epilogue warps of each CTA
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS);
+    uint64_t* full = bars;                          // [STAGES] leader CTA: 1 (TMA expect_tx) + 8 converter warps of each CTA
+    uint64_t* afull = bars + Cfg::MAX_STAGES;       // [STAGES] 8 local converter warps (operand-cache store)
+    uint64_t* empty = bars + 2 * Cfg::MAX_STAGES;   // [STAGES] 1 (tcgen05.commit, multicast to both CTAs) + 1 (operand-cache store warp)
+    uint64_t* tfull = bars + 3 * Cfg::MAX_STAGES;   // [2] 1 (tcgen05.commit, multicast)
+    uint64_t* tempty = tfull + 2;                   // [2] leader CTA: 8 epilogue warps of each CTA
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
     const int unit0 = (int)(blockIdx.x >> 1), ustride = (int)(gridDim.x >> 1);
-    const int n_units = (int)ceil_div64(p.N, TP_TF);  // pair tiles of 128 frames
+    const int n_units = (int)ceil_div64(p.N, TF);  // pair tiles
 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tm_w0hi); tc::prefetch_tmap(&tm_w0lo); tc::prefetch_tmap(&tm_w1hi); tc::prefetch_tmap(&tm_w1lo);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < TP_STAGES; ++s) {
-            tc::mbar_init(&full[s], 1 + (FWD_CONV_WARPS / 2) * 2);
-            tc::mbar_init(&afull[s], FWD_CONV_WARPS / 2);
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&full[s], 1 + 8 * 2);  // one team of eight converter warps per CTA fills a stage
+            tc::mbar_init(&afull[s], 8);
             tc::mbar_init(&empty[s], 1 + (p.cache ? 1 : 0));
         }
-        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], N_EPI_WARPS * 2); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], EPI_WARPS * 2); }
         tc::fence_barrier_init();
     }
     tc::cluster_sync();  // the peer's barriers exist before anyone arrives on them remotely
@@ -864,56 +906,56 @@ k_enc_fwd_tp(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
 
     if (warp == 0) {
         // ===================== TMA producer: this CTA's 128 hidden units of both nets, hi / lo =====================
-        tc::reg_dec<32>();
+        if (SETREG) tc::reg_dec<32>();
         if (lane == 0) {
             const uint32_t full_remote = tc::mapa(tc::smem_u32(full), 0);
             const int r0 = (int)rank * 128;
             uint32_t it = 0;
             for (int u = unit0; u < n_units; u += ustride)
                 for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const uint32_t s = it % TP_STAGES, ph = (it / TP_STAGES) & 1;
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     tc::mbar_wait(&empty[s], ph ^ 1);
-                    uint8_t* w0 = smem + s * TP_STAGE + TP_OFF_W;
-                    if ((p.dbg & 2) && it >= (uint32_t)TP_STAGES) {  // timing experiment: W stays what the first fill left
+                    uint8_t* w0 = smem + s * Cfg::STAGE + Cfg::OFF_W;
+                    if ((p.dbg & 2) && it >= (uint32_t)STAGES) {  // timing experiment: W stays what the first fill left
                         if (rank == 0) tc::mbar_arrive(&full[s]);
                         continue;
                     }
-                    if (rank == 0) tc::mbar_arrive_expect_tx(&full[s], 2 * 4 * TP_WB);  // the bytes of BOTH CTAs land on the leader's barrier
+                    if (rank == 0) tc::mbar_arrive_expect_tx(&full[s], 2 * 4 * Cfg::WB);  // the bytes of BOTH CTAs land on the leader's barrier
                     const uint32_t fb = full_remote + s * 8u;
                     tc::tma_load_2d_pair(w0, &tm_w0hi, fb, kb * BK, r0);
-                    tc::tma_load_2d_pair(w0 + TP_WB, &tm_w0lo, fb, kb * BK, r0);
-                    tc::tma_load_2d_pair(w0 + 2 * TP_WB, &tm_w1hi, fb, kb * BK, r0);
-                    tc::tma_load_2d_pair(w0 + 3 * TP_WB, &tm_w1lo, fb, kb * BK, r0);
+                    tc::tma_load_2d_pair(w0 + Cfg::WB, &tm_w0lo, fb, kb * BK, r0);
+                    tc::tma_load_2d_pair(w0 + 2 * Cfg::WB, &tm_w1hi, fb, kb * BK, r0);
+                    tc::tma_load_2d_pair(w0 + 3 * Cfg::WB, &tm_w1lo, fb, kb * BK, r0);
                 }
-            for (int k = 0; k < TP_STAGES; ++k, ++it) {  // every (multicast) commit to this CTA's empty[] has landed before the CTA may exit
-                const uint32_t s = it % TP_STAGES, ph = (it / TP_STAGES) & 1;
+            for (int k = 0; k < STAGES; ++k, ++it) {  // every (multicast) commit to this CTA's empty[] has landed before the CTA may exit
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                 tc::mbar_wait(&empty[s], ph ^ 1);
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA): A = W rows (M = 256 over the pair), B = converted frames (N = 128) ==========
-        tc::reg_dec<32>();
+        // ===================== MMA issuer (leader CTA): A = W rows (M = 256 over the pair), B = converted frames (N = TF) ==========
+        if (SETREG) tc::reg_dec<32>();
         if (rank == 0) {
-            constexpr uint32_t idesc = tc::make_idesc_f16(256, TP_TF, 0, 0);
+            constexpr uint32_t idesc = tc::make_idesc_f16(256, (int)TF, 0, 0);
             uint32_t it = 0, ti = 0;
             for (int u = unit0; u < n_units; u += ustride, ++ti) {
-                const uint32_t ab = ti & 1, tph = (ti >> 1) & 1;
+                const uint32_t ab = NBUF == 2 ? (ti & 1) : 0u, tph = NBUF == 2 ? ((ti >> 1) & 1) : (ti & 1);
                 tc::mbar_wait_cluster(&tempty[ab], tph ^ 1);
                 tc::tcgen05_fence_after();
                 for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const uint32_t s = it % TP_STAGES, ph = (it / TP_STAGES) & 1;
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     tc::mbar_wait_cluster(&full[s], ph);
                     tc::tcgen05_fence_after();
                     if (lane == 0) {
-                        const uint32_t base = tc::smem_u32(smem + s * TP_STAGE);
+                        const uint32_t base = tc::smem_u32(smem + s * Cfg::STAGE);
 #pragma unroll
                         for (int v = 0; v < 2; ++v) {
-                            const uint32_t d_tmem = tmem_base + ab * 256u + (uint32_t)v * TP_TF;
+                            const uint32_t d_tmem = tmem_base + ab * 2u * TF + (uint32_t)v * TF;
 #pragma unroll
                             for (int prod = 0; prod < 3; ++prod) {  // x_hi*W_hi, x_hi*W_lo, x_lo*W_hi
                                 if ((p.dbg & 1) && prod > 0) break;
-                                const uint32_t w_off = TP_OFF_W + v * 2 * TP_WB + ((prod == 1) ? TP_WB : 0u);
-                                const uint32_t x_off = TP_OFF_X + v * 2 * TP_XB + ((prod == 2) ? TP_XB : 0u);
+                                const uint32_t w_off = Cfg::OFF_W + v * 2 * Cfg::WB + ((prod == 1) ? Cfg::WB : 0u);
+                                const uint32_t x_off = Cfg::OFF_X + v * 2 * Cfg::XB + ((prod == 2) ? Cfg::XB : 0u);
 #pragma unroll
                                 for (int k = 0; k < BK / 16; ++k) {
                                     const uint64_t ad = tc::make_smem_desc_sw64(base + w_off + k * 32);
@@ -929,34 +971,37 @@ k_enc_fwd_tp(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
                 }
             }
         }
-    } else if (warp >= CONV_WARP0 && warp < CONV_WARP0 + FWD_CONV_WARPS) {
-        tc::reg_inc<88>();
+    } else if (warp >= CONV_WARP0 && warp < EPI_W0) {
+        if (SETREG) tc::reg_inc<88>();
         const int cw = warp - CONV_WARP0;
-        if (p.v[1].ap.noise_src == 1) tp_convert<true, 3>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units);
-        else tp_convert<false, 3>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units);
-    } else if (warp >= FWD_EPI_WARP0) {
+        if (p.v[1].ap.noise_src == 1) tp_convert<NF, true, TEAMS>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units);
+        else tp_convert<NF, false, TEAMS>(p, smem, full, afull, empty, cw, lane, rank, unit0, ustride, n_units);
+    } else if (warp >= EPI_W0) {
         // ===================== epilogue: lane = hidden unit, column = frame =====================
         // warp (q = ew & 3, view = ew >> 2) drains TMEM lanes 32 q .. 32 q + 31 (units rank*128 + 32 q + lane) of its view: per
         // 32-frame group a serial per-lane sum of relu(pre) over the valid frames (slot 0: frames of the group's first utterance,
         // slot 1: of the second, T >= 32) and one ballot per frame = the ReLU word (frame, units 32 (4 rank + q) ..) of the backward.
-        tc::reg_dec<56>();
-        const int ew = warp - FWD_EPI_WARP0;
-        const int q = ew & 3, view = ew >> 2;
-        const FwdView& V = p.v[view];
+        if (SETREG) tc::reg_dec<56>();
+        const int ew = warp - EPI_W0;
+        const int q = ew & 3, view0 = EPI_WARPS == 8 ? (ew >> 2) : 0;
         const int unit = (int)rank * 128 + q * 32 + lane;
-        const float bias = __ldg(V.bias + unit);
         const uint32_t wword = rank * 4u + (uint32_t)q;
-        const uint32_t scratch = tc::smem_u32(smem + TP_OFF_SCRATCH) + (uint32_t)ew * 128u;
+        const uint32_t scratch = tc::smem_u32(smem + Cfg::OFF_SCRATCH) + (uint32_t)ew * 128u;
         const uint32_t tempty_remote = tc::mapa(tc::smem_u32(tempty), 0);
         uint32_t ti = 0;
         for (int u = unit0; u < n_units; u += ustride, ++ti) {
-            const uint32_t ab = ti & 1, tph = (ti >> 1) & 1;
+            const uint32_t ab = NBUF == 2 ? (ti & 1) : 0u, tph = NBUF == 2 ? ((ti >> 1) & 1) : (ti & 1);
             tc::mbar_wait(&tfull[ab], tph);
             tc::tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256u + (uint32_t)view * TP_TF;
 #pragma unroll 1
-            for (int kg = 0; kg < 4; ++kg) {
-                const int64_t n0g = (int64_t)u * TP_TF + 32 * kg;
+            for (int vi = 0; vi < VIEWS_PER_EPI; ++vi) {
+            const int view = view0 + vi;
+            const FwdView& V = p.v[view];
+            const float bias = __ldg(V.bias + unit);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 2u * TF + (uint32_t)view * TF;
+#pragma unroll 1
+            for (int kg = 0; kg < (int)TF / 32; ++kg) {
+                const int64_t n0g = (int64_t)u * TF + 32 * kg;
                 const int64_t n = n0g + lane;
                 const bool in = n < p.N;
                 const uint32_t validw = __ballot_sync(0xffffffffu, in && !(p.pad && p.pad[n]));
@@ -995,30 +1040,31 @@ k_enc_fwd_tp(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
                 const uint32_t myw = tc::lds32(scratch + (uint32_t)lane * 4u);  // the ReLU word of frame n0g + lane
                 __syncwarp();
                 if (V.bits && in) V.bits[n * DAD_HW + wword] = myw;
-                const int64_t gidx = (int64_t)u * 4 + kg;
+                const int64_t gidx = n0g >> 5;
                 V.part[(gidx * 2 + 0) * DAD_H + unit] = s0;
                 V.part[(gidx * 2 + 1) * DAD_H + unit] = s1;
+            }
             }
             tc::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_cluster(tempty_remote + ab * 8u);
         }
     } else if (warp == 3) {
-        // ===================== operand-cache store: the strong view's hi (/ lo) tiles of THIS CTA's 64 frames, shared -> global by TMA =====
-        tc::reg_dec<32>();
+        // ===================== operand-cache store: the strong view's hi (/ lo) tiles of THIS CTA's frames, shared -> global by TMA =====
+        if (SETREG) tc::reg_dec<32>();
         if (p.cache && lane == 0) {
             tc::prefetch_tmap(&tm_xhi);
             if (p.cache > 1) tc::prefetch_tmap(&tm_xlo);
             uint32_t it = 0;
             for (int u = unit0; u < n_units; u += ustride) {
-                const int64_t f0 = (int64_t)u * TP_TF + (int64_t)rank * TP_CF;
+                const int64_t f0 = (int64_t)u * TF + (int64_t)rank * Cfg::CF;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const uint32_t s = it % TP_STAGES, ph = (it / TP_STAGES) & 1;
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     tc::mbar_wait(&afull[s], ph);
-                    const uint8_t* a = smem + s * TP_STAGE + TP_OFF_X + 2 * TP_XB;
+                    const uint8_t* a = smem + s * Cfg::STAGE + Cfg::OFF_X + 2 * Cfg::XB;
                     if (f0 < p.N) {
                         tc::tma_store_2d(&tm_xhi, a, kb * BK, (int)f0);
-                        if (p.cache > 1) tc::tma_store_2d(&tm_xlo, a + TP_XB, kb * BK, (int)f0);
+                        if (p.cache > 1) tc::tma_store_2d(&tm_xlo, a + Cfg::XB, kb * BK, (int)f0);
                         tc::bulk_commit();
                         tc::bulk_wait_read0();
                     }
@@ -1028,7 +1074,7 @@ k_enc_fwd_tp(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
             tc::bulk_wait0();
         }
     } else {
-        tc::reg_dec<32>();  // warp 2 (TMEM allocator)
+        if (SETREG) tc::reg_dec<32>();  // warp 2 (TMEM allocator)
     }
     tc::tcgen05_fence_before();
     __syncthreads();
@@ -1039,14 +1085,34 @@ k_enc_fwd_tp(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
     }
 }
 
+// frames per CTA and tile of the transposed kernel: 64; DAD_TC_TP_NF=128 selects the N = 256 form (kept for experiments)
+int tp_frames_per_cta(int64_t N) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("DAD_TC_TP_NF"); forced = e ? atoi(e) : 0; }
+    if (forced == 64 || forced == 128) return forced;
+    (void)N;
+    return 64;  // measured (B=4096, T=200): 2.28-2.36 ms with 64 frames per CTA, 2.44-2.55 ms with 128
+}
+
+// converter teams of the transposed kernel: 2; DAD_TC_TP_TEAMS=3 selects the 24-converter-warp form (kept for experiments: measured
+// SLOWER, 2.49-2.62 ms against 2.18-2.41 ms at B=4096, T=200 -- more warps in flight do not help a kernel that runs at the board's
+// power limit, and at 64 registers the converter body loses instruction-level parallelism)
+int tp_teams() {
+    static int t = -1;
+    if (t < 0) { const char* e = getenv("DAD_TC_TP_TEAMS"); t = e ? atoi(e) : 2; if (t != 2 && t != 3) t = 2; }
+    return t;
+}
+
+template <int NF, int TEAMS>
 int launch_fwd_tp(const CUtensorMap (&tw)[4], const CUtensorMap& txh, const CUtensorMap& txl, const FwdParams& p, cudaStream_t st) {
+    using Cfg = TpCfg<NF>;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_enc_fwd_tp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM);
-        if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "aug_encoder_fwd(tp): cannot opt in to %u B shared memory: %s", TP_SMEM, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(k_enc_fwd_tp<NF, TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "aug_encoder_fwd(tp): cannot opt in to %u B shared memory: %s", Cfg::SMEM, cudaGetErrorString(e));
         attr = true;
     }
-    const int units = (int)ceil_div64(p.N, TP_TF), max_pairs = sm_count() / 2;
+    const int units = (int)ceil_div64(p.N, Cfg::TF), max_pairs = sm_count() / 2;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cudaLaunchAttribute at[1];
@@ -1054,11 +1120,11 @@ int launch_fwd_tp(const CUtensorMap (&tw)[4], const CUtensorMap& txh, const CUte
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cfg.blockDim = dim3(FWD_THREADS);
-    cfg.dynamicSmemBytes = TP_SMEM;
+    cfg.blockDim = dim3(128 + TEAMS * 256 + (TEAMS == 3 ? 128 : 256));
+    cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = st;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_enc_fwd_tp, tw[0], tw[1], tw[2], tw[3], txh, txl, p);
-    if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "k_enc_fwd_tp launch: %s", cudaGetErrorString(e));
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_enc_fwd_tp<NF, TEAMS>, tw[0], tw[1], tw[2], tw[3], txh, txl, p);
+    if (e != cudaSuccess) return dad_set_error(DAD_ERR_CUDA, "k_enc_fwd_tp<%d> launch: %s", NF, cudaGetErrorString(e));
     return DAD_OK;
 }
 
@@ -1106,6 +1172,7 @@ int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W0_hi, con
     }
     const bool noisy = ap0.mode != 0;
     const bool tp = nv == 2 && !shared && cta2_mode() == 2;  // training's fused noisy forward: the transposed CTA-pair kernel
+    const int tp_nf = tp ? tp_frames_per_cta(B * T) : 0;
     const bool cta2 = tp || cta2_mode() == 1 || (cta2_mode() == 2 && !noisy);
     const uint32_t wrows = cta2 ? 128 : 256;
     CUtensorMap tw[4], txh, txl;
@@ -1133,12 +1200,13 @@ int launch_enc_fwd_tc(const float* x, const uint8_t* pad, const void* W0_hi, con
     p.shared_a = shared ? 1 : 0;
     p.cache = xs_hi ? (xs_lo ? 2 : 1) : 0;
     if (p.cache) {
-        rc = make_tmap_f16_sw64(&txh, xs_hi, (uint64_t)(B * T), tp ? TP_CF : BM);
-        if (!rc && p.cache > 1) rc = make_tmap_f16_sw64(&txl, xs_lo, (uint64_t)(B * T), tp ? TP_CF : BM);
+        rc = make_tmap_f16_sw64(&txh, xs_hi, (uint64_t)(B * T), tp ? (uint32_t)tp_nf : BM);
+        if (!rc && p.cache > 1) rc = make_tmap_f16_sw64(&txl, xs_lo, (uint64_t)(B * T), tp ? (uint32_t)tp_nf : BM);
         if (rc) return rc;
     }
     p.N = B * T; p.T = (int)T; p.num_tiles = (int)ceil_div64(B * T, BM);
-    if (tp) rc = launch_fwd_tp(tw, txh, txl, p, st);
+    if (tp && tp_nf == 128) rc = launch_fwd_tp<128, 2>(tw, txh, txl, p, st);
+    else if (tp) rc = tp_teams() == 3 ? launch_fwd_tp<64, 3>(tw, txh, txl, p, st) : launch_fwd_tp<64, 2>(tw, txh, txl, p, st);
     else if (nv == 2) rc = cta2 ? launch_fwd_variant<2, true>(tw, txh, txl, p, st) : launch_fwd_variant<2, false>(tw, txh, txl, p, st);
     else rc = cta2 ? launch_fwd_variant<1, true>(tw, txh, txl, p, st) : launch_fwd_variant<1, false>(tw, txh, txl, p, st);
     if (rc) return rc;
