@@ -400,6 +400,9 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         eng.step(args.epoch)
     sync()
+    if eng.exchange == "p2p":
+        eng._sym[32:64].zero_()  # wait statistics of the flag barriers (csrc/dad_optim.cuh peer_flag_barrier)
+        torch.cuda.synchronize(dev)
     sampler = ClockSampler(local)
     sampler.start()
     small = 2 * B * T * D_IN * 4 < 2 * 126e6  # working set not >> L2: flush L2 between steps and time steps individually
@@ -415,16 +418,34 @@ def run_ours(args):
         ms = tot / args.steps
     else:
         e0.record()
+        th0 = time.perf_counter()
         for _ in range(args.steps):
             eng.step(args.epoch)
+        host_enqueue_ms = (time.perf_counter() - th0) * 1e3 / args.steps  # host time to enqueue one step (no sync inside the loop)
         e1.record()
         sync()
         ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.summary()
+    ms_own = ms
     if world > 1:
         t = torch.tensor([ms], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = float(t)
+    barrier_wait = None
+    host_enqueue = None
+    if world > 1 and not small:
+        he = torch.tensor([host_enqueue_ms, ms_own], device=dev, dtype=torch.float64)
+        allh = [torch.zeros_like(he) for _ in range(world)]
+        torch.distributed.all_gather(allh, he)
+        host_enqueue = {"host_ms_per_step": [round(float(a[0]), 4) for a in allh], "device_ms_per_step": [round(float(a[1]), 4) for a in allh]}
+    if eng.exchange == "p2p":
+        # average microseconds per step that rank i (row) waited for rank j (column) at the pack / gradient barrier: the row maximum
+        # is what the barrier cost that rank, a column of large values names a late rank
+        w = eng._sym[32:64].view(torch.int64).to(torch.float64).reshape(2, 8)[:, :world] / (1e3 * args.steps)
+        allw = [torch.zeros_like(w) for _ in range(world)]
+        torch.distributed.all_gather(allw, w.contiguous())
+        barrier_wait = {"gradient_us": [[round(float(v), 1) for v in a[0]] for a in allw],
+                        "pack_us": [[round(float(v), 1) for v in a[1]] for a in allw]}
     launches = eng.launches_per_step * args.steps
     losses = eng.losses()
     value = Bg / (ms * 1e-3)
@@ -602,7 +623,7 @@ def run_ours(args):
                        "cta_pair": cfg_snapshot["cta_pair"], "bwd_products": cfg_snapshot["bwd_products"],
                        "l2": "inputs >> L2 (126 MB)" if not small else "L2 flushed (256 MB write) between individually timed steps"},
             "clocks": clocks, "e2e": e2e, "e2e_resident": e2e_resident, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "losses_last_step": losses, "dp_check": dpc, "extra_workloads": extra,
+            "losses_last_step": losses, "dp_check": dpc, "barrier_wait": barrier_wait, "per_rank": host_enqueue, "extra_workloads": extra,
         }))
     if world > 1:
         if eng is not None:

@@ -23,9 +23,17 @@ __device__ __forceinline__ void peer_flag_barrier(const PeerPtrs& peers, int wor
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(seq) : "memory");
         const unsigned* mine = reinterpret_cast<const unsigned*>(reinterpret_cast<char*>(peers.p[rank]) + flag_off) + r;
         unsigned v;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
         } while ((int)(v - seq) < 0);
+        // wait statistics (diagnostics, read by bench.py --gpus N): nanoseconds this rank spent waiting for rank r at the odd (pack)
+        // and even (gradient) barriers of a step, accumulated in the unused upper half of the flag block [16 x u64 at byte 128]
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        unsigned long long* dbg = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peers.p[rank]) + flag_off + 128) + (seq & 1u) * 8u + r;
+        *dbg += t1 - t0;
     }
 }
 
