@@ -118,9 +118,12 @@ int dad_predict(const float* x, const uint8_t* pad, const void* Ws_hi, const voi
                 size_t ws_bytes, int64_t B, int64_t T, void* stream);
 
 /* Process-wide switches of the tcgen05 encoder kernels (also DAD_TC_CTA2 / DAD_TC_BWD_PRODUCTS in the environment):
- *  cta_pair      forward kernels as CTA pairs (cluster of 2, tcgen05.mma.cta_group::2): 0 = never, 1 = always, 2 (default) = for
- *                the clean / inference launches (bound by the MMAs' shared-memory operand traffic), not for the noisy ones
- *                (bound by their converters)
+ *  cta_pair      forward kernels as CTA pairs (cluster of 2, tcgen05.mma.cta_group::2): 0 = never, 1 = always ([frames x units]
+ *                orientation), 2 (default) = CTA pairs for the clean / inference launches (bound by the MMAs' shared-memory operand
+ *                traffic), single CTAs for the one-view noisy launches, and the TRANSPOSED CTA-pair kernel k_enc_fwd_tp for
+ *                dad_aug_encoder_fwd (weights as the A operand, frames as B, two tiles of accumulators in TMEM: DESIGN.md 5.1).
+ *                Experiment switches of that kernel, environment only: DAD_TC_TP_NF=128 (256-frame tiles), DAD_TC_TP_TEAMS=3
+ *                (24 converter warps), DAD_TC_DBG (timing experiments, wrong results)
  *  bwd_products  3 (default) = dW GEMM as dpre_hi*x_hi + dpre_hi*x_lo + dpre_lo*x_hi (fp32-grade); 2 = x_hi only (xs_lo unused):
  *                a third less tensor work and half the operand cache, but gradient errors of ~1e-4 relative on cancelling
  *                elements -- outside the parity tolerances, opt-in */
