@@ -401,7 +401,7 @@ def run_ours(args):
         eng.step(args.epoch)
     sync()
     if eng.exchange == "p2p":
-        eng._sym[32:64].zero_()  # wait statistics of the flag barriers (csrc/dad_optim.cuh peer_flag_barrier)
+        eng._sym[16:64].zero_()  # wait statistics of the flag barriers (csrc/dad_optim.cuh peer_flag_barrier)
         torch.cuda.synchronize(dev)
     sampler = ClockSampler(local)
     sampler.start()
@@ -444,8 +444,12 @@ def run_ours(args):
         w = eng._sym[32:64].view(torch.int64).to(torch.float64).reshape(2, 8)[:, :world] / (1e3 * args.steps)
         allw = [torch.zeros_like(w) for _ in range(world)]
         torch.distributed.all_gather(allw, w.contiguous())
+        pd = eng._sym[16:32].view(torch.int64)[1:2].to(torch.float64) / (1e3 * args.steps)  # push duration (k_peer_push_barrier)
+        allp = [torch.zeros_like(pd) for _ in range(world)]
+        torch.distributed.all_gather(allp, pd.contiguous())
         barrier_wait = {"gradient_us": [[round(float(v), 1) for v in a[0]] for a in allw],
-                        "pack_us": [[round(float(v), 1) for v in a[1]] for a in allw]}
+                        "pack_us": [[round(float(v), 1) for v in a[1]] for a in allw],
+                        "pack_push_us": [round(float(a[0]), 1) for a in allp]}
     launches = eng.launches_per_step * args.steps
     losses = eng.losses()
     value = Bg / (ms * 1e-3)

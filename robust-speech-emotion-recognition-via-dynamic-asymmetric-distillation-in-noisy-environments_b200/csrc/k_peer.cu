@@ -49,6 +49,14 @@ __global__ void __launch_bounds__(32) k_peer_barrier(PeerPtrs peers, int world, 
 __global__ void __launch_bounds__(256) k_peer_push_barrier(const char* __restrict__ src, PeerPtrs peers, int world, int self_rank, size_t dst_off,
                                                            size_t bytes, size_t flag_off, unsigned* local_seq, unsigned* counter) {
     __shared__ unsigned s_last, s_seq;
+    // diagnostics (bench.py --gpus N): [flag block + 64] = start time of this launch, [+72] = accumulated ns from start to the
+    // moment the last CTA has fenced its stores (= duration of the push itself, before the barrier)
+    unsigned long long* dbg = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peers.p[self_rank]) + flag_off + 64);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        dbg[0] = t;
+    }
     const size_t n16 = bytes >> 4;  // segments are 16-byte multiples (launcher check)
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     // every 16-byte chunk is loaded once and stored to all peers back to back (remote stores are posted: nothing waits per store)
@@ -70,6 +78,12 @@ __global__ void __launch_bounds__(256) k_peer_push_barrier(const char* __restric
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const unsigned long long t0 = *reinterpret_cast<volatile unsigned long long*>(dbg);
+        if (t > t0) dbg[1] += t - t0;
+    }
     peer_flag_barrier(peers, world, self_rank, flag_off, s_seq);
     __syncthreads();
     __threadfence_system();
