@@ -37,6 +37,7 @@ _COMMON = dict(
     PRINT_MODEL_INFO=True, DEBUG_MODE=False, VERBOSE_LOGGING=True,
     # B200 additions (not in the reference): kernel arithmetic + noise source of the fused step
     DAD_GEMM_MODE=os.environ.get("DAD_GEMM", "tc"), DAD_USE_CUDA_GRAPH=True,
+    DAD_T_BUCKET=0,  # > 0: training batches are padded to a multiple of this many frames so that step shapes repeat (CUDA-graph replay); 0 = reference padding
     DAD_DEVICE_DATA=True,  # keep each split's features resident in HBM and assemble batches on the device (dataload.DeviceUtteranceLoader)
     DAD_SYNTHETIC_DATA=False,  # trainers built without explicit loaders use synthetic stand-in features (offline runs, runner tests)
 )

@@ -116,10 +116,20 @@ class UtteranceLoader:
     def __len__(self):
         return (len(self.dataset) + self.batch_size - 1) // self.batch_size
 
+    # 0 = pad every batch to ITS OWN longest utterance, exactly as the reference collator (I/dataload_clean.py:177-193).  b > 0 pads to
+    # the next multiple of b frames (cfg.DAD_T_BUCKET, training loaders only): shuffled batches then fall into a few dozen padded
+    # lengths and the step engine replays captured CUDA graphs instead of enqueueing ~30 launches eagerly per step.  Opt-in because
+    # the strong augmentation's span length is int(T_padded * TEMPORAL_MASK_RATIO) (I/utils.py:366): bucketing moves it by < b/10 frames.
+    t_bucket = 0
+
+    def _padded_len(self, t_max):
+        b = int(self.t_bucket)
+        return t_max if b <= 0 else (t_max + b - 1) // b * b
+
     def collate(self, ids):
         """ids [b] (positions inside the split) -> reference batch dict (I/dataload_clean.py:177-193), one vectorised gather."""
         sizes, offs = self.sizes[ids], self.offsets[ids]
-        b, T = len(ids), int(sizes.max())
+        b, T = len(ids), self._padded_len(int(sizes.max()))
         t = torch.arange(T)
         pad = t[None, :] >= sizes[:, None]
         src = (offs[:, None] + t[None, :]).masked_fill(pad, 0)
@@ -181,7 +191,7 @@ class DeviceUtteranceLoader(UtteranceLoader):
 
     def collate(self, ids):
         from . import ops
-        T = int(self.sizes[ids].max())  # host copy of the lengths: no device sync
+        T = self._padded_len(int(self.sizes[ids].max()))  # host copy of the lengths: no device sync
         ids_dev = ids.to(self.device, non_blocking=True)
         x_out = pad_out = None
         if self.sink is not None:

@@ -197,6 +197,9 @@ class CrossDomainTrainer:
         clean, noisy = self._loaders(self.cfg.BATCH_SIZE) if self._loaders is not None else self._make_loaders(self.cfg.BATCH_SIZE)
         self.clean_train_loader, self.clean_val_loader, self.clean_test_loader, self.class_names, self.num_classes = clean
         self.noisy_student_loader, self.noisy_teacher_loader, self.noisy_val_loader, self.noisy_test_loader = noisy
+        for ld in (self.clean_train_loader, self.noisy_student_loader, self.noisy_teacher_loader):
+            if hasattr(ld, "t_bucket"):
+                ld.t_bucket = int(getattr(self.cfg, "DAD_T_BUCKET", 0))  # 0: the reference's per-batch padding (dataload.UtteranceLoader.t_bucket)
         logger.info(f"loaders: clean {len(self.clean_train_loader)}/{len(self.clean_val_loader)}/{len(self.clean_test_loader)} batches, "
                     f"noisy {len(self.noisy_student_loader)}/{len(self.noisy_val_loader)}/{len(self.noisy_test_loader)} batches")
         if self.TRACK_BIAS:
@@ -255,6 +258,9 @@ class CrossDomainTrainer:
             else:
                 for b in ld:
                     T = max(T, int(b["net_input"]["feats"].shape[1]))
+        bk = int(getattr(self.cfg, "DAD_T_BUCKET", 0))
+        if bk > 0:
+            T = (T + bk - 1) // bk * bk  # bucketed padding (dataload.UtteranceLoader.t_bucket) rounds the longest batch up
         return int(self.cfg.BATCH_SIZE), T
 
     def _setup_training_components(self):
