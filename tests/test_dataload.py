@@ -40,6 +40,21 @@ def test_vectorised_collator_equals_reference_layout():
     assert seen == 6 and len(va) == 2 and len(va.dataset) == 6  # ragged last batch kept, like DataLoader(drop_last=False)
 
 
+def test_bucketed_padding_is_opt_in_and_only_appends_padding():
+    """cfg.DAD_T_BUCKET / UtteranceLoader.t_bucket: default 0 = the reference's per-batch padding; b > 0 rounds the padded length
+    up to a multiple of b and changes nothing but the number of trailing padded (zero, masked) frames."""
+    fs, _ = dataload.synthetic_feature_sets(5, 6, t_min=3, t_max=17, seed=3)
+    _, va, _, _, _ = dataload.get_cv_dataloaders(None, 4, fold_id=1, label_dict=LD, feature_set=fs)
+    assert va.t_bucket == 0
+    ref = [b for b in va]
+    va.t_bucket = 8
+    for b, r in zip(va, ref):
+        x, pad, T0 = b["net_input"]["feats"], b["net_input"]["padding_mask"], r["net_input"]["feats"].shape[1]
+        assert x.shape[1] % 8 == 0 and T0 <= x.shape[1] < T0 + 8
+        assert torch.equal(x[:, :T0], r["net_input"]["feats"]) and torch.equal(pad[:, :T0], r["net_input"]["padding_mask"])
+        assert bool(pad[:, T0:].all()) and float(x[:, T0:].abs().sum()) == 0.0
+
+
 def test_fold_tables_and_speaker_isolation():
     assert dataload.iemocap_fold_sessions(1) == ([1, 2, 3], 4, 5) and dataload.iemocap_fold_sessions(5) == ([5, 1, 2], 3, 4)
     with pytest.raises(ValueError):
