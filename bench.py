@@ -518,6 +518,9 @@ def run_ours(args):
                 "avg_launch_ms": dk["avg_launch_ms"], "achieved": dk["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": dk["GBps"] / peaks["hbm_gbs"], "traffic": dk["traffic"], "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dk["alg_bytes_per_launch"], "kernels": kern,
+                "note": ("the dominant launch is the fused noisy forward: ONE read of x_noisy (its algorithmic bytes) feeds two GEMMs (weak -> teacher, "
+                         "strong -> student), so its HBM fraction is low by construction and `tensor_3pass` is the roofline that binds it"
+                         if dk["kernel"] == "k_enc_fwd_tp" else None),
                 # the same launches seen from the tensor pipe (executed fp16 products; fp32-grade accuracy costs 3 per algorithmic FLOP in
                 # the forward), against the BURST peak: these kernels are timed in isolation
                 "tensor_3pass": {"achieved": dk["tensor_TFLOPs"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
