@@ -1,5 +1,8 @@
 """GPU (-m gpu): op-level parity of the CUDA kernels, called through the C ABI, against the oracle and the
 reference-generated golden vectors.  Augmentation must be BIT-EXACT; floating-point ops within the stated tolerances."""
+import os
+import sys
+
 import pytest
 import torch
 
@@ -286,6 +289,19 @@ def test_fused_noisy_forward_vs_oracle(B, T, cta_pair, tc_switch):
     assert torch.allclose(emb_t.cpu(), ref_t, rtol=1e-4, atol=2e-5), float((emb_t.cpu() - ref_t).abs().max())
     assert torch.allclose(emb_s.cpu(), ref_s, rtol=1e-4, atol=2e-5), float((emb_s.cpu() - ref_s).abs().max())
     assert torch.equal(lens.cpu(), (~ph).sum(1).float())
+
+
+@pytest.mark.parametrize("env", [{"DAD_TC_TP_NF": "128"}, {"DAD_TC_TP_TEAMS": "3"}], ids=["256-frame-tiles", "three-converter-teams"])
+def test_transposed_kernel_experiment_variants_pass_the_same_parity_tests(env):
+    """The two opt-in forms of k_enc_fwd_tp that DESIGN.md 5.1 reports as measured-and-slower (N = 256 frames per tile; 24 converter
+    warps) are selected by environment variables read once per process, so they are exercised in a child process: the fused-forward
+    parity tests above (bit-identical ReLU bits / operand cache, embeddings to fp32 rounding, oracle) must pass unchanged."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_ops.py"), "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider",
+                        "-k", "fused_noisy and transposed and not experiment"], env={**os.environ, **env}, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
 
 
 @pytest.mark.parametrize("B,T,padded", [(6, 64, True), (37, 41, True), (64, 200, False), (5, 97, True)])
