@@ -123,7 +123,7 @@ int dad_predict(const float* x, const uint8_t* pad, const void* Ws_hi, const voi
  *                traffic), single CTAs for the one-view noisy launches, and the TRANSPOSED CTA-pair kernel k_enc_fwd_tp for
  *                dad_aug_encoder_fwd (weights as the A operand, frames as B, two tiles of accumulators in TMEM: DESIGN.md 5.1).
  *                Experiment switches of that kernel, environment only: DAD_TC_TP_NF=128 (256-frame tiles), DAD_TC_TP_TEAMS=3
- *                (24 converter warps), DAD_TC_DBG (timing experiments, wrong results)
+ *                (24 converter warps), DAD_TC_DBG (timing experiments with wrong results; only in builds with -DDAD_TC_EXPERIMENTS)
  *  bwd_products  3 (default) = dW GEMM as dpre_hi*x_hi + dpre_hi*x_lo + dpre_lo*x_hi (fp32-grade); 2 = x_hi only (xs_lo unused):
  *                a third less tensor work and half the operand cache, but gradient errors of ~1e-4 relative on cancelling
  *                elements -- outside the parity tolerances, opt-in */

@@ -32,9 +32,11 @@ def build(force=False, verbose=False):
         if force or not _newer(obj, [src] + hdrs):
             jobs.append((src, obj))
 
+    extra = os.environ.get("DAD_NVCC_FLAGS", "").split()  # e.g. -DDAD_TC_EXPERIMENTS (timing-experiment switches, tools/gpu_dbg.sh)
+
     def cc(job):
         src, obj = job
-        cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [nvcc] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, r
 

@@ -34,6 +34,15 @@
 
 namespace {
 
+// Timing experiments (DAD_TC_DBG=<bits> in the environment: 1 one product instead of three, 2 no W re-loads, 4 no noise, 8 no A
+// stores -- wrong results, tools/gpu_dbg.sh) exist only in builds with -DDAD_TC_EXPERIMENTS (DAD_NVCC_FLAGS=-DDAD_TC_EXPERIMENTS
+// python csrc/build.py --force); in the product build the switch is a compile-time zero and the branches vanish.
+#ifdef DAD_TC_EXPERIMENTS
+#define TC_DBG(p, bit) (((p).dbg & (bit)) != 0)
+#else
+#define TC_DBG(p, bit) false
+#endif
+
 constexpr int BM = 128, BK = 32, KB = DAD_D / BK;  // 24 k-blocks of 32
 constexpr int FWD_THREADS = 896;                                          // 4 control + 16 converter + 8 epilogue warps
 constexpr int FWD_CONV_WARPS = 16, FWD_EPI_WARP0 = 20, N_EPI_WARPS = 8;
@@ -386,7 +395,7 @@ k_enc_fwd_tc(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
                             const uint32_t d_tmem = tmem_base + (NV == 1 ? acc : (uint32_t)v) * DAD_H;
 #pragma unroll
                             for (int prod = 0; prod < 3; ++prod) {
-                                if ((p.dbg & 1) && prod > 0) break;
+                                if (TC_DBG(p, 1) && prod > 0) break;
                                 const uint32_t a_off = Cfg::OFF_A + (p.shared_a ? 0 : v) * 2 * A_BYTES + ((prod == 2) ? A_BYTES : 0u);  // hi*hi, hi*lo, lo*hi
                                 const uint32_t b_off = Cfg::OFF_W + v * 2 * Cfg::W_BYTES + ((prod == 1) ? Cfg::W_BYTES : 0u);
 #pragma unroll
@@ -811,7 +820,7 @@ __device__ __forceinline__ void tp_convert(const FwdParams& p, uint8_t* smem, ui
                     const int rb = hh * 2 + i;
                     float4 vw = buf[j][i], vs = buf[j][i];
                     if (PHILOX) {
-                        if (!(p.dbg & 4)) {
+                        if (!TC_DBG(p, 4)) {
                             const uint4 w = noise_words(seed, blk, gn0 + 64 * hh + 4 * i, (uint32_t)(kb * (BK / 4) + c4));
                             NoiseBM4 z;
                             bm4_from_words(w.x, w.y, rk_w, z);
@@ -835,7 +844,7 @@ __device__ __forceinline__ void tp_convert(const FwdParams& p, uint8_t* smem, ui
                     }
                     const uint32_t a_row = stage_off + (i ? so1 : so0);
                     const float sc_s = ((zspan >> rb) & 1u) ? 0.f : TC_XS;
-                    if (!(p.dbg & 8) || vw.x == 12345.f) {
+                    if (!TC_DBG(p, 8) || vw.x == 12345.f) {
                         store_row(a_row, vw, TC_XS);
                         store_row(a_row + 2 * Cfg::XB, vs, sc_s);
                     }
@@ -916,7 +925,7 @@ k_enc_fwd_tp(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     tc::mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* w0 = smem + s * Cfg::STAGE + Cfg::OFF_W;
-                    if ((p.dbg & 2) && it >= (uint32_t)STAGES) {  // timing experiment: W stays what the first fill left
+                    if (TC_DBG(p, 2) && it >= (uint32_t)STAGES) {  // timing experiment: W stays what the first fill left
                         if (rank == 0) tc::mbar_arrive(&full[s]);
                         continue;
                     }
@@ -953,7 +962,7 @@ k_enc_fwd_tp(const __grid_constant__ CUtensorMap tm_w0hi, const __grid_constant_
                             const uint32_t d_tmem = tmem_base + ab * 2u * TF + (uint32_t)v * TF;
 #pragma unroll
                             for (int prod = 0; prod < 3; ++prod) {  // x_hi*W_hi, x_hi*W_lo, x_lo*W_hi
-                                if ((p.dbg & 1) && prod > 0) break;
+                                if (TC_DBG(p, 1) && prod > 0) break;
                                 const uint32_t w_off = Cfg::OFF_W + v * 2 * Cfg::WB + ((prod == 1) ? Cfg::WB : 0u);
                                 const uint32_t x_off = Cfg::OFF_X + v * 2 * Cfg::XB + ((prod == 2) ? Cfg::XB : 0u);
 #pragma unroll

@@ -1,5 +1,6 @@
 #!/bin/bash
-# Timing experiments on the transposed-pair fused forward (DAD_TC_DBG bits: 1 one product, 2 no W reloads, 4 no noise, 8 no A stores)
+# Timing experiments on the transposed-pair fused forward (DAD_TC_DBG bits: 1 one product, 2 no W reloads, 4 no noise, 8 no A stores).
+# Needs a library built with the experiment switches: DAD_NVCC_FLAGS=-DDAD_TC_EXPERIMENTS python <pkg>/csrc/build.py --force
 OUT=gpurun_out; mkdir -p $OUT
 for d in 0 1 2 4 8 3 6 12 15; do
   echo -n "dbg=$d "; DAD_TC_DBG=$d timeout 200 python - <<'PY'
