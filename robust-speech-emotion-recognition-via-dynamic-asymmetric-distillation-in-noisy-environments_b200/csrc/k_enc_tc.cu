@@ -1795,7 +1795,7 @@ int launch_enc_bwd_tc(const float* x, const uint8_t* pad, const AugParams& ap, c
     if (frames_per_lane >= 16384)
         return dad_set_error(DAD_ERR_UNSUPPORTED, "encoder_bwd: T = %lld frames is beyond the bias-gradient counters (T < 65536)", (long long)T);
     if (splits != enc_bwd_tc_splits(B)) return dad_set_error(DAD_ERR_ARG, "encoder_bwd(tc): splits must equal dad_encoder_bwd_splits()");
-    SideLane* lane = side_lane(g_bwd_lane);
+    SideLane* lane = side_lane(g_bwd_lane, st);
     const bool forked = side_fork(lane, st);
     cudaStream_t sdb = forked ? lane->side : st;
     if (frames_per_lane < 256)

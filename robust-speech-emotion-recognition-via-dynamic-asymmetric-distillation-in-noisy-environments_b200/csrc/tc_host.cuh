@@ -54,7 +54,7 @@ struct SideLane {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int dev = -1;
 };
-inline SideLane* side_lane(int which) {
+inline SideLane* side_lane(int which, cudaStream_t st) {
     static SideLane lanes[16][2];
     static std::mutex mu;
     int dev = 0;
@@ -62,6 +62,10 @@ inline SideLane* side_lane(int which) {
     std::lock_guard<std::mutex> lk(mu);
     SideLane& l = lanes[dev][which & 1];
     if (!l.side) {
+        // never create streams / events while `st` is being captured (resource creation is not a capturable operation): a launcher
+        // whose very first call on this device happens under capture simply stays on its main stream for that graph
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
         if (cudaStreamCreateWithFlags(&l.side, cudaStreamNonBlocking) != cudaSuccess) { l.side = nullptr; return nullptr; }
         if (cudaEventCreateWithFlags(&l.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&l.ev_join, cudaEventDisableTiming) != cudaSuccess) return nullptr;

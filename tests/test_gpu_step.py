@@ -190,6 +190,31 @@ def test_philox_mode_runs_and_is_deterministic():
     assert l["supervised_ce_loss"] > 0 and l["total_loss"] == l["total_loss"]  # finite
 
 
+def test_step_captured_on_first_sight_equals_eager_first():
+    """graph_after = 0 captures a (shape, schedule) key the first time it is seen, i.e. the library's launchers may run for the
+    very first time on this device UNDER stream capture (the bias-gradient helper lane of dad_encoder_bwd must not create streams
+    or events there): the run must equal the default eager-first policy bit for bit."""
+    from dad_b200 import _lib, synth
+    from dad_b200.engine import DADStepEngine
+    from helpers import cfg_for, pretrained_state
+    cfg = cfg_for("iemocap")
+    outs = []
+    for graph_after in (0, 1):
+        eng = DADStepEngine(cfg, 16, 64, gemm_mode=_lib.GEMM_TC, use_graph=True, noise_mode="philox", seed=3)
+        eng.graph_after = graph_after
+        eng.load_state_dict(pretrained_state())
+        eng.init_teacher()
+        eng.set_lr(5e-4)
+        c, n = synth.make_batches(16, 64, 5)
+        eng.set_inputs(_to_dev(c), _to_dev(n))
+        for _ in range(3):
+            eng.step(45)
+        torch.cuda.synchronize()
+        assert eng.graph_stats["eager"] == graph_after and eng.graph_stats["captured"] == 1
+        outs.append((eng.p.clone(), eng.t.clone(), eng.losses()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+
+
 @pytest.mark.parametrize("mode", ["fp32", "tc"])
 @pytest.mark.parametrize("Bc,Tc,Bn,Tn", [(13, 40, 16, 50), (16, 64, 9, 33), (5, 20, 5, 48)])
 def test_ragged_batches_and_capacity_engine(mode, Bc, Tc, Bn, Tn):
