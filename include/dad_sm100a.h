@@ -248,8 +248,11 @@ int dad_scl(const dad_scl_args* a, void* stream);
  *   dad_peer_push     copy `bytes` (multiple of 4) from `src_local` to offset `dst_offset` of every peer's buffer
  *                     (own buffer too when include_self)
  *   dad_peer_barrier  all ranks' earlier pushes are complete and visible; `flag_offset` = byte offset of a zero-initialised
- *                     array of `world` u32 inside the exchange buffer, `local_seq` = zero-initialised device counter private to
- *                     this rank.  Every rank must call its barriers in the same order.
+ *                     256-BYTE flag block inside the exchange buffer -- bytes [0, 4*world): the barrier flags (one u32 per rank);
+ *                     [64, 80): start time / accumulated duration of dad_peer_push_barrier's copy; [128, 256): 16 x u64
+ *                     accumulated nanoseconds this rank waited for rank r at the odd / even barriers (diagnostics written by
+ *                     the barrier itself, read by bench.py --gpus N) -- `local_seq` = zero-initialised device counter private
+ *                     to this rank.  Every rank must call its barriers in the same order.
  *   dad_grad_sum_ranks  out[e] = sum over r = 0..world-1 of stage[r][e]  (fixed order: identical result on every rank) */
 int dad_peer_push(const void* src_local, void* const* peers, int32_t world, int32_t self_rank, int32_t include_self,
                   size_t dst_offset, size_t bytes, void* stream);
